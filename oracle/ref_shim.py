@@ -1,0 +1,90 @@
+"""Run the UNMODIFIED reference classes (filippocastelli/GPnet, mounted read-only at /root/reference in
+the build container) under the three shims of SURVEY.md Appendix B.  TEST INFRASTRUCTURE ONLY
+(see oracle/__init__.py); used by oracle/make_golden.py to produce tests/golden/*.npz.  The reference
+does not exist on the GPU box, so nothing imported by -m gpu tests, smoke() or bench.py touches this.
+
+Shims (none edits a reference file):
+ 1. a stub ``matplotlib`` package (the reference imports pyplot/pylab/lines at module level,
+    GPnet.py:4,8; matplotlib is not installed here);
+ 2. ``GPnet.sl`` -> proxy of scipy.linalg whose ``expm`` accepts the sparse matrix the reference passes
+    (GPnet.py:340, delegated to scipy.sparse.linalg.expm as 2018 scipy did) and whose ``inv`` returns
+    an ndarray subclass with ``.toarray()`` (GPnet.py:342);
+ 3. the eager all-pairs shortest paths + Kamada-Kawai layout of ``__init__`` (GPnet.py:204-207) are
+    patched out for speed (unused by the hot path).
+"""
+import importlib
+import sys
+import types
+
+import numpy as np
+import scipy.linalg
+import scipy.sparse
+import scipy.sparse.linalg
+
+REFERENCE_PATH = "/root/reference"
+
+
+class _Inert:
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Inert()
+
+    def __getattr__(self, name):
+        return _Inert()
+
+    def __iter__(self):
+        return iter(())
+
+
+def _install_matplotlib_stub():
+    if "matplotlib" in sys.modules and not getattr(sys.modules["matplotlib"], "_gpnet_stub", False):
+        return
+    root = types.ModuleType("matplotlib")
+    root._gpnet_stub = True
+    root.__path__ = []
+    for sub in ("pyplot", "pylab", "lines", "patches", "cm", "colors"):
+        m = types.ModuleType("matplotlib." + sub)
+        m.__getattr__ = lambda name, _m=sub: _Inert()
+        setattr(root, sub, m)
+        sys.modules["matplotlib." + sub] = m
+    sys.modules["matplotlib"] = root
+
+
+class _ArrayWithToarray(np.ndarray):
+    def toarray(self):
+        return np.asarray(self)
+
+
+class _ScipyLinalgProxy:
+    def __getattr__(self, name):
+        return getattr(scipy.linalg, name)
+
+    @staticmethod
+    def expm(A):
+        if scipy.sparse.issparse(A):
+            return scipy.sparse.linalg.expm(scipy.sparse.csc_matrix(A))
+        return scipy.linalg.expm(A)
+
+    @staticmethod
+    def inv(A):
+        return np.asarray(scipy.linalg.inv(np.asarray(A))).view(_ArrayWithToarray)
+
+
+def load_reference(path=REFERENCE_PATH):
+    """Returns (GPnet module, GPnetRegressor class, GPnetClassifier class) of the shimmed reference."""
+    _install_matplotlib_stub()
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    for name in ("GPnet", "GPnetRegressor", "GPnetClassifier"):
+        mod = sys.modules.get(name)
+        if mod is not None and not str(getattr(mod, "__file__", "")).startswith(path):
+            del sys.modules[name]
+    gp = importlib.import_module("GPnet")
+    gp.sl = _ScipyLinalgProxy()
+    gp.GPnetBase.calc_shortest_paths = lambda self: setattr(self, "dist", None)
+    gp.nx.kamada_kawai_layout = lambda G, *a, **k: {}
+    reg = importlib.import_module("GPnetRegressor").GPnetRegressor
+    cls = importlib.import_module("GPnetClassifier").GPnetClassifier
+    return gp, reg, cls
