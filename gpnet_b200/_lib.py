@@ -1,0 +1,278 @@
+"""ctypes binding of libgpnet_b200.so (the C-ABI declared in include/gpnet_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or no sm_100a GPU is visible, loading /
+context creation raises.  torch is used only as plumbing by callers (device tensors for the unit-level
+primitives, torch.distributed for the sharded landscape); the drop-in classes work without importing it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpnet_b200.so")
+
+KERNEL_IDS = {"diffusion": 0, "regularized_laplacian": 1, "pstep_walk": 2}
+
+c_int_p = C.POINTER(C.c_int)
+c_dbl_p = C.POINTER(C.c_double)
+c_long_p = C.POINTER(C.c_long)
+
+# name -> (restype, argtypes); every symbol declared in include/gpnet_b200.h
+SIGNATURES = {
+    "gpn_create": (C.c_void_p, [C.c_int, C.c_void_p]),
+    "gpn_destroy": (None, [C.c_void_p]),
+    "gpn_last_error": (C.c_char_p, []),
+    "gpn_sync": (C.c_int, [C.c_void_p]),
+    "gpn_launch_count": (C.c_longlong, [C.c_void_p]),
+    "gpn_flop_count": (C.c_double, [C.c_void_p]),
+    "gpn_reset_counters": (None, [C.c_void_p]),
+    "gpn_set_graph": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_dbl_p]),
+    "gpn_set_nodes": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int, c_int_p]),
+    "gpn_laplacian_dense": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_long]),
+    "gpn_gemm_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_long,
+                               C.c_void_p, C.c_long, C.c_double, C.c_void_p, C.c_long]),
+    "gpn_potrf_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, c_int_p]),
+    "gpn_spd_inverse_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, c_int_p]),
+    "gpn_gather_block_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double,
+                                       C.c_void_p, C.c_long]),
+    "gpn_kernel_build": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, C.c_int]),
+    "gpn_kernel_ptr": (C.c_void_p, [C.c_void_p, c_long_p]),
+    "gpn_expm_info": (None, [C.c_void_p, c_int_p, c_int_p]),
+    "gpn_kernel_block_h": (C.c_int, [C.c_void_p, c_int_p, C.c_int, c_int_p, C.c_int, C.c_double, c_dbl_p]),
+    "gpn_gpr_logp_grad": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_int_p]),
+    "gpn_gpr_predict": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p]),
+    "gpn_gpr_fetch": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p]),
+    "gpn_gpc_newton": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, C.c_int, C.c_void_p, C.c_long, C.c_double,
+                                 C.c_double, C.c_double, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p]),
+    "gpn_gpc_predict": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_dbl_p,
+                                  c_dbl_p, c_dbl_p, c_int_p]),
+    "gpn_landscape": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dbl_p, C.c_int, C.c_int, C.c_int, c_dbl_p, C.c_int, c_dbl_p,
+                                C.c_int, c_dbl_p, C.c_long, C.c_long, C.c_long, C.c_int, c_dbl_p]),
+}
+
+_lib = None
+
+
+class GpnetError(RuntimeError):
+    """A C-ABI call returned a negative status (bad argument or CUDA error)."""
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the in-tree shared library and attach the prototypes.  Raises if it is missing (build it
+    with ``python -c 'import __graft_entry__ as g; g.build()'`` or ``make -C gpnet_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found: the CUDA library has not been built (no CPU fallback exists)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(c_dbl_p)
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(c_int_p)
+
+
+def _f64(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+
+
+def _i32(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int32).reshape(-1))
+
+
+class Context:
+    """One library context (one GPU, one stream).  Thin, explicit wrapper: every method is one C-ABI call."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load_library()
+        self.h = self.lib.gpn_create(int(device), C.c_void_p(stream) if stream else None)
+        if not self.h:
+            raise GpnetError("gpn_create failed: " + self.lib.gpn_last_error().decode())
+        self.device = int(device)
+        self.N = 0
+        self.n_train = 0
+        self.n_test = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gpn_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- status handling ---------------------------------------------------------------------------
+    def _check(self, st: int, what: str):
+        if st < 0:
+            raise GpnetError(f"{what} failed with status {st}: {self.lib.gpn_last_error().decode()}")
+        return st
+
+    # -- graph / node sets ---------------------------------------------------------------------------
+    def set_graph(self, indptr, indices, weights=None):
+        indptr, indices = _i32(indptr), _i32(indices)
+        N = len(indptr) - 1
+        w = None if weights is None else _f64(weights)
+        if w is not None and np.all(w == 1.0):
+            w = None
+        self._check(self.lib.gpn_set_graph(self.h, N, _ip(indptr), _ip(indices), None if w is None else _dp(w)), "gpn_set_graph")
+        self.N = N
+        self.n_train = self.n_test = 0
+
+    def set_nodes(self, train, test=()):
+        tr, te = _i32(sorted(int(x) for x in train)), _i32(sorted(int(x) for x in test))
+        self._check(self.lib.gpn_set_nodes(self.h, len(tr), _ip(tr), len(te), _ip(te)), "gpn_set_nodes")
+        self.n_train, self.n_test = len(tr), len(te)
+
+    # -- counters -----------------------------------------------------------------------------------
+    def sync(self):
+        self._check(self.lib.gpn_sync(self.h), "gpn_sync")
+
+    def launch_count(self) -> int:
+        return int(self.lib.gpn_launch_count(self.h))
+
+    def flop_count(self) -> float:
+        return float(self.lib.gpn_flop_count(self.h))
+
+    def reset_counters(self):
+        self.lib.gpn_reset_counters(self.h)
+
+    # -- device-pointer primitives (pointers are ints, e.g. torch.Tensor.data_ptr()) --------------------
+    def laplacian_dense(self, alpha, gamma, out_ptr, ld):
+        self._check(self.lib.gpn_laplacian_dense(self.h, alpha, gamma, C.c_void_p(out_ptr), ld), "gpn_laplacian_dense")
+
+    def gemm(self, transa, transb, M, N, K, alpha, a_ptr, lda, b_ptr, ldb, beta, c_ptr, ldc):
+        self._check(self.lib.gpn_gemm_f64(self.h, int(transa), int(transb), M, N, K, alpha, C.c_void_p(a_ptr), lda, C.c_void_p(b_ptr),
+                                          ldb, beta, C.c_void_p(c_ptr), ldc), "gpn_gemm_f64")
+
+    def potrf(self, n, a_ptr, lda) -> int:
+        info = C.c_int(0)
+        self._check(self.lib.gpn_potrf_f64(self.h, n, C.c_void_p(a_ptr), lda, C.byref(info)), "gpn_potrf_f64")
+        return info.value
+
+    def spd_inverse(self, n, a_ptr, lda, out_ptr, ldo, work_ptr) -> int:
+        info = C.c_int(0)
+        self._check(self.lib.gpn_spd_inverse_f64(self.h, n, C.c_void_p(a_ptr), lda, C.c_void_p(out_ptr), ldo, C.c_void_p(work_ptr),
+                                                 C.byref(info)), "gpn_spd_inverse_f64")
+        return info.value
+
+    def gather_block_add(self, k_ptr, ld, rows_ptr, nr, cols_ptr, nc, addc, out_ptr, ldo):
+        self._check(self.lib.gpn_gather_block_add(self.h, C.c_void_p(k_ptr), ld, C.c_void_p(rows_ptr), nr, C.c_void_p(cols_ptr), nc, addc,
+                                                  C.c_void_p(out_ptr), ldo), "gpn_gather_block_add")
+
+    # -- full kernel ---------------------------------------------------------------------------------
+    def kernel_build(self, kind: int, theta, want_grad=False) -> int:
+        th = _f64(theta)
+        st = self.lib.gpn_kernel_build(self.h, kind, _dp(th), len(th), int(want_grad))
+        if st in (-100, -101):
+            return st
+        return self._check(st, "gpn_kernel_build")
+
+    def kernel_ptr(self):
+        ld = C.c_long(0)
+        p = self.lib.gpn_kernel_ptr(self.h, C.byref(ld))
+        return p, ld.value
+
+    def expm_info(self):
+        m, s = C.c_int(0), C.c_int(0)
+        self.lib.gpn_expm_info(self.h, C.byref(m), C.byref(s))
+        return m.value, s.value
+
+    def kernel_block(self, rows, cols, addc) -> np.ndarray:
+        r, c = _i32(rows), _i32(cols)
+        out = np.empty((len(r), len(c)), dtype=np.float64)
+        if out.size:
+            self._check(self.lib.gpn_kernel_block_h(self.h, _ip(r), len(r), _ip(c), len(c), float(addc), _dp(out)), "gpn_kernel_block_h")
+        return out
+
+    # -- regression ----------------------------------------------------------------------------------
+    def gpr_logp_grad(self, kind, theta, t, want_grad):
+        th, tt = _f64(theta), _f64(t)
+        if len(tt) != self.n_train:
+            raise ValueError("len(t) != number of training nodes")
+        out = np.zeros(1 + len(th), dtype=np.float64)
+        info = C.c_int(0)
+        st = self.lib.gpn_gpr_logp_grad(self.h, kind, _dp(th), len(th), _dp(tt), int(want_grad), _dp(out), C.byref(info))
+        if st in (-100, -101):
+            return st, out, 0
+        self._check(st, "gpn_gpr_logp_grad")
+        return 0, out, info.value
+
+    def gpr_predict(self, kind, theta, t):
+        th, tt = _f64(theta), _f64(t)
+        if len(tt) != self.n_train:
+            raise ValueError("len(t) != number of training nodes")
+        n, m = self.n_train, self.n_test
+        alpha, fstar, s, kss = (np.zeros(n), np.zeros(m), np.zeros(m), np.zeros(m))
+        info = (C.c_int * 2)(0, 0)
+        st = self.lib.gpn_gpr_predict(self.h, kind, _dp(th), len(th), _dp(tt), _dp(alpha), _dp(fstar), _dp(s), _dp(kss), info)
+        if st in (-100, -101):
+            return st, None
+        self._check(st, "gpn_gpr_predict")
+        return 0, dict(alpha=alpha, fstar=fstar, s=s, kstarstar_diag=kss, info_k=info[0], info_kss=info[1])
+
+    def gpr_fetch(self, which: str) -> np.ndarray:
+        n, m = self.n_train, self.n_test
+        shape = {"k": (n, n), "kstar": (m, n), "L": (n, n), "v": (n, m), "kstarstar": (m, m)}[which]
+        idx = {"k": 0, "kstar": 1, "L": 2, "v": 3, "kstarstar": 4}[which]
+        out = np.empty(shape, dtype=np.float64)
+        if out.size:
+            self._check(self.lib.gpn_gpr_fetch(self.h, idx, _dp(out)), "gpn_gpr_fetch")
+        return out
+
+    # -- classification ------------------------------------------------------------------------------
+    def gpc_newton(self, kind, theta, y, tol=0.1, phif=1e100, scale=1.0, variant=0, K_ptr=None, ldk=0):
+        th, yy = _f64(theta), _f64(y)
+        n = len(yy)
+        f, a = np.zeros(n), np.zeros(n)
+        logq, iters, info = C.c_double(0), C.c_int(0), C.c_int(0)
+        st = self.lib.gpn_gpc_newton(self.h, kind, _dp(th), len(th), _dp(yy), n, C.c_void_p(K_ptr) if K_ptr else None, ldk, tol, phif,
+                                     scale, variant, _dp(f), _dp(a), C.byref(logq), C.byref(iters), C.byref(info))
+        if st in (-100, -101):
+            return st, None
+        self._check(st, "gpn_gpc_newton")
+        return 0, dict(f=f, a=a, logq=logq.value, iters=iters.value, info=info.value)
+
+    def gpc_predict(self, kind, theta, y):
+        th, yy = _f64(theta), _f64(y)
+        n, m = self.n_train, self.n_test
+        if len(yy) != n:
+            raise ValueError("len(y) != number of training nodes")
+        f, a, fstar, V, pi = np.zeros(n), np.zeros(n), np.zeros(m), np.zeros(m), np.zeros(m)
+        logq, iters, info = C.c_double(0), C.c_int(0), C.c_int(0)
+        st = self.lib.gpn_gpc_predict(self.h, kind, _dp(th), len(th), _dp(yy), _dp(f), _dp(a), C.byref(logq), C.byref(iters), _dp(fstar),
+                                      _dp(V), _dp(pi), C.byref(info))
+        if st in (-100, -101):
+            return st, None
+        self._check(st, "gpn_gpc_predict")
+        return 0, dict(f=f, a=a, logq=logq.value, iters=iters.value, info=info.value, fstar=fstar, V=V, pi_star=pi)
+
+    # -- landscape slice ------------------------------------------------------------------------------
+    def landscape(self, kind, classifier, theta, axidx, ax1, ax2, t, begin, end, stride, want_grad=False):
+        th, a1, a2, tt = _f64(theta), _f64(ax1), _f64(ax2), _f64(t)
+        total = len(a1) * len(a2)
+        end = min(end, total)
+        count = max(0, (end - begin + stride - 1) // stride)
+        out = np.zeros((count, 1 + len(th)), dtype=np.float64)
+        if count:
+            st = self.lib.gpn_landscape(self.h, kind, int(classifier), _dp(th), len(th), int(axidx[0]), int(axidx[1]), _dp(a1), len(a1),
+                                        _dp(a2), len(a2), _dp(tt), begin, end, stride, int(want_grad), _dp(out))
+            if st in (-100, -101):
+                return st, out
+            self._check(st, "gpn_landscape")
+        return 0, out

@@ -1,0 +1,132 @@
+// gpnet_b200 -- shared declarations of the sm_100a library (internal; the public C-ABI is include/gpnet_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+#include "../../include/gpnet_b200.h"
+
+// Status convention: 0 ok, >0 LAPACK-style info, <0 bad argument, <=-1000 CUDA error.
+#define GPN_CUDA_ERR(e) (-1000 - (int)(e))
+#define GPN_CK(call)                                                                          \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            gpn_set_last_error(__FILE__, __LINE__, cudaGetErrorString(_e));                   \
+            return GPN_CUDA_ERR(_e);                                                          \
+        }                                                                                     \
+    } while (0)
+#define GPN_TRY(call)                                                                         \
+    do {                                                                                      \
+        int _s = (call);                                                                      \
+        if (_s != 0) return _s;                                                               \
+    } while (0)
+
+void gpn_set_last_error(const char* file, int line, const char* msg);
+
+// A growable device buffer owned by the context.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+// GEMM flags (tile-level structure exploitation; see gemm_f64.cu)
+enum : int {
+    GF_LOWER = 1,    // compute only tiles with tile_m >= tile_n (square C, BM == BN)
+    GF_MIRROR = 2,   // with GF_LOWER: also store the transposed tile (symmetric result)
+    GF_KLO_M = 4,    // contributions only for k >= m0   (op(A)[m][k] == 0 for k < m)
+    GF_KLO_N = 8,    // contributions only for k >= n0   (op(B)[k][n] == 0 for k < n)
+    GF_KHI_M = 16,   // contributions only for k <  m0+BM (op(A)[m][k] == 0 for k > m)
+    GF_KHI_N = 32,   // contributions only for k <  n0+BN (op(B)[k][n] == 0 for k > n)
+    GF_FORCE_SMALL = 64,   // force the 64x64 tile configuration
+    GF_FORCE_BIG = 128,    // force the 128x128 tile configuration
+};
+
+struct gpn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    long long launches = 0;        // kernels launched through this context (bench "gpu_launches")
+    double flops = 0.0;            // executed tensor flops accounted by the GEMM launcher
+
+    // graph (resident)
+    int N = 0;
+    long long nnz = 0;
+    DevBuf indptr, indices, weights, dinv;
+
+    // training / test sets (resident)
+    int n_train = 0, n_test = 0;
+    DevBuf train_idx, test_idx, tvec;
+
+    // full-kernel state
+    int kind = -1;
+    int P = 0;
+    double theta_exp[8] = {0};
+    int pstep_p = 0;
+    int expm_m = 0, expm_s = 0;
+    bool have_full = false;
+    bool have_aux = false;       // derivative by-product present (A = -beta*L~ for diffusion, B^(p-1) for p-step)
+    long ldN = 0;
+
+    // named work buffers (N x N unless noted)
+    DevBuf mat[10];
+    DevBuf nb[16];               // n-sized / n x n / n x m buffers of the GP algebra
+    DevBuf winv;                 // inverted diagonal blocks of the running Cholesky (N x 128)
+    DevBuf scal;                 // small device scalars (reductions, info)
+    DevBuf partial;              // reduction partials
+    void* pinned = nullptr;      // pinned host staging for scalar read-back
+    size_t pinned_cap = 0;
+};
+
+int gpn_buf_ensure(gpn_ctx* c, DevBuf& b, size_t bytes);
+
+static inline long gpn_round_ld(long n) { return (n + 15) / 16 * 16; }   // 128-byte rows: TMA-friendly, sector aligned
+
+// ---- internal device-level primitives (all stream-ordered on c->stream, device pointers) -----------------
+// C[M x N] = alpha * op(A) op(B) + beta * C.   a_kmajor: A stored [M][K] (row-major, K contiguous); else [K][M].
+// b_kmajor: B stored [N][K]; else [K][N].  Batched over `batch` problems with element strides sA/sB/sC.
+int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, long lda, bool a_kmajor, const double* B,
+             long ldb, bool b_kmajor, double beta, double* C, long ldc, int flags, int batch = 1, long sA = 0,
+             long sB = 0, long sC = 0);
+
+// Cholesky (lower, in place, row-major), triangular inverse and SPD inverse.  info: device int (0 = ok).
+int gpn_potrf(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset = 0);
+int gpn_trtri_from_winv(gpn_ctx* c, int n, const double* L, long ldl, const double* winv, double* W, long ldw);
+int gpn_lauum(gpn_ctx* c, int n, const double* W, long ldw, double* out, long ldo, bool mirror);
+
+// elementwise / reductions (elementwise.cu)
+int gpn_k_fill_zero(gpn_ctx* c, double* A, long ld, int rows, int cols);
+int gpn_k_laplacian_scatter(gpn_ctx* c, int N, const int* indptr, const int* indices, const double* w, const double* dinv,
+                            double alpha, double gamma, double* out, long ld);
+int gpn_k_degree_dinv(gpn_ctx* c, int N, const int* indptr, const int* indices, const double* w, double* dinv);
+// pad_r/pad_c < 0: write zeros up to the next multiple of 128 rows / min(next multiple of 128, ldo) columns
+int gpn_k_gather(gpn_ctx* c, const double* K, long ld, const int* rows, int nr, const int* cols, int nc, double addc,
+                 double* out, long ldo, int pad_r = -1, int pad_c = -1);
+int gpn_k_gather_rows(gpn_ctx* c, const double* K, long ld, const int* rows, int nr, int ncols, double* out, long ldo);
+int gpn_k_zero_upper(gpn_ctx* c, double* A, long ld, int n);
+int gpn_k_mirror_lower(gpn_ctx* c, double* A, long ld, int n);
+int gpn_k_lincomb(gpn_ctx* c, int n, double* out, long ldo, double diag, int nterms, const double* const* X, const long* ldx,
+                  const double* coef);
+int gpn_k_onenorm(gpn_ctx* c, int n, const double* A, long ld, double* d_out /*device scalar*/);
+int gpn_k_copy(gpn_ctx* c, int rows, int cols, const double* A, long lda, double* B, long ldb);
+int gpn_k_gemv(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* x, double* y, int mode);
+int gpn_k_gemv_t(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* x, double* y, int mode);
+int gpn_k_dot(gpn_ctx* c, int n, const double* x, const double* y, double* d_out);
+int gpn_k_sum(gpn_ctx* c, int n, const double* x, double* d_out);
+int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out);
+int gpn_k_colnorm2(gpn_ctx* c, int rows, int cols, const double* V, long ld, double* out);
+int gpn_k_diag_gather(gpn_ctx* c, const double* K, long ld, const int* idx, int m, double addc, double* out);
+int gpn_k_grad_trace(gpn_ctx* c, int n, const double* Kinv, long ldi, const double* G, long ldg, const double* Ktt, long ldk,
+                     double g_scale, double k_scale, double k_shift, const double* alpha, double* d_out3);
+int gpn_k_form_B(gpn_ctx* c, int n, const double* K, long ldk, const double* sw, double* B, long ldb);
+int gpn_k_scale_rows(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* s, double* out, long ldo);
+
+enum { GEMV_FULL = 0, GEMV_LOWER = 1 /* treat entries with col > row as zero */ };

@@ -1,0 +1,441 @@
+// HBM-bound kernels of the GP hot path: Laplacian assembly, block gather, linear combinations, norms, GEMV,
+// reductions, and the fused elementwise pieces of the Laplace Newton loop.  All fp64, all coalesced along rows
+// (row-major, 128-byte-aligned leading dimensions), 16-byte vector accesses where the layout allows.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide sum; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sh[32];
+    __syncthreads();
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (l < (blockDim.x >> 5)) ? sh[l] : 0.0;
+        v = warp_sum(v);
+    }
+    return v;
+}
+
+// ---- K1: Laplacian assembly (GPnet.py:329 + the gamma*I + alpha*L~ forms of GPnet.py:340,342,346) -----------------
+// (a) degree row sums and dinv = 1/sqrt(d) (inf -> 0), once per graph
+__global__ void degree_dinv_kernel(int N, const int* __restrict__ indptr, const int* __restrict__ indices,
+                                   const double* __restrict__ w, double* __restrict__ dinv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double d = 0.0;
+    for (int e = indptr[i]; e < indptr[i + 1]; ++e) d += w ? w[e] : 1.0;   // CSR order == scipy's row-sum order
+    double r = 1.0 / sqrt(d);
+    if (isinf(r)) r = 0.0;
+    dinv[i] = r;
+    dinv[N + i] = d;
+}
+// (b) vectorised zero fill of the rows x cols region (rows padded with zeros up to ld by the caller's choice of cols)
+__global__ void fill_zero_kernel(double* __restrict__ A, long ld, int rows, int cols) {
+    const long nvec = ((long)cols + 1) / 2;
+    const long total = (long)rows * nvec;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long r = idx / nvec, v = idx - r * nvec;
+        reinterpret_cast<double2*>(A + r * ld)[v] = make_double2(0.0, 0.0);
+    }
+}
+// (c) scatter of the nnz + diagonal: out[i][j] = alpha * (dinv_i * ((D-A)_ij * dinv_j)) (+ gamma on the diagonal),
+//     same operation order as networkx's  DH @ ((D - A) @ DH).  One warp per row.
+__global__ void laplacian_scatter_kernel(int N, const int* __restrict__ indptr, const int* __restrict__ indices,
+                                         const double* __restrict__ w, const double* __restrict__ dinv, double alpha, double gamma,
+                                         double* __restrict__ out, long ld) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= N) return;
+    const double di = dinv[row], deg = dinv[N + row];
+    const int e0 = indptr[row], e1 = indptr[row + 1];
+    double self = 0.0;
+    for (int e = e0 + lane; e < e1; e += 32) {
+        const int j = indices[e];
+        const double a = w ? w[e] : 1.0;
+        if (j == row) {
+            self = a;
+        } else {
+            const double l = di * ((-a) * dinv[j]);
+            out[(long)row * ld + j] = alpha * l;
+        }
+    }
+    self = warp_sum(self);   // at most one lane holds a self-loop weight
+    if (lane == 0) {
+        const double l = di * ((deg - self) * di);
+        out[(long)row * ld + row] = gamma + alpha * l;
+    }
+}
+
+// ---- K6: block gather + noise (GPnet.py:362-365) -----------------------------------------------------------------
+__global__ void gather_kernel(const double* __restrict__ K, long ld, const int* __restrict__ rows, int nr,
+                              const int* __restrict__ cols, int nc, double addc, double* __restrict__ out, long ldo, int pad_r,
+                              int pad_c) {
+    const int r = blockIdx.y;
+    const long src = (r < nr) ? (long)rows[r] * ld : 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < pad_c; c += gridDim.x * blockDim.x) {
+        double v = 0.0;
+        if (r < nr && c < nc) v = K[src + cols[c]] + addc;
+        out[(long)r * ldo + c] = v;
+    }
+    (void)pad_r;
+}
+__global__ void gather_rows_kernel(const double* __restrict__ K, long ld, const int* __restrict__ rows, int ncols,
+                                   double* __restrict__ out, long ldo) {
+    const int r = blockIdx.y;
+    const double2* src = reinterpret_cast<const double2*>(K + (long)rows[r] * ld);
+    double2* dst = reinterpret_cast<double2*>(out + (long)r * ldo);
+    const int nvec = (ncols + 1) / 2;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) dst[v] = src[v];
+}
+__global__ void diag_gather_kernel(const double* __restrict__ K, long ld, const int* __restrict__ idx, int m, double addc,
+                                   double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = K[(long)idx[i] * ld + idx[i]] + addc;
+}
+
+__global__ void zero_upper_kernel(double* __restrict__ A, long ld, int n) {
+    const int r = blockIdx.y;
+    for (int c = r + 1 + blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) A[(long)r * ld + c] = 0.0;
+}
+
+// out = diag*I + sum_t coef[t] * X_t    (Pade polynomial pieces; up to 5 terms)
+struct LinArgs {
+    const double* X[5];
+    long ld[5];
+    double coef[5];
+    int nterms;
+};
+__global__ void lincomb_kernel(int n, double* __restrict__ out, long ldo, double diag, LinArgs a) {
+    const int r = blockIdx.y;
+    const int nvec = (n + 1) / 2;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+        double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
+            if (t < a.nterms) {
+                const double2 x = reinterpret_cast<const double2*>(a.X[t] + (long)r * a.ld[t])[v];
+                s.x += a.coef[t] * x.x;
+                s.y += a.coef[t] * x.y;
+            }
+        const int c = 2 * v;
+        if (c == r) s.x += diag;
+        if (c + 1 == r) s.y += diag;
+        if (c + 1 >= n) s.y = 0.0;
+        reinterpret_cast<double2*>(out + (long)r * ldo)[v] = s;
+    }
+}
+
+// 1-norm of a symmetric matrix == max row abs-sum.  Stage 1: one warp per row -> rowsum; stage 2: max.
+__global__ void rowabs_kernel(int n, const double* __restrict__ A, long ld, double* __restrict__ rows) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double2* p = reinterpret_cast<const double2*>(A + (long)row * ld);
+    double s = 0.0;
+    const int nvec = n / 2;
+    for (int v = lane; v < nvec; v += 32) {
+        const double2 x = p[v];
+        s += fabs(x.x) + fabs(x.y);
+    }
+    if ((n & 1) && lane == 0) s += fabs(A[(long)row * ld + n - 1]);
+    s = warp_sum(s);
+    if (lane == 0) rows[row] = s;
+}
+__global__ void max_kernel(int n, const double* __restrict__ x, double* __restrict__ out) {
+    __shared__ double sh[32];
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, x[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+        m = warp_max(m);
+        if (threadIdx.x == 0) *out = m;
+    }
+}
+
+__global__ void copy_kernel(int rows, int cols, const double* __restrict__ A, long lda, double* __restrict__ B, long ldb) {
+    const int r = blockIdx.y;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) B[(long)r * ldb + c] = A[(long)r * lda + c];
+}
+
+// ---- GEMV (K11): y = A x, one warp per row; mode GEMV_LOWER treats col > row as zero -------------------------------
+__global__ void gemv_kernel(int rows, int cols, const double* __restrict__ A, long lda, const double* __restrict__ x,
+                            double* __restrict__ y, int mode) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int lim = (mode == GEMV_LOWER) ? min(cols, row + 1) : cols;
+    const double* a = A + (long)row * lda;
+    double s = 0.0;
+    for (int c = lane; c < lim; c += 32) s += a[c] * x[c];
+    s = warp_sum(s);
+    if (lane == 0) y[row] = s;
+}
+// y = A^T x : each thread owns one column, rows are split across blockIdx.y and combined with atomics (y pre-zeroed)
+__global__ void gemv_t_kernel(int rows, int cols, const double* __restrict__ A, long lda, const double* __restrict__ x,
+                              double* __restrict__ y, int mode, int rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    if (mode == GEMV_LOWER) r0 = max(r0, c);   // A[r][c] nonzero only for r >= c
+    double s = 0.0;
+    for (int r = r0; r < r1; ++r) s += A[(long)r * lda + c] * x[r];
+    if (r1 > r0) atomicAdd(&y[c], s);
+}
+__global__ void zero_vec_kernel(int n, double* y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = 0.0;
+}
+
+// ---- K8: reductions (single block; n is at most a few 10^4) ---------------------------------------------------------
+__global__ void dot_kernel(int n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i] * y[i];
+    s = block_sum(s);
+    if (threadIdx.x == 0) *out = s;
+}
+__global__ void sum_kernel(int n, const double* __restrict__ x, double* __restrict__ out) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+    s = block_sum(s);
+    if (threadIdx.x == 0) *out = s;
+}
+__global__ void sumlogdiag_kernel(int n, const double* __restrict__ A, long ld, double* __restrict__ out) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += log(A[(long)i * ld + i]);
+    s = block_sum(s);
+    if (threadIdx.x == 0) *out = s;
+}
+
+// ---- K9: column squared norms of V (rows x cols): out[c] = sum_r V[r][c]^2 -------------------------------------------
+__global__ void colnorm2_kernel(int rows, int cols, const double* __restrict__ V, long ld, double* __restrict__ out, int rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    double s = 0.0;
+    for (int r = r0; r < r1; ++r) {
+        const double v = V[(long)r * ld + c];
+        s += v * v;
+    }
+    atomicAdd(&out[c], s);
+}
+
+// ---- gradient traces: out[0] = sum_ij Kinv_ij (symmetric, lower stored), out[1] = sum_ij (a_i a_j - Kinv_ij) * D_ij
+//      with D = g_scale*G + k_scale*Ktt (lower triangles; off-diagonal counted twice), out[2] = sum_i a_i -------------
+__global__ void grad_trace_kernel(int n, const double* __restrict__ Kinv, long ldi, const double* __restrict__ G, long ldg,
+                                  const double* __restrict__ Ktt, long ldk, double g_scale, double k_scale, double k_shift,
+                                  const double* __restrict__ alpha, double* __restrict__ out) {
+    const int r = blockIdx.x;
+    double s_inv = 0.0, s_tr = 0.0;
+    const double ar = alpha[r];
+    for (int c = threadIdx.x; c <= r; c += blockDim.x) {
+        const double w = (c == r) ? 1.0 : 2.0;
+        const double ki = Kinv[(long)r * ldi + c];
+        double d = 0.0;
+        if (G) d += g_scale * G[(long)r * ldg + c];
+        if (Ktt) d += k_scale * (Ktt[(long)r * ldk + c] - k_shift);
+        s_inv += w * ki;
+        s_tr += w * (ar * alpha[c] - ki) * d;
+    }
+    s_inv = block_sum(s_inv);
+    s_tr = block_sum(s_tr);
+    if (threadIdx.x == 0) {
+        atomicAdd(&out[0], s_inv);
+        atomicAdd(&out[1], s_tr);
+    }
+}
+
+// ---- K10: B = I + sw_i K_ij sw_j (GPnetClassifier.py:110), zero padding up to pad x pad ------------------------------
+__global__ void form_B_kernel(int n, int pad, const double* __restrict__ K, long ldk, const double* __restrict__ sw,
+                              double* __restrict__ B, long ldb) {
+    const int r = blockIdx.y;
+    const double sr = (r < n) ? sw[r] : 0.0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < pad; c += gridDim.x * blockDim.x) {
+        double v = 0.0;
+        if (r < n && c < n) v = sr * K[(long)r * ldk + c] * sw[c] + ((r == c) ? 1.0 : 0.0);
+        B[(long)r * ldb + c] = v;
+    }
+}
+__global__ void scale_rows_kernel(int rows, int cols, const double* __restrict__ A, long lda, const double* __restrict__ s,
+                                  double* __restrict__ out, long ldo) {
+    const int r = blockIdx.y;
+    const double sr = s[r];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+        out[(long)r * ldo + c] = sr * A[(long)r * lda + c];
+}
+
+inline int grid1(long n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
+inline int gridx_cols(int cols) { return max(1, min(64, grid1(cols))); }
+
+}   // namespace
+
+#define LAUNCHED(c)                \
+    do {                           \
+        (c)->launches++;           \
+        GPN_CK(cudaGetLastError()); \
+    } while (0)
+
+int gpn_k_degree_dinv(gpn_ctx* c, int N, const int* indptr, const int* indices, const double* w, double* dinv) {
+    degree_dinv_kernel<<<grid1(N), TPB, 0, c->stream>>>(N, indptr, indices, w, dinv);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_fill_zero(gpn_ctx* c, double* A, long ld, int rows, int cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    const long total = (long)rows * ((cols + 1) / 2);
+    const int blocks = (int)min((long)c->num_sms * 16, (total + TPB - 1) / TPB);
+    fill_zero_kernel<<<blocks, TPB, 0, c->stream>>>(A, ld, rows, cols);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_laplacian_scatter(gpn_ctx* c, int N, const int* indptr, const int* indices, const double* w, const double* dinv,
+                            double alpha, double gamma, double* out, long ld) {
+    laplacian_scatter_kernel<<<grid1((long)N * 32), TPB, 0, c->stream>>>(N, indptr, indices, w, dinv, alpha, gamma, out, ld);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_gather(gpn_ctx* c, const double* K, long ld, const int* rows, int nr, const int* cols, int nc, double addc, double* out,
+                 long ldo, int pad_r, int pad_c) {
+    // default: writes the full padded (round128(nr) x round128(nc)) region, zeros outside nr x nc
+    const int pr = pad_r >= 0 ? pad_r : (nr + 127) / 128 * 128;
+    const int pc = pad_c >= 0 ? pad_c : (int)min((long)(nc + 127) / 128 * 128, ldo);
+    if (pr <= 0 || pc <= 0) return 0;
+    dim3 grid(gridx_cols(pc), pr);
+    gather_kernel<<<grid, TPB, 0, c->stream>>>(K, ld, rows, nr, cols, nc, addc, out, ldo, pr, pc);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_gather_rows(gpn_ctx* c, const double* K, long ld, const int* rows, int nr, int ncols, double* out, long ldo) {
+    if (nr <= 0) return 0;
+    dim3 grid(gridx_cols((ncols + 1) / 2), nr);
+    gather_rows_kernel<<<grid, TPB, 0, c->stream>>>(K, ld, rows, ncols, out, ldo);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_diag_gather(gpn_ctx* c, const double* K, long ld, const int* idx, int m, double addc, double* out) {
+    if (m <= 0) return 0;
+    diag_gather_kernel<<<grid1(m), TPB, 0, c->stream>>>(K, ld, idx, m, addc, out);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_zero_upper(gpn_ctx* c, double* A, long ld, int n) {
+    if (n <= 1) return 0;
+    dim3 grid(gridx_cols(n), n);
+    zero_upper_kernel<<<grid, TPB, 0, c->stream>>>(A, ld, n);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_lincomb(gpn_ctx* c, int n, double* out, long ldo, double diag, int nterms, const double* const* X, const long* ldx,
+                  const double* coef) {
+    if (nterms > 5) return -5;
+    LinArgs a;
+    a.nterms = nterms;
+    for (int t = 0; t < 5; ++t) {
+        a.X[t] = t < nterms ? X[t] : nullptr;
+        a.ld[t] = t < nterms ? ldx[t] : 0;
+        a.coef[t] = t < nterms ? coef[t] : 0.0;
+    }
+    dim3 grid(gridx_cols((n + 1) / 2), n);
+    lincomb_kernel<<<grid, TPB, 0, c->stream>>>(n, out, ldo, diag, a);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_onenorm(gpn_ctx* c, int n, const double* A, long ld, double* d_out) {
+    GPN_TRY(gpn_buf_ensure(c, c->partial, sizeof(double) * (size_t)(n + 64)));
+    double* rows = (double*)c->partial.p;
+    rowabs_kernel<<<grid1((long)n * 32), TPB, 0, c->stream>>>(n, A, ld, rows);
+    LAUNCHED(c);
+    max_kernel<<<1, 1024, 0, c->stream>>>(n, rows, d_out);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_copy(gpn_ctx* c, int rows, int cols, const double* A, long lda, double* B, long ldb) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid(gridx_cols(cols), rows);
+    copy_kernel<<<grid, TPB, 0, c->stream>>>(rows, cols, A, lda, B, ldb);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_gemv(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* x, double* y, int mode) {
+    if (rows <= 0) return 0;
+    gemv_kernel<<<grid1((long)rows * 32), TPB, 0, c->stream>>>(rows, cols, A, lda, x, y, mode);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_gemv_t(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* x, double* y, int mode) {
+    if (cols <= 0) return 0;
+    zero_vec_kernel<<<grid1(cols), TPB, 0, c->stream>>>(cols, y);
+    LAUNCHED(c);
+    if (rows <= 0) return 0;
+    const int rpb = 128;
+    dim3 grid(grid1(cols, 128), (rows + rpb - 1) / rpb);
+    gemv_t_kernel<<<grid, 128, 0, c->stream>>>(rows, cols, A, lda, x, y, mode, rpb);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_dot(gpn_ctx* c, int n, const double* x, const double* y, double* d_out) {
+    dot_kernel<<<1, 1024, 0, c->stream>>>(n, x, y, d_out);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_sum(gpn_ctx* c, int n, const double* x, double* d_out) {
+    sum_kernel<<<1, 1024, 0, c->stream>>>(n, x, d_out);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out) {
+    sumlogdiag_kernel<<<1, 1024, 0, c->stream>>>(n, A, ld, d_out);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_colnorm2(gpn_ctx* c, int rows, int cols, const double* V, long ld, double* out) {
+    if (cols <= 0) return 0;
+    zero_vec_kernel<<<grid1(cols), TPB, 0, c->stream>>>(cols, out);
+    LAUNCHED(c);
+    if (rows <= 0) return 0;
+    const int rpb = 128;
+    dim3 grid(grid1(cols, 128), (rows + rpb - 1) / rpb);
+    colnorm2_kernel<<<grid, 128, 0, c->stream>>>(rows, cols, V, ld, out, rpb);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_grad_trace(gpn_ctx* c, int n, const double* Kinv, long ldi, const double* G, long ldg, const double* Ktt, long ldk,
+                     double g_scale, double k_scale, double k_shift, const double* alpha, double* d_out3) {
+    zero_vec_kernel<<<1, 32, 0, c->stream>>>(3, d_out3);
+    LAUNCHED(c);
+    grad_trace_kernel<<<n, 256, 0, c->stream>>>(n, Kinv, ldi, G, ldg, Ktt, ldk, g_scale, k_scale, k_shift, alpha, d_out3);
+    LAUNCHED(c);
+    return gpn_k_sum(c, n, alpha, d_out3 + 2);
+}
+int gpn_k_form_B(gpn_ctx* c, int n, const double* K, long ldk, const double* sw, double* B, long ldb) {
+    const int pad = (int)min((long)(n + 127) / 128 * 128, ldb);
+    dim3 grid(gridx_cols(pad), pad);
+    form_B_kernel<<<grid, TPB, 0, c->stream>>>(n, pad, K, ldk, sw, B, ldb);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_scale_rows(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* s, double* out, long ldo) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid(gridx_cols(cols), rows);
+    scale_rows_kernel<<<grid, TPB, 0, c->stream>>>(rows, cols, A, lda, s, out, ldo);
+    LAUNCHED(c);
+    return 0;
+}

@@ -1,0 +1,1029 @@
+// GP drivers behind the C-ABI: context, graph upload, full-kernel construction (diffusion / regularized Laplacian /
+// p-step walk), GP-regression log marginal likelihood + analytic gradient + predictive mean/variance, the Laplace
+// Newton loop of the classifier and its predictive probabilities, and the landscape slice evaluator.
+// Reference lines are cited per function; the numerical kernels live in gemm_f64.cu / factor.cu / elementwise.cu.
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+#include <algorithm>
+
+int gpn_trtri_from_winv_tmp(gpn_ctx* c, int n, const double* L, long ldl, const double* winv, double* W, long ldw, double* tmp);
+
+static thread_local char g_last_error[512] = "";
+void gpn_set_last_error(const char* file, int line, const char* msg) {
+    snprintf(g_last_error, sizeof g_last_error, "%s:%d: %s", file, line, msg);
+}
+
+int gpn_buf_ensure(gpn_ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) {
+        GPN_CK(cudaStreamSynchronize(c->stream));
+        GPN_CK(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    bytes = (bytes + 255) & ~(size_t)255;
+    GPN_CK(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return 0;
+}
+
+namespace {
+
+constexpr double LOG_2PI = 1.8378770664093454835606594728112;
+
+inline long pad128(long n) { return (n + 127) / 128 * 128; }
+
+// n-sized work buffers
+enum NB {
+    NB_KY = 0, NB_KC, NB_W, NB_T, NB_ROWS1, NB_ROWS2, NB_G, NB_KSTAR, NB_KSS, NB_V, NB_S, NB_B, NB_WB, NB_WK, NB_COUNT
+};
+static_assert(NB_COUNT <= 16, "nb[] too small");
+
+struct Scal {           // layout of c->scal (doubles), followed by ints
+    enum { DOT = 0, LOGDET, SUM, TR0, TR1, TR2, CONV, Q, LIK, AF, NORM0, NORM1, NORM2, NORM3, NDBL = 32 };
+};
+
+double* dscal(gpn_ctx* c, int i) { return (double*)c->scal.p + i; }
+int* iscal(gpn_ctx* c, int i) { return (int*)((double*)c->scal.p + Scal::NDBL) + i; }
+
+int read_scalars(gpn_ctx* c, double* out_d, int nd, int* out_i, int ni) {
+    // one D2H of the whole scalar block through pinned memory, then a stream sync
+    const size_t bytes = sizeof(double) * Scal::NDBL + sizeof(int) * 16;
+    GPN_CK(cudaMemcpyAsync(c->pinned, c->scal.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    GPN_CK(cudaStreamSynchronize(c->stream));
+    if (out_d) memcpy(out_d, c->pinned, sizeof(double) * nd);
+    if (out_i) memcpy(out_i, (char*)c->pinned + sizeof(double) * Scal::NDBL, sizeof(int) * ni);
+    return 0;
+}
+int clear_info(gpn_ctx* c) {
+    GPN_CK(cudaMemsetAsync(iscal(c, 0), 0, sizeof(int) * 16, c->stream));
+    return 0;
+}
+int upload(gpn_ctx* c, void* dst, const void* src_h, size_t bytes) {
+    // small host vectors: stage through pinned memory when they fit, so the copy is truly asynchronous
+    GPN_CK(cudaMemcpyAsync(dst, src_h, bytes, cudaMemcpyHostToDevice, c->stream));
+    GPN_CK(cudaStreamSynchronize(c->stream));   // the host buffer may be a temporary of the caller
+    return 0;
+}
+int download(gpn_ctx* c, void* dst_h, const void* src, size_t bytes) {
+    GPN_CK(cudaMemcpyAsync(dst_h, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+int download_matrix(gpn_ctx* c, double* dst_h, const double* src, long ld, int rows, int cols) {
+    GPN_CK(cudaMemcpy2DAsync(dst_h, sizeof(double) * cols, src, sizeof(double) * ld, sizeof(double) * cols, rows,
+                             cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+double* mat(gpn_ctx* c, int i) { return (double*)c->mat[i].p; }
+int ensure_mat(gpn_ctx* c, int i) {
+    const long np = pad128(c->N);
+    return gpn_buf_ensure(c, c->mat[i], sizeof(double) * (size_t)np * np);
+}
+int ensure_nb(gpn_ctx* c, int i, long rows, long cols) { return gpn_buf_ensure(c, c->nb[i], sizeof(double) * (size_t)rows * cols); }
+double* nbp(gpn_ctx* c, int i) { return (double*)c->nb[i].p; }
+
+// ---- vector kernels of the Laplace Newton loop (GPnetClassifier.py:106-112,124-145,204-231) -------------------------
+__global__ void newton_pre_kernel(int n, const double* __restrict__ f, const double* __restrict__ y, double* __restrict__ w,
+                                  double* __restrict__ sw, double* __restrict__ p, double* __restrict__ b, double* __restrict__ g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double fi = f[i];
+    const double e = exp(-fabs(fi));
+    const double d = 1.0 + e;
+    const double pi = (fi >= 0.0) ? 1.0 / d : e / d;     // sigma(f)           (:111 / :209)
+    const double wi = e / (d * d);                        // sigma(1-sigma)     (:106 / :204-206)
+    w[i] = wi;
+    sw[i] = sqrt(wi);
+    p[i] = pi;
+    const double gi = 0.5 * (y[i] + 1.0) - pi;
+    b[i] = wi * fi + gi;                                  // :112
+    g[i] = gi;                                            // (y+1)/2 - p        (:210)
+}
+__global__ void vec_mul_kernel(int n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = x[i] * y[i];
+}
+// a = scale * (b - sw * sol)                                                  (:113-121)
+__global__ void newton_a_kernel(int n, double scale, const double* __restrict__ b, const double* __restrict__ sw,
+                                const double* __restrict__ sol, double* __restrict__ a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = scale * (b[i] - sw[i] * sol[i]);
+}
+// phif_i = log p_i - q/2 - logdet/2 - n/2 log 2pi; conv = sum (old - new)^2 (:124-132).  Single block.
+__global__ void newton_phif_kernel(int n, const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ logdet,
+                                   double* __restrict__ phif, int first, double phif0, double* __restrict__ conv) {
+    __shared__ double sh[32];
+    const double common = -0.5 * (*q) - 0.5 * (*logdet) - 0.5 * n * LOG_2PI;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = log(p[i]) + common;
+        const double old = first ? phif0 : phif[i];
+        const double d = old - v;
+        s += d * d;
+        phif[i] = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) *conv = s;
+    }
+}
+// lik = sum log(1 + log(1 + exp(-s))), s = -y f  (:138-143, quirk A-10); variant 1: scripts/prova.py:197-200
+__global__ void newton_lik_kernel(int n, const double* __restrict__ f, const double* __restrict__ y, int variant,
+                                  double* __restrict__ out) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double s = -y[i] * f[i];
+        if (variant == 0) {
+            acc += log(1.0 + log(1.0 + exp(-s)));
+        } else {
+            const double ps = s > 0.0 ? s : 0.0;
+            acc += log(ps + log(exp(-ps) + exp(s - ps)));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) *out = acc;
+    }
+}
+// K12: V = kss - ||v||^2 and the 5-erf averaged sigmoid (GPnetClassifier.py:217-231, constants GPnet.py:59-62)
+__global__ void pistar_kernel(int m, const double* __restrict__ fstar, const double* __restrict__ kss, const double* __restrict__ vn,
+                              double* __restrict__ V, double* __restrict__ pistar) {
+    const double LAM[5] = {0.41, 0.4, 0.37, 0.44, 0.39};
+    const double COEF[5] = {-1854.8214151, 3516.89893646, 221.29346712, 128.12323805, -2010.49422654};
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double v = kss[i] - vn[i];
+    V[i] = v;
+    const double alpha = 1.0 / (2.0 * v);
+    const double fs = fstar[i];
+    double acc = 0.0, csum = 0.0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const double gamma = LAM[k] * fs;
+        const double integ = sqrt(M_PI / alpha) * erf(gamma * sqrt(alpha / (alpha + LAM[k] * LAM[k]))) / (2.0 * sqrt(v * 2.0 * M_PI));
+        acc += COEF[k] * integ;
+        csum += COEF[k];
+    }
+    pistar[i] = acc + 0.5 * csum;
+}
+
+inline int g1(long n) { return (int)((n + 255) / 256); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// full kernel construction (GPnet.py:335-349)
+// ---------------------------------------------------------------------------------------------------------------------
+int laplacian_into(gpn_ctx* c, double alpha, double gamma, double* out, long ld) {
+    const long np = pad128(c->N);
+    GPN_TRY(gpn_k_fill_zero(c, out, ld, (int)np, (int)np));
+    return gpn_k_laplacian_scatter(c, c->N, (const int*)c->indptr.p, (const int*)c->indices.p,
+                                   c->weights.p ? (const double*)c->weights.p : nullptr, (const double*)c->dinv.p, alpha, gamma, out,
+                                   ld);
+}
+
+// symmetric product of two symmetric (commuting) matrices: lower tiles + mirrored store
+int symm_mul(gpn_ctx* c, const double* A, const double* B, double* C) {
+    const long ld = c->ldN;
+    return gpn_gemm(c, c->N, c->N, c->N, 1.0, A, ld, true, B, ld, true, 0.0, C, ld, GF_LOWER | GF_MIRROR);
+}
+
+// SPD inverse of the N x N matrix in `a` (destroyed -> L); result (full symmetric) in `out`; w/t scratch
+int spd_inverse(gpn_ctx* c, int n, double* a, long ld, double* w, double* t, double* out, int info_slot) {
+    GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(n) * 128));
+    GPN_TRY(gpn_potrf(c, n, a, ld, (double*)c->winv.p, iscal(c, info_slot)));
+    GPN_TRY(gpn_trtri_from_winv_tmp(c, n, a, ld, (const double*)c->winv.p, w, ld, t));
+    return gpn_lauum(c, n, w, ld, out, ld, true);
+}
+
+int build_reglap(gpn_ctx* c, double beta) {
+    for (int i = 0; i < 3; ++i) GPN_TRY(ensure_mat(c, i));
+    GPN_TRY(laplacian_into(c, beta, 1.0, mat(c, 0), c->ldN));                       // M = I + beta L~   (:342)
+    GPN_TRY(spd_inverse(c, c->N, mat(c, 0), c->ldN, mat(c, 1), mat(c, 2), mat(c, 0), 0));
+    c->mat[9] = c->mat[0];   // alias: slot 9 designates the resident kernel
+    return 0;
+}
+
+// np.linalg.matrix_power structure (binary powering: z squared every step, multiplied into the result on set bits);
+// all factors are polynomials in B => symmetric products.  Z0/Z1 and R0/R1 are ping-pong scratch matrices.
+int matpow(gpn_ctx* c, const double* src, int p, double* Z0, double* Z1, double* R0, double* R1, const double** res) {
+    const double* z = src;
+    const double* r = nullptr;
+    double* Zb[2] = {Z0, Z1};
+    double* Rb[2] = {R0, R1};
+    int zi = 0, ri = 0;
+    bool first = true;
+    for (int e = p; e > 0; e >>= 1) {
+        if (!first) {
+            GPN_TRY(symm_mul(c, z, z, Zb[zi]));
+            z = Zb[zi];
+            zi ^= 1;
+        }
+        first = false;
+        if (e & 1) {
+            if (r == nullptr) {
+                if ((e >> 1) == 0) {
+                    r = z;                       // last bit: no further squaring can clobber z
+                } else {
+                    GPN_TRY(gpn_k_copy(c, c->N, c->N, z, c->ldN, Rb[ri], c->ldN));
+                    r = Rb[ri];
+                    ri ^= 1;
+                }
+            } else {
+                GPN_TRY(symm_mul(c, r, z, Rb[ri]));
+                r = Rb[ri];
+                ri ^= 1;
+            }
+        }
+    }
+    *res = r;
+    return 0;
+}
+
+int build_pstep(gpn_ctx* c, double a, int p, int want_grad) {
+    for (int i = 0; i < 8; ++i) GPN_TRY(ensure_mat(c, i));
+    const long ld = c->ldN;
+    GPN_TRY(laplacian_into(c, -1.0, a, mat(c, 0), ld));                              // B = a I - L~      (:346)
+    c->have_aux = false;
+    if (p <= 0) {   // matrix_power(B, 0) = I
+        GPN_TRY(gpn_k_fill_zero(c, mat(c, 5), ld, (int)pad128(c->N), (int)pad128(c->N)));
+        const double* X[1] = {mat(c, 0)};
+        const long l1[1] = {ld};
+        const double cf[1] = {0.0};
+        GPN_TRY(gpn_k_lincomb(c, c->N, mat(c, 5), ld, 1.0, 1, X, l1, cf));
+        c->mat[9] = c->mat[5];
+        return 0;
+    }
+    const double* res = nullptr;
+    if (want_grad && p >= 2) {
+        // K = B^(p-1) * B, keeping B^(p-1) for dK/dtheta0 = a p B^(p-1)
+        GPN_TRY(matpow(c, mat(c, 0), p - 1, mat(c, 1), mat(c, 2), mat(c, 3), mat(c, 6), &res));
+        if (res != mat(c, 4)) GPN_TRY(gpn_k_copy(c, c->N, c->N, res, ld, mat(c, 4), ld));
+        GPN_TRY(symm_mul(c, mat(c, 4), mat(c, 0), mat(c, 5)));
+        c->have_aux = true;       // aux = mat 4
+        c->mat[9] = c->mat[5];
+        return 0;
+    }
+    GPN_TRY(matpow(c, mat(c, 0), p, mat(c, 1), mat(c, 2), mat(c, 3), mat(c, 6), &res));
+    if (res != mat(c, 5)) GPN_TRY(gpn_k_copy(c, c->N, c->N, res, ld, mat(c, 5), ld));
+    c->mat[9] = c->mat[5];
+    return 0;
+}
+
+// expm(-beta L~): scaling-and-squaring Pade (Al-Mohy & Higham 2009 order selection with exact 1-norms of the
+// even powers; the odd-power "ell" refinement of scipy is not needed for symmetric A), all
+// products symmetric, and Q X = P solved through the SPD inverse of Q (GPnet.py:340).
+int build_diffusion(gpn_ctx* c, double beta) {
+    for (int i = 0; i < 8; ++i) GPN_TRY(ensure_mat(c, i));
+    const long ld = c->ldN;
+    const int N = c->N;
+    double *A = mat(c, 0), *A2 = mat(c, 1), *A4 = mat(c, 2), *A6 = mat(c, 3), *Z = mat(c, 4), *U = mat(c, 5), *V = mat(c, 6),
+           *X8 = mat(c, 7);
+    GPN_TRY(laplacian_into(c, -beta, 0.0, A, ld));
+    GPN_TRY(symm_mul(c, A, A, A2));
+    GPN_TRY(symm_mul(c, A2, A2, A4));
+    GPN_TRY(symm_mul(c, A4, A2, A6));
+    GPN_TRY(gpn_k_onenorm(c, N, A, ld, dscal(c, Scal::NORM0)));
+    GPN_TRY(gpn_k_onenorm(c, N, A2, ld, dscal(c, Scal::NORM1)));
+    GPN_TRY(gpn_k_onenorm(c, N, A4, ld, dscal(c, Scal::NORM2)));
+    GPN_TRY(gpn_k_onenorm(c, N, A6, ld, dscal(c, Scal::NORM3)));
+    double sc[Scal::NDBL];
+    GPN_TRY(read_scalars(c, sc, Scal::NDBL, nullptr, 0));
+    const double n2 = sc[Scal::NORM1], n4 = sc[Scal::NORM2], n6 = sc[Scal::NORM3];
+    const double d4 = pow(n4, 0.25), d6 = pow(n6, 1.0 / 6.0);
+    const double d8 = fmin(d4, pow(n2 * n6, 0.125)), d10 = pow(n4 * n6, 0.1);
+    const double eta1 = fmax(d4, d6), eta3 = fmax(d6, d8);
+    int m, s = 0;
+    if (eta1 < 1.495585217958292e-002) m = 3;
+    else if (eta1 < 2.539398330063230e-001) m = 5;
+    else if (eta3 < 9.504178996162932e-001) m = 7;
+    else if (eta3 < 2.097847961257068e+000) m = 9;
+    else {
+        m = 13;
+        const double eta4 = fmax(d8, d10), eta5 = fmin(eta3, eta4);
+        if (eta5 > 0) s = (int)fmax(ceil(log2(eta5 / 4.25)), 0.0);
+    }
+    c->expm_m = m;
+    c->expm_s = s;
+    static const double b3[] = {120., 60., 12., 1.};
+    static const double b5[] = {30240., 15120., 3360., 420., 30., 1.};
+    static const double b7[] = {17297280., 8648640., 1995840., 277200., 25200., 1512., 56., 1.};
+    static const double b9[] = {17643225600., 8821612800., 2075673600., 302702400., 30270240., 2162160., 110880., 3960., 90., 1.};
+    static const double b13[] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
+                                 10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.};
+    const double* X3[3] = {A2, A4, A6};
+    const long l3[3] = {ld, ld, ld};
+    if (m <= 9) {
+        const double* b = (m == 3) ? b3 : (m == 5) ? b5 : (m == 7) ? b7 : b9;
+        const int nt = (m - 1) / 2;          // number of even powers A2.. used
+        const double* X4[4] = {A2, A4, A6, X8};
+        const long l4[4] = {ld, ld, ld, ld};
+        if (m == 9) GPN_TRY(symm_mul(c, A6, A2, X8));
+        double cu[4], cv[4];
+        for (int i = 0; i < nt; ++i) {
+            cu[i] = b[2 * i + 3];
+            cv[i] = b[2 * i + 2];
+        }
+        GPN_TRY(gpn_k_lincomb(c, N, Z, ld, b[1], nt, X4, l4, cu));       // Z = b1 I + b3 A2 + ...
+        GPN_TRY(symm_mul(c, A, Z, U));                                     // U = A Z
+        GPN_TRY(gpn_k_lincomb(c, N, V, ld, b[0], nt, X4, l4, cv));        // V = b0 I + b2 A2 + ...
+    } else {
+        const double* b = b13;
+        const double s2 = ldexp(1.0, -2 * s), s4 = ldexp(1.0, -4 * s), s6 = ldexp(1.0, -6 * s), s1 = ldexp(1.0, -s);
+        {   // U2 = B6 (b13 B6 + b11 B4 + b9 B2);  U = B (U2 + b7 B6 + b5 B4 + b3 B2 + b1 I)
+            const double cf[3] = {b[9] * s2, b[11] * s4, b[13] * s6};
+            GPN_TRY(gpn_k_lincomb(c, N, Z, ld, 0.0, 3, X3, l3, cf));
+            GPN_TRY(gpn_gemm(c, N, N, N, s6, A6, ld, true, Z, ld, true, 0.0, X8, ld, GF_LOWER | GF_MIRROR));
+            const double* X4[4] = {A2, A4, A6, X8};
+            const long l4[4] = {ld, ld, ld, ld};
+            const double c2[4] = {b[3] * s2, b[5] * s4, b[7] * s6, 1.0};
+            GPN_TRY(gpn_k_lincomb(c, N, Z, ld, b[1], 4, X4, l4, c2));
+            GPN_TRY(gpn_gemm(c, N, N, N, s1, A, ld, true, Z, ld, true, 0.0, U, ld, GF_LOWER | GF_MIRROR));
+        }
+        {   // V2 = B6 (b12 B6 + b10 B4 + b8 B2);  V = V2 + b6 B6 + b4 B4 + b2 B2 + b0 I
+            const double cf[3] = {b[8] * s2, b[10] * s4, b[12] * s6};
+            GPN_TRY(gpn_k_lincomb(c, N, Z, ld, 0.0, 3, X3, l3, cf));
+            GPN_TRY(gpn_gemm(c, N, N, N, s6, A6, ld, true, Z, ld, true, 0.0, X8, ld, GF_LOWER | GF_MIRROR));
+            const double* X4[4] = {A2, A4, A6, X8};
+            const long l4[4] = {ld, ld, ld, ld};
+            const double c2[4] = {b[2] * s2, b[4] * s4, b[6] * s6, 1.0};
+            GPN_TRY(gpn_k_lincomb(c, N, V, ld, b[0], 4, X4, l4, c2));
+        }
+    }
+    {   // Q = V - U -> Z (zero padded);  P = V + U -> X8
+        GPN_TRY(gpn_k_fill_zero(c, Z, ld, (int)pad128(N), (int)pad128(N)));
+        const double* X2[2] = {V, U};
+        const long l2[2] = {ld, ld};
+        const double cq[2] = {1.0, -1.0}, cp[2] = {1.0, 1.0};
+        GPN_TRY(gpn_k_lincomb(c, N, Z, ld, 0.0, 2, X2, l2, cq));
+        GPN_TRY(gpn_k_lincomb(c, N, X8, ld, 0.0, 2, X2, l2, cp));
+    }
+    // X = Q^-1 P  (Q SPD: q_m(x) = p_m(-x) has positive coefficients and spec(A) <= 0)
+    GPN_TRY(spd_inverse(c, N, Z, ld, A2, A4, A6, 0));          // Qinv -> A6 (A2, A4 scratch)
+    GPN_TRY(symm_mul(c, A6, X8, U));                            // X -> U
+    double* cur = U;
+    double* oth = V;
+    for (int i = 0; i < s; ++i) {
+        GPN_TRY(symm_mul(c, cur, cur, oth));
+        double* t = cur; cur = oth; oth = t;
+    }
+    c->mat[9] = (cur == U) ? c->mat[5] : c->mat[6];
+    c->have_aux = true;     // aux = A (mat 0) for dK/dtheta0 = A K
+    return 0;
+}
+
+const double* kfull(gpn_ctx* c) { return (const double*)c->mat[9].p; }
+
+int kernel_build(gpn_ctx* c, int kind, const double* theta_h, int P, int want_grad) {
+    if (c->N <= 0) return -1;
+    if (P < 1 || P > 8) return -4;
+    c->have_full = false;
+    c->kind = kind;
+    c->P = P;
+    for (int i = 0; i < P; ++i) c->theta_exp[i] = exp(theta_h[i]);     // GPnet.py:303
+    c->ldN = pad128(c->N);
+    GPN_TRY(clear_info(c));
+    int st;
+    if (kind == GPN_KERNEL_DIFFUSION) {
+        if (!(c->theta_exp[0] < 1.0)) return -100;                        // GPnet.py:339
+        st = build_diffusion(c, c->theta_exp[0]);
+    } else if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN) {
+        st = build_reglap(c, c->theta_exp[0]);
+    } else if (kind == GPN_KERNEL_PSTEP_WALK) {
+        if (!(c->theta_exp[0] >= 2.0)) return -101;                       // GPnet.py:344
+        if (P < 2) return -4;
+        c->pstep_p = (int)c->theta_exp[1];                                // int(theta[1]) after exp, quirk A-4
+        st = build_pstep(c, c->theta_exp[0], c->pstep_p, want_grad);
+    } else {
+        return -2;                                                        // "kerneltype not implemented" (:337)
+    }
+    if (st == 0) c->have_full = true;
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GP regression
+// ---------------------------------------------------------------------------------------------------------------------
+struct GprFactor {
+    int n;
+    long ldn;
+    double *Ky, *W, *T;
+};
+
+// Ky = K[tr,tr] + c; L = chol(Ky) (in NB_KY); W = L^-1 (NB_W).  keep_copy: NB_KC = Ky before factorisation.
+int gpr_factor(gpn_ctx* c, bool keep_copy, GprFactor* f) {
+    const int n = c->n_train;
+    const long ldn = pad128(n);
+    GPN_TRY(ensure_nb(c, NB_KY, ldn, ldn));
+    GPN_TRY(ensure_nb(c, NB_W, ldn, ldn));
+    GPN_TRY(ensure_nb(c, NB_T, ldn, ldn));
+    const double noise = c->theta_exp[c->P - 1];                           // measnoise * theta[-1], quirk A-3
+    const int* tr = (const int*)c->train_idx.p;
+    GPN_TRY(gpn_k_gather(c, kfull(c), c->ldN, tr, n, tr, n, noise, nbp(c, NB_KY), ldn));
+    if (keep_copy) {
+        GPN_TRY(ensure_nb(c, NB_KC, ldn, ldn));
+        GPN_TRY(gpn_k_copy(c, n, n, nbp(c, NB_KY), ldn, nbp(c, NB_KC), ldn));
+    }
+    GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(std::max(n, c->N)) * 128));
+    GPN_TRY(gpn_potrf(c, n, nbp(c, NB_KY), ldn, (double*)c->winv.p, iscal(c, 1)));
+    GPN_TRY(gpn_trtri_from_winv_tmp(c, n, nbp(c, NB_KY), ldn, (const double*)c->winv.p, nbp(c, NB_W), ldn, nbp(c, NB_T)));
+    f->n = n; f->ldn = ldn; f->Ky = nbp(c, NB_KY); f->W = nbp(c, NB_W); f->T = nbp(c, NB_T);
+    return 0;
+}
+
+// vectors: partition of c->tvec (doubles): slot k at offset k*vstride
+double* vecp(gpn_ctx* c, int k) {
+    const long vs = pad128(std::max(std::max(c->n_train, c->n_test), 1)) + 128;
+    return (double*)c->tvec.p + (long)k * vs;
+}
+int ensure_vecs(gpn_ctx* c) {
+    const long vs = pad128(std::max(std::max(c->n_train, c->n_test), 1)) + 128;
+    return gpn_buf_ensure(c, c->tvec, sizeof(double) * (size_t)vs * 24);
+}
+enum VEC { V_T = 0, V_Z, V_ALPHA, V_F, V_A, V_B, V_P, V_W, V_SW, V_G, V_KB, V_RHS, V_Z2, V_SOL, V_Y, V_PHIF, V_U, V_FSTAR, V_VN, V_KSS, V_VV, V_PI };
+
+int gpr_logp_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
+    if (c->n_train <= 0) return -1;
+    int st = kernel_build(c, kind, theta_h, P, want_grad);
+    if (st != 0) return st;
+    GPN_TRY(ensure_vecs(c));
+    const int n = c->n_train, N = c->N;
+    GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
+    GprFactor f;
+    GPN_TRY(gpr_factor(c, want_grad && kind == GPN_KERNEL_REGULARIZED_LAPLACIAN, &f));
+    // z = L^-1 t, alpha = L^-T z, t^T alpha = z^T z                         (GPnetRegressor.py:144-148)
+    GPN_TRY(gpn_k_gemv(c, n, n, f.W, f.ldn, vecp(c, V_T), vecp(c, V_Z), GEMV_LOWER));
+    GPN_TRY(gpn_k_dot(c, n, vecp(c, V_Z), vecp(c, V_Z), dscal(c, Scal::DOT)));
+    GPN_TRY(gpn_k_sumlogdiag(c, n, f.Ky, f.ldn, dscal(c, Scal::LOGDET)));
+    const double noise = c->theta_exp[P - 1];
+    if (want_grad) {
+        GPN_TRY(gpn_k_gemv_t(c, n, n, f.W, f.ldn, vecp(c, V_Z), vecp(c, V_ALPHA), GEMV_LOWER));
+        // Kinv = W^T W (lower) -> NB_T
+        GPN_TRY(gpn_lauum(c, n, f.W, f.ldn, f.T, f.ldn, false));
+        const int* tr = (const int*)c->train_idx.p;
+        const double* G = nullptr;
+        const double* Ktt = nullptr;
+        double gs = 0.0, ks = 0.0, kshift = 0.0;
+        GPN_TRY(ensure_nb(c, NB_G, f.ldn, f.ldn));
+        if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN) {
+            // dK/dtheta0 = K^2 - K  => (K^2)[tr,tr] = K[tr,:] K[tr,:]^T  (SYRK n x n x N)
+            GPN_TRY(ensure_nb(c, NB_ROWS1, n, c->ldN));
+            GPN_TRY(gpn_k_gather_rows(c, kfull(c), c->ldN, tr, n, N, nbp(c, NB_ROWS1), c->ldN));
+            GPN_TRY(gpn_gemm(c, n, n, N, 1.0, nbp(c, NB_ROWS1), c->ldN, true, nbp(c, NB_ROWS1), c->ldN, true, 0.0, nbp(c, NB_G), f.ldn,
+                             GF_LOWER));
+            G = nbp(c, NB_G); gs = 1.0;
+            Ktt = nbp(c, NB_KC); ks = -1.0; kshift = noise;
+        } else if (kind == GPN_KERNEL_DIFFUSION) {
+            // dK/dtheta0 = -beta L~ K = A K  => (A K)[tr,tr] = A[tr,:] K[tr,:]^T (symmetric: A and K commute)
+            GPN_TRY(ensure_nb(c, NB_ROWS1, n, c->ldN));
+            GPN_TRY(ensure_nb(c, NB_ROWS2, n, c->ldN));
+            GPN_TRY(gpn_k_gather_rows(c, mat(c, 0), c->ldN, tr, n, N, nbp(c, NB_ROWS1), c->ldN));
+            GPN_TRY(gpn_k_gather_rows(c, kfull(c), c->ldN, tr, n, N, nbp(c, NB_ROWS2), c->ldN));
+            GPN_TRY(gpn_gemm(c, n, n, N, 1.0, nbp(c, NB_ROWS1), c->ldN, true, nbp(c, NB_ROWS2), c->ldN, true, 0.0, nbp(c, NB_G), f.ldn,
+                             GF_LOWER));
+            G = nbp(c, NB_G); gs = 1.0;
+        } else {
+            // dK/dtheta0 = a p B^(p-1); p = 1: B^0 = I; p <= 0: K = I, derivative 0
+            const int p = c->pstep_p;
+            if (p >= 2) {
+                GPN_TRY(gpn_k_gather(c, mat(c, 4), c->ldN, tr, n, tr, n, 0.0, nbp(c, NB_G), f.ldn));
+                G = nbp(c, NB_G); gs = c->theta_exp[0] * p;
+            } else if (p == 1) {
+                GPN_TRY(gpn_k_fill_zero(c, nbp(c, NB_G), f.ldn, n, n));
+                const double* X[1] = {nbp(c, NB_G)};
+                const long l1[1] = {f.ldn};
+                const double cf[1] = {0.0};
+                GPN_TRY(gpn_k_lincomb(c, n, nbp(c, NB_G), f.ldn, 1.0, 1, X, l1, cf));
+                G = nbp(c, NB_G); gs = c->theta_exp[0];
+            }
+        }
+        GPN_TRY(gpn_k_grad_trace(c, n, f.T, f.ldn, G, f.ldn, Ktt, f.ldn, gs, ks, kshift, vecp(c, V_ALPHA), dscal(c, Scal::TR0)));
+    }
+    double sc[Scal::NDBL];
+    int info[16];
+    GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
+    if (info_h) *info_h = info[1] ? info[1] : info[0];
+    out_h[0] = 0.5 * sc[Scal::DOT] + sc[Scal::LOGDET] + 0.5 * n * LOG_2PI;     // -logp (GPnetRegressor.py:145-150)
+    if (want_grad) {
+        for (int j = 0; j < P; ++j) out_h[1 + j] = 0.0;
+        const double sinv = sc[Scal::TR0], tr0 = sc[Scal::TR1], sa = sc[Scal::TR2];
+        out_h[1 + 0] += -0.5 * tr0;                                              // -(1/2)(a^T D a - tr(K^-1 D))
+        out_h[1 + (P - 1)] += -0.5 * noise * (sa * sa - sinv);                   // D_last = c 1 1^T
+    }
+    return 0;
+}
+
+int gpr_predict(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, double* alpha_h, double* fstar_h, double* s_h,
+                double* kss_diag_h, int* info_h) {
+    if (c->n_train <= 0) return -1;
+    int st = kernel_build(c, kind, theta_h, P, 0);
+    if (st != 0) return st;
+    GPN_TRY(ensure_vecs(c));
+    const int n = c->n_train, m = c->n_test;
+    const long ldm = pad128(m);
+    double mean = 0.0;
+    for (int i = 0; i < n; ++i) mean += t_h[i];
+    mean /= n;                                                  // np.mean: pairwise in numpy; difference is O(ulp), see DESIGN.md
+    std::vector<double> ts(n);
+    for (int i = 0; i < n; ++i) ts[i] = t_h[i] - mean;          // GPnetRegressor.py:86-87
+    GPN_TRY(upload(c, vecp(c, V_T), ts.data(), sizeof(double) * n));
+    GprFactor f;
+    GPN_TRY(gpr_factor(c, true, &f));
+    const int* tr = (const int*)c->train_idx.p;
+    const int* te = (const int*)c->test_idx.p;
+    const double noise = c->theta_exp[P - 1];
+    GPN_TRY(gpn_k_gemv(c, n, n, f.W, f.ldn, vecp(c, V_T), vecp(c, V_Z), GEMV_LOWER));
+    GPN_TRY(gpn_k_gemv_t(c, n, n, f.W, f.ldn, vecp(c, V_Z), vecp(c, V_ALPHA), GEMV_LOWER));      // :124
+    if (m > 0) {
+        GPN_TRY(ensure_nb(c, NB_KSTAR, ldm, f.ldn));
+        GPN_TRY(gpn_k_gather(c, kfull(c), c->ldN, te, m, tr, n, 0.0, nbp(c, NB_KSTAR), f.ldn));   // kstar, measnoise=False (:96-102)
+        GPN_TRY(gpn_k_gemv(c, m, n, nbp(c, NB_KSTAR), f.ldn, vecp(c, V_ALPHA), vecp(c, V_FSTAR), GEMV_FULL));   // :125
+        // v = L^-1 kstar^T = W kstar^T  (n x m)                                                   (:126)
+        GPN_TRY(ensure_nb(c, NB_V, f.ldn, ldm));
+        GPN_TRY(gpn_gemm(c, n, m, n, 1.0, f.W, f.ldn, true, nbp(c, NB_KSTAR), f.ldn, true, 0.0, nbp(c, NB_V), ldm, GF_KHI_M));
+        GPN_TRY(gpn_k_colnorm2(c, n, m, nbp(c, NB_V), ldm, vecp(c, V_VN)));                         // diag(v^T v) (:127-128)
+        GPN_TRY(gpn_k_diag_gather(c, kfull(c), c->ldN, te, m, noise, vecp(c, V_KSS)));             // kstarstar_diag (:110)
+        // PD gate on kstarstar (:117-121) through a Cholesky instead of eigvals (quirk A-7)
+        GPN_TRY(ensure_nb(c, NB_KSS, ldm, ldm));
+        GPN_TRY(gpn_k_gather(c, kfull(c), c->ldN, te, m, te, m, noise, nbp(c, NB_KSS), ldm));
+        GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(std::max(std::max(n, m), c->N)) * 128));
+        GPN_TRY(gpn_potrf(c, m, nbp(c, NB_KSS), ldm, (double*)c->winv.p, iscal(c, 2)));
+    }
+    std::vector<double> fs(m), vn(m), kss(m);
+    GPN_TRY(download(c, alpha_h, vecp(c, V_ALPHA), sizeof(double) * n));
+    if (m > 0) {
+        GPN_TRY(download(c, fs.data(), vecp(c, V_FSTAR), sizeof(double) * m));
+        GPN_TRY(download(c, vn.data(), vecp(c, V_VN), sizeof(double) * m));
+        GPN_TRY(download(c, kss.data(), vecp(c, V_KSS), sizeof(double) * m));
+    }
+    int info[16];
+    GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
+    info_h[0] = info[1] ? info[1] : info[0];
+    info_h[1] = info[2];
+    for (int i = 0; i < m; ++i) {
+        fstar_h[i] = fs[i] + mean;
+        kss_diag_h[i] = kss[i];
+        s_h[i] = sqrt(kss[i] - vn[i]);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GP classification: Laplace Newton loop (GPnetClassifier.py:90-147)
+// ---------------------------------------------------------------------------------------------------------------------
+struct NewtonState {
+    int n;
+    long ldn;
+    const double* K;
+    long ldk;
+    bool have_wk;
+};
+
+// factor B = I + sw K sw from the current V_SW; leaves L_B in NB_B, W_B in NB_WB
+int factor_B(gpn_ctx* c, const NewtonState& s) {
+    GPN_TRY(gpn_k_form_B(c, s.n, s.K, s.ldk, vecp(c, V_SW), nbp(c, NB_B), s.ldn));
+    GPN_TRY(gpn_potrf(c, s.n, nbp(c, NB_B), s.ldn, (double*)c->winv.p, iscal(c, 3)));
+    return gpn_trtri_from_winv_tmp(c, s.n, nbp(c, NB_B), s.ldn, (const double*)c->winv.p, nbp(c, NB_WB), s.ldn, nbp(c, NB_T));
+}
+
+int gpc_newton(gpn_ctx* c, const double* K, long ldk, int n, const double* y_h, double tol, double phif0, double scale, int variant,
+               double* f_h, double* a_h, double* logq_h, int* iters_h, int* info_h) {
+    GPN_TRY(ensure_vecs(c));
+    NewtonState s;
+    s.n = n; s.ldn = pad128(n); s.K = K; s.ldk = ldk;
+    GPN_TRY(ensure_nb(c, NB_B, s.ldn, s.ldn));
+    GPN_TRY(ensure_nb(c, NB_WB, s.ldn, s.ldn));
+    GPN_TRY(ensure_nb(c, NB_T, s.ldn, s.ldn));
+    GPN_TRY(ensure_nb(c, NB_WK, s.ldn, s.ldn));
+    GPN_TRY(ensure_nb(c, NB_KC, s.ldn, s.ldn));
+    GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(std::max(n, c->N)) * 128));
+    GPN_TRY(upload(c, vecp(c, V_Y), y_h, sizeof(double) * n));
+    GPN_CK(cudaMemsetAsync(vecp(c, V_F), 0, sizeof(double) * n, c->stream));                    // f = 0 (:96)
+    // f^T K^-1 f of the convergence test (:126) through one Cholesky of K (K is fixed during the loop)
+    GPN_TRY(gpn_k_fill_zero(c, nbp(c, NB_KC), s.ldn, (int)s.ldn, (int)s.ldn));
+    GPN_TRY(gpn_k_copy(c, n, n, K, ldk, nbp(c, NB_KC), s.ldn));
+    GPN_TRY(gpn_potrf(c, n, nbp(c, NB_KC), s.ldn, (double*)c->winv.p, iscal(c, 4)));
+    GPN_TRY(gpn_trtri_from_winv_tmp(c, n, nbp(c, NB_KC), s.ldn, (const double*)c->winv.p, nbp(c, NB_WK), s.ldn, nbp(c, NB_T)));
+    int info[16];
+    GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
+    s.have_wk = (info[4] == 0);     // K not numerically PD: use f^T a (== f^T K^-1 f since f = K a), see DESIGN.md
+    int count = 0, iters = 0;
+    double sc[Scal::NDBL];
+    while (true) {
+        ++count;
+        ++iters;
+        newton_pre_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_F), vecp(c, V_Y), vecp(c, V_W), vecp(c, V_SW), vecp(c, V_P),
+                                                         vecp(c, V_B), vecp(c, V_G));
+        c->launches++;
+        GPN_TRY(factor_B(c, s));                                                                 // :110
+        GPN_TRY(gpn_k_gemv(c, n, n, K, ldk, vecp(c, V_B), vecp(c, V_KB), GEMV_FULL));            // K b
+        vec_mul_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_SW), vecp(c, V_KB), vecp(c, V_RHS));
+        c->launches++;
+        GPN_TRY(gpn_k_gemv(c, n, n, nbp(c, NB_WB), s.ldn, vecp(c, V_RHS), vecp(c, V_Z2), GEMV_LOWER));
+        GPN_TRY(gpn_k_gemv_t(c, n, n, nbp(c, NB_WB), s.ldn, vecp(c, V_Z2), vecp(c, V_SOL), GEMV_LOWER));
+        newton_a_kernel<<<g1(n), 256, 0, c->stream>>>(n, scale, vecp(c, V_B), vecp(c, V_SW), vecp(c, V_SOL), vecp(c, V_A));
+        c->launches++;
+        GPN_TRY(gpn_k_gemv(c, n, n, K, ldk, vecp(c, V_A), vecp(c, V_F), GEMV_FULL));             // f = K a (:122)
+        if (s.have_wk) {
+            GPN_TRY(gpn_k_gemv(c, n, n, nbp(c, NB_WK), s.ldn, vecp(c, V_F), vecp(c, V_U), GEMV_LOWER));
+            GPN_TRY(gpn_k_dot(c, n, vecp(c, V_U), vecp(c, V_U), dscal(c, Scal::Q)));
+        } else {
+            GPN_TRY(gpn_k_dot(c, n, vecp(c, V_F), vecp(c, V_A), dscal(c, Scal::Q)));
+        }
+        GPN_TRY(gpn_k_sumlogdiag(c, n, nbp(c, NB_B), s.ldn, dscal(c, Scal::LOGDET)));
+        newton_phif_kernel<<<1, 1024, 0, c->stream>>>(n, vecp(c, V_P), dscal(c, Scal::Q), dscal(c, Scal::LOGDET), vecp(c, V_PHIF),
+                                                       iters == 1, phif0, dscal(c, Scal::CONV));
+        c->launches++;
+        GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
+        if (info[3] != 0) {     // np.linalg.cholesky raised inside the loop: propagate (GPnetClassifier.py:110)
+            *info_h = info[3];
+            *iters_h = iters;
+            return 0;
+        }
+        if (sc[Scal::CONV] < tol) break;                                                         // :132
+        if (count > 100) {                                                                       // :134-136
+            count = 0;
+            scale /= 2.0;
+        }
+        if (iters > 100000) return -95;
+    }
+    // logq (:138-145): uses L of the LAST iteration (computed from the previous f)
+    GPN_TRY(gpn_k_dot(c, n, vecp(c, V_A), vecp(c, V_F), dscal(c, Scal::AF)));
+    newton_lik_kernel<<<1, 1024, 0, c->stream>>>(n, vecp(c, V_F), vecp(c, V_Y), variant, dscal(c, Scal::LIK));
+    c->launches++;
+    if (f_h) GPN_TRY(download(c, f_h, vecp(c, V_F), sizeof(double) * n));
+    if (a_h) GPN_TRY(download(c, a_h, vecp(c, V_A), sizeof(double) * n));
+    GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
+    *logq_h = -0.5 * sc[Scal::AF] - sc[Scal::LIK] - sc[Scal::LOGDET];
+    *iters_h = iters;
+    *info_h = 0;
+    return 0;
+}
+
+int gpc_train_block(gpn_ctx* c) {   // K = kernel(train, train) with noise on every entry -> NB_KY
+    const int n = c->n_train;
+    const long ldn = pad128(n);
+    GPN_TRY(ensure_nb(c, NB_KY, ldn, ldn));
+    const int* tr = (const int*)c->train_idx.p;
+    return gpn_k_gather(c, kfull(c), c->ldN, tr, n, tr, n, c->theta_exp[c->P - 1], nbp(c, NB_KY), ldn);
+}
+
+}   // namespace
+
+// =====================================================================================================================
+// C-ABI
+// =====================================================================================================================
+extern "C" {
+
+const char* gpn_last_error(void) { return g_last_error; }
+
+gpn_ctx* gpn_create(int device, void* cuda_stream) {
+    if (cudaSetDevice(device) != cudaSuccess) {
+        gpn_set_last_error(__FILE__, __LINE__, "cudaSetDevice failed (no CUDA device? this library has no CPU fallback)");
+        return nullptr;
+    }
+    gpn_ctx* c = new gpn_ctx();
+    c->device = device;
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            gpn_set_last_error(__FILE__, __LINE__, "cudaStreamCreate failed");
+            delete c;
+            return nullptr;
+        }
+        c->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        gpn_set_last_error(__FILE__, __LINE__, "cudaGetDeviceProperties failed");
+        delete c;
+        return nullptr;
+    }
+    c->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        gpn_set_last_error(__FILE__, __LINE__, "gpnet_b200 requires an sm_100a device (B200)");
+        delete c;
+        return nullptr;
+    }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+        gpn_set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available from the driver");
+        delete c;
+        return nullptr;
+    }
+    c->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    if (cudaMalloc(&c->scal.p, 1024) != cudaSuccess || cudaMallocHost(&c->pinned, 4096) != cudaSuccess) {
+        gpn_set_last_error(__FILE__, __LINE__, "initial allocations failed");
+        delete c;
+        return nullptr;
+    }
+    c->scal.cap = 1024;
+    c->pinned_cap = 4096;
+    cudaMemsetAsync(c->scal.p, 0, 1024, c->stream);
+    return c;
+}
+
+void gpn_destroy(gpn_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->mat[9] = DevBuf();   // alias slot
+    DevBuf* all[] = {&c->indptr, &c->indices, &c->weights, &c->dinv, &c->train_idx, &c->test_idx, &c->tvec, &c->winv, &c->scal, &c->partial};
+    for (DevBuf* b : all)
+        if (b->p) cudaFree(b->p);
+    for (auto& b : c->mat)
+        if (b.p) cudaFree(b.p);
+    for (auto& b : c->nb)
+        if (b.p) cudaFree(b.p);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int gpn_sync(gpn_ctx* c) {
+    GPN_CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+long long gpn_launch_count(gpn_ctx* c) { return c->launches; }
+double gpn_flop_count(gpn_ctx* c) { return c->flops; }
+void gpn_reset_counters(gpn_ctx* c) {
+    c->launches = 0;
+    c->flops = 0.0;
+}
+
+int gpn_set_graph(gpn_ctx* c, int N, const int* indptr_h, const int* indices_h, const double* weights_h) {
+    if (!c) return -1;
+    if (N <= 0) return -2;
+    if (!indptr_h) return -3;
+    GPN_CK(cudaSetDevice(c->device));
+    const long long nnz = indptr_h[N];
+    if (nnz < 0) return -3;
+    if (nnz > 0 && !indices_h) return -4;
+    for (long long e = 0; e < nnz; ++e)
+        if (indices_h[e] < 0 || indices_h[e] >= N) return -4;
+    GPN_TRY(gpn_buf_ensure(c, c->indptr, sizeof(int) * (size_t)(N + 1)));
+    GPN_TRY(gpn_buf_ensure(c, c->indices, sizeof(int) * (size_t)(nnz + 1)));
+    GPN_TRY(gpn_buf_ensure(c, c->dinv, sizeof(double) * (size_t)(2 * N)));
+    GPN_TRY(upload(c, c->indptr.p, indptr_h, sizeof(int) * (size_t)(N + 1)));
+    if (nnz > 0) GPN_TRY(upload(c, c->indices.p, indices_h, sizeof(int) * (size_t)nnz));
+    if (weights_h && nnz > 0) {
+        GPN_TRY(gpn_buf_ensure(c, c->weights, sizeof(double) * (size_t)nnz));
+        GPN_TRY(upload(c, c->weights.p, weights_h, sizeof(double) * (size_t)nnz));
+    } else if (c->weights.p) {
+        GPN_CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->weights.p);
+        c->weights = DevBuf();
+    }
+    c->N = N;
+    c->nnz = nnz;
+    c->ldN = pad128(N);
+    c->have_full = false;
+    c->n_train = c->n_test = 0;
+    return gpn_k_degree_dinv(c, N, (const int*)c->indptr.p, (const int*)c->indices.p, (const double*)c->weights.p, (double*)c->dinv.p);
+}
+
+int gpn_set_nodes(gpn_ctx* c, int n_train, const int* train_h, int n_test, const int* test_h) {
+    if (!c) return -1;
+    if (n_train < 0 || n_train > c->N) return -2;
+    if (n_test < 0 || n_test > c->N) return -4;
+    for (int i = 0; i < n_train; ++i)
+        if (train_h[i] < 0 || train_h[i] >= c->N) return -3;
+    for (int i = 0; i < n_test; ++i)
+        if (test_h[i] < 0 || test_h[i] >= c->N) return -5;
+    GPN_TRY(gpn_buf_ensure(c, c->train_idx, sizeof(int) * (size_t)(n_train + 1)));
+    GPN_TRY(gpn_buf_ensure(c, c->test_idx, sizeof(int) * (size_t)(n_test + 1)));
+    if (n_train) GPN_TRY(upload(c, c->train_idx.p, train_h, sizeof(int) * (size_t)n_train));
+    if (n_test) GPN_TRY(upload(c, c->test_idx.p, test_h, sizeof(int) * (size_t)n_test));
+    c->n_train = n_train;
+    c->n_test = n_test;
+    return ensure_vecs(c);
+}
+
+int gpn_laplacian_dense(gpn_ctx* c, double alpha, double gamma, double* out, long ld) {
+    if (!c || c->N <= 0) return -1;
+    if (ld < c->N || (ld & 1)) return -5;
+    GPN_TRY(gpn_k_fill_zero(c, out, ld, c->N, c->N));
+    return gpn_k_laplacian_scatter(c, c->N, (const int*)c->indptr.p, (const int*)c->indices.p,
+                                   c->weights.p ? (const double*)c->weights.p : nullptr, (const double*)c->dinv.p, alpha, gamma, out,
+                                   ld);
+}
+
+int gpn_gemm_f64(gpn_ctx* c, int transa, int transb, int M, int N, int K, double alpha, const double* A, long lda, const double* B,
+                 long ldb, double beta, double* C, long ldc) {
+    if (!c) return -1;
+    return gpn_gemm(c, M, N, K, alpha, A, lda, transa == 0, B, ldb, transb != 0, beta, C, ldc, 0);
+}
+
+int gpn_potrf_f64(gpn_ctx* c, int n, double* A, long lda, int* info_h) {
+    if (!c) return -1;
+    GPN_TRY(clear_info(c));
+    GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(n) * 128));
+    GPN_TRY(gpn_potrf(c, n, A, lda, (double*)c->winv.p, iscal(c, 0)));
+    GPN_TRY(gpn_k_zero_upper(c, A, lda, n));
+    int info[16];
+    GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
+    if (info_h) *info_h = info[0];
+    return 0;
+}
+
+int gpn_spd_inverse_f64(gpn_ctx* c, int n, double* A, long lda, double* out, long ldo, double* work, int* info_h) {
+    if (!c) return -1;
+    if (lda != ldo) return -6;
+    GPN_TRY(clear_info(c));
+    GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(n) * 128));
+    GPN_TRY(gpn_potrf(c, n, A, lda, (double*)c->winv.p, iscal(c, 0)));
+    // W -> out, scratch -> work, then K = W^T W needs a third buffer: reuse A (L is dead once W exists)
+    GPN_TRY(gpn_trtri_from_winv_tmp(c, n, A, lda, (const double*)c->winv.p, out, ldo, work));
+    GPN_TRY(gpn_k_copy(c, n, n, out, ldo, work, ldo));
+    GPN_TRY(gpn_lauum(c, n, work, ldo, out, ldo, true));
+    int info[16];
+    GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
+    if (info_h) *info_h = info[0];
+    return 0;
+}
+
+int gpn_gather_block_add(gpn_ctx* c, const double* K, long ld, const int* rows, int nr, const int* cols, int nc, double addc,
+                         double* out, long ldo) {
+    if (!c) return -1;
+    return gpn_k_gather(c, K, ld, rows, nr, cols, nc, addc, out, ldo, nr, nc);
+}
+
+int gpn_kernel_build(gpn_ctx* c, int kind, const double* theta_h, int P, int want_grad) {
+    if (!c) return -1;
+    return kernel_build(c, kind, theta_h, P, want_grad);
+}
+const double* gpn_kernel_ptr(gpn_ctx* c, long* ld) {
+    if (!c || !c->have_full) return nullptr;
+    if (ld) *ld = c->ldN;
+    return kfull(c);
+}
+void gpn_expm_info(gpn_ctx* c, int* m, int* s) {
+    if (m) *m = c->expm_m;
+    if (s) *s = c->expm_s;
+}
+
+int gpn_kernel_block_h(gpn_ctx* c, const int* rows_h, int nr, const int* cols_h, int nc, double addc, double* out_h) {
+    if (!c || !c->have_full) return -1;
+    if (nr <= 0 || nc <= 0) return 0;
+    DevBuf& ib = c->partial;
+    const long ldo = (nc + 1) & ~1L;
+    GPN_TRY(gpn_buf_ensure(c, ib, sizeof(int) * (size_t)(nr + nc + 2)));
+    GPN_TRY(ensure_nb(c, NB_S, nr, ldo));
+    int* dr = (int*)ib.p;
+    int* dc = dr + nr;
+    GPN_TRY(upload(c, dr, rows_h, sizeof(int) * (size_t)nr));
+    GPN_TRY(upload(c, dc, cols_h, sizeof(int) * (size_t)nc));
+    GPN_TRY(gpn_k_gather(c, kfull(c), c->ldN, dr, nr, dc, nc, addc, nbp(c, NB_S), ldo, nr, nc));
+    GPN_TRY(download_matrix(c, out_h, nbp(c, NB_S), ldo, nr, nc));
+    return gpn_sync(c);
+}
+
+int gpn_gpr_logp_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
+    if (!c) return -1;
+    return gpr_logp_grad(c, kind, theta_h, P, t_h, want_grad, out_h, info_h);
+}
+
+int gpn_gpr_predict(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, double* alpha_h, double* fstar_h, double* s_h,
+                    double* kss_diag_h, int* info_h) {
+    if (!c) return -1;
+    return gpr_predict(c, kind, theta_h, P, t_h, alpha_h, fstar_h, s_h, kss_diag_h, info_h);
+}
+
+int gpn_gpr_fetch(gpn_ctx* c, int which, double* out_h) {
+    if (!c || !c->have_full) return -1;
+    const int n = c->n_train, m = c->n_test;
+    const long ldn = pad128(n), ldm = pad128(m);
+    switch (which) {
+        case 0: GPN_TRY(download_matrix(c, out_h, nbp(c, NB_KC), ldn, n, n)); break;
+        case 1: GPN_TRY(download_matrix(c, out_h, nbp(c, NB_KSTAR), ldn, m, n)); break;
+        case 2:
+            GPN_TRY(gpn_k_zero_upper(c, nbp(c, NB_KY), ldn, n));
+            GPN_TRY(download_matrix(c, out_h, nbp(c, NB_KY), ldn, n, n));
+            break;
+        case 3: GPN_TRY(download_matrix(c, out_h, nbp(c, NB_V), ldm, n, m)); break;
+        case 4: {
+            const int* te = (const int*)c->test_idx.p;
+            GPN_TRY(gpn_k_gather(c, kfull(c), c->ldN, te, m, te, m, c->theta_exp[c->P - 1], nbp(c, NB_KSS), ldm, m, m));
+            GPN_TRY(download_matrix(c, out_h, nbp(c, NB_KSS), ldm, m, m));
+            break;
+        }
+        default: return -2;
+    }
+    return gpn_sync(c);
+}
+
+int gpn_gpc_newton(gpn_ctx* c, int kind, const double* theta_h, int P, const double* y_h, int n, const double* K_dev, long ldk, double tol,
+                   double phif0, double scale, int variant, double* f_h, double* a_h, double* logq_h, int* iters_h, int* info_h) {
+    if (!c) return -1;
+    const double* K = K_dev;
+    if (K == nullptr) {
+        int st = kernel_build(c, kind, theta_h, P, 0);
+        if (st != 0) return st;
+        if (n != c->n_train) return -6;
+        GPN_TRY(gpc_train_block(c));
+        K = nbp(c, NB_KY);
+        ldk = pad128(n);
+    } else {
+        // external K: vectors are sized from the node sets, make sure they can hold n
+        if (c->n_train < n) c->n_train = n;
+        GPN_TRY(clear_info(c));
+    }
+    return gpc_newton(c, K, ldk, n, y_h, tol, phif0, scale, variant, f_h, a_h, logq_h, iters_h, info_h);
+}
+
+int gpn_gpc_predict(gpn_ctx* c, int kind, const double* theta_h, int P, const double* y_h, double* f_h, double* a_h, double* logq_h,
+                    int* iters_h, double* fstar_h, double* V_h, double* pistar_h, int* info_h) {
+    if (!c) return -1;
+    int st = kernel_build(c, kind, theta_h, P, 0);
+    if (st != 0) return st;
+    const int n = c->n_train, m = c->n_test;
+    const long ldn = pad128(n), ldm = pad128(m);
+    GPN_TRY(gpc_train_block(c));
+    const double* K = nbp(c, NB_KY);
+    GPN_TRY(gpc_newton(c, K, ldn, n, y_h, 0.1, 1e100, 1.0, 0, f_h, a_h, logq_h, iters_h, info_h));   // :200-202 defaults
+    if (*info_h != 0 || m <= 0) return 0;
+    NewtonState s;
+    s.n = n; s.ldn = ldn; s.K = K; s.ldk = ldn; s.have_wk = false;
+    // W, p from the FINAL f (:203-209); B refactored (:208)
+    newton_pre_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_F), vecp(c, V_Y), vecp(c, V_W), vecp(c, V_SW), vecp(c, V_P), vecp(c, V_B),
+                                                     vecp(c, V_G));
+    c->launches++;
+    GPN_TRY(factor_B(c, s));
+    const int* tr = (const int*)c->train_idx.p;
+    const int* te = (const int*)c->test_idx.p;
+    GPN_TRY(ensure_nb(c, NB_KSTAR, ldn, ldm));
+    GPN_TRY(ensure_nb(c, NB_S, ldn, ldm));
+    GPN_TRY(ensure_nb(c, NB_V, ldn, ldm));
+    GPN_TRY(gpn_k_gather(c, kfull(c), c->ldN, tr, n, te, m, 0.0, nbp(c, NB_KSTAR), ldm, n, m));           // kstar n x m, measnoise=0 (:193-199)
+    GPN_TRY(gpn_k_gemv_t(c, n, m, nbp(c, NB_KSTAR), ldm, vecp(c, V_G), vecp(c, V_FSTAR), GEMV_FULL));     // fstar (:210)
+    GPN_TRY(gpn_k_scale_rows(c, n, m, nbp(c, NB_KSTAR), ldm, vecp(c, V_SW), nbp(c, NB_S), ldm));          // sqrtW kstar
+    // v = L_B^-1 (sqrtW kstar) = W_B S                                                                  (:211)
+    GPN_TRY(gpn_gemm(c, n, m, n, 1.0, nbp(c, NB_WB), ldn, true, nbp(c, NB_S), ldm, false, 0.0, nbp(c, NB_V), ldm, GF_KHI_M));
+    GPN_TRY(gpn_k_colnorm2(c, n, m, nbp(c, NB_V), ldm, vecp(c, V_VN)));
+    GPN_TRY(gpn_k_diag_gather(c, kfull(c), c->ldN, te, m, 0.0, vecp(c, V_KSS)));                          // :212-214
+    pistar_kernel<<<g1(m), 256, 0, c->stream>>>(m, vecp(c, V_FSTAR), vecp(c, V_KSS), vecp(c, V_VN), vecp(c, V_VV), vecp(c, V_PI));
+    c->launches++;
+    GPN_TRY(download(c, fstar_h, vecp(c, V_FSTAR), sizeof(double) * m));
+    GPN_TRY(download(c, V_h, vecp(c, V_VV), sizeof(double) * m));
+    GPN_TRY(download(c, pistar_h, vecp(c, V_PI), sizeof(double) * m));
+    int info[16];
+    GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
+    if (info[3] != 0) *info_h = info[3];
+    return 0;
+}
+
+int gpn_landscape(gpn_ctx* c, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1, const double* ax1_h, int n1,
+                  const double* ax2_h, int n2, const double* t_h, long idx_begin, long idx_end, long idx_stride, int want_grad,
+                  double* out_h) {
+    if (!c) return -1;
+    if (ax0 < 0 || ax0 >= P) return -6;
+    if (ax1 < 0 || ax1 >= P) return -7;
+    if (idx_stride <= 0) return -15;
+    double th[8];
+    const int rec = 1 + P;
+    long q = 0;
+    for (long idx = idx_begin; idx < idx_end && idx < (long)n1 * n2; idx += idx_stride, ++q) {
+        for (int j = 0; j < P; ++j) th[j] = theta_h[j];
+        th[ax0] = ax1_h[idx / n2];          // GPnet.py:544-546 (ax0 written first, then ax1, as the reference)
+        th[ax1] = ax2_h[idx % n2];
+        double* o = out_h + q * rec;
+        for (int j = 0; j < rec; ++j) o[j] = 0.0;
+        int info = 0, st;
+        if (!classifier) {
+            double tmp[9];
+            st = gpr_logp_grad(c, kind, th, P, t_h, want_grad, tmp, &info);
+            if (st != 0) return st;
+            if (info > 0) {
+                o[0] = INFINITY;            // logPosterior returned -inf (A-8) => lml = +inf
+            } else {
+                o[0] = -tmp[0];
+                if (want_grad)
+                    for (int j = 0; j < P; ++j) o[1 + j] = -tmp[1 + j];
+            }
+        } else {
+            double logq = 0.0;
+            int iters = 0;
+            st = kernel_build(c, kind, th, P, 0);
+            if (st != 0) return st;
+            GPN_TRY(gpc_train_block(c));
+            st = gpc_newton(c, nbp(c, NB_KY), pad128(c->n_train), c->n_train, t_h, 0.1, 1e100, 1.0, 0, nullptr, nullptr, &logq, &iters,
+                            &info);
+            if (st != 0) return st;
+            o[0] = (info > 0) ? NAN : logq;
+        }
+    }
+    return 0;
+}
+
+}   // extern "C"

@@ -1,0 +1,112 @@
+/* gpnet_b200 -- C-ABI of the B200-native dense-GP hot path of filippocastelli/GPnet.
+ *
+ * The reference is pure Python and has no FFI: the boundary it offers is the Python class API
+ * (GPnetRegressor / GPnetClassifier).  This header is the C-ABI introduced BENEATH that API; each entry point
+ * names the reference code it replaces (file:line in the reference repository).  The Python drop-in classes in
+ * gpnet_b200/ bind it with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - one context per process per GPU; every call is stream-ordered on the context's stream and returns after
+ *    the work is enqueued, except calls with `_h` output pointers, which synchronise before returning;
+ *  - pointers are DEVICE pointers unless the parameter name ends in `_h` (host);
+ *  - matrices are row-major fp64 with an explicit leading dimension (elements); leading dimensions and any
+ *    sub-matrix column offset must be even and base pointers 16-byte aligned (TMA stride rule);
+ *  - return value: 0 ok; >0 LAPACK-style info (order of the leading minor that is not positive definite);
+ *    <0 bad argument (-i = i-th argument); <= -1000 CUDA/driver error (gpn_last_error() has the text);
+ *  - never throws, never calls back into the host language.
+ */
+#ifndef GPNET_B200_H
+#define GPNET_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpn_ctx gpn_ctx;
+
+/* kernel types, GPnet.py:333 kernel_list */
+enum { GPN_KERNEL_DIFFUSION = 0, GPN_KERNEL_REGULARIZED_LAPLACIAN = 1, GPN_KERNEL_PSTEP_WALK = 2 };
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+gpn_ctx* gpn_create(int device, void* cuda_stream /* NULL: the library creates its own stream */);
+void gpn_destroy(gpn_ctx* ctx);
+const char* gpn_last_error(void);
+int gpn_sync(gpn_ctx* ctx);
+/* counters: kernels launched through this context and tensor flops executed by the GEMM launcher */
+long long gpn_launch_count(gpn_ctx* ctx);
+double gpn_flop_count(gpn_ctx* ctx);
+void gpn_reset_counters(gpn_ctx* ctx);
+
+/* ---- graph and node sets (host -> device once; resident afterwards) -------------------------------------- */
+/* CSR adjacency in graph-position order (row i = i-th node of list(G)); weights_h may be NULL (all ones).
+ * Replaces the per-call nx.normalized_laplacian_matrix(self.Graph) of GPnet.py:329: degrees and D^-1/2 are
+ * computed once here. */
+int gpn_set_graph(gpn_ctx* ctx, int N, const int* indptr_h, const int* indices_h, const double* weights_h);
+/* sorted graph positions of the training / test nodes (GPnet.py:305-323 set algebra, quirk A-5) */
+int gpn_set_nodes(gpn_ctx* ctx, int n_train, const int* train_h, int n_test, const int* test_h);
+
+/* ---- device-level primitives (unit-testable; device pointers) ------------------------------------------- */
+/* out = gamma*I + alpha*L~ with L~ = D^-1/2 (D-A) D^-1/2 (GPnet.py:329 and the operands of :340,:342,:346) */
+int gpn_laplacian_dense(gpn_ctx* ctx, double alpha, double gamma, double* out, long ld);
+/* C = alpha*op(A)*op(B) + beta*C; transX != 0 means the operand is stored transposed ([K][M] resp. [N][K]).
+ * Replaces the dgemm behind np.dot / np.linalg.matrix_power (GPnet.py:346). */
+int gpn_gemm_f64(gpn_ctx* ctx, int transa, int transb, int M, int N, int K, double alpha, const double* A, long lda,
+                 const double* B, long ldb, double beta, double* C, long ldc);
+/* lower Cholesky in place (strict upper zeroed); replaces np.linalg.cholesky (GPnetRegressor.py:123,141;
+ * GPnetClassifier.py:110,159,208).  info_h receives 0 or the failing minor. */
+int gpn_potrf_f64(gpn_ctx* ctx, int n, double* A, long lda, int* info_h);
+/* out = inverse of the SPD matrix A (A is destroyed: it holds L afterwards); replaces scipy.linalg.inv (GPnet.py:342)
+ * and the inv(K) of GPnetClassifier.py:126.  work: n*ld doubles of scratch. */
+int gpn_spd_inverse_f64(gpn_ctx* ctx, int n, double* A, long lda, double* out, long ldo, double* work, int* info_h);
+/* out[i][j] = K[rows[i]][cols[j]] + addc  (GPnet.py:362-365: np.delete x2 + scalar noise on every entry) */
+int gpn_gather_block_add(gpn_ctx* ctx, const double* K, long ld, const int* rows, int nr, const int* cols, int nc,
+                         double addc, double* out, long ldo);
+
+/* ---- full kernel (GPnet.py:335-349) ------------------------------------------------------------------------ */
+/* Builds the N x N kernel for log-parameters theta_h[0..P) and keeps it resident.  Parameter-domain violations
+ * return -100 (diffusion: exp(theta0) >= 1, GPnet.py:339) / -101 (p-step: exp(theta0) < 2, GPnet.py:344) so the
+ * host can raise the reference's AssertionError.  want_grad keeps the derivative by-products. */
+int gpn_kernel_build(gpn_ctx* ctx, int kind, const double* theta_h, int P, int want_grad);
+/* device pointer / leading dimension of the resident full kernel */
+const double* gpn_kernel_ptr(gpn_ctx* ctx, long* ld);
+/* Pade order and number of squarings used by the last diffusion build */
+void gpn_expm_info(gpn_ctx* ctx, int* m, int* s);
+/* K[rows][cols] + addc copied to the host (the return value of GPnetBase.kernel, GPnet.py:362-367) */
+int gpn_kernel_block_h(gpn_ctx* ctx, const int* rows_h, int nr, const int* cols_h, int nc, double addc, double* out_h);
+
+/* ---- GP regression (GPnetRegressor.py:79-150) ---------------------------------------------------------------- */
+/* out_h[0] = -logp (GPnetRegressor.py:136-150, quirk A-8: *info_h>0 means Cholesky failed and the caller returns
+ * -inf); with want_grad, out_h[1..P] = d(-logp)/d theta_j (analytic form of old_implementation/GPR.py:52-64).
+ * Rebuilds the full kernel from theta (as the reference does on every call). t_h: n_train un-shifted targets. */
+int gpn_gpr_logp_grad(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* t_h, int want_grad,
+                      double* out_h, int* info_h);
+/* GPnetRegressor.predict body (:86-128).  Outputs (host): alpha[n], fstar[m], s[m] (sqrt of the predictive
+ * variance), kss_diag[m]; info_h[0]: Cholesky info of k, info_h[1]: info of kstarstar (the two PD gates, A-7). */
+int gpn_gpr_predict(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* t_h, double* alpha_h,
+                    double* fstar_h, double* s_h, double* kss_diag_h, int* info_h);
+/* after gpn_gpr_predict: which = 0 k (n x n), 1 kstar (m x n), 2 L (n x n), 3 v (n x m), 4 kstarstar (m x m) */
+int gpn_gpr_fetch(gpn_ctx* ctx, int which, double* out_h);
+
+/* ---- GP classification, Laplace approximation (GPnetClassifier.py:90-147,184-240) ---------------------------- */
+/* Newton loop on K = kernel(train,train) (built from theta unless K_dev != NULL, in which case the n x n device
+ * matrix is used as is -- the notebook KAT path).  variant 0 = GPnetClassifier.py:138-145 logq, 1 = the older
+ * expression of scripts/prova.py:197-200.  Outputs (host): f[n], a[n], logq, iterations. */
+int gpn_gpc_newton(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* y_h, int n, const double* K_dev,
+                   long ldk, double tol, double phif0, double scale, int variant, double* f_h, double* a_h, double* logq_h,
+                   int* iters_h, int* info_h);
+/* GPnetClassifier.predict (:184-233): Newton + fstar[m], V[m], pi_star[m] */
+int gpn_gpc_predict(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* y_h, double* f_h, double* a_h,
+                    double* logq_h, int* iters_h, double* fstar_h, double* V_h, double* pistar_h, int* info_h);
+
+/* ---- landscape slice (GPnet.py:539-552) ---------------------------------------------------------------------- */
+/* For flat grid indices idx = idx_begin + q*idx_stride < idx_end: theta[ax0] = ax1_h[idx / n2], theta[ax1] =
+ * ax2_h[idx % n2]; out_h[q*(1+P) ..] = (lml = +logp, dlogp/dtheta) (gradient only if want_grad).  classifier != 0
+ * evaluates -logq... of the Laplace loop instead (y in t_h).  Used by the multi-GPU sharded landscape. */
+int gpn_landscape(gpn_ctx* ctx, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1, const double* ax1_h,
+                  int n1, const double* ax2_h, int n2, const double* t_h, long idx_begin, long idx_end, long idx_stride,
+                  int want_grad, double* out_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPNET_B200_H */
