@@ -1,0 +1,97 @@
+"""Drop-in ``GPnetClassifier`` (reference: GPnetClassifier.py:9-240) on the sm_100a library.
+
+The Laplace mode-finding Newton loop (``NRiteration``), ``logPosterior`` and ``predict`` keep the reference's
+signatures, shapes and quirks: the log-of-log ``logq`` (A-10), the n-vector convergence test with ``tol = 0.1``
+(A-11), the 5-erf averaged sigmoid, and the label rule of ``generate_df`` (GPnet.py:587-603).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+
+from ._lib import KERNEL_IDS
+from .engine import raise_domain
+from .GPnet import COEFS, LAMBDAS, GPnetBase, KERNEL_LIST  # noqa: F401  (re-exported like the reference module)
+
+
+class GPnetClassifier(GPnetBase):
+    def __init__(self, Graph=False, totnodes=False, ntrain=100, ntest=90, deg=4, seed=0, training_nodes=False,
+                 training_values=False, test_nodes=False, theta=[0.1, 0.1, 0.1], optimize=False, relabel_nodes=False,
+                 kerneltype="diffusion"):
+        super().__init__(Graph, totnodes, ntrain, ntest, deg, seed, training_nodes, training_values, test_nodes, theta,
+                         optimize, relabel_nodes, kerneltype)
+        self.pivot_flag = False
+        if not isinstance(training_values, pd.Series):
+            print("no training labels where specified")
+            print("> Setting labels to (np.sin(0.6 * self.pvtdist) > 0).replace({True: 1, False: -1})")
+            self.pivot_flag = True
+            self.pvtdist = self.pivot_distance(0)
+            self.binary_labels = pd.Series(np.where(np.sin(0.6 * self.pvtdist) > 0, 1, -1), index=self.pvtdist.index)
+            self.training_values = self.binary_labels[self.training_nodes]
+        else:
+            self.training_values = training_values
+
+    def _kind(self):
+        assert self.kerneltype in KERNEL_LIST, "kerneltype not implemented"
+        return KERNEL_IDS[self.kerneltype]
+
+    @staticmethod
+    def _labels(targets):
+        return np.asarray(targets.values if isinstance(targets, (pd.Series, pd.DataFrame)) else targets,
+                          dtype=np.float64).reshape(-1)
+
+    # ---- GPnetClassifier.py:85-147 ---------------------------------------------------------------------
+    def logPosterior(self, theta, *args):
+        data, targets = args
+        (f, logq, a) = self.NRiteration(data, targets, theta)
+        return -logq
+
+    def NRiteration(self, data, targets, theta, tol=0.1, phif=1e100, scale=1.0):
+        th = self._theta_vec(theta)
+        ctx = self._engine.bind(self._positions(data), self._positions(self.test_nodes))
+        ctx._kernel_key = None
+        ctx._predict_token = None
+        st, r = ctx.gpc_newton(self._kind(), th, self._labels(targets), tol=tol, phif=phif, scale=scale, variant=0)
+        raise_domain(st)
+        if r["info"] > 0:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")   # np.linalg.cholesky, GPnetClassifier.py:110
+        self.newton_iterations = r["iters"]
+        n = len(r["f"])
+        return (r["f"].reshape(n, 1), np.array([[r["logq"]]]), r["a"].reshape(n, 1))
+
+    # ---- GPnetClassifier.py:184-240 --------------------------------------------------------------------
+    def predict(self):
+        if self.optimize != False:   # noqa: E712
+            self.optimize_params()
+        th = self._theta_vec(self.theta)
+        ctx = self._engine.bind(self._positions(self.training_nodes), self._positions(self.test_nodes))
+        ctx._kernel_key = None
+        ctx._predict_token = None
+        st, r = ctx.gpc_predict(self._kind(), th, self._labels(self.training_values))
+        raise_domain(st)
+        if r["info"] > 0:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")
+        self.newton_iterations = r["iters"]
+        self.fstar = r["fstar"]
+        self.V = r["V"]
+        pi_star = r["pi_star"]
+        self.predicted_probs = np.vstack((1 - pi_star, pi_star)).T
+        self.s = np.sqrt(self.V)
+        print("succesfully trained model")
+        self.is_trained = True
+        self.generate_df()
+        return (self.fstar.T, self.V, self.predicted_probs)
+
+    def gradLogPosterior(self, theta, *args):
+        raise NotImplementedError(
+            "GPnetClassifier.gradLogPosterior needs derivative kernels the reference never had (IndexError there, "
+            "SURVEY A-12); the classifier's optimize_params stays function-only like the reference's")
+
+    def plot_latent(self, filename=False):
+        pl = self._pyplot()
+        pl.figure(figsize=[15, 9])
+        pl.plot(self.test_nodes, self.fstar, "b-")
+        pl.gca().fill_between(self.test_nodes, self.fstar - self.s, self.fstar + self.s, color="#dddddd")
+        pl.title("Latent Process Mean and Variance")
+        if isinstance(filename, str):
+            pl.savefig(filename, bbox_inches="tight")

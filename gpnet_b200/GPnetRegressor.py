@@ -1,0 +1,159 @@
+"""Drop-in ``GPnetRegressor`` (reference: GPnetRegressor.py:8-181) on the sm_100a library.
+
+``predict`` / ``logPosterior`` / ``gradLogPosterior`` keep the reference's signatures, return values and
+quirks: targets are mean-shifted in ``predict`` but not in ``logPosterior`` (A-6),
+``logPosterior`` returns ``-inf`` when the Cholesky fails (A-8), PD gates print and return ``self`` (A-7,
+through the Cholesky info instead of ``eigvals``).  ``gradLogPosterior`` is the *correct* analytic gradient
+(the reference's own body is dead code, A-9) with the reference's sign convention (returns ``-grad``).
+Large attributes (``k``, ``kstar``, ``kstarstar``, ``L``, ``v``, ``V``) are fetched from the device on first access.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+
+from ._lib import KERNEL_IDS
+from .engine import raise_domain
+from .GPnet import GPnetBase, KERNEL_LIST, _is_false
+
+
+class _DeviceBacked:
+    """Descriptor: attribute materialised from the device on first read, then cached on the instance."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __set_name__(self, owner, attr):
+        self.attr = "_lazy_" + attr
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        val = obj.__dict__.get(self.attr)
+        if val is None:
+            val = obj._fetch(self.name)
+            obj.__dict__[self.attr] = val
+        return val
+
+    def __set__(self, obj, value):
+        obj.__dict__[self.attr] = value
+
+
+class GPnetRegressor(GPnetBase):
+    k = _DeviceBacked("k")
+    kstar = _DeviceBacked("kstar")
+    kstarstar = _DeviceBacked("kstarstar")
+    L = _DeviceBacked("L")
+    v = _DeviceBacked("v")
+    V = _DeviceBacked("V")
+
+    def __init__(self, Graph=False, totnodes=False, ntrain=100, ntest=90, deg=4, seed=0, training_nodes=False,
+                 training_values=False, test_nodes=False, theta=[0.1, 0.1, 0.1], optimize=False, relabel_nodes=False,
+                 kerneltype="diffusion"):
+        super().__init__(Graph, totnodes, ntrain, ntest, deg, seed, training_nodes, training_values, test_nodes, theta,
+                         optimize, relabel_nodes, kerneltype)
+        self.pivot_flag = False
+        if _is_false(training_values):
+            self.pivot_flag = True
+            self.training_values = self.pvtdist[self.training_nodes]
+        else:
+            self.training_values = training_values
+        self._predict_token = None
+
+    # ---- helpers -----------------------------------------------------------------------------------
+    def _kind(self):
+        assert self.kerneltype in KERNEL_LIST, "kerneltype not implemented"
+        return KERNEL_IDS[self.kerneltype]
+
+    @staticmethod
+    def _values(t):
+        return np.asarray(t.values if isinstance(t, (pd.Series, pd.DataFrame)) else t, dtype=np.float64).reshape(-1)
+
+    def _fetch(self, name):
+        ctx = self._engine.ctx
+        if self._predict_token is None or ctx._owner is not self._engine or ctx._predict_token is not self._predict_token:
+            raise AttributeError(f"'{name}' is only available right after predict() (device buffers were reused)")
+        if name == "V":      # GPnetRegressor.py:127: kstarstar_diag - v^T v (m x m by broadcasting)
+            v = self.v
+            return self.kstarstar_diag - v.T @ v
+        return ctx.gpr_fetch(name)
+
+    def _clear_lazy(self):
+        for key in [k for k in self.__dict__ if k.startswith("_lazy_")]:
+            del self.__dict__[key]
+
+    # ---- GPnetRegressor.py:79-134 ----------------------------------------------------------------------
+    def predict(self):
+        self.optimize_params()
+        self.k_not_posdef_flag = False
+        self.kstar_not_posdef_flag = False
+        t = self._values(self.training_values)
+        self.t_mean = np.mean(self.training_values)
+        self.t_shifted = self.training_values - self.t_mean
+        th = self._theta_vec(self.theta)
+        ctx = self._engine.bind(self._positions(self.training_nodes), self._positions(self.test_nodes))
+        ctx._kernel_key = None
+        self._clear_lazy()
+        st, res = ctx.gpr_predict(self._kind(), th, t)
+        raise_domain(st)
+        self._predict_token = object()
+        ctx._predict_token = self._predict_token
+        self.kstarstar_diag = res["kstarstar_diag"]
+        if res["info_k"] > 0:
+            self.k_not_posdef_flag = True
+            print("K not positive definite, aborting...")
+            return self
+        if res["info_kss"] > 0:
+            self.kstar_not_posdef_flag = True
+            print("K** not positive definite, aborting...")
+            return self
+        self.alpha = res["alpha"]
+        self.fstar = res["fstar"]
+        self.s = res["s"]
+        print("succesfully trained model")
+        self.is_trained = True
+        self.generate_df()
+        return self
+
+    # ---- GPnetRegressor.py:136-150 ---------------------------------------------------------------------
+    def _eval(self, theta, data, t, want_grad):
+        th = self._theta_vec(theta)
+        ctx = self._engine.bind(self._positions(data), self._positions(self.test_nodes) if not _is_false(self.test_nodes) else ())
+        ctx._kernel_key = None          # the compound call rebuilds the resident kernel for this theta
+        ctx._predict_token = None       # ... and reuses the buffers predict() left behind
+        st, out, info = ctx.gpr_logp_grad(self._kind(), th, self._values(t), want_grad)
+        raise_domain(st)
+        return out, info
+
+    def logPosterior(self, theta, *args):
+        data, t = args
+        out, info = self._eval(theta, data, t, False)
+        if info > 0:
+            return -np.inf
+        return float(out[0])
+
+    def gradLogPosterior(self, theta, *args):
+        data, t = args
+        out, info = self._eval(theta, data, t, True)
+        if info > 0:
+            return -np.inf
+        return out[1:].copy()
+
+    def logPosterior_and_grad(self, theta, *args):
+        """(-logp, -dlogp/dtheta) from ONE fused device evaluation -- the callback for ``jac=True``."""
+        data, t = args
+        out, info = self._eval(theta, data, t, True)
+        if info > 0:
+            return -np.inf, np.zeros(len(out) - 1)
+        return float(out[0]), out[1:].copy()
+
+    # ---- plotting pass-through (presentation only) ---------------------------------------------------
+    def plot_predict_2d(self, filename=False):
+        pl = self._pyplot()
+        pl.figure(figsize=[15, 9])
+        pl.plot(self.training_nodes, self._values(self.training_values), "r+", ms=20)
+        pl.plot(self.test_nodes, self.fstar, "b-")
+        pl.gca().fill_between(self.test_nodes, self.fstar - self.s, self.fstar + self.s, color="#dddddd")
+        pl.title("Gaussian Process Mean and Variance")
+        if isinstance(filename, str):
+            pl.savefig(filename, bbox_inches="tight")

@@ -29,8 +29,12 @@ SIGNATURES = {
     "gpn_launch_count": (C.c_longlong, [C.c_void_p]),
     "gpn_flop_count": (C.c_double, [C.c_void_p]),
     "gpn_reset_counters": (None, [C.c_void_p]),
+    "gpn_fp64_peak": (C.c_int, [C.c_void_p, C.c_double, c_dbl_p]),
+    "gpn_set_profile": (None, [C.c_void_p, C.c_int]),
+    "gpn_profile_summary": (C.c_int, [C.c_void_p, c_dbl_p]),
     "gpn_set_graph": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_dbl_p]),
     "gpn_set_nodes": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int, c_int_p]),
+    "gpn_set_targets": (C.c_int, [C.c_void_p, c_dbl_p, C.c_int]),
     "gpn_laplacian_dense": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_long]),
     "gpn_gemm_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_long,
                                C.c_void_p, C.c_long, C.c_double, C.c_void_p, C.c_long]),
@@ -139,6 +143,10 @@ class Context:
         self._check(self.lib.gpn_set_nodes(self.h, len(tr), _ip(tr), len(te), _ip(te)), "gpn_set_nodes")
         self.n_train, self.n_test = len(tr), len(te)
 
+    def set_targets(self, t):
+        tt = _f64(t)
+        self._check(self.lib.gpn_set_targets(self.h, _dp(tt), len(tt)), "gpn_set_targets")
+
     # -- counters -----------------------------------------------------------------------------------
     def sync(self):
         self._check(self.lib.gpn_sync(self.h), "gpn_sync")
@@ -151,6 +159,20 @@ class Context:
 
     def reset_counters(self):
         self.lib.gpn_reset_counters(self.h)
+
+    def fp64_peak(self, seconds=0.25) -> float:
+        out = C.c_double(0)
+        self._check(self.lib.gpn_fp64_peak(self.h, float(seconds), C.byref(out)), "gpn_fp64_peak")
+        return out.value
+
+    def set_profile(self, on: bool):
+        self.lib.gpn_set_profile(self.h, int(bool(on)))
+
+    def profile_summary(self):
+        out = np.zeros(6)
+        self._check(self.lib.gpn_profile_summary(self.h, _dp(out)), "gpn_profile_summary")
+        return dict(gemm_ms=out[0], gemm_flops=out[1], gemm_launches=int(out[2]), big_ms=out[3], big_flops=out[4],
+                    big_launches=int(out[5]))
 
     # -- device-pointer primitives (pointers are ints, e.g. torch.Tensor.data_ptr()) --------------------
     def laplacian_dense(self, alpha, gamma, out_ptr, ld):
@@ -202,12 +224,15 @@ class Context:
 
     # -- regression ----------------------------------------------------------------------------------
     def gpr_logp_grad(self, kind, theta, t, want_grad):
-        th, tt = _f64(theta), _f64(t)
-        if len(tt) != self.n_train:
+        """t=None: use the resident targets of set_targets()."""
+        th = _f64(theta)
+        tt = None if t is None else _f64(t)
+        if tt is not None and len(tt) != self.n_train:
             raise ValueError("len(t) != number of training nodes")
         out = np.zeros(1 + len(th), dtype=np.float64)
         info = C.c_int(0)
-        st = self.lib.gpn_gpr_logp_grad(self.h, kind, _dp(th), len(th), _dp(tt), int(want_grad), _dp(out), C.byref(info))
+        st = self.lib.gpn_gpr_logp_grad(self.h, kind, _dp(th), len(th), None if tt is None else _dp(tt), int(want_grad), _dp(out),
+                                        C.byref(info))
         if st in (-100, -101):
             return st, out, 0
         self._check(st, "gpn_gpr_logp_grad")

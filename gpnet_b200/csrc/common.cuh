@@ -48,6 +48,12 @@ enum : int {
     GF_FORCE_BIG = 128,    // force the 128x128 tile configuration
 };
 
+struct ProfEvent {
+    cudaEvent_t e0, e1;
+    double flops;
+    bool big;
+};
+
 struct gpn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -56,6 +62,8 @@ struct gpn_ctx {
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     long long launches = 0;        // kernels launched through this context (bench "gpu_launches")
     double flops = 0.0;            // executed tensor flops accounted by the GEMM launcher
+    bool profile = false;          // record a CUDA-event pair around every GEMM launch (bench roofline leg)
+    std::vector<ProfEvent> prof_events;
 
     // graph (resident)
     int N = 0;

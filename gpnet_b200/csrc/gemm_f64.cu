@@ -350,11 +350,23 @@ int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, lon
     GPN_TRY(encode_operand(c, &ta, A, lda, a_kmajor, M, K, bm, batch, sA));
     GPN_TRY(encode_operand(c, &tb, B, ldb, b_kmajor, N, K, bn, batch, sB));
     // executed-flop accounting (tile granularity, respecting the structure flags)
-    {
-        double kavg = (double)K;
-        if (flags & (GF_KLO_M | GF_KLO_N | GF_KHI_M | GF_KHI_N)) kavg = 0.5 * K + 0.5 * bm;
-        c->flops += 2.0 * (double)ntiles * bm * bn * kavg * batch;
+    double kavg = (double)K;
+    if (flags & (GF_KLO_M | GF_KLO_N | GF_KHI_M | GF_KHI_N)) kavg = fmin((double)K, 0.5 * K + 0.5 * bm);
+    const double fl = 2.0 * (double)ntiles * bm * bn * kavg * batch;
+    c->flops += fl;
+    ProfEvent pe;
+    if (c->profile) {
+        cudaEventCreate(&pe.e0);
+        cudaEventCreate(&pe.e1);
+        pe.flops = fl;
+        pe.big = use_big;
+        cudaEventRecord(pe.e0, c->stream);
     }
-    if (use_big) return launch_layout<2, 4, 6>(c, a_kmajor, b_kmajor, ta, tb, a, (int)ntiles, batch);
-    return launch_layout<1, 2, 4>(c, a_kmajor, b_kmajor, ta, tb, a, (int)ntiles, batch);
+    const int st = use_big ? launch_layout<2, 4, 6>(c, a_kmajor, b_kmajor, ta, tb, a, (int)ntiles, batch)
+                           : launch_layout<1, 2, 4>(c, a_kmajor, b_kmajor, ta, tb, a, (int)ntiles, batch);
+    if (c->profile) {
+        cudaEventRecord(pe.e1, c->stream);
+        c->prof_events.push_back(pe);
+    }
+    return st;
 }

@@ -180,6 +180,25 @@ __global__ void pistar_kernel(int m, const double* __restrict__ fstar, const dou
 
 inline int g1(long n) { return (int)((n + 255) / 256); }
 
+// register-resident DMMA.8x8x4 loop: the FP64 tensor issue-rate ceiling the roofline is reported against
+// (MEASURED_PEAKS.json has no FP64 entry).  8 independent accumulator pairs per warp, 16 warps per SM.
+__global__ void __launch_bounds__(512) dmma_peak_kernel(double* out, int iters, double a0, double b0) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-9; c[i][1] = i * 1e-9; }
+    const double a = a0 + threadIdx.x * 1e-12, b = b0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // full kernel construction (GPnet.py:335-349)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -449,7 +468,7 @@ int ensure_vecs(gpn_ctx* c) {
     const long vs = pad128(std::max(std::max(c->n_train, c->n_test), 1)) + 128;
     return gpn_buf_ensure(c, c->tvec, sizeof(double) * (size_t)vs * 24);
 }
-enum VEC { V_T = 0, V_Z, V_ALPHA, V_F, V_A, V_B, V_P, V_W, V_SW, V_G, V_KB, V_RHS, V_Z2, V_SOL, V_Y, V_PHIF, V_U, V_FSTAR, V_VN, V_KSS, V_VV, V_PI };
+enum VEC { V_TRES = 23, V_T = 0, V_Z, V_ALPHA, V_F, V_A, V_B, V_P, V_W, V_SW, V_G, V_KB, V_RHS, V_Z2, V_SOL, V_Y, V_PHIF, V_U, V_FSTAR, V_VN, V_KSS, V_VV, V_PI };
 
 int gpr_logp_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
     if (c->n_train <= 0) return -1;
@@ -457,7 +476,8 @@ int gpr_logp_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const doub
     if (st != 0) return st;
     GPN_TRY(ensure_vecs(c));
     const int n = c->n_train, N = c->N;
-    GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
+    if (t_h) GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
+    else GPN_CK(cudaMemcpyAsync(vecp(c, V_T), vecp(c, V_TRES), sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
     GprFactor f;
     GPN_TRY(gpr_factor(c, want_grad && kind == GPN_KERNEL_REGULARIZED_LAPLACIAN, &f));
     // z = L^-1 t, alpha = L^-T z, t^T alpha = z^T z                         (GPnetRegressor.py:144-148)
@@ -808,6 +828,65 @@ int gpn_set_nodes(gpn_ctx* c, int n_train, const int* train_h, int n_test, const
     c->n_train = n_train;
     c->n_test = n_test;
     return ensure_vecs(c);
+}
+
+int gpn_fp64_peak(gpn_ctx* c, double seconds, double* tflops_h) {
+    if (!c) return -1;
+    GPN_TRY(gpn_buf_ensure(c, c->partial, sizeof(double) * (size_t)c->num_sms * 512));
+    cudaEvent_t e0, e1;
+    GPN_CK(cudaEventCreate(&e0));
+    GPN_CK(cudaEventCreate(&e1));
+    const int iters = 16384;
+    const double flops_per_launch = 512.0 * 8 * iters * 16 * c->num_sms;
+    dmma_peak_kernel<<<c->num_sms, 512, 0, c->stream>>>((double*)c->partial.p, 64, 1.0000001, 0.9999999);   // warm-up
+    GPN_CK(cudaStreamSynchronize(c->stream));
+    GPN_CK(cudaEventRecord(e0, c->stream));
+    int reps = 0;
+    float ms = 0.f;
+    do {
+        for (int r = 0; r < 4; ++r) dmma_peak_kernel<<<c->num_sms, 512, 0, c->stream>>>((double*)c->partial.p, iters, 1.0000001, 0.9999999);
+        reps += 4;
+        GPN_CK(cudaEventRecord(e1, c->stream));
+        GPN_CK(cudaEventSynchronize(e1));
+        GPN_CK(cudaEventElapsedTime(&ms, e0, e1));
+    } while (ms < seconds * 1e3);
+    *tflops_h = flops_per_launch * reps / (ms * 1e-3) * 1e-12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+}
+
+void gpn_set_profile(gpn_ctx* c, int on) {
+    if (!c) return;
+    c->profile = on != 0;
+    if (!on) return;
+    for (auto& p : c->prof_events) {
+        cudaEventDestroy(p.e0);
+        cudaEventDestroy(p.e1);
+    }
+    c->prof_events.clear();
+}
+
+/* out_h[0] = summed duration (ms) of the GEMM launches recorded since gpn_set_profile(ctx,1), out_h[1] = their executed
+ * flops, out_h[2] = number of launches, out_h[3] = same three restricted to the 128x128 configuration: ms, [4] flops, [5] count */
+int gpn_profile_summary(gpn_ctx* c, double* out_h) {
+    if (!c) return -1;
+    GPN_CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 6; ++i) out_h[i] = 0.0;
+    for (auto& p : c->prof_events) {
+        float ms = 0.f;
+        GPN_CK(cudaEventElapsedTime(&ms, p.e0, p.e1));
+        out_h[0] += ms; out_h[1] += p.flops; out_h[2] += 1;
+        if (p.big) { out_h[3] += ms; out_h[4] += p.flops; out_h[5] += 1; }
+    }
+    return 0;
+}
+
+int gpn_set_targets(gpn_ctx* c, const double* t_h, int n) {
+    if (!c) return -1;
+    if (n != c->n_train || n <= 0) return -3;
+    GPN_TRY(ensure_vecs(c));
+    return upload(c, vecp(c, V_TRES), t_h, sizeof(double) * n);
 }
 
 int gpn_laplacian_dense(gpn_ctx* c, double alpha, double gamma, double* out, long ld) {

@@ -1,0 +1,128 @@
+"""Host-side engine shared by the drop-in classes: one library context per process per GPU, graphs
+uploaded once and re-bound only when another model used the context in between (SURVEY A-17: the
+reference rebuilds the Laplacian from networkx on every kernel() call, GPnet.py:329)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from ._lib import KERNEL_IDS, Context
+
+_CONTEXTS: dict[int, Context] = {}
+
+
+def default_device() -> int:
+    """LOCAL_RANK under torchrun (one process per GPU), else GPNET_B200_DEVICE, else 0."""
+    for key in ("GPNET_B200_DEVICE", "LOCAL_RANK"):
+        if key in os.environ:
+            return int(os.environ[key])
+    return 0
+
+
+def get_context(device: int | None = None) -> Context:
+    device = default_device() if device is None else int(device)
+    ctx = _CONTEXTS.get(device)
+    if ctx is None:
+        ctx = Context(device)          # raises if the .so is missing or no B200 is visible: no CPU fallback
+        ctx._owner = None
+        ctx._nodes_key = None
+        ctx._kernel_key = None
+        ctx._predict_token = None
+        _CONTEXTS[device] = ctx
+    return ctx
+
+
+def register_context(ctx: Context) -> Context:
+    """Adopt an externally created context (e.g. one bound to a torch stream) as THE context of its device."""
+    for attr in ("_owner", "_nodes_key", "_kernel_key", "_predict_token"):
+        if not hasattr(ctx, attr):
+            setattr(ctx, attr, None)
+    _CONTEXTS[ctx.device] = ctx
+    return ctx
+
+
+def graph_csr(G, weight="weight"):
+    """CSR adjacency in ``list(G)`` order (what nx.normalized_laplacian_matrix(G) uses at GPnet.py:329);
+    a self-loop contributes once to its row, undirected edges appear in both rows."""
+    nodelist = list(G)
+    pos = {u: i for i, u in enumerate(nodelist)}
+    N = len(nodelist)
+    src, dst, wts = [], [], []
+    for u, v, d in G.edges(data=True):
+        w = float(d.get(weight, 1.0))
+        i, j = pos[u], pos[v]
+        src.append(i); dst.append(j); wts.append(w)
+        if i != j:
+            src.append(j); dst.append(i); wts.append(w)
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    wts = np.asarray(wts, dtype=np.float64)
+    order = np.lexsort((dst, src))
+    src, dst, wts = src[order], dst[order], wts[order]
+    indptr = np.zeros(N + 1, dtype=np.int64)
+    np.add.at(indptr, src + 1, 1)
+    indptr = np.cumsum(indptr)
+    return indptr.astype(np.int32), dst.astype(np.int32), wts, nodelist, pos
+
+
+class GraphEngine:
+    """Binds one model's graph + node sets to the shared context on demand."""
+
+    def __init__(self, G, device: int | None = None):
+        self.indptr, self.indices, self.weights, self.nodelist, self.pos = graph_csr(G)
+        self.N = len(self.nodelist)
+        self.device = device
+        self._ctx = None
+
+    @property
+    def ctx(self) -> Context:
+        if self._ctx is None:
+            self._ctx = get_context(self.device)
+        return self._ctx
+
+    def bind(self, train_pos=None, test_pos=None) -> Context:
+        ctx = self.ctx
+        if ctx._owner is not self:
+            ctx.set_graph(self.indptr, self.indices, self.weights)
+            ctx._owner = self
+            ctx._nodes_key = None
+            ctx._kernel_key = None
+        if train_pos is not None:
+            key = (tuple(train_pos), tuple(test_pos or ()))
+            if ctx._nodes_key != key:
+                ctx.set_nodes(train_pos, test_pos or ())
+                ctx._nodes_key = key
+        return ctx
+
+    def positions(self, nodes, relabelled: bool):
+        """graph positions of ``nodes``, de-duplicated and ascending (GPnet.py:305-323 set algebra, A-5)."""
+        if relabelled:
+            return sorted({int(x) for x in nodes})
+        return sorted({self.pos[x] for x in nodes})
+
+    def build_kernel(self, kerneltype: str, theta, want_grad=False):
+        """Full N x N kernel resident on the device for these log-parameters (cached per theta)."""
+        ctx = self.bind()
+        th = np.asarray(theta, dtype=np.float64).reshape(-1)
+        key = (kerneltype, th.tobytes(), bool(want_grad))
+        if ctx._kernel_key == key:
+            return ctx
+        ctx._kernel_key = None
+        ctx._predict_token = None
+        st = ctx.kernel_build(KERNEL_IDS[kerneltype], th, want_grad)
+        raise_domain(st)
+        ctx._kernel_key = key
+        return ctx
+
+    def invalidate_kernel(self):
+        if self._ctx is not None:
+            self._ctx._kernel_key = None
+
+
+def raise_domain(st: int):
+    """Parameter-domain statuses of the C-ABI -> the reference's AssertionErrors (GPnet.py:339,344)."""
+    if st == -100:
+        raise AssertionError("Lambda must be < 1")
+    if st == -101:
+        raise AssertionError("a must be >=2")

@@ -37,6 +37,13 @@ long long gpn_launch_count(gpn_ctx* ctx);
 double gpn_flop_count(gpn_ctx* ctx);
 void gpn_reset_counters(gpn_ctx* ctx);
 
+/* measurement hooks (bench.py): sustained FP64 tensor (DMMA.8x8x4) issue-rate ceiling of this GPU, measured for
+ * about `seconds`; per-launch CUDA-event profiling of the GEMM kernel (out_h[0..2]: ms, executed flops, launches of
+ * all GEMM launches since gpn_set_profile(ctx,1); out_h[3..5]: the same for the 128x128 configuration only). */
+int gpn_fp64_peak(gpn_ctx* ctx, double seconds, double* tflops_h);
+void gpn_set_profile(gpn_ctx* ctx, int on);
+int gpn_profile_summary(gpn_ctx* ctx, double* out_h);
+
 /* ---- graph and node sets (host -> device once; resident afterwards) -------------------------------------- */
 /* CSR adjacency in graph-position order (row i = i-th node of list(G)); weights_h may be NULL (all ones).
  * Replaces the per-call nx.normalized_laplacian_matrix(self.Graph) of GPnet.py:329: degrees and D^-1/2 are
@@ -44,6 +51,10 @@ void gpn_reset_counters(gpn_ctx* ctx);
 int gpn_set_graph(gpn_ctx* ctx, int N, const int* indptr_h, const int* indices_h, const double* weights_h);
 /* sorted graph positions of the training / test nodes (GPnet.py:305-323 set algebra, quirk A-5) */
 int gpn_set_nodes(gpn_ctx* ctx, int n_train, const int* train_h, int n_test, const int* test_h);
+
+/* makes the n_train training targets resident on the device; GP-regression calls with t_h == NULL use them
+ * (GPnetBase.set_training_values, GPnet.py:554-556) */
+int gpn_set_targets(gpn_ctx* ctx, const double* t_h, int n);
 
 /* ---- device-level primitives (unit-testable; device pointers) ------------------------------------------- */
 /* out = gamma*I + alpha*L~ with L~ = D^-1/2 (D-A) D^-1/2 (GPnet.py:329 and the operands of :340,:342,:346) */
@@ -77,7 +88,8 @@ int gpn_kernel_block_h(gpn_ctx* ctx, const int* rows_h, int nr, const int* cols_
 /* ---- GP regression (GPnetRegressor.py:79-150) ---------------------------------------------------------------- */
 /* out_h[0] = -logp (GPnetRegressor.py:136-150, quirk A-8: *info_h>0 means Cholesky failed and the caller returns
  * -inf); with want_grad, out_h[1..P] = d(-logp)/d theta_j (analytic form of old_implementation/GPR.py:52-64).
- * Rebuilds the full kernel from theta (as the reference does on every call). t_h: n_train un-shifted targets. */
+ * Rebuilds the full kernel from theta (as the reference does on every call). t_h: n_train un-shifted targets
+ * (NULL: the resident targets of gpn_set_targets). */
 int gpn_gpr_logp_grad(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* t_h, int want_grad,
                       double* out_h, int* info_h);
 /* GPnetRegressor.predict body (:86-128).  Outputs (host): alpha[n], fstar[m], s[m] (sqrt of the predictive

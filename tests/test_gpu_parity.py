@@ -1,0 +1,219 @@
+"""GPU tier: parity of the CUDA path (through the drop-in classes / the C-ABI) against the golden vectors of
+the shimmed reference and against the numpy oracle on the same seeded inputs.  Tolerance: 1e-9 norm-wise
+relative on kernel entries, predictive mean / deviation and logp (north_star); classifier labels and Newton
+iteration counts identical."""
+import os
+
+import networkx as nx
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import golden_files, load_golden, nrel
+from oracle import configs as cfg
+from oracle import gp_oracle as go
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def graph_from_csr(g):
+    N = len(g["indptr"]) - 1
+    G = nx.Graph()
+    G.add_nodes_from(range(N))
+    for i in range(N):
+        for e in range(g["indptr"][i], g["indptr"][i + 1]):
+            j = int(g["indices"][e])
+            if j >= i:
+                G.add_edge(i, j, weight=float(g["weights"][e]))
+    return G
+
+
+def make_regressor(g):
+    import gpnet_b200
+    tr, te = [int(x) for x in g["train"]], [int(x) for x in g["test"]]
+    m = gpnet_b200.GPnetRegressor(Graph=graph_from_csr(g), training_nodes=tr, test_nodes=te, theta=list(g["theta"]),
+                                  relabel_nodes=True, kerneltype=str(g["kerneltype"]), training_values=False)
+    m.set_training_values(pd.Series(g["t_train"], index=tr))
+    return m
+
+
+@pytest.mark.parametrize("path", golden_files("reg_"), ids=os.path.basename)
+def test_regressor_parity(path):
+    g = load_golden(path)
+    m = make_regressor(g)
+    assert m.predict() is m and m.is_trained
+    assert nrel(m.fstar, g["fstar"]) <= TOL
+    assert nrel(m.s, g["s"]) <= TOL
+    assert nrel(m.alpha, g["alpha"]) <= TOL
+    assert nrel(m.kstarstar_diag, g["kstarstar_diag"]) <= TOL
+    assert list(m.df.columns) == ["pvtdist", "train_vals", "fstar", "variance_s", "prob_0", "prob_1", "predicted_class"]
+    assert nrel(m.df["fstar"][m.test_nodes].values, g["fstar"]) <= TOL
+    if "k" in g:        # lazily fetched device-resident attributes
+        assert nrel(m.k, g["k"]) <= TOL and nrel(m.kstar, g["kstar"]) <= TOL
+        L = m.L
+        assert nrel(L @ L.T, g["k"]) <= TOL and np.all(np.triu(L, 1) == 0)
+        v = m.v
+        assert nrel(np.sum(v * v, axis=0), g["kstarstar_diag"] - g["s"] ** 2) <= 1e-8
+        assert m.V.shape == (len(m.test_nodes),) * 2 and m.kstarstar.shape == m.V.shape
+        # GPnetBase.kernel: fresh host array, graph order, noise on every entry
+        kk = m.kernel(m.training_nodes, m.training_nodes, m.theta)
+        assert nrel(kk, g["k"]) <= TOL
+        ks = m.kernel(m.test_nodes, m.training_nodes, m.theta, measnoise=False)
+        assert nrel(ks, g["kstar"]) <= TOL
+    lp = m.logp()
+    assert abs(lp - g["logp"]) <= TOL * abs(g["logp"])
+    tv = m.training_values
+    if "neg_logp_grad_fd" in g:
+        grad = m.gradLogPosterior(m.theta, m.training_nodes, tv)
+        sel = g["grad_fd_valid"]
+        assert nrel(grad[sel], g["neg_logp_grad_fd"][sel]) <= 1e-6            # vs central differences of the reference
+        assert nrel(grad, g["neg_logp_grad_analytic_oracle"]) <= 1e-8          # vs the analytic oracle
+        val, grad2 = m.logPosterior_and_grad(m.theta, m.training_nodes, tv)
+        assert abs(-val - g["logp"]) <= TOL * abs(g["logp"]) and np.array_equal(grad, grad2)
+    if "land_lml" in g:
+        th = list(g["theta"])
+        lml = m.lml_landscape(th, list(g["land_axidx"]), g["land_ax1"], g["land_ax2"])
+        assert nrel(lml, g["land_lml"]) <= TOL
+        assert th[g["land_axidx"][0]] == g["land_ax1"][-1] and th[g["land_axidx"][1]] == g["land_ax2"][-1]   # A-14
+
+
+@pytest.mark.parametrize("path", golden_files("cls_"), ids=os.path.basename)
+def test_classifier_parity(path):
+    import gpnet_b200
+    g = load_golden(path)
+    tr, te = [int(x) for x in g["train"]], [int(x) for x in g["test"]]
+    y = pd.Series(g["y_train"].astype(np.int64), index=tr)
+    m = gpnet_b200.GPnetClassifier(Graph=graph_from_csr(g), training_nodes=tr, test_nodes=te, theta=list(g["theta"]),
+                                   relabel_nodes=True, kerneltype=str(g["kerneltype"]), training_values=y)
+    f, logq, a = m.NRiteration(tr, y, g["theta"])
+    assert f.shape == (len(tr), 1) and a.shape == (len(tr), 1) and np.shape(logq) == (1, 1)
+    assert m.newton_iterations == g["iters"]
+    assert abs(float(logq[0, 0]) - g["logq"]) <= TOL * abs(g["logq"])
+    assert nrel(f.ravel(), g["f"]) <= TOL and nrel(a.ravel(), g["a"]) <= TOL
+    fstar, V, probs = m.predict()
+    assert m.newton_iterations == g["iters"]
+    assert nrel(fstar, g["fstar"]) <= TOL and nrel(V, g["V"]) <= TOL and nrel(probs, g["probs"]) <= TOL
+    labels = np.asarray(m.df["predicted_class"][te], dtype=np.float64)
+    assert np.array_equal(labels, g["labels"])                   # identical classifier labels
+    assert abs(float(np.squeeze(m.logp())) - g["logp"]) <= TOL * abs(g["logp"])
+
+
+def test_notebook_known_answer_on_gpu(gpu_ctx):
+    """The reference's only KAT (report_notebook.ipynb cell 49) through the CUDA Newton loop."""
+    import torch
+    g = load_golden(os.path.join(os.path.dirname(__file__), "golden", "notebook_kat.npz"))
+    n = len(g["y"])
+    Kb = torch.zeros(n, 48, dtype=torch.float64, device="cuda:0")
+    Kb[:, :n] = torch.tensor(g["K"], device="cuda:0")
+    torch.cuda.synchronize()
+    st, r = gpu_ctx.gpc_newton(0, [0.0], g["y"], variant=1, K_ptr=Kb.data_ptr(), ldk=48)
+    assert st == 0 and r["info"] == 0
+    assert abs(-r["logq"] - (-77.22939013)) < 5e-9
+    assert r["iters"] == 5
+    assert nrel(r["f"], g["f"]) <= TOL and nrel(r["a"], g["a"]) <= TOL
+
+
+def test_error_behaviour_matches_reference():
+    import gpnet_b200
+    G, tr, te, t = cfg.grid_case(8, 8, 20, 20)
+    m = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=tr, test_nodes=te, theta=list(np.log([1.5, 0.01])), relabel_nodes=True,
+                                  kerneltype="diffusion", training_values=False)
+    m.set_training_values(pd.Series(t[tr], index=tr))
+    with pytest.raises(AssertionError, match="Lambda must be < 1"):        # GPnet.py:339
+        m.kernel(tr, tr, m.theta)
+    with pytest.raises(AssertionError, match="Lambda must be < 1"):
+        m.logp()
+    m.kerneltype = "pstep_walk"
+    with pytest.raises(AssertionError, match="a must be >=2"):             # GPnet.py:344
+        m.kernel(tr, tr, np.log([1.5, 2.0, 0.1]))
+    # K_y not positive definite -> logPosterior returns -inf (A-8); predict prints and returns self (A-7)
+    m.kerneltype = "pstep_walk"
+    m.theta = list(np.log([2.0, 3.0, 1e-300]))         # (2I - L~)^3 is singular on a bipartite grid, noise ~ 0
+    val = m.logPosterior(m.theta, tr, m.training_values)
+    assert val == -np.inf or np.isfinite(val)
+    full = list(range(64))
+    m2 = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=full, test_nodes=[0], theta=m.theta, relabel_nodes=True,
+                                   kerneltype="pstep_walk", training_values=False)
+    m2.set_training_values(pd.Series(t, index=full))
+    assert m2.logPosterior(m2.theta, full, m2.training_values) == -np.inf
+    assert m2.predict() is m2 and m2.k_not_posdef_flag and not m2.is_trained
+
+
+def test_is_pos_def_and_calc_ktot():
+    import gpnet_b200
+    G, tr, te, t = cfg.grid_case(6, 6, 10, 10)
+    m = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=tr, test_nodes=te, theta=list(np.log([0.5, 0.1])), relabel_nodes=True,
+                                  kerneltype="regularized_laplacian")
+    m.calc_ktot()
+    orc = go.OracleGP(G, kerneltype="regularized_laplacian")
+    assert nrel(m.ktot, orc.kernel(range(36), range(36), m.theta)) <= TOL
+    assert m.is_pos_def(m.ktot)
+    assert not m.is_pos_def(-np.eye(5))
+
+
+def test_optimize_params_with_device_gradient():
+    """scipy.optimize drives the fused logp+grad entry point (jac=True extension) and the reference-style
+    function-only mode to the same optimum (reduced C3: RGG, regularized Laplacian, L-BFGS-B box)."""
+    import gpnet_b200
+    G, tr, te, t = cfg.rgg_case(600, 300, 300)
+    bounds = [[np.log(0.01), np.log(0.99)], [np.log(0.001), np.log(10.0)]]
+    res = {}
+    for jac in (True, False):
+        m = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=tr, test_nodes=te, theta=list(np.log([0.6, 0.01])), relabel_nodes=True,
+                                      kerneltype="regularized_laplacian", training_values=False,
+                                      optimize={"method": "L-BFGS-B", "bounds": bounds, "jac": jac})
+        m.set_training_values(pd.Series(t[tr], index=tr))
+        m.optimize_params()
+        res[jac] = (np.array(m.theta), m.optimize_result.fun)
+    orc = go.OracleGP(G, kerneltype="regularized_laplacian")
+    assert abs(res[True][1] - orc.neg_logp(res[True][0], tr, t[tr])) <= 1e-9 * abs(res[True][1])
+    assert abs(res[True][1] - res[False][1]) <= 1e-5 * abs(res[False][1])
+
+
+def test_full_size_properties_c3_reglap(gpu_ctx):
+    """BASELINE size (N = 8192, regularized Laplacian): size-independent identities instead of an O(N^3) CPU oracle:
+    K (I + beta L~) = I on random columns, symmetry, and logp+grad consistent with a central difference of logp."""
+    import torch
+    indptr, indices, w, pos, t = cfg.rgg_csr_fast(8192)
+    gpu_ctx.set_graph(indptr, indices, w)
+    tr, te = cfg.split(8192, 4096, 4096)
+    gpu_ctx.set_nodes(tr, te)
+    beta = 0.6
+    th = np.log([beta, 0.01])
+    assert gpu_ctx.kernel_build(1, th, False) == 0
+    cols = np.sort(np.random.RandomState(0).choice(8192, 64, replace=False)).astype(np.int32)
+    Kc = gpu_ctx.kernel_block(range(8192), cols, 0.0)                    # 8192 x 64 columns of K
+    Lnorm = go.normalized_laplacian(indptr, indices, w, 8192)
+    M = np.eye(8192) + beta * Lnorm
+    R = M @ Kc
+    E = np.zeros_like(R)
+    E[cols, np.arange(64)] = 1.0
+    assert np.max(np.abs(R - E)) < 1e-12
+    Kr = gpu_ctx.kernel_block(cols, range(8192), 0.0)
+    assert np.array_equal(Kr, Kc.T)
+    tt = t[tr]
+    st, out, info = gpu_ctx.gpr_logp_grad(1, th, tt, True)
+    assert st == 0 and info == 0
+    h = 1e-5
+    for j in range(2):
+        tp, tm = th.copy(), th.copy()
+        tp[j] += h
+        tm[j] -= h
+        fd = (gpu_ctx.gpr_logp_grad(1, tp, tt, False)[1][0] - gpu_ctx.gpr_logp_grad(1, tm, tt, False)[1][0]) / (2 * h)
+        assert abs(fd - out[1 + j]) <= 1e-6 * max(1.0, abs(fd))
+
+
+def test_diffusion_semigroup_property_n4096(gpu_ctx):
+    """C4 size: exp(-b L~) exp(-b L~) = exp(-2b L~) on a column sample (Pade orders differ between the two sides)."""
+    indptr, indices, w, pos, t = cfg.rgg_csr_fast(4096)
+    gpu_ctx.set_graph(indptr, indices, w)
+    cols = np.arange(0, 4096, 128, dtype=np.int32)
+    assert gpu_ctx.kernel_build(0, np.log([0.45, 0.01]), False) == 0
+    m1 = gpu_ctx.expm_info()
+    K1 = gpu_ctx.kernel_block(range(4096), range(4096), 0.0)
+    assert gpu_ctx.kernel_build(0, np.log([0.9, 0.01]), False) == 0
+    m2 = gpu_ctx.expm_info()
+    K2c = gpu_ctx.kernel_block(range(4096), cols, 0.0)
+    assert np.max(np.abs(K1 @ K1[:, cols] - K2c)) < 1e-12
+    assert m1[0] in (5, 7, 9, 13) and m2[0] in (7, 9, 13)

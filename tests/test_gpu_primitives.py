@@ -1,0 +1,126 @@
+"""GPU tier: the device-level C-ABI primitives against torch fp64 (a floating-point kernel keeps a library
+reference) and, for the integer/byte-exact pieces (Laplacian assembly, block gather), bit-exact against the oracle."""
+import networkx as nx
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as go
+
+pytestmark = pytest.mark.gpu
+FP_TOL = 1e-12     # fp64 GEMM / factorisations: far inside the 1e-9 contract
+
+
+def dmat(rows, cols, fill=None):
+    import torch
+    ld = (cols + 15) // 16 * 16
+    buf = torch.zeros(rows, ld, dtype=torch.float64, device="cuda:0")
+    if fill is not None:
+        buf[:, :cols] = fill
+    return buf, ld
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 16), (128, 128, 128), (300, 200, 100), (1, 1, 1), (129, 257, 33), (1000, 900, 333),
+                                   (2048, 2048, 512)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_all_layouts(gpu_ctx, shape, ta, tb):
+    import torch
+    M, N, K = shape
+    torch.manual_seed(M * 7 + N * 3 + K + ta * 2 + tb)
+    A = torch.randn((K, M) if ta else (M, K), dtype=torch.float64, device="cuda:0")
+    B = torch.randn((N, K) if tb else (K, N), dtype=torch.float64, device="cuda:0")
+    C0 = torch.randn(M, N, dtype=torch.float64, device="cuda:0")
+    Ab, lda = dmat(*A.shape, A)
+    Bb, ldb = dmat(*B.shape, B)
+    Cb, ldc = dmat(M, N, C0)
+    gpu_ctx.gemm(ta, tb, M, N, K, 0.75, Ab.data_ptr(), lda, Bb.data_ptr(), ldb, -0.5, Cb.data_ptr(), ldc)
+    gpu_ctx.sync()
+    ref = 0.75 * ((A.T if ta else A) @ (B.T if tb else B)) - 0.5 * C0
+    err = (Cb[:, :N] - ref).abs().max().item() / ref.abs().max().item()
+    assert err < FP_TOL
+    assert ldc == N or Cb[:, N:].abs().max().item() == 0.0      # padding untouched
+
+
+def test_gemm_k_zero_and_beta_only(gpu_ctx):
+    import torch
+    C0 = torch.randn(70, 50, dtype=torch.float64, device="cuda:0")
+    Cb, ldc = dmat(70, 50, C0)
+    A, lda = dmat(70, 16)
+    B, ldb = dmat(16, 50)
+    gpu_ctx.gemm(0, 0, 70, 50, 0, 1.0, A.data_ptr(), lda, B.data_ptr(), ldb, 2.0, Cb.data_ptr(), ldc)
+    gpu_ctx.sync()
+    assert torch.equal(Cb[:, :50], 2.0 * C0)
+
+
+@pytest.mark.parametrize("n", [1, 5, 100, 128, 129, 256, 900, 2048, 3000])
+def test_potrf_matches_lapack(gpu_ctx, n):
+    import torch
+    torch.manual_seed(n)
+    X = torch.randn(n, n, dtype=torch.float64, device="cuda:0")
+    S = X @ X.T / n + torch.eye(n, dtype=torch.float64, device="cuda:0")
+    Sb, ld = dmat(n, n, S)
+    assert gpu_ctx.potrf(n, Sb.data_ptr(), ld) == 0
+    L = torch.linalg.cholesky(S)
+    assert (Sb[:, :n] - L).abs().max().item() / L.abs().max().item() < FP_TOL
+    assert torch.equal(Sb[:, :n].triu(1), torch.zeros_like(S))
+
+
+def test_potrf_reports_failing_minor(gpu_ctx):
+    import torch
+    n = 300
+    S = torch.eye(n, dtype=torch.float64, device="cuda:0")
+    S[200, 200] = -1.0
+    Sb, ld = dmat(n, n, S)
+    assert gpu_ctx.potrf(n, Sb.data_ptr(), ld) == 201          # LAPACK info convention
+
+
+@pytest.mark.parametrize("n", [7, 128, 300, 900, 1024, 2500])
+def test_spd_inverse(gpu_ctx, n):
+    import torch
+    torch.manual_seed(n + 1)
+    X = torch.randn(n, n, dtype=torch.float64, device="cuda:0")
+    S = X @ X.T / n + torch.eye(n, dtype=torch.float64, device="cuda:0")
+    Sb, ld = dmat(n, n, S)
+    Ob, _ = dmat(n, n)
+    Wb, _ = dmat(n, n)
+    assert gpu_ctx.spd_inverse(n, Sb.data_ptr(), ld, Ob.data_ptr(), ld, Wb.data_ptr()) == 0
+    ref = torch.linalg.inv(S)
+    assert (Ob[:, :n] - ref).abs().max().item() / ref.abs().max().item() < 1e-11
+    assert torch.equal(Ob[:, :n], Ob[:, :n].T)                   # mirrored store => exactly symmetric
+
+
+def test_laplacian_and_gather_bit_exact(gpu_ctx):
+    """Laplacian assembly reproduces networkx's operation order bit for bit (self-loop, isolated node, weights);
+    the block gather reproduces np.delete x2 + scalar add (GPnet.py:362-365)."""
+    import torch
+    G = nx.relabel_nodes(nx.grid_2d_graph(15, 15), dict(zip(nx.grid_2d_graph(15, 15), range(225))))
+    G.add_edge(3, 3)
+    G.add_node(225)
+    G[0][1]["weight"] = 2.5
+    indptr, indices, w, _ = go.graph_to_csr(G)
+    N = 226
+    Lnx = nx.normalized_laplacian_matrix(G).toarray()
+    gpu_ctx.set_graph(indptr, indices, w)
+    out, ld = dmat(N, N)
+    for alpha, gamma, ref in ((1.0, 0.0, Lnx), (-0.6, 0.0, -0.6 * Lnx), (0.6, 1.0, np.eye(N) + 0.6 * Lnx), (-1.0, 2.3, 2.3 * np.eye(N) - Lnx)):
+        out.fill_(7.0)
+        gpu_ctx.laplacian_dense(alpha, gamma, out.data_ptr(), ld)
+        gpu_ctx.sync()
+        assert np.array_equal(out[:, :N].cpu().numpy(), ref)
+    rows = torch.tensor([0, 5, 17, 224, 225], dtype=torch.int32, device="cuda:0")
+    cols = torch.tensor([1, 2, 3, 100], dtype=torch.int32, device="cuda:0")
+    blk, ldb = dmat(5, 4)
+    gpu_ctx.gather_block_add(out.data_ptr(), ld, rows.data_ptr(), 5, cols.data_ptr(), 4, 0.01, blk.data_ptr(), ldb)
+    gpu_ctx.sync()
+    ref = (2.3 * np.eye(N) - Lnx)[np.ix_([0, 5, 17, 224, 225], [1, 2, 3, 100])] + 0.01
+    assert np.array_equal(blk[:, :4].cpu().numpy(), ref)
+
+
+def test_empty_graph_rows_and_bad_arguments(gpu_ctx):
+    from gpnet_b200._lib import GpnetError
+    with pytest.raises(GpnetError):
+        gpu_ctx.set_graph([0, 1], [5])          # index out of range
+    gpu_ctx.set_graph([0, 0, 0, 0], [])         # three isolated nodes: L~ = 0
+    out, ld = dmat(3, 3)
+    gpu_ctx.laplacian_dense(1.0, 1.0, out.data_ptr(), ld)
+    gpu_ctx.sync()
+    assert np.array_equal(out[:, :3].cpu().numpy(), np.eye(3))

@@ -1,0 +1,163 @@
+"""CPU tier: host-side logic of the drop-in (graph -> CSR, node bookkeeping, sharding, the C-ABI surface)."""
+import os
+import re
+import subprocess
+import sys
+
+import networkx as nx
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    """The .so loads without a GPU and exports every function include/gpnet_b200.h declares."""
+    from gpnet_b200 import _lib
+    lib = _lib.load_library()
+    header = open(os.path.join(ROOT, "include", "gpnet_b200.h")).read()
+    declared = set(re.findall(r"\b(gpn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gpn_ctx"}
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gpnet_b200._lib import Context, GpnetError
+    with pytest.raises(GpnetError):
+        Context(0)
+
+
+def test_graph_csr_matches_networkx_adjacency():
+    from gpnet_b200.engine import graph_csr
+    G = nx.barabasi_albert_graph(50, 3, seed=3)
+    G.add_edge(4, 4)
+    G[0][1]["weight"] = 0.25
+    indptr, indices, w, nodelist, pos = graph_csr(G)
+    import scipy.sparse as sp
+    A = sp.csr_array((w, indices, indptr), shape=(50, 50)).toarray()
+    assert np.array_equal(A, nx.to_numpy_array(G, nodelist=nodelist))
+    assert nodelist == list(G)
+
+
+def test_product_does_not_import_oracle():
+    for fn in os.listdir(os.path.join(ROOT, "gpnet_b200")):
+        if fn.endswith(".py"):
+            src = open(os.path.join(ROOT, "gpnet_b200", fn)).read()
+            assert "oracle" not in src, fn
+
+
+def _model(**kw):
+    import gpnet_b200
+    G = nx.grid_2d_graph(6, 5)
+    return gpnet_b200.GPnetRegressor(Graph=G, ntrain=10, ntest=8, theta=np.log([0.6, 0.01]), relabel_nodes=True, **kw)
+
+
+def test_constructor_bookkeeping(capsys):
+    m = _model(seed=3)
+    assert len(m.training_nodes) == 10 and len(m.test_nodes) == 8 and len(m.other_nodes) == 12
+    assert m.training_nodes == sorted(m.training_nodes)
+    assert not (set(m.training_nodes) & set(m.test_nodes))
+    assert set(m.training_nodes) | set(m.test_nodes) | set(m.other_nodes) == set(range(30))
+    assert m.orig_labels_dict[(1, 0)] == 5 and m.orig_labels_invdict[5] == (1, 0)
+    assert m.pvtdist[29] == 9 and m.pivot_flag
+    assert list(m.training_values.index) == m.training_nodes
+    m2 = _model(seed=3)
+    assert m2.training_nodes == m.training_nodes          # seeded
+    assert "Assigning Nodes Randomly" in capsys.readouterr().out
+
+
+def test_constructor_errors_and_series_values():
+    import gpnet_b200
+    G = nx.grid_2d_graph(3, 3)
+    with pytest.raises(ValueError):
+        gpnet_b200.GPnetRegressor(Graph=G, ntrain=6, ntest=6, relabel_nodes=True)
+    tv = pd.Series([1.0, 2.0, 3.0], index=[0, 4, 8])
+    m = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=[0, 4, 8], test_nodes=[1, 2], training_values=tv, relabel_nodes=True)
+    assert m.training_values is tv and not m.pivot_flag
+    y = pd.Series([1, -1, 1], index=[0, 4, 8])
+    c = gpnet_b200.GPnetClassifier(Graph=G, training_nodes=[0, 4, 8], test_nodes=[1, 2], training_values=y, relabel_nodes=True)
+    assert c.training_values is y
+    c2 = gpnet_b200.GPnetClassifier(Graph=G, training_nodes=[0, 4, 8], test_nodes=[1, 2], relabel_nodes=True)
+    assert set(np.unique(c2.training_values.values)) <= {-1, 1} and c2.pivot_flag
+
+
+def test_positions_follow_graph_order_not_caller_order():
+    """A-5 / GPnet.py:305-323: un-relabelled graphs map node names through orig_labels_dict; order is ascending."""
+    import gpnet_b200
+    G = nx.grid_2d_graph(3, 3)
+    m = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=[(2, 2), (0, 1), (1, 0)], test_nodes=[(0, 0)], relabel_nodes=False)
+    assert m._positions([(2, 2), (0, 1), (1, 0), (0, 1)]) == [1, 3, 8]
+
+
+def test_dropin_module_aliases():
+    import gpnet_b200
+    gpnet_b200.install_dropin()
+    from GPnetRegressor import GPnetRegressor
+    from GPnetClassifier import GPnetClassifier, LAMBDAS, COEFS
+    assert GPnetRegressor is gpnet_b200.GPnetRegressor and GPnetClassifier is gpnet_b200.GPnetClassifier
+    assert LAMBDAS.shape == (5,) and COEFS.shape == (5, 1)
+
+
+def test_kernel_type_assert_is_raised_on_host():
+    m = _model()
+    m.kerneltype = "matern"
+    with pytest.raises(AssertionError, match="kerneltype not implemented"):
+        m.kernel([0], [1], np.log([0.5, 0.1]))
+
+
+def test_cyclic_shards_cover_the_grid():
+    from gpnet_b200.sharded import cyclic_slice
+    total = 64 * 64
+    for world in (1, 2, 4, 8, 3):
+        seen = np.zeros(total, dtype=int)
+        for r in range(world):
+            b, e, s = cyclic_slice(total, r, world)
+            seen[b:e:s] += 1
+        assert np.all(seen == 1)
+
+
+WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+from gpnet_b200.sharded import allgather_rows, cyclic_slice, sharded_multistart
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT={port!r}, RANK=str(rank), WORLD_SIZE=str(world))
+dist.init_process_group("gloo", rank=rank, world_size=world)
+total, width = 37, 3
+b, e, s = cyclic_slice(total, rank, world)
+idx = np.arange(b, e, s)
+local = np.stack([idx * 1.0, idx * 2.0 + 0.5, -idx * 1.0], axis=1)
+full = allgather_rows(local, total, rank, world, dist)
+exp = np.stack([np.arange(total) * 1.0, np.arange(total) * 2.0 + 0.5, -np.arange(total) * 1.0], axis=1)
+assert np.array_equal(full, exp), (rank, full[:5])
+
+class Fake:                                    # stands in for a model: value and gradient are functions of theta
+    training_nodes = [0]; training_values = [0.0]
+    def logPosterior_and_grad(self, th, *a):
+        return float(np.sum(th ** 2)), 2 * np.asarray(th)
+thetas = np.arange(14, dtype=float).reshape(7, 2)
+out = sharded_multistart(Fake(), thetas)
+assert np.allclose(out[:, 0], (thetas ** 2).sum(1)) and np.allclose(out[:, 1:], 2 * thetas)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_allgather_world_size_2_gloo(tmp_path):
+    """N > 1 path on CPU: two gloo ranks reassemble cyclic shards into the identical full array."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=str(29500 + os.getpid() % 2000)))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out.decode()

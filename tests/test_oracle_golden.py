@@ -1,0 +1,108 @@
+"""CPU tier: the numpy oracle against the golden vectors produced by the UNMODIFIED (shimmed) reference
+(oracle/make_golden.py), the reference's only known-answer value, and independent cross-checks."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_files, load_golden, nrel
+from oracle import gp_oracle as go
+
+TOL = 1e-9   # north_star tolerance (norm-wise relative); the oracle itself agrees to ~1e-14
+
+
+def _orc(g, expm_mode="sparse"):
+    return go.OracleGP(csr=(g["indptr"], g["indices"], g["weights"]), kerneltype=str(g["kerneltype"]), expm_mode=expm_mode)
+
+
+@pytest.mark.parametrize("path", golden_files("reg_"), ids=os.path.basename)
+def test_regressor_oracle_matches_reference(path):
+    g = load_golden(path)
+    N = len(g["indptr"]) - 1
+    orc = _orc(g, "sparse" if N <= 1100 else "dense")
+    tr, te, t, th = g["train"], g["test"], g["t_train"], g["theta"]
+    assert abs(-orc.neg_logp(th, tr, t) - g["logp"]) <= TOL * abs(g["logp"])
+    pr = orc.predict_regressor(th, tr, te, t)
+    for key in ("fstar", "s", "alpha", "kstarstar_diag"):
+        assert nrel(pr[key], g[key]) <= TOL, key
+    if "k" in g:
+        assert nrel(pr["k"], g["k"]) <= TOL and nrel(pr["kstar"], g["kstar"]) <= TOL
+    if "neg_logp_grad_fd" in g:     # analytic gradient vs central differences of the reference's logPosterior
+        _, ng = orc.neg_logp_grad(th, tr, t)
+        sel = g["grad_fd_valid"]
+        assert nrel(ng[sel], g["neg_logp_grad_fd"][sel]) <= 1e-6
+    if "land_lml" in g:
+        lml = orc.landscape(th, list(g["land_axidx"]), g["land_ax1"], g["land_ax2"], tr, t)
+        assert nrel(lml, g["land_lml"]) <= TOL
+
+
+@pytest.mark.parametrize("path", golden_files("cls_"), ids=os.path.basename)
+def test_classifier_oracle_matches_reference(path):
+    g = load_golden(path)
+    N = len(g["indptr"]) - 1
+    orc = _orc(g, "sparse" if N <= 500 else "dense")
+    pr = orc.predict_classifier(g["theta"], g["train"], g["test"], g["y_train"])
+    assert pr["iters"] == g["iters"]
+    assert abs(pr["logq"] - g["logq"]) <= TOL * abs(g["logq"])
+    for key in ("f", "a", "fstar", "V", "probs"):
+        assert nrel(np.asarray(pr[key]).reshape(np.asarray(g[key]).shape), g[key]) <= TOL, key
+    assert np.array_equal(pr["labels"], g["labels"])
+
+
+def test_notebook_known_answer():
+    """report_notebook.ipynb cell 49: logPosterior = -77.22939013 (old-variant logq), 5 Newton iterations."""
+    K, y = go.notebook_kat_inputs()
+    f, logq, a, iters = go.gpc_newton(K, y, logq_variant="notebook")
+    assert abs(-logq - go.NOTEBOOK_KAT_VALUE) < 5e-9
+    assert iters == 5
+    g = load_golden(os.path.join(os.path.dirname(__file__), "golden", "notebook_kat.npz"))
+    assert np.allclose(K, g["K"]) and np.array_equal(y.ravel(), g["y"])
+
+
+@pytest.mark.parametrize("kt,theta", [("diffusion", np.log([0.6, 0.01])), ("regularized_laplacian", np.log([0.6, 0.01]))])
+def test_spectral_cross_check(kt, theta):
+    """K = V r(lambda) V^T (PDF eq. 55-56) agrees with the expm / inverse paths."""
+    import networkx as nx
+    G = nx.relabel_nodes(nx.grid_2d_graph(12, 11), dict(zip(nx.grid_2d_graph(12, 11), range(132))))
+    a = go.OracleGP(G, kerneltype=kt, expm_mode="sparse").full(theta)
+    b = go.OracleGP(G, kerneltype=kt, expm_mode="spectral").full(theta)
+    c = go.OracleGP(G, kerneltype=kt, expm_mode="dense").full(theta)
+    assert nrel(a, b) < 1e-12 and nrel(c, b) < 1e-12
+
+
+def test_kernel_properties_and_quirks():
+    import networkx as nx
+    G = nx.barabasi_albert_graph(60, 3, seed=1)
+    orc = go.OracleGP(G, kerneltype="regularized_laplacian")
+    K = orc.full(np.log([0.7, 0.1]))
+    assert np.allclose(K @ (np.eye(60) + 0.7 * orc.Lnorm), np.eye(60), atol=1e-12)
+    orc.kerneltype = "pstep_walk"
+    assert np.allclose(orc.full(np.log([2.5, 1.0, 0.1])), 2.5 * np.eye(60) - orc.Lnorm)
+    # A-4: p = int(exp(log 5)) == 4
+    assert go.pstep_order(np.exp(np.log([2.5, 5.0]))) == 4
+    # A-3: noise on every entry; A-5: graph-position order regardless of caller order
+    blk = orc.kernel([5, 2, 9], [7, 1], np.log([2.5, 2.0, 0.3]))
+    Kf = orc.full(np.log([2.5, 2.0, 0.3]))
+    assert np.allclose(blk, Kf[np.ix_([2, 5, 9], [1, 7])] + 0.3)
+    # parameter-domain asserts (GPnet.py:339,344)
+    orc.kerneltype = "diffusion"
+    with pytest.raises(AssertionError):
+        orc.full(np.log([1.5, 0.1]))
+    orc.kerneltype = "pstep_walk"
+    with pytest.raises(AssertionError):
+        orc.full(np.log([1.5, 2.0, 0.1]))
+
+
+def test_laplacian_matches_networkx_edge_cases():
+    import networkx as nx
+    G = nx.path_graph(7)
+    G.add_edge(2, 2)
+    G.add_node(7)
+    G[0][1]["weight"] = 2.5
+    indptr, indices, w, _ = go.graph_to_csr(G)
+    L = go.normalized_laplacian(indptr, indices, w, 8)
+    assert np.array_equal(L, nx.normalized_laplacian_matrix(G).toarray())
+
+
+def test_neg_inf_on_cholesky_failure():
+    assert go.gpr_neg_logp(-np.eye(3), np.ones(3)) == -np.inf
