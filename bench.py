@@ -223,8 +223,10 @@ def main():
     value = world * K / (ms_total * 1e-3)
 
     # ---- e2e: the public API (drop-in class) with HOST buffers, copies inside the timed region -----------------
-    model = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=train, test_nodes=test, theta=list(theta), relabel_nodes=True,
-                                      kerneltype=KERNEL, training_values=False)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # the drop-in prints like the reference; stdout carries ONE JSON line
+        model = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=train, test_nodes=test, theta=list(theta), relabel_nodes=True,
+                                          kerneltype=KERNEL, training_values=False)
     tv = pd.Series(t[train], index=train)
     model.set_training_values(tv)
     from gpnet_b200.engine import register_context

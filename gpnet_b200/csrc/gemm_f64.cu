@@ -268,6 +268,7 @@ int encode_operand(gpn_ctx* c, CUtensorMap* tm, const double* ptr, long ld, bool
     if (((uintptr_t)ptr & 15) || (ld & 1) || (batch > 1 && (stride & 1))) return -3;
     cuuint64_t gdim[3], gstr[2];
     cuuint32_t box[3], estr[3] = {1, 1, 1};
+    if (k_extent < 1) k_extent = 1;   // K == 0: no k-steps are issued, the map only has to be encodable
     if (kmajor) {   // [mn][k]
         gdim[0] = (cuuint64_t)k_extent;
         gdim[1] = (cuuint64_t)mn_extent;

@@ -112,6 +112,42 @@ def test_kernel_type_assert_is_raised_on_host():
         m.kernel([0], [1], np.log([0.5, 0.1]))
 
 
+class _FakeCtx:
+    """Stands in for the device context so the host-side mapping of LAPACK-style info codes can be tested on CPU."""
+    _owner = None; _nodes_key = None; _kernel_key = None; _predict_token = None; device = 0
+
+    def __init__(self, info_k=0, info_kss=0):
+        self.info_k, self.info_kss = info_k, info_kss
+
+    def set_graph(self, *a): pass
+    def set_nodes(self, tr, te=()): self.n_train, self.n_test = len(tr), len(te)
+
+    def gpr_logp_grad(self, kind, theta, t, want_grad):
+        return 0, np.array([12.5] + [0.25] * len(theta)), self.info_k
+
+    def gpr_predict(self, kind, theta, t):
+        n, m = self.n_train, self.n_test
+        return 0, dict(alpha=np.zeros(n), fstar=np.ones(m), s=np.ones(m), kstarstar_diag=np.ones(m), info_k=self.info_k,
+                       info_kss=self.info_kss)
+
+
+def test_cholesky_failure_maps_to_reference_behaviour(capsys):
+    """A-8: logPosterior returns -inf when the Cholesky fails (GPnetRegressor.py:140-143); A-7: the PD gates of predict
+    print, set the flag and return self without training (GPnetRegressor.py:112-121)."""
+    m = _model()
+    m._engine._ctx = _FakeCtx(info_k=3)
+    assert m.logPosterior(m.theta, m.training_nodes, m.training_values) == -np.inf
+    assert m.predict() is m and m.k_not_posdef_flag and not m.kstar_not_posdef_flag and not m.is_trained
+    assert "K not positive definite, aborting..." in capsys.readouterr().out
+    m._engine._ctx = _FakeCtx(info_kss=2)
+    assert m.logPosterior(m.theta, m.training_nodes, m.training_values) == 12.5
+    assert np.array_equal(m.gradLogPosterior(m.theta, m.training_nodes, m.training_values), [0.25, 0.25])
+    assert m.predict() is m and m.kstar_not_posdef_flag and not m.is_trained
+    assert "K** not positive definite, aborting..." in capsys.readouterr().out
+    m._engine._ctx = _FakeCtx()
+    assert m.predict().is_trained and list(m.df["fstar"][m.test_nodes]) == [1.0] * 8
+
+
 def test_cyclic_shards_cover_the_grid():
     from gpnet_b200.sharded import cyclic_slice
     total = 64 * 64
