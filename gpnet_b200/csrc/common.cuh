@@ -88,6 +88,10 @@ struct gpn_ctx {
     DevBuf mat[10];
     DevBuf nb[16];               // n-sized / n x n / n x m buffers of the GP algebra
     DevBuf winv;                 // inverted diagonal blocks of the running Cholesky (N x 128)
+    DevBuf flags;                // dataflow Cholesky: epoch-stamped tile-ready flags (T x T ints)
+    int epoch = 0;
+    void* leaf_prof = nullptr;   // optional device buffer (32 x int64) receiving clock64 stamps of the leaf phases
+    int potrf_mode = 0;          // 0: dataflow kernel (default), 1: recursive multi-launch (GPNET_B200_POTRF=recursive)
     DevBuf scal;                 // small device scalars (reductions, info)
     DevBuf partial;              // reduction partials
     void* pinned = nullptr;      // pinned host staging for scalar read-back
@@ -107,6 +111,7 @@ int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, lon
 
 // Cholesky (lower, in place, row-major), triangular inverse and SPD inverse.  info: device int (0 = ok).
 int gpn_potrf(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset = 0);
+int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset);
 int gpn_trtri_from_winv(gpn_ctx* c, int n, const double* L, long ldl, const double* winv, double* W, long ldw);
 int gpn_lauum(gpn_ctx* c, int n, const double* W, long ldw, double* out, long ldo, bool mirror);
 

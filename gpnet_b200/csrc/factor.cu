@@ -11,24 +11,21 @@
 //                  (W21 = -W22 * (L21 * W11)), triangular structure skipped at tile granularity.
 //  * gpn_lauum   : W^T W as a single structure-aware GEMM (k >= max(m0,n0), lower tiles + mirrored store).
 #include "common.cuh"
+#include "leaf.cuh"
 
 namespace {
 
-constexpr int LB = 128;          // leaf block
-constexpr int LDS_ = LB + 1;     // padded shared-memory leading dimension (conflict-free column access)
+constexpr int LB = leaf::LB;
 
 // One CTA (256 threads): factor the nv x nv (nv <= 128) diagonal block at A (lower Cholesky, written back, strict upper
-// zeroed) and write inv(L) (identity-padded to 128x128, upper zero) to winv (ld 128).
+// zeroed) and write inv(L) (identity-padded to 128x128, upper zero) to winv (ld 128).  Body: leaf.cuh.
 __global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ A, long lda, int nv, double* __restrict__ winv,
-                                                            int* __restrict__ info, int info_off) {
+                                                            int* __restrict__ info, int info_off, long long* prof) {
     extern __shared__ double sm[];
-    double* S = sm;                       // [128][129]
-    double* T = S + LB * LDS_;            // [96][33] temp block column
-    double* rinv = T + 96 * 33;           // [128]
-    __shared__ double sh_l[8][9];
-    __shared__ double sh_piv;
+    double* S = sm;
+    double* Wd = S + LB * leaf::LDS_;
+    double* T = Wd + 4 * 32 * leaf::WLD;
     const int tid = threadIdx.x;
-
     for (int idx = tid; idx < LB * LB; idx += 256) {
         const int r = idx >> 7, c = idx & 127;
         double v = 0.0;
@@ -36,136 +33,14 @@ __global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ 
             if (r < nv) v = A[(long)r * lda + c];
             else if (r == c) v = 1.0;
         }
-        S[r * LDS_ + c] = v;
+        S[r * leaf::LDS_ + c] = v;
     }
     __syncthreads();
-
-    // ---------------- factorization: 8-column micro panels, right looking ----------------
-    for (int kb = 0; kb < LB; kb += 8) {
-        double x[8];
-        const bool owner = (tid < LB) && (tid >= kb);
-        if (owner) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) x[c] = S[tid * LDS_ + kb + c];
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            if (tid == kb + c) {
-                double d = x[c];
-                if (!(d > 0.0)) atomicCAS(info, 0, info_off + kb + c + 1);
-                d = sqrt(d);
-                x[c] = d;
-                sh_piv = d;
-            }
-            __syncthreads();
-            if (owner && tid > kb + c) {
-                x[c] = x[c] / sh_piv;
-                if (tid < kb + 8) sh_l[tid - kb][c] = x[c];
-            }
-            __syncthreads();
-            if (owner && tid > kb + c) {
-#pragma unroll
-                for (int c2 = c + 1; c2 < 8; ++c2) x[c2] -= x[c] * sh_l[c2][c];
-            }
-        }
-        if (owner) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) S[tid * LDS_ + kb + c] = (kb + c <= tid) ? x[c] : 0.0;
-        }
-        __syncthreads();
-        // trailing update S[r][c'] -= sum_k S[r][kb+k] * S[c'][kb+k]   (r >= c' >= kb+8), 4x4 register tiles
-        const int t0 = kb + 8;
-        const int rem = LB - t0;
-        const int nt = (rem + 3) >> 2;
-        for (int ti = tid; ti < nt * nt; ti += 256) {
-            const int tr = ti / nt, tc = ti - tr * nt;
-            if (tc > tr) continue;
-            const int r0 = t0 + 4 * tr, c0 = t0 + 4 * tc;
-            double a[4][8], b[4][8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    a[i][k] = S[(r0 + i) * LDS_ + kb + k];
-                    b[i][k] = S[(c0 + i) * LDS_ + kb + k];
-                }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) s += a[i][k] * b[j][k];
-                    if (c0 + j <= r0 + i) S[(r0 + i) * LDS_ + c0 + j] -= s;
-                }
-        }
-        __syncthreads();
-    }
-
-    // ---------------- write L back (valid region; strict upper zeroed) ----------------
-    for (int idx = tid; idx < LB * LB; idx += 256) {
-        const int r = idx >> 7, c = idx & 127;
-        if (r < nv && c < nv) A[(long)r * lda + c] = S[r * LDS_ + c];
-    }
-    if (tid < LB) rinv[tid] = 1.0 / S[tid * LDS_ + tid];
-    __syncthreads();
-
-    // ---------------- in-place inverse, 32x32 blocks ----------------
-    // (1) diagonal blocks: warp b inverts block b, lane j owns column j (forward substitution in registers)
-    {
-        const int b = tid >> 5, j = tid & 31;
-        double x[32];
-        if (b < 4) {
-            const double* Sb = S + (b * 32) * LDS_ + b * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                double s0 = (i == j) ? 1.0 : 0.0, s1 = 0.0;
-#pragma unroll
-                for (int k = 0; k + 1 < i; k += 2) {
-                    s0 -= Sb[i * LDS_ + k] * x[k];
-                    s1 -= Sb[i * LDS_ + k + 1] * x[k + 1];
-                }
-                if (i & 1) s0 -= Sb[i * LDS_ + i - 1] * x[i - 1];
-                x[i] = (s0 + s1) * rinv[b * 32 + i];
-            }
-        }
-        __syncthreads();
-        if (b < 4) {
-            double* Sb = S + (b * 32) * LDS_ + b * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (i >= j) Sb[i * LDS_ + j] = x[i];
-        }
-        __syncthreads();
-    }
-    // (2) block columns right to left: X = -W_trail * (L_col * W_kk)
-    for (int k = 2; k >= 0; --k) {
-        const int r0 = 32 * (k + 1);
-        const int nr = LB - r0;
-        const int j = tid & 31;
-        for (int r = tid >> 5; r < nr; r += 8) {
-            double s = 0.0;
-            const double* Lr = S + (r0 + r) * LDS_ + 32 * k;
-            const double* Wk = S + (32 * k) * LDS_ + 32 * k;
-            for (int q = j; q < 32; ++q) s += Lr[q] * Wk[q * LDS_ + j];
-            T[r * 33 + j] = s;
-        }
-        __syncthreads();
-        for (int r = tid >> 5; r < nr; r += 8) {
-            double s = 0.0;
-            const double* Wr = S + (r0 + r) * LDS_ + r0;
-            for (int q = 0; q <= r; ++q) s += Wr[q] * T[q * 33 + j];
-            S[(r0 + r) * LDS_ + 32 * k + j] = -s;
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < LB * LB; idx += 256) {
-        const int r = idx >> 7, c = idx & 127;
-        winv[idx] = (c <= r) ? S[r * LDS_ + c] : 0.0;
-    }
+    if (prof && tid == 0) prof[31] = clock64();
+    leaf::potf2_inverse<0>(S, Wd, T, A, lda, nv, winv, info, info_off, tid, prof);
 }
 
-constexpr size_t LEAF_SMEM = (size_t)(LB * LDS_ + 96 * 33 + LB) * sizeof(double);
+constexpr size_t LEAF_SMEM = leaf::SMEM_BYTES;
 
 int launch_leaf(gpn_ctx* c, double* A, long lda, int nv, double* winv, int* d_info, int info_off) {
     static bool configured = false;
@@ -173,7 +48,7 @@ int launch_leaf(gpn_ctx* c, double* A, long lda, int nv, double* winv, int* d_in
         GPN_CK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
         configured = true;
     }
-    potf2_inv_kernel<<<1, 256, LEAF_SMEM, c->stream>>>(A, lda, nv, winv, d_info, info_off);
+    potf2_inv_kernel<<<1, 256, LEAF_SMEM, c->stream>>>(A, lda, nv, winv, d_info, info_off, (long long*)c->leaf_prof);
     c->launches++;
     GPN_CK(cudaGetLastError());
     return 0;
@@ -222,6 +97,7 @@ __global__ void copy_diag_blocks_kernel(const double* __restrict__ winv, double*
 
 int gpn_potrf(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset) {
     if (n <= 0) return 0;
+    if (n > LB && c->potrf_mode == 0) return gpn_potrf_dataflow(c, n, A, lda, winv, d_info, info_offset);
     return potrf_rec(c, n, A, lda, winv, d_info, info_offset);
 }
 

@@ -743,6 +743,7 @@ gpn_ctx* gpn_create(int device, void* cuda_stream) {
         return nullptr;
     }
     c->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    if (const char* m = getenv("GPNET_B200_POTRF")) c->potrf_mode = (strcmp(m, "recursive") == 0) ? 1 : 0;
     if (cudaMalloc(&c->scal.p, 1024) != cudaSuccess || cudaMallocHost(&c->pinned, 4096) != cudaSuccess) {
         gpn_set_last_error(__FILE__, __LINE__, "initial allocations failed");
         delete c;
@@ -759,7 +760,8 @@ void gpn_destroy(gpn_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->mat[9] = DevBuf();   // alias slot
-    DevBuf* all[] = {&c->indptr, &c->indices, &c->weights, &c->dinv, &c->train_idx, &c->test_idx, &c->tvec, &c->winv, &c->scal, &c->partial};
+    DevBuf* all[] = {&c->indptr, &c->indices, &c->weights, &c->dinv, &c->train_idx, &c->test_idx, &c->tvec, &c->winv, &c->scal, &c->partial,
+                     &c->flags};
     for (DevBuf* b : all)
         if (b->p) cudaFree(b->p);
     for (auto& b : c->mat)
@@ -856,6 +858,10 @@ int gpn_fp64_peak(gpn_ctx* c, double seconds, double* tflops_h) {
     return 0;
 }
 
+void gpn_debug_leaf_prof(gpn_ctx* c, void* dev_buf32) {
+    if (c) c->leaf_prof = dev_buf32;
+}
+
 void gpn_set_profile(gpn_ctx* c, int on) {
     if (!c) return;
     c->profile = on != 0;
@@ -910,9 +916,10 @@ int gpn_potrf_f64(gpn_ctx* c, int n, double* A, long lda, int* info_h) {
     GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(n) * 128));
     GPN_TRY(gpn_potrf(c, n, A, lda, (double*)c->winv.p, iscal(c, 0)));
     GPN_TRY(gpn_k_zero_upper(c, A, lda, n));
+    if (!info_h) return 0;       // asynchronous use: no read-back
     int info[16];
     GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
-    if (info_h) *info_h = info[0];
+    *info_h = info[0];
     return 0;
 }
 

@@ -1,0 +1,301 @@
+// Dataflow (task-parallel) Cholesky for sm_100a: ONE persistent kernel factors the whole matrix.
+//
+// Replaces np.linalg.cholesky (GPnetRegressor.py:123,141; GPnetClassifier.py:110,159,208) and the Cholesky inside the
+// SPD inverse that stands in for scipy.linalg.inv (GPnet.py:342).
+//
+// The matrix is cut into 128x128 tiles; a task is one output tile (i, j), i >= j, processed left-looking:
+//     C   = A_ij - sum_{k<j} L_ik L_jk^T        TMA -> smem ring -> DMMA.8x8x4, accumulators stay in registers (K = 128 j)
+//     i == j : L_jj = chol(C), W_j = L_jj^-1     in shared memory by the same CTA (leaf.cuh)
+//     i >  j : L_ij = C W_j^T                    second in-CTA DMMA GEMM, C staged through shared memory
+// Tasks are enumerated column-major and dealt round-robin to a co-resident grid (one CTA per SM, cooperative launch);
+// a task only waits on tasks that precede it in that order (tiles (i,k), (j,k), k < j, and (j,j)), so the schedule is
+// deadlock-free, and several tile columns are in flight at once: the serial chain chol(j) -> trsm(j+1,j) -> chol(j+1)
+// overlaps the bulk updates of later columns.  Dependencies are epoch-stamped flags in global memory
+// (st.release / ld.acquire at gpu scope, fence.proxy.async before the TMA reads of tiles written by other SMs).
+#include "leaf.cuh"
+#include "tile_primitives.cuh"
+
+namespace {
+
+using namespace tp;
+
+constexpr int TB = 128;
+constexpr int STAGES = 6;
+constexpr uint32_t TILE_BYTES = TB * 128;               // one operand tile per k-step: 128 rows x 16 doubles
+constexpr uint32_t STAGE_BYTES = 2 * TILE_BYTES;
+constexpr uint32_t RING_BYTES = STAGES * STAGE_BYTES;   // 192 KB
+constexpr uint32_t CREG_BYTES = 8 * TILE_BYTES;         // C staged as 8 K-major sub-tiles (stages 0..3 of the ring)
+constexpr int WSTAGES = 4;                              // W_j ring in stages 4..5 of the ring
+constexpr size_t DF_SMEM = RING_BYTES + 256 + 1024;
+
+static_assert(leaf::SMEM_BYTES <= RING_BYTES, "leaf scratch must fit in the ring");
+
+struct DfArgs {
+    double* A;
+    long lda;
+    int n, T, ntasks;
+    double* winv;
+    int* flags;
+    int epoch;
+    int* info;
+    int info_off;
+};
+
+__device__ __forceinline__ void wait_flag(const int* f, int epoch) {
+    while (ld_acquire(f) != epoch) __nanosleep(32);
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
+__global__ void __launch_bounds__(384, 1)
+potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmW, const DfArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+    const uint32_t bar_full = smem0 + RING_BYTES, bar_empty = bar_full + STAGES * 8;
+    const uint32_t bar_wfull = bar_empty + STAGES * 8, bar_wempty = bar_wfull + WSTAGES * 8;
+    const uint32_t bar_mdone = bar_wempty + WSTAGES * 8, bar_fdone = bar_mdone + 8;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int T = g.T;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + s * 8, 1);
+            mbar_init(bar_empty + s * 8, 8);
+        }
+#pragma unroll
+        for (int s = 0; s < WSTAGES; ++s) {
+            mbar_init(bar_wfull + s * 8, 1);
+            mbar_init(bar_wempty + s * 8, 8);
+        }
+        mbar_init(bar_mdone, 8);
+        mbar_init(bar_fdone, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= 8) {
+        // ============================== TMA producer ==============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 8 && lane == 0) {
+            uint32_t it = 0, wit = 0;
+            int task_idx = 0, j = 0, q0 = 0;
+            for (int q = blockIdx.x; q < g.ntasks; q += gridDim.x, ++task_idx) {
+                while (q >= q0 + (T - j)) { q0 += T - j; ++j; }
+                const int i = j + (q - q0);
+                if (task_idx > 0) mbar_wait(bar_fdone, (task_idx - 1) & 1);      // consumers left the C region / leaf scratch
+                for (int kb = 0; kb < j; ++kb) {
+                    wait_flag(g.flags + (long)i * T + kb, g.epoch);
+                    if (i != j) wait_flag(g.flags + (long)j * T + kb, g.epoch);
+                    fence_proxy_async();
+#pragma unroll 1
+                    for (int s = 0; s < 8; ++s, ++it) {
+                        const int st = it % STAGES;
+                        mbar_wait(bar_empty + st * 8, ((it / STAGES) & 1) ^ 1);
+                        const uint32_t full = bar_full + st * 8;
+                        mbar_expect_tx(full, STAGE_BYTES);
+                        const uint32_t sa = smem0 + st * STAGE_BYTES;
+                        tma_load_3d(sa, &tmL, full, kb * TB + s * KSTEP, i * TB, 0);
+                        tma_load_3d(sa + TILE_BYTES, &tmL, full, kb * TB + s * KSTEP, j * TB, 0);
+                    }
+                }
+                if (i != j) {
+                    wait_flag(g.flags + (long)j * T + j, g.epoch);                // L_jj factored, W_j written
+                    fence_proxy_async();
+                    mbar_wait(bar_mdone, task_idx & 1);                           // ring drained by every consumer warp
+#pragma unroll 1
+                    for (int s = 0; s < 8; ++s, ++wit) {
+                        const int ws = wit % WSTAGES;
+                        mbar_wait(bar_wempty + ws * 8, ((wit / WSTAGES) & 1) ^ 1);
+                        const uint32_t full = bar_wfull + ws * 8;
+                        mbar_expect_tx(full, TILE_BYTES);
+                        tma_load_3d(smem0 + CREG_BYTES + ws * TILE_BYTES, &tmW, full, s * KSTEP, j * TB, 0);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ============================== DMMA consumers (8 warps, 64 x 32 each) ==============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int wm = warp >> 2, wn = warp & 3;
+    const int gq = lane >> 2, t = lane & 3;
+    const int pg = (gq >> 1) | ((gq & 1) << 2);
+    double* S = reinterpret_cast<double*>(smem_gen);
+    double* Wd = S + leaf::LB * leaf::LDS_;
+    double* Tt = Wd + 4 * 32 * leaf::WLD;
+
+    uint32_t it = 0, wit = 0;
+    int task_idx = 0, j = 0, q0 = 0;
+    for (int q = blockIdx.x; q < g.ntasks; q += gridDim.x, ++task_idx) {
+        while (q >= q0 + (T - j)) { q0 += T - j; ++j; }
+        const int i = j + (q - q0);
+
+        double acc[8][4][2];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+        const int niter = j * 8;
+        for (int n = 0; n < niter; ++n, ++it) {
+            const int st = it % STAGES;
+            mbar_wait(bar_full + st * 8, (it / STAGES) & 1);
+            const uint32_t sa = smem0 + st * STAGE_BYTES, sb = sa + TILE_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double af[8][2], bf[4][2];
+                load_frags<8, true>(af, sa, wm * 64, h, gq, t);
+                load_frags<4, true>(bf, sb, wn * 32, h, gq, t);
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) dmma884(acc[a][b], af[a][u], bf[b][u]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + st * 8);
+        }
+        bar_consumers();                        // every consumer warp has finished reading the ring
+        if (lane == 0) mbar_arrive(bar_mdone);
+
+        const long grow0 = (long)i * TB + wm * 64, gcol0 = (long)j * TB + wn * 32;
+        if (i == j) {
+            // ---- C = A_jj - acc -> S (identity padded); factor + invert in shared memory ----
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int r = wm * 64 + a * 8 + pg;
+                const long gr = (long)i * TB + r;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int cc = wn * 32 + b * 8 + t + 4 * e;
+                        const long gc = (long)j * TB + cc;
+                        double v;
+                        if (gr < g.n && gc < g.n) v = g.A[gr * g.lda + gc] - acc[a][b][e];
+                        else v = (r == cc) ? 1.0 : 0.0;
+                        S[r * leaf::LDS_ + cc] = v;
+                    }
+            }
+            bar_consumers();
+            const int nv = min(TB, g.n - j * TB);
+            leaf::potf2_inverse<1>(S, Wd, Tt, g.A + ((long)j * TB) * g.lda + (long)j * TB, g.lda, nv, g.winv + (long)j * TB * TB, g.info,
+                                   g.info_off + j * TB, tid);
+            __threadfence();
+            bar_consumers();
+            if (tid == 0) {
+                fence_proxy_async();
+                st_release(g.flags + (long)j * T + j, g.epoch);
+            }
+        } else {
+            // ---- C = A_ij - acc -> K-major swizzled sub-tiles; L_ij = C W_j^T ----
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int r = wm * 64 + a * 8 + pg;
+                const long gr = (long)i * TB + r;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int cc = wn * 32 + b * 8 + t + 4 * e;
+                        const long gc = (long)j * TB + cc;
+                        const double v = (gr < g.n) ? g.A[gr * g.lda + gc] - acc[a][b][e] : 0.0;
+                        const int cw = cc & 15;
+                        sts64(smem0 + (cc >> 4) * TILE_BYTES + r * 128 + ((((cw >> 1) ^ (r & 7)) << 4) | ((cw & 1) << 3)), v);
+                        acc[a][b][e] = 0.0;
+                    }
+            }
+            bar_consumers();
+            for (int s = 0; s < 8; ++s, ++wit) {
+                const int ws = wit % WSTAGES;
+                mbar_wait(bar_wfull + ws * 8, (wit / WSTAGES) & 1);
+                const uint32_t sa = smem0 + s * TILE_BYTES, sb = smem0 + CREG_BYTES + ws * TILE_BYTES;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double af[8][2], bf[4][2];
+                    load_frags<8, true>(af, sa, wm * 64, h, gq, t);
+                    load_frags<4, true>(bf, sb, wn * 32, h, gq, t);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int a = 0; a < 8; ++a)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) dmma884(acc[a][b], af[a][u], bf[b][u]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_wempty + ws * 8);
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const long gr = grow0 + a * 8 + pg;
+                if (gr < g.n) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) g.A[gr * g.lda + gcol0 + b * 8 + t + 4 * e] = acc[a][b][e];
+                }
+            }
+            __threadfence();
+            bar_consumers();
+            if (tid == 0) {
+                fence_proxy_async();
+                st_release(g.flags + (long)i * T + j, g.epoch);
+            }
+        }
+        fence_proxy_async();                    // generic smem traffic of this task before the next task's TMA writes
+        if (lane == 0) mbar_arrive(bar_fdone);
+    }
+}
+
+int encode_tiles(gpn_ctx* c, CUtensorMap* tm, const double* ptr, long ld, long rows, long cols) {
+    if (((uintptr_t)ptr & 15) || (ld & 1)) return -3;
+    cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 1};
+    cuuint64_t gstr[2] = {(cuuint64_t)ld * 8, (cuuint64_t)ld * 8 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {KSTEP, TB, 1}, estr[3] = {1, 1, 1};
+    CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        gpn_set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled failed (dataflow potrf)");
+        return -1100 - (int)r;
+    }
+    return 0;
+}
+
+}   // namespace
+
+// Lower Cholesky of the n x n matrix A in place (tiles strictly above the diagonal are left untouched, the strict upper
+// triangle of the diagonal tiles is zeroed); inverted diagonal blocks go to winv (ceil(n/128) blocks of 128x128).
+int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset) {
+    const int T = (n + TB - 1) / TB;
+    const int ntasks = T * (T + 1) / 2;
+    if (c->flags.cap < sizeof(int) * (size_t)T * T) {
+        GPN_TRY(gpn_buf_ensure(c, c->flags, sizeof(int) * (size_t)T * T));
+        GPN_CK(cudaMemsetAsync(c->flags.p, 0, c->flags.cap, c->stream));
+        c->epoch = 0;
+    }
+    DfArgs a;
+    a.A = A; a.lda = lda; a.n = n; a.T = T; a.ntasks = ntasks; a.winv = winv; a.flags = (int*)c->flags.p;
+    a.epoch = ++c->epoch; a.info = d_info; a.info_off = info_offset;
+    CUtensorMap tl, tw;
+    GPN_TRY(encode_tiles(c, &tl, A, lda, n, n));
+    GPN_TRY(encode_tiles(c, &tw, winv, TB, (long)T * TB, TB));
+    static bool configured = false;
+    if (!configured) {
+        GPN_CK(cudaFuncSetAttribute(potrf_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM));
+        configured = true;
+    }
+    const int grid = ntasks < c->num_sms ? ntasks : c->num_sms;
+    void* args[] = {(void*)&tl, (void*)&tw, (void*)&a};
+    GPN_CK(cudaLaunchCooperativeKernel((const void*)potrf_dataflow_kernel, dim3(grid), dim3(384), args, DF_SMEM, c->stream));
+    c->launches++;
+    // executed flops: every task runs j k-blocks of 128^3 MACs (+ the in-CTA trsm / leaf)
+    double kb = 0.0;
+    for (int j = 0; j < T; ++j) kb += (double)(T - j) * j + (T - j - 1);
+    c->flops += 2.0 * kb * TB * TB * TB;
+    return 0;
+}

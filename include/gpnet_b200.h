@@ -43,6 +43,8 @@ void gpn_reset_counters(gpn_ctx* ctx);
 int gpn_fp64_peak(gpn_ctx* ctx, double seconds, double* tflops_h);
 void gpn_set_profile(gpn_ctx* ctx, int on);
 int gpn_profile_summary(gpn_ctx* ctx, double* out_h);
+/* development aid: device buffer of 32 int64 receiving clock64() stamps of the phases of the next leaf-kernel launch */
+void gpn_debug_leaf_prof(gpn_ctx* ctx, void* dev_buf32);
 
 /* ---- graph and node sets (host -> device once; resident afterwards) -------------------------------------- */
 /* CSR adjacency in graph-position order (row i = i-th node of list(G)); weights_h may be NULL (all ones).

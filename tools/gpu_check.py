@@ -106,6 +106,37 @@ def stage_perf(ctx):
         print(f"cusolver potrf {n}: {ms:.3f} ms", flush=True)
 
 
+def stage_leaf(ctx):
+    n = 128
+    X = torch.randn(n, n, dtype=torch.float64, device=dev)
+    S = X @ X.T / n + torch.eye(n, dtype=torch.float64, device=dev)
+    bufs = [dmat(n, n, S)[0] for _ in range(50)]
+
+    def run():
+        for b in bufs:
+            ctx.lib.gpn_potrf_f64(ctx.h, n, b.data_ptr(), 128, None)   # async (no info read-back)
+    import ctypes
+    ctx.lib.gpn_potrf_f64.argtypes[4] = ctypes.c_void_p
+    ms = ev(lambda: (run(), ctx.sync()))
+    print(f"leaf potf2+inverse 128x128: {ms/50*1e3:.1f} us per launch (incl. zero_upper + launch overhead)", flush=True)
+    prof = torch.zeros(32, dtype=torch.int64, device=dev)
+    ctx.lib.gpn_debug_leaf_prof(ctx.h, prof.data_ptr())
+    ctx.lib.gpn_potrf_f64(ctx.h, n, bufs[0].data_ptr(), 128, None)
+    ctx.sync()
+    ctx.lib.gpn_debug_leaf_prof(ctx.h, None)
+    p = prof.cpu().numpy()
+    print("diag32 factor-end stamps (relative to kernel start):", [int(x) - int(p[31]) for x in p[24:28]])
+    stamps = [int(x) for x in p[:24] if x != 0]
+    print("leaf phase cycles (load, then [diag32, panel, trailing] x kb, L write, inverse k=2,1,0, winv write):")
+    print("  load:", stamps[0] - int(p[31]), " phases:", [b - a for a, b in zip(stamps[:-1], stamps[1:])], " total:", stamps[-1] - int(p[31]), flush=True)
+    for nn in (256, 512, 1024, 2048):
+        X = torch.randn(nn, nn, dtype=torch.float64, device=dev)
+        S = X @ X.T / nn + torch.eye(nn, dtype=torch.float64, device=dev)
+        Sb, ld = dmat(nn, nn, S)
+        ms = ev(lambda: (ctx.potrf(nn, Sb.data_ptr(), ld)))
+        print(f"potrf {nn}: {ms*1e3:.1f} us  ({nn//128} tile columns -> {ms*1e3/(nn//128):.1f} us per column)", flush=True)
+
+
 def stage_potrf(ctx):
     torch.manual_seed(1)
     for n in (5, 100, 128, 129, 256, 900, 1024, 2048, 3000):

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for s in "$@"; do
   echo "##### stage $s" 
-  timeout 240 python tools/gpu_check.py $s > gpurun_out/stage_$s.log 2>&1
+  timeout 150 python tools/gpu_check.py $s > gpurun_out/stage_$s.log 2>&1
   echo "rc=$?"
   tail -n 60 gpurun_out/stage_$s.log
 done
