@@ -275,10 +275,23 @@ int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, lon
     CUtensorMap ta, tb;
     GPN_TRY(encode_operand(c, &ta, A, lda, a_kmajor, M, K, bm, batch, sA));
     GPN_TRY(encode_operand(c, &tb, B, ldb, b_kmajor, N, K, bn, batch, sB));
-    // executed-flop accounting (tile granularity, respecting the structure flags)
-    double kavg = (double)K;
-    if (flags & (GF_KLO_M | GF_KLO_N | GF_KHI_M | GF_KHI_N)) kavg = fmin((double)K, 0.5 * K + 0.5 * bm);
-    const double fl = 2.0 * (double)ntiles * bm * bn * kavg * batch;
+    // executed-flop accounting: exact sum over the tiles of the k-steps each one runs (structure flags respected)
+    double ksum = 0.0;
+    if (flags & (GF_KLO_M | GF_KLO_N | GF_KHI_M | GF_KHI_N)) {
+        for (int tm = 0; tm < a.tiles_m; ++tm)
+            for (int tn = 0; tn < ((flags & GF_LOWER) ? tm + 1 : a.tiles_n); ++tn) {
+                int k_lo = 0, k_hi = K;
+                if (flags & GF_KLO_M) k_lo = k_lo > tm * bm ? k_lo : tm * bm;
+                if (flags & GF_KLO_N) k_lo = k_lo > tn * bn ? k_lo : tn * bn;
+                if (flags & GF_KHI_M) k_hi = k_hi < (tm + 1) * bm ? k_hi : (tm + 1) * bm;
+                if (flags & GF_KHI_N) k_hi = k_hi < (tn + 1) * bn ? k_hi : (tn + 1) * bn;
+                k_lo &= ~(KSTEP - 1);
+                if (k_hi > k_lo) ksum += (double)((k_hi - k_lo + KSTEP - 1) / KSTEP * KSTEP);
+            }
+    } else {
+        ksum = (double)ntiles * ((K + KSTEP - 1) / KSTEP * KSTEP);
+    }
+    const double fl = 2.0 * bm * bn * ksum * batch;
     c->flops += fl;
     ProfEvent pe;
     if (c->profile) {

@@ -74,36 +74,65 @@ __device__ __forceinline__ void for_tiles(int R, int Cn, int tid, bool lower_onl
     }
 }
 
-// One warp: factor the 32x32 diagonal block at S[b0.., b0..] (lower Cholesky, in place, strict upper zeroed) and write
-// its inverse to Wb (row-major, ld WLD, upper zero).  Compact rolled loops on purpose: a fully unrolled version is
-// ~10k straight-line instructions executed once, i.e. instruction-fetch bound (measured 55k cycles per block).
-__device__ __forceinline__ void diag32(double* __restrict__ S, int b0, double* __restrict__ Wb, double* __restrict__ rdiag, int* info, int info_off,
-                                       int lane, long long* dprof = nullptr) {
+// FP64 arithmetic has ~36 cycles of dependent-issue latency on B200 (DFMA at ILP16 on 1 warp/SMSP reaches 88% of peak),
+// so the leaf is organised around the length of its dependent chains, not around its flop count.
+//
+// One warp: factor the 32x32 diagonal block at S[b0.., b0..] (lower Cholesky, in place, strict upper zeroed) and store
+// 1/L_cc in rdiag[c].  Lane r keeps row r in registers; y[q] is element (r, c+q) so the current column is always y[0]
+// (rolled loop, static register indices).  Software pipelined: the rank-1 update of column c-1 on columns c+1.. is
+// issued while rsqrt(d_c) is in flight; only the update of the next pivot column sits on the per-pivot chain
+// shfl -> rsqrt -> mul -> shfl -> fma.
+__device__ __forceinline__ void diag32_factor(double* __restrict__ S, int b0, double* __restrict__ rdiag, int* info, int info_off, int lane) {
     const unsigned full = 0xffffffffu;
     double* Sd = S + b0 * LDS_ + b0;
-    // y[q] = row `lane`, column c+q of the (partially updated) block: the current column is always y[0]
     double y[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) y[q] = Sd[lane * LDS_ + q];
+    double lp = 0.0;                       // this row's multiplier of the previous column
 #pragma unroll 1
     for (int c = 0; c < 32; ++c) {
         const double d = __shfl_sync(full, y[0], c);
         if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, info_off + b0 + c + 1);
         const double rd = rsqrt(d);
-        const double l = (lane > c) ? y[0] * rd : 0.0;
-        Sd[lane * LDS_ + c] = (lane == c) ? d * rd : l;          // column c of L (zero above the diagonal)
-        if (lane == c) rdiag[c] = rd;
 #pragma unroll
-        for (int q = 1; q < 32; ++q) {
-            const double lq = __shfl_sync(full, l, (c + q) & 31);     // l of row c+q (junk once c+q wraps: unused columns)
-            y[q - 1] = y[q] - l * lq;
+        for (int q = 1; q < 32; ++q) {     // column c-1 applied to columns c+1 .. (wrapped lanes hold lp == 0)
+            const double lq = __shfl_sync(full, lp, (c + q) & 31);
+            y[q] -= lp * lq;
         }
+        const double l = (lane > c) ? y[0] * rd : 0.0;
+        Sd[lane * LDS_ + c] = (lane == c) ? d * rd : l;
+        if (lane == c) rdiag[c] = rd;
+        const double l1 = __shfl_sync(full, l, (c + 1) & 31);
+        y[0] = y[1] - l * l1;              // next pivot column, fully updated
+#pragma unroll
+        for (int q = 2; q < 32; ++q) y[q - 1] = y[q];
+        lp = l;
     }
     __syncwarp();
-    if (dprof && lane == 0) dprof[0] = clock64();
-    // inverse by forward substitution, lane j owns column j of W = L^-1; X kept in shared memory (Wb).  FP64 latency on
-    // this part is ~36 cycles, so the dot products run on 8 independent accumulators and the division is a multiply
-    // by the reciprocal diagonal (1/L_ii == rsqrt(d_i), kept from the factorisation).
+}
+
+// One thread per row below the diagonal block: row <- row * L_kk^-T by a column sweep against L_kk in shared memory
+// (broadcast reads), i.e. the panel solve without forming the inverse of the diagonal block.  Chain per column: mul -> fma.
+__device__ __forceinline__ void panel_sweep(double* __restrict__ S, int b0, int row, const double* __restrict__ rdiag) {
+    const double* Sd = S + b0 * LDS_ + b0;
+    double* Sr = S + row * LDS_ + b0;
+    double y[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) y[q] = Sr[q];
+#pragma unroll 1
+    for (int c = 0; c < 32; ++c) {
+        const double x = y[0] * rdiag[c];
+        Sr[c] = x;
+#pragma unroll
+        for (int q = 1; q < 32; ++q) y[q - 1] = y[q] - x * Sd[((c + q) & 31) * LDS_ + c];   // wrapped rows read zeros (upper part)
+    }
+}
+
+// One warp: W = L_kk^-1 by forward substitution, lane j owns column j; X kept in shared memory (Wb, ld WLD).
+// Dot products on 8 independent accumulators; the division is a multiply by the stored reciprocal diagonal.
+__device__ __forceinline__ void diag32_inverse(const double* __restrict__ S, int b0, double* __restrict__ Wb, const double* __restrict__ rdiag,
+                                               int lane) {
+    const double* Sd = S + b0 * LDS_ + b0;
 #pragma unroll 1
     for (int i = 0; i < 32; ++i) {
         double s[8];
@@ -138,33 +167,15 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
 #define LEAF_STAMP() do { if (prof && tid == 0) prof[pidx++] = clock64(); } while (0)
     LEAF_STAMP();
     // ---------------- factorisation, 32-wide block columns ----------------
+    double* rdiag = T + 96 * WLD;
 #pragma unroll 1
     for (int kb = 0; kb < 4; ++kb) {
         const int b0 = 32 * kb, r1 = b0 + 32, R = LB - r1;
-        if (warp == 0) diag32(S, b0, Wd + kb * 32 * WLD, T + 96 * WLD + b0, info, info_off, lane, prof ? prof + 24 + kb : nullptr);
+        if (warp == 0) diag32_factor(S, b0, rdiag + b0, info, info_off, lane);
         bar256<BAR_ID>();
         LEAF_STAMP();
         if (R > 0) {
-            // panel: P = A21 * W11^T  (W11 lower => k <= c; computed with full K = 32 on a zero-padded W11)
-            double keep[3][4][4];
-            int kr[3], kc[3], cnt = 0;
-            for_tiles(R, 32, tid, false, [&](int r0, int c0) {
-                double acc[4][4];
-                tile4x4<false>(S + r1 * LDS_ + b0, LDS_, Wd + kb * 32 * WLD, WLD, 1, 32, r0, c0, acc);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) keep[cnt][i][j] = acc[i][j];
-                kr[cnt] = r0;
-                kc[cnt] = c0;
-                ++cnt;
-            });
-            bar256<BAR_ID>();
-            for (int q = 0; q < cnt; ++q)
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) S[(r1 + kr[q] + i) * LDS_ + b0 + kc[q] + j] = keep[q][i][j];
+            if (tid < R) panel_sweep(S, b0, r1 + tid, rdiag + b0);
             bar256<BAR_ID>();
             LEAF_STAMP();
             // trailing update: A22 -= P P^T (lower tiles)
@@ -191,7 +202,10 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
     }
     bar256<BAR_ID>();
     LEAF_STAMP();
-    // ---------------- inverse: diagonal blocks from Wd, then block columns right to left ----------------
+    // ---------------- inverse: the four diagonal blocks in parallel (one warp each), then block columns right to left ------
+    if (warp < 4) diag32_inverse(S, 32 * warp, Wd + warp * 32 * WLD, rdiag + 32 * warp, lane);
+    bar256<BAR_ID>();
+    LEAF_STAMP();
     for (int idx = tid; idx < 4 * 32 * 32; idx += 256) {
         const int b = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
         S[(32 * b + r) * LDS_ + 32 * b + c] = Wd[b * 32 * WLD + r * WLD + c];
