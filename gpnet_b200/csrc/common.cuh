@@ -99,6 +99,7 @@ struct gpn_ctx {
 };
 
 int gpn_buf_ensure(gpn_ctx* c, DevBuf& b, size_t bytes);
+int gpn_winv_ensure(gpn_ctx* c, size_t bytes);
 
 static inline long gpn_round_ld(long n) { return (n + 15) / 16 * 16; }   // 128-byte rows: TMA-friendly, sector aligned
 

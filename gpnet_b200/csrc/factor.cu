@@ -22,10 +22,11 @@ constexpr int LB = leaf::LB;
 __global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ A, long lda, int nv, double* __restrict__ winv,
                                                             int* __restrict__ info, int info_off, long long* prof) {
     extern __shared__ double sm[];
-    double* S = sm;
+    double* S = sm + leaf::GUARD;
     double* Wd = S + LB * leaf::LDS_;
     double* T = Wd + 4 * 32 * leaf::WLD;
     const int tid = threadIdx.x;
+    if (tid < leaf::GUARD) sm[tid] = 0.0;
     for (int idx = tid; idx < LB * LB; idx += 256) {
         const int r = idx >> 7, c = idx & 127;
         double v = 0.0;

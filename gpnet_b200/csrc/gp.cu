@@ -14,6 +14,14 @@ void gpn_set_last_error(const char* file, int line, const char* msg) {
     snprintf(g_last_error, sizeof g_last_error, "%s:%d: %s", file, line, msg);
 }
 
+// winv must be zero above the diagonal of every 128x128 block (the leaf writes lower triangles only)
+int gpn_winv_ensure(gpn_ctx* c, size_t bytes) {
+    if (bytes <= c->winv.cap) return 0;
+    GPN_TRY(gpn_buf_ensure(c, c->winv, bytes));
+    GPN_CK(cudaMemsetAsync(c->winv.p, 0, c->winv.cap, c->stream));
+    return 0;
+}
+
 int gpn_buf_ensure(gpn_ctx* c, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return 0;
     if (b.p) {
@@ -218,7 +226,7 @@ int symm_mul(gpn_ctx* c, const double* A, const double* B, double* C) {
 
 // SPD inverse of the N x N matrix in `a` (destroyed -> L); result (full symmetric) in `out`; w/t scratch
 int spd_inverse(gpn_ctx* c, int n, double* a, long ld, double* w, double* t, double* out, int info_slot) {
-    GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(n) * 128));
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(n) * 128));
     GPN_TRY(gpn_potrf(c, n, a, ld, (double*)c->winv.p, iscal(c, info_slot)));
     GPN_TRY(gpn_trtri_from_winv_tmp(c, n, a, ld, (const double*)c->winv.p, w, ld, t));
     return gpn_lauum(c, n, w, ld, out, ld, true);
@@ -452,7 +460,7 @@ int gpr_factor(gpn_ctx* c, bool keep_copy, GprFactor* f) {
         GPN_TRY(ensure_nb(c, NB_KC, ldn, ldn));
         GPN_TRY(gpn_k_copy(c, n, n, nbp(c, NB_KY), ldn, nbp(c, NB_KC), ldn));
     }
-    GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(std::max(n, c->N)) * 128));
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(std::max(n, c->N)) * 128));
     GPN_TRY(gpn_potrf(c, n, nbp(c, NB_KY), ldn, (double*)c->winv.p, iscal(c, 1)));
     GPN_TRY(gpn_trtri_from_winv_tmp(c, n, nbp(c, NB_KY), ldn, (const double*)c->winv.p, nbp(c, NB_W), ldn, nbp(c, NB_T)));
     f->n = n; f->ldn = ldn; f->Ky = nbp(c, NB_KY); f->W = nbp(c, NB_W); f->T = nbp(c, NB_T);
@@ -575,7 +583,7 @@ int gpr_predict(gpn_ctx* c, int kind, const double* theta_h, int P, const double
         // PD gate on kstarstar (:117-121) through a Cholesky instead of eigvals (quirk A-7)
         GPN_TRY(ensure_nb(c, NB_KSS, ldm, ldm));
         GPN_TRY(gpn_k_gather(c, kfull(c), c->ldN, te, m, te, m, noise, nbp(c, NB_KSS), ldm));
-        GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(std::max(std::max(n, m), c->N)) * 128));
+        GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(std::max(std::max(n, m), c->N)) * 128));
         GPN_TRY(gpn_potrf(c, m, nbp(c, NB_KSS), ldm, (double*)c->winv.p, iscal(c, 2)));
     }
     std::vector<double> fs(m), vn(m), kss(m);
@@ -625,7 +633,7 @@ int gpc_newton(gpn_ctx* c, const double* K, long ldk, int n, const double* y_h, 
     GPN_TRY(ensure_nb(c, NB_T, s.ldn, s.ldn));
     GPN_TRY(ensure_nb(c, NB_WK, s.ldn, s.ldn));
     GPN_TRY(ensure_nb(c, NB_KC, s.ldn, s.ldn));
-    GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(std::max(n, c->N)) * 128));
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(std::max(n, c->N)) * 128));
     GPN_TRY(upload(c, vecp(c, V_Y), y_h, sizeof(double) * n));
     GPN_CK(cudaMemsetAsync(vecp(c, V_F), 0, sizeof(double) * n, c->stream));                    // f = 0 (:96)
     // f^T K^-1 f of the convergence test (:126) through one Cholesky of K (K is fixed during the loop)
@@ -913,7 +921,7 @@ int gpn_gemm_f64(gpn_ctx* c, int transa, int transb, int M, int N, int K, double
 int gpn_potrf_f64(gpn_ctx* c, int n, double* A, long lda, int* info_h) {
     if (!c) return -1;
     GPN_TRY(clear_info(c));
-    GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(n) * 128));
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(n) * 128));
     GPN_TRY(gpn_potrf(c, n, A, lda, (double*)c->winv.p, iscal(c, 0)));
     GPN_TRY(gpn_k_zero_upper(c, A, lda, n));
     if (!info_h) return 0;       // asynchronous use: no read-back
@@ -927,7 +935,7 @@ int gpn_spd_inverse_f64(gpn_ctx* c, int n, double* A, long lda, double* out, lon
     if (!c) return -1;
     if (lda != ldo) return -6;
     GPN_TRY(clear_info(c));
-    GPN_TRY(gpn_buf_ensure(c, c->winv, sizeof(double) * (size_t)pad128(n) * 128));
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(n) * 128));
     GPN_TRY(gpn_potrf(c, n, A, lda, (double*)c->winv.p, iscal(c, 0)));
     // W -> out, scratch -> work, then K = W^T W needs a third buffer: reuse A (L is dead once W exists)
     GPN_TRY(gpn_trtri_from_winv_tmp(c, n, A, lda, (const double*)c->winv.p, out, ldo, work));

@@ -14,7 +14,8 @@ namespace leaf {
 constexpr int LB = 128;
 constexpr int LDS_ = LB + 1;
 constexpr int WLD = 33;
-constexpr size_t SMEM_DOUBLES = (size_t)LB * LDS_ + 4 * 32 * WLD + 96 * WLD + LB;   // S, Wd, T, reciprocal diagonal
+constexpr int GUARD = 32;                   // doubles in front of S (diag32_inverse reads up to 31 doubles before a row start)
+constexpr size_t SMEM_DOUBLES = GUARD + (size_t)LB * LDS_ + 4 * 32 * WLD + 96 * WLD + LB + 128;   // guard, S, Wd, T, 1/diag, column broadcast
 constexpr size_t SMEM_BYTES = SMEM_DOUBLES * sizeof(double);
 
 template <int BAR_ID>
@@ -23,29 +24,34 @@ __device__ __forceinline__ void bar256() {
     else asm volatile("bar.sync %0, 256;" ::"n"(BAR_ID) : "memory");
 }
 
-// acc[i][j] = sum_{k < klim(tile)} A[(r0+i)*sAr + k] * B[(c0+j)*sBc + k*sBk] for the 4x4 tile (r0, c0).
+// acc[i][j] = sum_{k < klim(tile)} A[(r0+i)*SAR + k] * B[(c0+j)*SBC + k*SBK] for the 4x4 tile (r0, c0); strides are
+// compile-time so that every load address is pointer + immediate (a single warp issues integer ops at 1 per 2 cycles:
+// address arithmetic, not FP64, was the bottleneck of the first version).
 // KTRI: the A operand is lower triangular in (row, k) => k <= r0+3 suffices.
-template <bool KTRI>
-__device__ __forceinline__ void tile4x4(const double* __restrict__ A, int sAr, const double* __restrict__ B, int sBc, int sBk, int K,
-                                        int r0, int c0, double (&acc)[4][4]) {
+template <bool KTRI, int SAR, int SBC, int SBK>
+__device__ __forceinline__ void tile4x4(const double* __restrict__ A, const double* __restrict__ B, int K, int r0, int c0,
+                                        double (&acc)[4][4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    const int klim = KTRI ? min(K, r0 + 4) : K;
-    const double* a0 = A + r0 * sAr;
-    const double* b0 = B + c0 * sBc;
-#pragma unroll 4
-    for (int k = 0; k < klim; ++k) {
-        double a[4], b[4];
+    const int klim = KTRI ? min(K, r0 + 4) : K;       // always a multiple of 4 here
+    const double* a0 = A + r0 * SAR;
+    const double* b0 = B + c0 * SBC;
+#pragma unroll 1
+    for (int k = 0; k < klim; k += 4, a0 += 4, b0 += 4 * SBK) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = a0[i * sAr + k];
+        for (int kk = 0; kk < 4; ++kk) {
+            double a[4], b[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = b0[j * sBc + k * sBk];
+            for (int i = 0; i < 4; ++i) a[i] = a0[i * SAR + kk];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) b[j] = b0[j * SBC + kk * SBK];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
     }
 }
 
@@ -82,75 +88,77 @@ __device__ __forceinline__ void for_tiles(int R, int Cn, int tid, bool lower_onl
 // (rolled loop, static register indices).  Software pipelined: the rank-1 update of column c-1 on columns c+1.. is
 // issued while rsqrt(d_c) is in flight; only the update of the next pivot column sits on the per-pivot chain
 // shfl -> rsqrt -> mul -> shfl -> fma.
-__device__ __forceinline__ void diag32_factor(double* __restrict__ S, int b0, double* __restrict__ rdiag, int* info, int info_off, int lane) {
+__device__ __forceinline__ void diag32_factor(double* __restrict__ S, int b0, double* __restrict__ rdiag, double* __restrict__ colbuf,
+                                              int* info, int info_off, int lane) {
     const unsigned full = 0xffffffffu;
     double* Sd = S + b0 * LDS_ + b0;
     double y[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) y[q] = Sd[lane * LDS_ + q];
+    // colbuf: 2 x 64 doubles; entries 32..63 of each half stay zero so that "row c+q" needs no wrap-around arithmetic
+    colbuf[lane] = 0.0; colbuf[32 + lane] = 0.0; colbuf[64 + lane] = 0.0; colbuf[96 + lane] = 0.0;
+    __syncwarp();
     double lp = 0.0;                       // this row's multiplier of the previous column
+    double* sp = Sd + lane * LDS_;         // &L[lane][c]
 #pragma unroll 1
-    for (int c = 0; c < 32; ++c) {
+    for (int c = 0; c < 32; ++c, ++sp) {
         const double d = __shfl_sync(full, y[0], c);
         if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, info_off + b0 + c + 1);
         const double rd = rsqrt(d);
+        // column c-1 applied to columns c+1 .. : multipliers of rows c+1.. are broadcast from shared memory (pointer +
+        // immediate loads); results are written one slot down so that column c+1 becomes y[0] for the next pivot
+        const double* lc = colbuf + ((c & 1) << 6) + c;      // lc[q] = l_{c+q, c-1}  (zero beyond row 31)
+        const double t1 = y[1] - lp * lc[1];
 #pragma unroll
-        for (int q = 1; q < 32; ++q) {     // column c-1 applied to columns c+1 .. (wrapped lanes hold lp == 0)
-            const double lq = __shfl_sync(full, lp, (c + q) & 31);
-            y[q] -= lp * lq;
-        }
+        for (int q = 2; q < 32; ++q) y[q - 1] = y[q] - lp * lc[q];
         const double l = (lane > c) ? y[0] * rd : 0.0;
-        Sd[lane * LDS_ + c] = (lane == c) ? d * rd : l;
+        *sp = (lane == c) ? d * rd : l;
         if (lane == c) rdiag[c] = rd;
+        colbuf[(((c + 1) & 1) << 6) + lane] = l;             // published for the next iteration's bulk update
         const double l1 = __shfl_sync(full, l, (c + 1) & 31);
-        y[0] = y[1] - l * l1;              // next pivot column, fully updated
-#pragma unroll
-        for (int q = 2; q < 32; ++q) y[q - 1] = y[q];
+        y[0] = t1 - l * l1;                // next pivot column, fully updated
         lp = l;
+        __syncwarp();
     }
-    __syncwarp();
 }
 
 // One thread per row below the diagonal block: row <- row * L_kk^-T by a column sweep against L_kk in shared memory
 // (broadcast reads), i.e. the panel solve without forming the inverse of the diagonal block.  Chain per column: mul -> fma.
 __device__ __forceinline__ void panel_sweep(double* __restrict__ S, int b0, int row, const double* __restrict__ rdiag) {
-    const double* Sd = S + b0 * LDS_ + b0;
+    const double* lp = S + b0 * LDS_ + b0;      // &L_kk[c][c], advanced along the diagonal
     double* Sr = S + row * LDS_ + b0;
     double y[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) y[q] = Sr[q];
 #pragma unroll 1
-    for (int c = 0; c < 32; ++c) {
+    for (int c = 0; c < 32; ++c, lp += LDS_ + 1) {
         const double x = y[0] * rdiag[c];
         Sr[c] = x;
+        // y[q] is column c+q; L[c+q][c] = lp[q*LDS_].  For c+q >= 32 the load leaves the diagonal block (finite junk from
+        // the rows below / the scratch after S) and only feeds slots of columns >= 32, which are never used.
 #pragma unroll
-        for (int q = 1; q < 32; ++q) y[q - 1] = y[q] - x * Sd[((c + q) & 31) * LDS_ + c];   // wrapped rows read zeros (upper part)
+        for (int q = 1; q < 32; ++q) y[q - 1] = y[q] - x * lp[q * LDS_];
     }
 }
 
-// One warp: W = L_kk^-1 by forward substitution, lane j owns column j; X kept in shared memory (Wb, ld WLD).
-// Dot products on 8 independent accumulators; the division is a multiply by the stored reciprocal diagonal.
+// One warp: W = L_kk^-1, lane r owns ROW r of W (x L_kk = e_r), columns swept from 31 down to 0 against the rows of
+// L_kk in shared memory (broadcast reads).  z[q] is the pending value of column c-q, so the current column is z[0]
+// (static register indices in a rolled loop); chain per column: mul -> fma.  Wrapped columns read the zero upper part.
 __device__ __forceinline__ void diag32_inverse(const double* __restrict__ S, int b0, double* __restrict__ Wb, const double* __restrict__ rdiag,
                                                int lane) {
-    const double* Sd = S + b0 * LDS_ + b0;
+    const double* lc = S + (b0 + 31) * LDS_ + b0 + 31;     // &L_kk[c][c], walked up the diagonal
+    double* wp = Wb + lane * WLD + 31;
+    double z[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) z[q] = (lane == 31 - q) ? 1.0 : 0.0;
 #pragma unroll 1
-    for (int i = 0; i < 32; ++i) {
-        double s[8];
+    for (int c = 31; c >= 0; --c, lc -= LDS_ + 1, --wp) {
+        const double x = z[0] * rdiag[c];
+        *wp = x;                                      // zero for c > lane by construction
+        // z[q] is column c-q; L[c][c-q] = lc[-q].  For q > c the load runs into the columns left of the block / the previous
+        // row (finite values; the GUARD doubles in front of S cover the very first row) and only feeds unused slots.
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s[u] = 0.0;
-        s[0] = (i == lane) ? 1.0 : 0.0;
-        const double* Li = Sd + i * LDS_;
-        const int i8 = i & ~7;
-#pragma unroll 1
-        for (int k = 0; k < i8; k += 8) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s[u] -= Li[k + u] * Wb[(k + u) * WLD + lane];
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (i8 + u < i) s[u] -= Li[i8 + u] * Wb[(i8 + u) * WLD + lane];
-        const double tot = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-        Wb[i * WLD + lane] = (i >= lane) ? tot * rdiag[i] : 0.0;
+        for (int q = 1; q < 32; ++q) z[q - 1] = z[q] - x * lc[-q];
     }
     __syncwarp();
 }
@@ -171,7 +179,7 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
 #pragma unroll 1
     for (int kb = 0; kb < 4; ++kb) {
         const int b0 = 32 * kb, r1 = b0 + 32, R = LB - r1;
-        if (warp == 0) diag32_factor(S, b0, rdiag + b0, info, info_off, lane);
+        if (warp == 0) diag32_factor(S, b0, rdiag + b0, rdiag + LB, info, info_off, lane);
         bar256<BAR_ID>();
         LEAF_STAMP();
         if (R > 0) {
@@ -181,7 +189,7 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
             // trailing update: A22 -= P P^T (lower tiles)
             for_tiles(R, R, tid, true, [&](int r0, int c0) {
                 double acc[4][4];
-                tile4x4<false>(S + r1 * LDS_ + b0, LDS_, S + r1 * LDS_ + b0, LDS_, 1, 32, r0, c0, acc);
+                tile4x4<false, LDS_, LDS_, 1>(S + r1 * LDS_ + b0, S + r1 * LDS_ + b0, 32, r0, c0, acc);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -192,10 +200,12 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
         }
     }
     // ---------------- write L back ----------------
+    // lower triangle (+ the one pair straddling the diagonal); the strict upper triangle of a diagonal tile is never read
+    // by the library (the public gpn_potrf_f64 zeroes it afterwards)
     for (int idx = tid; idx < LB * LB / 2; idx += 256) {
         const int r = idx >> 6, c = (idx & 63) * 2;
-        if (r < nv && c < nv) {
-            const double v0 = (c <= r) ? S[r * LDS_ + c] : 0.0, v1 = (c + 1 <= r) ? S[r * LDS_ + c + 1] : 0.0;
+        if (r < nv && c <= r) {
+            const double v0 = S[r * LDS_ + c], v1 = (c + 1 <= r) ? S[r * LDS_ + c + 1] : 0.0;
             if (c + 1 < nv) *reinterpret_cast<double2*>(Lout + (long)r * ldl + c) = make_double2(v0, v1);
             else Lout[(long)r * ldl + c] = v0;
         }
@@ -217,7 +227,7 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
         // T = L_col * W_kk           (B[c=j][q] = W_kk[q][j])
         for_tiles(R, 32, tid, false, [&](int r0, int c0) {
             double acc[4][4];
-            tile4x4<false>(S + r1 * LDS_ + 32 * k, LDS_, Wd + k * 32 * WLD, 1, WLD, 32, r0, c0, acc);
+            tile4x4<false, LDS_, 1, WLD>(S + r1 * LDS_ + 32 * k, Wd + k * 32 * WLD, 32, r0, c0, acc);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -227,7 +237,7 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
         // X = -W_trail * T           (W_trail lower => k <= r)
         for_tiles(R, 32, tid, false, [&](int r0, int c0) {
             double acc[4][4];
-            tile4x4<true>(S + r1 * LDS_ + r1, LDS_, T, 1, WLD, R, r0, c0, acc);
+            tile4x4<true, LDS_, 1, WLD>(S + r1 * LDS_ + r1, T, R, r0, c0, acc);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -236,9 +246,10 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
         bar256<BAR_ID>();
         LEAF_STAMP();
     }
+    // lower triangle only: winv buffers are zero-initialised when they are allocated and the upper part is never written
     for (int idx = tid; idx < LB * LB / 2; idx += 256) {
         const int r = idx >> 6, c = (idx & 63) * 2;
-        reinterpret_cast<double2*>(winv)[idx] = make_double2((c <= r) ? S[r * LDS_ + c] : 0.0, (c + 1 <= r) ? S[r * LDS_ + c + 1] : 0.0);
+        if (c <= r) reinterpret_cast<double2*>(winv)[idx] = make_double2(S[r * LDS_ + c], (c + 1 <= r) ? S[r * LDS_ + c + 1] : 0.0);
     }
     LEAF_STAMP();
 #undef LEAF_STAMP

@@ -124,7 +124,7 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
     const int wm = warp >> 2, wn = warp & 3;
     const int gq = lane >> 2, t = lane & 3;
     const int pg = (gq >> 1) | ((gq & 1) << 2);
-    double* S = reinterpret_cast<double*>(smem_gen);
+    double* S = reinterpret_cast<double*>(smem_gen) + leaf::GUARD;
     double* Wd = S + leaf::LB * leaf::LDS_;
     double* Tt = Wd + 4 * 32 * leaf::WLD;
 
@@ -166,6 +166,7 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
         const long grow0 = (long)i * TB + wm * 64, gcol0 = (long)j * TB + wn * 32;
         if (i == j) {
             // ---- C = A_jj - acc -> S (identity padded); factor + invert in shared memory ----
+            if (tid < leaf::GUARD) reinterpret_cast<double*>(smem_gen)[tid] = 0.0;
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
                 const int r = wm * 64 + a * 8 + pg;
