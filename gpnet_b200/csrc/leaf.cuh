@@ -7,6 +7,8 @@
 //    4x4 register-tiled shared-memory GEMMs over all 8 warps.
 // Shared memory: S[128][129] (padded, conflict-free column access), Wd[4][32][33], T[96][33].
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace leaf {
@@ -100,8 +102,8 @@ __device__ __forceinline__ void diag32_factor(double* __restrict__ S, int b0, do
     __syncwarp();
     double lp = 0.0;                       // this row's multiplier of the previous column
     double* sp = Sd + lane * LDS_;         // &L[lane][c]
-#pragma unroll 1
-    for (int c = 0; c < 32; ++c, ++sp) {
+    auto pivot_step = [&](int c, auto qm_tag) {
+        constexpr int QM = decltype(qm_tag)::value;        // live slots: columns c .. c+QM
         const double d = __shfl_sync(full, y[0], c);
         if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, info_off + b0 + c + 1);
         const double rd = rsqrt(d);
@@ -110,7 +112,7 @@ __device__ __forceinline__ void diag32_factor(double* __restrict__ S, int b0, do
         const double* lc = colbuf + ((c & 1) << 6) + c;      // lc[q] = l_{c+q, c-1}  (zero beyond row 31)
         const double t1 = y[1] - lp * lc[1];
 #pragma unroll
-        for (int q = 2; q < 32; ++q) y[q - 1] = y[q] - lp * lc[q];
+        for (int q = 2; q <= QM; ++q) y[q - 1] = y[q] - lp * lc[q];
         const double l = (lane > c) ? y[0] * rd : 0.0;
         *sp = (lane == c) ? d * rd : l;
         if (lane == c) rdiag[c] = rd;
@@ -118,8 +120,13 @@ __device__ __forceinline__ void diag32_factor(double* __restrict__ S, int b0, do
         const double l1 = __shfl_sync(full, l, (c + 1) & 31);
         y[0] = t1 - l * l1;                // next pivot column, fully updated
         lp = l;
+        ++sp;
         __syncwarp();
-    }
+    };
+#pragma unroll 1
+    for (int c = 0; c < 16; ++c) pivot_step(c, std::integral_constant<int, 31>{});
+#pragma unroll 1
+    for (int c = 16; c < 32; ++c) pivot_step(c, std::integral_constant<int, 16>{});   // columns >= 32 do not exist
 }
 
 // One thread per row below the diagonal block: row <- row * L_kk^-T by a column sweep against L_kk in shared memory
@@ -130,15 +137,19 @@ __device__ __forceinline__ void panel_sweep(double* __restrict__ S, int b0, int 
     double y[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) y[q] = Sr[q];
-#pragma unroll 1
-    for (int c = 0; c < 32; ++c, lp += LDS_ + 1) {
+    auto step = [&](int c, auto qm_tag) {
+        constexpr int QM = decltype(qm_tag)::value;
         const double x = y[0] * rdiag[c];
         Sr[c] = x;
-        // y[q] is column c+q; L[c+q][c] = lp[q*LDS_].  For c+q >= 32 the load leaves the diagonal block (finite junk from
-        // the rows below / the scratch after S) and only feeds slots of columns >= 32, which are never used.
+        // y[q] is column c+q; L[c+q][c] = lp[q*LDS_]
 #pragma unroll
-        for (int q = 1; q < 32; ++q) y[q - 1] = y[q] - x * lp[q * LDS_];
-    }
+        for (int q = 1; q <= QM; ++q) y[q - 1] = y[q] - x * lp[q * LDS_];
+        lp += LDS_ + 1;
+    };
+#pragma unroll 1
+    for (int c = 0; c < 16; ++c) step(c, std::integral_constant<int, 31>{});
+#pragma unroll 1
+    for (int c = 16; c < 32; ++c) step(c, std::integral_constant<int, 15>{});     // columns >= 32 do not exist
 }
 
 // One warp: W = L_kk^-1, lane r owns ROW r of W (x L_kk = e_r), columns swept from 31 down to 0 against the rows of
@@ -151,15 +162,20 @@ __device__ __forceinline__ void diag32_inverse(const double* __restrict__ S, int
     double z[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) z[q] = (lane == 31 - q) ? 1.0 : 0.0;
-#pragma unroll 1
-    for (int c = 31; c >= 0; --c, lc -= LDS_ + 1, --wp) {
+    auto step = [&](int c, auto qm_tag) {
+        constexpr int QM = decltype(qm_tag)::value;
         const double x = z[0] * rdiag[c];
         *wp = x;                                      // zero for c > lane by construction
-        // z[q] is column c-q; L[c][c-q] = lc[-q].  For q > c the load runs into the columns left of the block / the previous
-        // row (finite values; the GUARD doubles in front of S cover the very first row) and only feeds unused slots.
+        // z[q] is column c-q; L[c][c-q] = lc[-q]
 #pragma unroll
-        for (int q = 1; q < 32; ++q) z[q - 1] = z[q] - x * lc[-q];
-    }
+        for (int q = 1; q <= QM; ++q) z[q - 1] = z[q] - x * lc[-q];
+        lc -= LDS_ + 1;
+        --wp;
+    };
+#pragma unroll 1
+    for (int c = 31; c >= 16; --c) step(c, std::integral_constant<int, 31>{});
+#pragma unroll 1
+    for (int c = 15; c >= 0; --c) step(c, std::integral_constant<int, 15>{});     // columns < 0 do not exist
     __syncwarp();
 }
 

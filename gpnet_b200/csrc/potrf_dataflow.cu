@@ -121,9 +121,19 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
 
     // ============================== DMMA consumers (8 warps, 64 x 32 each) ==============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int wm = warp >> 2, wn = warp & 3;
+    // warp w runs on SMSP w % 4.  Column groups are dealt so that every SMSP hosts one "early" and one "late" column group
+    // (wn = w for warps 0-3, 7 - w for warps 4-7): the triangular skips below (diagonal tiles need only their lower
+    // triangle, W_j is lower triangular) then remove ~45 % of the DMMA work from EVERY SMSP instead of idling two of them.
+    const int wm = warp >> 2, wn = (warp < 4) ? warp : 7 - warp;
     const int gq = lane >> 2, t = lane & 3;
     const int pg = (gq >> 1) | ((gq & 1) << 2);
+    // bit (a*4+b): 8x8 block (a, b) of this warp's 64x32 tile touches the lower triangle of a diagonal tile
+    uint32_t diag_mask = 0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (32 * wn + 8 * b <= 64 * wm + 8 * a + 7) diag_mask |= 1u << (a * 4 + b);
     double* S = reinterpret_cast<double*>(smem_gen) + leaf::GUARD;
     double* Wd = S + leaf::LB * leaf::LDS_;
     double* Tt = Wd + 4 * 32 * leaf::WLD;
@@ -141,21 +151,38 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
             for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
         const int niter = j * 8;
+        const uint32_t mask = (i == j) ? diag_mask : 0xffffffffu;
         for (int n = 0; n < niter; ++n, ++it) {
             const int st = it % STAGES;
             mbar_wait(bar_full + st * 8, (it / STAGES) & 1);
             const uint32_t sa = smem0 + st * STAGE_BYTES, sb = sa + TILE_BYTES;
+            if (mask == 0xffffffffu) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                double af[8][2], bf[4][2];
-                load_frags<8, true>(af, sa, wm * 64, h, gq, t);
-                load_frags<4, true>(bf, sb, wn * 32, h, gq, t);
+                for (int h = 0; h < 2; ++h) {
+                    double af[8][2], bf[4][2];
+                    load_frags<8, true>(af, sa, wm * 64, h, gq, t);
+                    load_frags<4, true>(bf, sb, wn * 32, h, gq, t);
 #pragma unroll
-                for (int u = 0; u < 2; ++u)
+                    for (int u = 0; u < 2; ++u)
 #pragma unroll
-                    for (int a = 0; a < 8; ++a)
+                        for (int a = 0; a < 8; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) dmma884(acc[a][b], af[a][u], bf[b][u]);
+                            for (int b = 0; b < 4; ++b) dmma884(acc[a][b], af[a][u], bf[b][u]);
+                }
+            } else if (mask != 0) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double af[8][2], bf[4][2];
+                    load_frags<8, true>(af, sa, wm * 64, h, gq, t);
+                    load_frags<4, true>(bf, sb, wn * 32, h, gq, t);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int a = 0; a < 8; ++a)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                if (mask & (1u << (a * 4 + b))) dmma884(acc[a][b], af[a][u], bf[b][u]);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + st * 8);
@@ -216,17 +243,22 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
                 const int ws = wit % WSTAGES;
                 mbar_wait(bar_wfull + ws * 8, (wit / WSTAGES) & 1);
                 const uint32_t sa = smem0 + s * TILE_BYTES, sb = smem0 + CREG_BYTES + ws * TILE_BYTES;
+                // W_j[n][k] == 0 for k > n: k-step s only reaches the 8-column blocks with 16 s <= 32 wn + 8 b + 7
+                if (16 * s <= 32 * wn + 31) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    double af[8][2], bf[4][2];
-                    load_frags<8, true>(af, sa, wm * 64, h, gq, t);
-                    load_frags<4, true>(bf, sb, wn * 32, h, gq, t);
+                    for (int h = 0; h < 2; ++h) {
+                        double af[8][2], bf[4][2];
+                        load_frags<8, true>(af, sa, wm * 64, h, gq, t);
+                        load_frags<4, true>(bf, sb, wn * 32, h, gq, t);
 #pragma unroll
-                    for (int u = 0; u < 2; ++u)
+                        for (int b = 0; b < 4; ++b)
+                            if (16 * s <= 32 * wn + 8 * b + 7) {
 #pragma unroll
-                        for (int a = 0; a < 8; ++a)
+                                for (int u = 0; u < 2; ++u)
 #pragma unroll
-                            for (int b = 0; b < 4; ++b) dmma884(acc[a][b], af[a][u], bf[b][u]);
+                                    for (int a = 0; a < 8; ++a) dmma884(acc[a][b], af[a][u], bf[b][u]);
+                            }
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_wempty + ws * 8);
