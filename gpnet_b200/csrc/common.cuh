@@ -108,13 +108,15 @@ static inline long gpn_round_ld(long n) { return (n + 15) / 16 * 16; }   // 128-
 // b_kmajor: B stored [N][K]; else [K][N].  Batched over `batch` problems with element strides sA/sB/sC.
 int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, long lda, bool a_kmajor, const double* B,
              long ldb, bool b_kmajor, double beta, double* C, long ldc, int flags, int batch = 1, long sA = 0,
-             long sB = 0, long sC = 0);
+             long sB = 0, long sC = 0, double* CT = nullptr, long ldct = 0, long sCT = 0);   // CT: optional transposed copy
 
 // Cholesky (lower, in place, row-major), triangular inverse and SPD inverse.  info: device int (0 = ok).
 int gpn_potrf(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset = 0);
 int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset);
-int gpn_trtri_from_winv(gpn_ctx* c, int n, const double* L, long ldl, const double* winv, double* W, long ldw);
-int gpn_lauum(gpn_ctx* c, int n, const double* W, long ldw, double* out, long ldo, bool mirror);
+// W = L^-1 (normal, lower) and WT = W^T (upper) from L and the inverted diagonal blocks; TT: n x n scratch.  All ld = ldw.
+int gpn_trtri(gpn_ctx* c, int n, const double* L, long ldl, const double* winv, double* W, double* WT, double* TT, long ldw);
+// out (lower [+ mirrored upper]) = W^T W computed from WT = W^T (both operands K-major)
+int gpn_lauum_t(gpn_ctx* c, int n, const double* WT, long ldw, double* out, long ldo, bool mirror);
 
 // elementwise / reductions (elementwise.cu)
 int gpn_k_fill_zero(gpn_ctx* c, double* A, long ld, int rows, int cols);

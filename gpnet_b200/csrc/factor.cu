@@ -85,12 +85,16 @@ int potrf_rec(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info,
     return potrf_rec(c, n2, A22, lda, winv + (long)n1 * LB, d_info, off + n1);
 }
 
-__global__ void copy_diag_blocks_kernel(const double* __restrict__ winv, double* __restrict__ W, long ldw, int n) {
+__global__ void copy_diag_blocks_kernel(const double* __restrict__ winv, double* __restrict__ W, double* __restrict__ WT, long ldw, int n) {
     const int b = blockIdx.x;
     for (int idx = threadIdx.x; idx < LB * LB; idx += blockDim.x) {
         const int r = idx >> 7, cc = idx & 127;
         const int gr = b * LB + r, gc = b * LB + cc;
-        if (gr < n && gc < n) W[(long)gr * ldw + gc] = winv[(long)b * LB * LB + idx];
+        if (gr < n && gc < n) {
+            const double v = winv[(long)b * LB * LB + idx];
+            W[(long)gr * ldw + gc] = v;
+            WT[(long)gc * ldw + gr] = v;
+        }
     }
 }
 
@@ -102,12 +106,14 @@ int gpn_potrf(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info,
     return potrf_rec(c, n, A, lda, winv, d_info, info_offset);
 }
 
-// W (n x n, ldw; fully overwritten incl. zero upper triangle) = L^-1.  `tmp` is an n x n scratch with leading dim ldw.
-int gpn_trtri_from_winv_tmp(gpn_ctx* c, int n, const double* L, long ldl, const double* winv, double* W, long ldw, double* tmp) {
+// W = L^-1 (lower, upper part zeroed) and WT = W^T, level by level; every GEMM reads K-major operands only (the 99 %
+// DMMA path): T^T is kept instead of T, and each W21 block is stored both ways by the GEMM epilogue.
+int gpn_trtri(gpn_ctx* c, int n, const double* L, long ldl, const double* winv, double* W, double* WT, double* TT, long ldw) {
     if (n <= 0) return 0;
     GPN_TRY(gpn_k_fill_zero(c, W, ldw, n, n));
+    GPN_TRY(gpn_k_fill_zero(c, WT, ldw, n, n));
     const int m = (n + LB - 1) / LB;
-    copy_diag_blocks_kernel<<<m, 256, 0, c->stream>>>(winv, W, ldw, n);
+    copy_diag_blocks_kernel<<<m, 256, 0, c->stream>>>(winv, W, WT, ldw, n);
     c->launches++;
     GPN_CK(cudaGetLastError());
     for (long b = LB; b < n; b *= 2) {       // b = half size of the pairs of this level
@@ -115,29 +121,26 @@ int gpn_trtri_from_winv_tmp(gpn_ctx* c, int n, const double* L, long ldl, const 
         const int full = (int)(n / pair);    // pairs entirely inside the valid n x n region
         if (full > 0) {
             const long sL = pair * ldl + pair, sW = pair * ldw + pair;
-            // T = L21 * W11       (W11 lower: only k >= n0 contributes)
-            GPN_TRY(gpn_gemm(c, (int)b, (int)b, (int)b, 1.0, L + b * ldl, ldl, true, W, ldw, false, 0.0, tmp + b * ldw, ldw, GF_KLO_N,
-                             full, sL, sW, sW));
-            // W21 = -W22 * T      (W22 lower: only k < m0+BM contributes)
-            GPN_TRY(gpn_gemm(c, (int)b, (int)b, (int)b, -1.0, W + b * ldw + b, ldw, true, tmp + b * ldw, ldw, false, 0.0, W + b * ldw,
-                             ldw, GF_KHI_M, full, sW, sW, sW));
+            // T = L21 * W11 (W11 lower: only k >= n0 contributes), stored transposed: TT[o+c][o+b+r]
+            GPN_TRY(gpn_gemm(c, (int)b, (int)b, (int)b, 1.0, L + b * ldl, ldl, true, WT, ldw, true, 0.0, nullptr, 0, GF_KLO_N, full, sL, sW, 0,
+                             TT + b, ldw, sW));
+            // W21 = -W22 * T (W22 lower: only k < m0+BM contributes); normal copy into W, transposed copy into WT
+            GPN_TRY(gpn_gemm(c, (int)b, (int)b, (int)b, -1.0, W + b * ldw + b, ldw, true, TT + b, ldw, true, 0.0, W + b * ldw, ldw, GF_KHI_M,
+                             full, sW, sW, sW, WT + b, ldw, sW));
         }
         const long o = (long)full * pair;    // ragged remainder: [o, o+b) full first half, [o+b, n) partial second half
         const long r = n - o - b;
         if (r > 0) {
-            const double* L21 = L + (o + b) * ldl + o;
-            double* T21 = tmp + (o + b) * ldw + o;
-            double* W21 = W + (o + b) * ldw + o;
-            GPN_TRY(gpn_gemm(c, (int)r, (int)b, (int)b, 1.0, L21, ldl, true, W + o * ldw + o, ldw, false, 0.0, T21, ldw, GF_KLO_N));
-            GPN_TRY(gpn_gemm(c, (int)r, (int)b, (int)r, -1.0, W + (o + b) * ldw + (o + b), ldw, true, T21, ldw, false, 0.0, W21, ldw,
-                             GF_KHI_M));
+            GPN_TRY(gpn_gemm(c, (int)r, (int)b, (int)b, 1.0, L + (o + b) * ldl + o, ldl, true, WT + o * ldw + o, ldw, true, 0.0, nullptr, 0,
+                             GF_KLO_N, 1, 0, 0, 0, TT + o * ldw + (o + b), ldw, 0));
+            GPN_TRY(gpn_gemm(c, (int)r, (int)b, (int)r, -1.0, W + (o + b) * ldw + (o + b), ldw, true, TT + o * ldw + (o + b), ldw, true, 0.0,
+                             W + (o + b) * ldw + o, ldw, GF_KHI_M, 1, 0, 0, 0, WT + o * ldw + (o + b), ldw, 0));
         }
     }
     return 0;
 }
 
-// out (lower [+ mirrored upper]) = W^T W for lower-triangular W.
-int gpn_lauum(gpn_ctx* c, int n, const double* W, long ldw, double* out, long ldo, bool mirror) {
-    return gpn_gemm(c, n, n, n, 1.0, W, ldw, false, W, ldw, false, 0.0, out, ldo,
-                    GF_LOWER | (mirror ? GF_MIRROR : 0) | GF_KLO_M | GF_KLO_N);
+// out (lower [+ mirrored upper]) = W^T W = sum_k WT[i][k] WT[j][k], k >= max(i, j)
+int gpn_lauum_t(gpn_ctx* c, int n, const double* WT, long ldw, double* out, long ldo, bool mirror) {
+    return gpn_gemm(c, n, n, n, 1.0, WT, ldw, true, WT, ldw, true, 0.0, out, ldo, GF_LOWER | (mirror ? GF_MIRROR : 0) | GF_KLO_M | GF_KLO_N);
 }

@@ -23,8 +23,9 @@ using namespace tp;
 
 struct GemmArgs {
     int M, N, K;
-    double* C;
-    long ldc, sC;
+    double* C;      // normal output (may be null when only the transposed copy is wanted)
+    double* CT;     // optional transposed output: CT[col][row] = value
+    long ldc, sC, ldct, sCT;
     double alpha, beta;
     int flags;
     int tiles_m, tiles_n;
@@ -157,7 +158,8 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 
     // ---- epilogue: C = alpha*acc + beta*C (+ mirrored store) ---------------------------------------------
-    double* __restrict__ C = g.C + (long)batch * g.sC;
+    double* __restrict__ C = g.C ? g.C + (long)batch * g.sC : nullptr;
+    double* __restrict__ CT = g.CT ? g.CT + (long)batch * g.sCT : nullptr;
     const bool mirror = (g.flags & GF_MIRROR) && (tm != tn);
     const int pg = (gq >> 1) | ((gq & 1) << 2);
     const int rsel = AK ? pg : gq;
@@ -173,10 +175,13 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int col = n0 + wn * 32 + j * 8 + (BK ? (t + 4 * e) : (2 * t + e));
                 if (col < g.N) {
                     double v = alpha * acc[i][j][e];
-                    double* p = C + (long)row * g.ldc + col;
-                    if (beta != 0.0) v += beta * (*p);
-                    *p = v;
-                    if (mirror) C[(long)col * g.ldc + row] = v;
+                    if (C) {
+                        double* p = C + (long)row * g.ldc + col;
+                        if (beta != 0.0) v += beta * (*p);
+                        *p = v;
+                        if (mirror) C[(long)col * g.ldc + row] = v;
+                    }
+                    if (CT) CT[(long)col * g.ldct + row] = v;
                 }
             }
         }
@@ -250,7 +255,8 @@ int launch_layout(gpn_ctx* c, bool ak, bool bk, const CUtensorMap& ta, const CUt
 }   // namespace
 
 int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, long lda, bool a_kmajor, const double* B, long ldb,
-             bool b_kmajor, double beta, double* C, long ldc, int flags, int batch, long sA, long sB, long sC) {
+             bool b_kmajor, double beta, double* C, long ldc, int flags, int batch, long sA, long sB, long sC, double* CT, long ldct,
+             long sCT) {
     if (M <= 0 || N <= 0 || batch <= 0) return 0;
     if (K < 0) return -4;
     if ((flags & GF_LOWER) && M != N) return -2;
@@ -268,7 +274,7 @@ int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, lon
     if (flags & GF_FORCE_BIG) use_big = true;
     const int bm = use_big ? 128 : 64, bn = bm;
     GemmArgs a;
-    a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = ldc; a.sC = sC; a.alpha = alpha; a.beta = beta; a.flags = flags;
+    a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = ldc; a.sC = sC; a.CT = CT; a.ldct = ldct; a.sCT = sCT; a.alpha = alpha; a.beta = beta; a.flags = flags;
     a.tiles_m = use_big ? tm_b : tm_s;
     a.tiles_n = use_big ? tn_b : tn_s;
     const long ntiles = (use_big ? big : small) / batch;

@@ -7,7 +7,6 @@
 #include <cudaTypedefs.h>
 #include <algorithm>
 
-int gpn_trtri_from_winv_tmp(gpn_ctx* c, int n, const double* L, long ldl, const double* winv, double* W, long ldw, double* tmp);
 
 static thread_local char g_last_error[512] = "";
 void gpn_set_last_error(const char* file, int line, const char* msg) {
@@ -44,7 +43,7 @@ inline long pad128(long n) { return (n + 127) / 128 * 128; }
 
 // n-sized work buffers
 enum NB {
-    NB_KY = 0, NB_KC, NB_W, NB_T, NB_ROWS1, NB_ROWS2, NB_G, NB_KSTAR, NB_KSS, NB_V, NB_S, NB_B, NB_WB, NB_WK, NB_COUNT
+    NB_KY = 0, NB_KC, NB_W, NB_T, NB_ROWS1, NB_ROWS2, NB_G, NB_KSTAR, NB_KSS, NB_V, NB_S, NB_B, NB_WB, NB_WK, NB_WT, NB_COUNT
 };
 static_assert(NB_COUNT <= 16, "nb[] too small");
 
@@ -225,17 +224,17 @@ int symm_mul(gpn_ctx* c, const double* A, const double* B, double* C) {
 }
 
 // SPD inverse of the N x N matrix in `a` (destroyed -> L); result (full symmetric) in `out`; w/t scratch
-int spd_inverse(gpn_ctx* c, int n, double* a, long ld, double* w, double* t, double* out, int info_slot) {
+int spd_inverse(gpn_ctx* c, int n, double* a, long ld, double* w, double* wt, double* tt, double* out, int info_slot) {
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(n) * 128));
     GPN_TRY(gpn_potrf(c, n, a, ld, (double*)c->winv.p, iscal(c, info_slot)));
-    GPN_TRY(gpn_trtri_from_winv_tmp(c, n, a, ld, (const double*)c->winv.p, w, ld, t));
-    return gpn_lauum(c, n, w, ld, out, ld, true);
+    GPN_TRY(gpn_trtri(c, n, a, ld, (const double*)c->winv.p, w, wt, tt, ld));
+    return gpn_lauum_t(c, n, wt, ld, out, ld, true);
 }
 
 int build_reglap(gpn_ctx* c, double beta) {
-    for (int i = 0; i < 3; ++i) GPN_TRY(ensure_mat(c, i));
+    for (int i = 0; i < 4; ++i) GPN_TRY(ensure_mat(c, i));
     GPN_TRY(laplacian_into(c, beta, 1.0, mat(c, 0), c->ldN));                       // M = I + beta L~   (:342)
-    GPN_TRY(spd_inverse(c, c->N, mat(c, 0), c->ldN, mat(c, 1), mat(c, 2), mat(c, 0), 0));
+    GPN_TRY(spd_inverse(c, c->N, mat(c, 0), c->ldN, mat(c, 1), mat(c, 2), mat(c, 3), mat(c, 0), 0));
     c->mat[9] = c->mat[0];   // alias: slot 9 designates the resident kernel
     return 0;
 }
@@ -395,7 +394,7 @@ int build_diffusion(gpn_ctx* c, double beta) {
         GPN_TRY(gpn_k_lincomb(c, N, X8, ld, 0.0, 2, X2, l2, cp));
     }
     // X = Q^-1 P  (Q SPD: q_m(x) = p_m(-x) has positive coefficients and spec(A) <= 0)
-    GPN_TRY(spd_inverse(c, N, Z, ld, A2, A4, A6, 0));          // Qinv -> A6 (A2, A4 scratch)
+    GPN_TRY(spd_inverse(c, N, Z, ld, A2, A4, V, A6, 0));       // Qinv -> A6 (A2, A4, V scratch: U and V are dead once Q, P exist)
     GPN_TRY(symm_mul(c, A6, X8, U));                            // X -> U
     double* cur = U;
     double* oth = V;
@@ -443,7 +442,7 @@ int kernel_build(gpn_ctx* c, int kind, const double* theta_h, int P, int want_gr
 struct GprFactor {
     int n;
     long ldn;
-    double *Ky, *W, *T;
+    double *Ky, *W, *T, *WT;
 };
 
 // Ky = K[tr,tr] + c; L = chol(Ky) (in NB_KY); W = L^-1 (NB_W).  keep_copy: NB_KC = Ky before factorisation.
@@ -462,8 +461,9 @@ int gpr_factor(gpn_ctx* c, bool keep_copy, GprFactor* f) {
     }
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(std::max(n, c->N)) * 128));
     GPN_TRY(gpn_potrf(c, n, nbp(c, NB_KY), ldn, (double*)c->winv.p, iscal(c, 1)));
-    GPN_TRY(gpn_trtri_from_winv_tmp(c, n, nbp(c, NB_KY), ldn, (const double*)c->winv.p, nbp(c, NB_W), ldn, nbp(c, NB_T)));
-    f->n = n; f->ldn = ldn; f->Ky = nbp(c, NB_KY); f->W = nbp(c, NB_W); f->T = nbp(c, NB_T);
+    GPN_TRY(ensure_nb(c, NB_WT, ldn, ldn));
+    GPN_TRY(gpn_trtri(c, n, nbp(c, NB_KY), ldn, (const double*)c->winv.p, nbp(c, NB_W), nbp(c, NB_WT), nbp(c, NB_T), ldn));
+    f->n = n; f->ldn = ldn; f->Ky = nbp(c, NB_KY); f->W = nbp(c, NB_W); f->T = nbp(c, NB_T); f->WT = nbp(c, NB_WT);
     return 0;
 }
 
@@ -496,7 +496,7 @@ int gpr_logp_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const doub
     if (want_grad) {
         GPN_TRY(gpn_k_gemv_t(c, n, n, f.W, f.ldn, vecp(c, V_Z), vecp(c, V_ALPHA), GEMV_LOWER));
         // Kinv = W^T W (lower) -> NB_T
-        GPN_TRY(gpn_lauum(c, n, f.W, f.ldn, f.T, f.ldn, false));
+        GPN_TRY(gpn_lauum_t(c, n, f.WT, f.ldn, f.T, f.ldn, false));
         const int* tr = (const int*)c->train_idx.p;
         const double* G = nullptr;
         const double* Ktt = nullptr;
@@ -620,7 +620,7 @@ struct NewtonState {
 int factor_B(gpn_ctx* c, const NewtonState& s) {
     GPN_TRY(gpn_k_form_B(c, s.n, s.K, s.ldk, vecp(c, V_SW), nbp(c, NB_B), s.ldn));
     GPN_TRY(gpn_potrf(c, s.n, nbp(c, NB_B), s.ldn, (double*)c->winv.p, iscal(c, 3)));
-    return gpn_trtri_from_winv_tmp(c, s.n, nbp(c, NB_B), s.ldn, (const double*)c->winv.p, nbp(c, NB_WB), s.ldn, nbp(c, NB_T));
+    return gpn_trtri(c, s.n, nbp(c, NB_B), s.ldn, (const double*)c->winv.p, nbp(c, NB_WB), nbp(c, NB_WT), nbp(c, NB_T), s.ldn);
 }
 
 int gpc_newton(gpn_ctx* c, const double* K, long ldk, int n, const double* y_h, double tol, double phif0, double scale, int variant,
@@ -633,6 +633,7 @@ int gpc_newton(gpn_ctx* c, const double* K, long ldk, int n, const double* y_h, 
     GPN_TRY(ensure_nb(c, NB_T, s.ldn, s.ldn));
     GPN_TRY(ensure_nb(c, NB_WK, s.ldn, s.ldn));
     GPN_TRY(ensure_nb(c, NB_KC, s.ldn, s.ldn));
+    GPN_TRY(ensure_nb(c, NB_WT, s.ldn, s.ldn));
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(std::max(n, c->N)) * 128));
     GPN_TRY(upload(c, vecp(c, V_Y), y_h, sizeof(double) * n));
     GPN_CK(cudaMemsetAsync(vecp(c, V_F), 0, sizeof(double) * n, c->stream));                    // f = 0 (:96)
@@ -640,7 +641,7 @@ int gpc_newton(gpn_ctx* c, const double* K, long ldk, int n, const double* y_h, 
     GPN_TRY(gpn_k_fill_zero(c, nbp(c, NB_KC), s.ldn, (int)s.ldn, (int)s.ldn));
     GPN_TRY(gpn_k_copy(c, n, n, K, ldk, nbp(c, NB_KC), s.ldn));
     GPN_TRY(gpn_potrf(c, n, nbp(c, NB_KC), s.ldn, (double*)c->winv.p, iscal(c, 4)));
-    GPN_TRY(gpn_trtri_from_winv_tmp(c, n, nbp(c, NB_KC), s.ldn, (const double*)c->winv.p, nbp(c, NB_WK), s.ldn, nbp(c, NB_T)));
+    GPN_TRY(gpn_trtri(c, n, nbp(c, NB_KC), s.ldn, (const double*)c->winv.p, nbp(c, NB_WK), nbp(c, NB_WT), nbp(c, NB_T), s.ldn));
     int info[16];
     GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
     s.have_wk = (info[4] == 0);     // K not numerically PD: use f^T a (== f^T K^-1 f since f = K a), see DESIGN.md
@@ -937,10 +938,10 @@ int gpn_spd_inverse_f64(gpn_ctx* c, int n, double* A, long lda, double* out, lon
     GPN_TRY(clear_info(c));
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(n) * 128));
     GPN_TRY(gpn_potrf(c, n, A, lda, (double*)c->winv.p, iscal(c, 0)));
-    // W -> out, scratch -> work, then K = W^T W needs a third buffer: reuse A (L is dead once W exists)
-    GPN_TRY(gpn_trtri_from_winv_tmp(c, n, A, lda, (const double*)c->winv.p, out, ldo, work));
-    GPN_TRY(gpn_k_copy(c, n, n, out, ldo, work, ldo));
-    GPN_TRY(gpn_lauum(c, n, work, ldo, out, ldo, true));
+    // W -> out, W^T -> internal buffer, T^T -> work; then K = W^T W overwrites out (W itself is not an operand any more)
+    GPN_TRY(ensure_nb(c, NB_WT, n, ldo));
+    GPN_TRY(gpn_trtri(c, n, A, lda, (const double*)c->winv.p, out, nbp(c, NB_WT), work, ldo));
+    GPN_TRY(gpn_lauum_t(c, n, nbp(c, NB_WT), ldo, out, ldo, true));
     int info[16];
     GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
     if (info_h) *info_h = info[0];
