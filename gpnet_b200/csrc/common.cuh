@@ -58,6 +58,9 @@ struct gpn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t stream2 = nullptr;      // side stream: independent GEMM work overlapped with a latency-bound Cholesky
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int potrf_grid_cap = 0;              // > 0: the next dataflow Cholesky may use at most this many CTAs
     int num_sms = 148;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     long long launches = 0;        // kernels launched through this context (bench "gpu_launches")

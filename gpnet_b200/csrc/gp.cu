@@ -445,13 +445,15 @@ struct GprFactor {
     double *Ky, *W, *T, *WT;
 };
 
-// Ky = K[tr,tr] + c; L = chol(Ky) (in NB_KY); W = L^-1 (NB_W).  keep_copy: NB_KC = Ky before factorisation.
-int gpr_factor(gpn_ctx* c, bool keep_copy, GprFactor* f) {
+// Ky = K[tr,tr] + c (NB_KY); keep_copy: NB_KC = Ky before factorisation.
+int gpr_gather_ky(gpn_ctx* c, bool keep_copy) {
     const int n = c->n_train;
     const long ldn = pad128(n);
     GPN_TRY(ensure_nb(c, NB_KY, ldn, ldn));
     GPN_TRY(ensure_nb(c, NB_W, ldn, ldn));
     GPN_TRY(ensure_nb(c, NB_T, ldn, ldn));
+    GPN_TRY(ensure_nb(c, NB_WT, ldn, ldn));
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(std::max(n, c->N)) * 128));
     const double noise = c->theta_exp[c->P - 1];                           // measnoise * theta[-1], quirk A-3
     const int* tr = (const int*)c->train_idx.p;
     GPN_TRY(gpn_k_gather(c, kfull(c), c->ldN, tr, n, tr, n, noise, nbp(c, NB_KY), ldn));
@@ -459,12 +461,20 @@ int gpr_factor(gpn_ctx* c, bool keep_copy, GprFactor* f) {
         GPN_TRY(ensure_nb(c, NB_KC, ldn, ldn));
         GPN_TRY(gpn_k_copy(c, n, n, nbp(c, NB_KY), ldn, nbp(c, NB_KC), ldn));
     }
-    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(std::max(n, c->N)) * 128));
+    return 0;
+}
+// L = chol(Ky) in place (NB_KY); W = L^-1 (NB_W), W^T (NB_WT)
+int gpr_factor_ky(gpn_ctx* c, GprFactor* f) {
+    const int n = c->n_train;
+    const long ldn = pad128(n);
     GPN_TRY(gpn_potrf(c, n, nbp(c, NB_KY), ldn, (double*)c->winv.p, iscal(c, 1)));
-    GPN_TRY(ensure_nb(c, NB_WT, ldn, ldn));
     GPN_TRY(gpn_trtri(c, n, nbp(c, NB_KY), ldn, (const double*)c->winv.p, nbp(c, NB_W), nbp(c, NB_WT), nbp(c, NB_T), ldn));
     f->n = n; f->ldn = ldn; f->Ky = nbp(c, NB_KY); f->W = nbp(c, NB_W); f->T = nbp(c, NB_T); f->WT = nbp(c, NB_WT);
     return 0;
+}
+int gpr_factor(gpn_ctx* c, bool keep_copy, GprFactor* f) {
+    GPN_TRY(gpr_gather_ky(c, keep_copy));
+    return gpr_factor_ky(c, f);
 }
 
 // vectors: partition of c->tvec (doubles): slot k at offset k*vstride
@@ -478,62 +488,99 @@ int ensure_vecs(gpn_ctx* c) {
 }
 enum VEC { V_TRES = 23, V_T = 0, V_Z, V_ALPHA, V_F, V_A, V_B, V_P, V_W, V_SW, V_G, V_KB, V_RHS, V_Z2, V_SOL, V_Y, V_PHIF, V_U, V_FSTAR, V_VN, V_KSS, V_VV, V_PI };
 
+// Number of CTAs a latency-bound dataflow Cholesky of n rows needs to keep up with its per-column dependency chain
+// (~100 us): the busiest tile column has (T/2)^2 k-blocks of ~17 us.  The rest of the GPU is left to the side stream.
+int chain_bound_ctas(int n) {
+    const int T = (n + 127) / 128;
+    const int need = (int)(0.25 * T * T * 17.0 / 90.0) + 8;
+    return need < 16 ? 16 : need;
+}
+
+// (d K / d theta_0)[tr,tr] pieces that are plain GEMM work and independent of the factorisation of K_y
+int gpr_grad_kernel_block(gpn_ctx* c, int kind, long ldn, const double** G, double* gs) {
+    const int n = c->n_train, N = c->N;
+    const int* tr = (const int*)c->train_idx.p;
+    *G = nullptr;
+    *gs = 0.0;
+    GPN_TRY(ensure_nb(c, NB_G, ldn, ldn));
+    if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN) {
+        // dK/dtheta0 = K^2 - K  => (K^2)[tr,tr] = K[tr,:] K[tr,:]^T  (SYRK n x n x N)
+        GPN_TRY(ensure_nb(c, NB_ROWS1, n, c->ldN));
+        GPN_TRY(gpn_k_gather_rows(c, kfull(c), c->ldN, tr, n, N, nbp(c, NB_ROWS1), c->ldN));
+        GPN_TRY(gpn_gemm(c, n, n, N, 1.0, nbp(c, NB_ROWS1), c->ldN, true, nbp(c, NB_ROWS1), c->ldN, true, 0.0, nbp(c, NB_G), ldn, GF_LOWER));
+        *G = nbp(c, NB_G); *gs = 1.0;
+    } else if (kind == GPN_KERNEL_DIFFUSION) {
+        // dK/dtheta0 = -beta L~ K = A K  => (A K)[tr,tr] = A[tr,:] K[tr,:]^T (symmetric: A and K commute)
+        GPN_TRY(ensure_nb(c, NB_ROWS1, n, c->ldN));
+        GPN_TRY(ensure_nb(c, NB_ROWS2, n, c->ldN));
+        GPN_TRY(gpn_k_gather_rows(c, mat(c, 0), c->ldN, tr, n, N, nbp(c, NB_ROWS1), c->ldN));
+        GPN_TRY(gpn_k_gather_rows(c, kfull(c), c->ldN, tr, n, N, nbp(c, NB_ROWS2), c->ldN));
+        GPN_TRY(gpn_gemm(c, n, n, N, 1.0, nbp(c, NB_ROWS1), c->ldN, true, nbp(c, NB_ROWS2), c->ldN, true, 0.0, nbp(c, NB_G), ldn, GF_LOWER));
+        *G = nbp(c, NB_G); *gs = 1.0;
+    } else {
+        // dK/dtheta0 = a p B^(p-1); p = 1: B^0 = I; p <= 0: K = I, derivative 0
+        const int p = c->pstep_p;
+        if (p >= 2) {
+            GPN_TRY(gpn_k_gather(c, mat(c, 4), c->ldN, tr, n, tr, n, 0.0, nbp(c, NB_G), ldn));
+            *G = nbp(c, NB_G); *gs = c->theta_exp[0] * p;
+        } else if (p == 1) {
+            GPN_TRY(gpn_k_fill_zero(c, nbp(c, NB_G), ldn, n, n));
+            const double* X[1] = {nbp(c, NB_G)};
+            const long l1[1] = {ldn};
+            const double cf[1] = {0.0};
+            GPN_TRY(gpn_k_lincomb(c, n, nbp(c, NB_G), ldn, 1.0, 1, X, l1, cf));
+            *G = nbp(c, NB_G); *gs = c->theta_exp[0];
+        }
+    }
+    return 0;
+}
+
 int gpr_logp_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
     if (c->n_train <= 0) return -1;
     int st = kernel_build(c, kind, theta_h, P, want_grad);
     if (st != 0) return st;
     GPN_TRY(ensure_vecs(c));
-    const int n = c->n_train, N = c->N;
+    const int n = c->n_train;
+    const long ldn = pad128(n);
     if (t_h) GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
     else GPN_CK(cudaMemcpyAsync(vecp(c, V_T), vecp(c, V_TRES), sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    const double noise = c->theta_exp[P - 1];
+    const double* G = nullptr;
+    double gs = 0.0;
+    bool forked = false;
+    GPN_TRY(gpr_gather_ky(c, want_grad && kind == GPN_KERNEL_REGULARIZED_LAPLACIAN));
     GprFactor f;
-    GPN_TRY(gpr_factor(c, want_grad && kind == GPN_KERNEL_REGULARIZED_LAPLACIAN, &f));
+    if (want_grad) {
+        // The Cholesky of K_y is bound by its per-column dependency chain, not by flops: give it only the CTAs it needs and
+        // run the (independent, flop-bound) gradient GEMM on the side stream at the same time.  The side stream is released
+        // by an event recorded right before the Cholesky launch so that the cooperative kernel is dispatched first.
+        cudaStream_t main_stream = c->stream;
+        GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
+        c->potrf_grid_cap = chain_bound_ctas(n);
+        st = gpr_factor_ky(c, &f);
+        c->potrf_grid_cap = 0;
+        if (st != 0) return st;
+        GPN_CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        c->stream = c->stream2;
+        st = gpr_grad_kernel_block(c, kind, ldn, &G, &gs);
+        c->stream = main_stream;
+        if (st != 0) return st;
+        GPN_CK(cudaEventRecord(c->ev_join, c->stream2));
+        forked = true;
+    } else {
+        GPN_TRY(gpr_factor_ky(c, &f));
+    }
     // z = L^-1 t, alpha = L^-T z, t^T alpha = z^T z                         (GPnetRegressor.py:144-148)
     GPN_TRY(gpn_k_gemv(c, n, n, f.W, f.ldn, vecp(c, V_T), vecp(c, V_Z), GEMV_LOWER));
     GPN_TRY(gpn_k_dot(c, n, vecp(c, V_Z), vecp(c, V_Z), dscal(c, Scal::DOT)));
     GPN_TRY(gpn_k_sumlogdiag(c, n, f.Ky, f.ldn, dscal(c, Scal::LOGDET)));
-    const double noise = c->theta_exp[P - 1];
     if (want_grad) {
         GPN_TRY(gpn_k_gemv_t(c, n, n, f.W, f.ldn, vecp(c, V_Z), vecp(c, V_ALPHA), GEMV_LOWER));
-        // Kinv = W^T W (lower) -> NB_T
-        GPN_TRY(gpn_lauum_t(c, n, f.WT, f.ldn, f.T, f.ldn, false));
-        const int* tr = (const int*)c->train_idx.p;
-        const double* G = nullptr;
+        GPN_TRY(gpn_lauum_t(c, n, f.WT, f.ldn, f.T, f.ldn, false));            // Kinv = W^T W (lower) -> NB_T
         const double* Ktt = nullptr;
-        double gs = 0.0, ks = 0.0, kshift = 0.0;
-        GPN_TRY(ensure_nb(c, NB_G, f.ldn, f.ldn));
-        if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN) {
-            // dK/dtheta0 = K^2 - K  => (K^2)[tr,tr] = K[tr,:] K[tr,:]^T  (SYRK n x n x N)
-            GPN_TRY(ensure_nb(c, NB_ROWS1, n, c->ldN));
-            GPN_TRY(gpn_k_gather_rows(c, kfull(c), c->ldN, tr, n, N, nbp(c, NB_ROWS1), c->ldN));
-            GPN_TRY(gpn_gemm(c, n, n, N, 1.0, nbp(c, NB_ROWS1), c->ldN, true, nbp(c, NB_ROWS1), c->ldN, true, 0.0, nbp(c, NB_G), f.ldn,
-                             GF_LOWER));
-            G = nbp(c, NB_G); gs = 1.0;
-            Ktt = nbp(c, NB_KC); ks = -1.0; kshift = noise;
-        } else if (kind == GPN_KERNEL_DIFFUSION) {
-            // dK/dtheta0 = -beta L~ K = A K  => (A K)[tr,tr] = A[tr,:] K[tr,:]^T (symmetric: A and K commute)
-            GPN_TRY(ensure_nb(c, NB_ROWS1, n, c->ldN));
-            GPN_TRY(ensure_nb(c, NB_ROWS2, n, c->ldN));
-            GPN_TRY(gpn_k_gather_rows(c, mat(c, 0), c->ldN, tr, n, N, nbp(c, NB_ROWS1), c->ldN));
-            GPN_TRY(gpn_k_gather_rows(c, kfull(c), c->ldN, tr, n, N, nbp(c, NB_ROWS2), c->ldN));
-            GPN_TRY(gpn_gemm(c, n, n, N, 1.0, nbp(c, NB_ROWS1), c->ldN, true, nbp(c, NB_ROWS2), c->ldN, true, 0.0, nbp(c, NB_G), f.ldn,
-                             GF_LOWER));
-            G = nbp(c, NB_G); gs = 1.0;
-        } else {
-            // dK/dtheta0 = a p B^(p-1); p = 1: B^0 = I; p <= 0: K = I, derivative 0
-            const int p = c->pstep_p;
-            if (p >= 2) {
-                GPN_TRY(gpn_k_gather(c, mat(c, 4), c->ldN, tr, n, tr, n, 0.0, nbp(c, NB_G), f.ldn));
-                G = nbp(c, NB_G); gs = c->theta_exp[0] * p;
-            } else if (p == 1) {
-                GPN_TRY(gpn_k_fill_zero(c, nbp(c, NB_G), f.ldn, n, n));
-                const double* X[1] = {nbp(c, NB_G)};
-                const long l1[1] = {f.ldn};
-                const double cf[1] = {0.0};
-                GPN_TRY(gpn_k_lincomb(c, n, nbp(c, NB_G), f.ldn, 1.0, 1, X, l1, cf));
-                G = nbp(c, NB_G); gs = c->theta_exp[0];
-            }
-        }
+        double ks = 0.0, kshift = 0.0;
+        if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN) { Ktt = nbp(c, NB_KC); ks = -1.0; kshift = noise; }
+        if (forked) GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         GPN_TRY(gpn_k_grad_trace(c, n, f.T, f.ldn, G, f.ldn, Ktt, f.ldn, gs, ks, kshift, vecp(c, V_ALPHA), dscal(c, Scal::TR0)));
     }
     double sc[Scal::NDBL];
@@ -752,6 +799,13 @@ gpn_ctx* gpn_create(int device, void* cuda_stream) {
         return nullptr;
     }
     c->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        gpn_set_last_error(__FILE__, __LINE__, "side stream / event creation failed");
+        delete c;
+        return nullptr;
+    }
     if (const char* m = getenv("GPNET_B200_POTRF")) c->potrf_mode = (strcmp(m, "recursive") == 0) ? 1 : 0;
     if (cudaMalloc(&c->scal.p, 1024) != cudaSuccess || cudaMallocHost(&c->pinned, 4096) != cudaSuccess) {
         gpn_set_last_error(__FILE__, __LINE__, "initial allocations failed");
@@ -778,6 +832,9 @@ void gpn_destroy(gpn_ctx* c) {
     for (auto& b : c->nb)
         if (b.p) cudaFree(b.p);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }

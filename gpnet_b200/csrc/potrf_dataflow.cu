@@ -322,7 +322,8 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
         GPN_CK(cudaFuncSetAttribute(potrf_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM));
         configured = true;
     }
-    const int grid = ntasks < c->num_sms ? ntasks : c->num_sms;
+    int grid = ntasks < c->num_sms ? ntasks : c->num_sms;
+    if (c->potrf_grid_cap > 0 && grid > c->potrf_grid_cap) grid = c->potrf_grid_cap;   // leave SMs to concurrent work
     void* args[] = {(void*)&tl, (void*)&tw, (void*)&a};
     GPN_CK(cudaLaunchCooperativeKernel((const void*)potrf_dataflow_kernel, dim3(grid), dim3(384), args, DF_SMEM, c->stream));
     c->launches++;
