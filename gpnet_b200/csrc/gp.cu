@@ -315,29 +315,48 @@ int build_diffusion(gpn_ctx* c, double beta) {
     double *A = mat(c, 0), *A2 = mat(c, 1), *A4 = mat(c, 2), *A6 = mat(c, 3), *Z = mat(c, 4), *U = mat(c, 5), *V = mat(c, 6),
            *X8 = mat(c, 7);
     GPN_TRY(laplacian_into(c, -beta, 0.0, A, ld));
-    GPN_TRY(symm_mul(c, A, A, A2));
-    GPN_TRY(symm_mul(c, A2, A2, A4));
-    GPN_TRY(symm_mul(c, A4, A2, A6));
-    GPN_TRY(gpn_k_onenorm(c, N, A, ld, dscal(c, Scal::NORM0)));
-    GPN_TRY(gpn_k_onenorm(c, N, A2, ld, dscal(c, Scal::NORM1)));
-    GPN_TRY(gpn_k_onenorm(c, N, A4, ld, dscal(c, Scal::NORM2)));
-    GPN_TRY(gpn_k_onenorm(c, N, A6, ld, dscal(c, Scal::NORM3)));
+    // Order selection with as few powers as possible (each power is an N^3 product): bounds ||A^(p+q)|| <= ||A^p|| ||A^q||
+    // stand in for the powers that have not been formed yet, so the choice can only err towards a HIGHER order than
+    // scipy's (which uses estimated norms), never a lower one.
     double sc[Scal::NDBL];
-    GPN_TRY(read_scalars(c, sc, Scal::NDBL, nullptr, 0));
-    const double n2 = sc[Scal::NORM1], n4 = sc[Scal::NORM2], n6 = sc[Scal::NORM3];
-    const double d4 = pow(n4, 0.25), d6 = pow(n6, 1.0 / 6.0);
-    const double d8 = fmin(d4, pow(n2 * n6, 0.125)), d10 = pow(n4 * n6, 0.1);
-    const double eta1 = fmax(d4, d6), eta3 = fmax(d6, d8);
     int m, s = 0;
-    if (eta1 < 1.495585217958292e-002) m = 3;
-    else if (eta1 < 2.539398330063230e-001) m = 5;
-    else if (eta3 < 9.504178996162932e-001) m = 7;
-    else if (eta3 < 2.097847961257068e+000) m = 9;
-    else {
-        m = 13;
-        const double eta4 = fmax(d8, d10), eta5 = fmin(eta3, eta4);
-        if (eta5 > 0) s = (int)fmax(ceil(log2(eta5 / 4.25)), 0.0);
+    GPN_TRY(symm_mul(c, A, A, A2));
+    GPN_TRY(gpn_k_onenorm(c, N, A2, ld, dscal(c, Scal::NORM1)));
+    GPN_TRY(read_scalars(c, sc, Scal::NDBL, nullptr, 0));
+    const double n2 = sc[Scal::NORM1];
+    bool have4 = false, have6 = false;
+    if (sqrt(n2) < 1.495585217958292e-002) {          // d4, d6 <= ||A^2||^(1/2)
+        m = 3;
+    } else {
+        GPN_TRY(symm_mul(c, A2, A2, A4));
+        have4 = true;
+        GPN_TRY(gpn_k_onenorm(c, N, A4, ld, dscal(c, Scal::NORM2)));
+        GPN_TRY(read_scalars(c, sc, Scal::NDBL, nullptr, 0));
+        const double n4 = sc[Scal::NORM2];
+        const double d4 = pow(n4, 0.25);
+        if (fmax(d4, pow(n2 * n4, 1.0 / 6.0)) < 2.539398330063230e-001) {   // d6 <= (||A^2|| ||A^4||)^(1/6)
+            m = 5;
+        } else {
+            GPN_TRY(symm_mul(c, A4, A2, A6));
+            have6 = true;
+            GPN_TRY(gpn_k_onenorm(c, N, A6, ld, dscal(c, Scal::NORM3)));
+            GPN_TRY(read_scalars(c, sc, Scal::NDBL, nullptr, 0));
+            const double n6 = sc[Scal::NORM3];
+            const double d6 = pow(n6, 1.0 / 6.0);
+            const double d8 = fmin(d4, pow(n2 * n6, 0.125)), d10 = pow(n4 * n6, 0.1);
+            const double eta1 = fmax(d4, d6), eta3 = fmax(d6, d8);
+            if (eta1 < 2.539398330063230e-001) m = 5;
+            else if (eta3 < 9.504178996162932e-001) m = 7;
+            else if (eta3 < 2.097847961257068e+000) m = 9;
+            else {
+                m = 13;
+                const double eta4 = fmax(d8, d10), eta5 = fmin(eta3, eta4);
+                if (eta5 > 0) s = (int)fmax(ceil(log2(eta5 / 4.25)), 0.0);
+            }
+        }
     }
+    (void)have4;
+    (void)have6;
     c->expm_m = m;
     c->expm_s = s;
     static const double b3[] = {120., 60., 12., 1.};

@@ -26,6 +26,74 @@ __device__ __forceinline__ void bar256() {
     else asm volatile("bar.sync %0, 256;" ::"n"(BAR_ID) : "memory");
 }
 
+// 1/sqrt(d) for normal positive d without the library's special-case branch (a branch in the pivot loop is a scheduling
+// barrier: the independent bulk update could not be issued under the latency of this chain).  MUFU.RSQ64H seed (~2^-22)
+// + one cubic Newton step (error ~ e^3), the same arithmetic the CUDA math library uses on its fast path.
+// d <= 0 / NaN give garbage; the caller records those pivots in `info`.
+__device__ __forceinline__ double rsqrt_nobranch(double d) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+    const double e = fma(-d, y0 * y0, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    return fma(p, y0 * e, y0);
+}
+
+// 1/d for normal positive d: MUFU.RCP64H seed + one cubic Newton step, branch free (see rsqrt_nobranch).
+__device__ __forceinline__ double rcp_nobranch(double d) {
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+    const double e = fma(-d, r0, 1.0);
+    return fma(r0, fma(e, e, e), r0);
+}
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+// Shared-memory GEMM on the FP64 tensor pipe for the small products of the leaf:
+//     C(m, n) = sum_k A[m][k] * Bop(k, n),   A row-major with stride SA,   Bop(k, n) = BT ? B[n*SB + k] : B[k*SB + n].
+// Work unit = 16 rows x 32 columns (2 x 4 DMMA blocks = 8 independent accumulators: a DMMA has ~140 cycles of latency, so
+// a warp needs about that many in flight), dealt round-robin to the 8 warps.  TRI = 1: A is lower triangular in (m, k)
+// (k-steps beyond the row blocks are skipped); TRI = 2: only units touching the lower triangle of a square C.
+// epi(row, col, value) receives the values a lane owns (C fragment: row g, cols 2t, 2t+1 of each 8x8 block).
+template <int SA, int SB, bool BT, int TRI, typename Epi>
+__device__ __forceinline__ void smem_dmma(const double* __restrict__ A, const double* __restrict__ B, int munits, int nunits, int K, int tid,
+                                          Epi epi) {
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    for (int u = warp; u < munits * nunits; u += 8) {
+        const int mu = u / nunits, nu = u - mu * nunits;
+        if (TRI == 2 && 32 * nu > 16 * mu + 15) continue;
+        double acc[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const int kend = (TRI == 1) ? min(K, 16 * mu + 16) : K;
+        const double* ap = A + (16 * mu + g) * SA + t;
+        const double* bp = BT ? B + (32 * nu + g) * SB + t : B + t * SB + 32 * nu + g;
+#pragma unroll 2
+        for (int k0 = 0; k0 < kend; k0 += 4) {
+            double a[2], b[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) a[i] = ap[i * 8 * SA + k0];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = BT ? bp[j * 8 * SB + k0] : bp[k0 * SB + 8 * j];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j], a[i], b[j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) epi(16 * mu + 8 * i + g, 32 * nu + 8 * j + 2 * t + e, acc[i][j][e]);
+    }
+}
+
 // acc[i][j] = sum_{k < klim(tile)} A[(r0+i)*SAR + k] * B[(c0+j)*SBC + k*SBK] for the 4x4 tile (r0, c0); strides are
 // compile-time so that every load address is pointer + immediate (a single warp issues integer ops at 1 per 2 cycles:
 // address arithmetic, not FP64, was the bottleneck of the first version).
@@ -102,11 +170,18 @@ __device__ __forceinline__ void diag32_factor(double* __restrict__ S, int b0, do
     __syncwarp();
     double lp = 0.0;                       // this row's multiplier of the previous column
     double* sp = Sd + lane * LDS_;         // &L[lane][c]
+    int first_bad = 32;                    // first column whose pivot is not positive (LAPACK info), reported after the loop
     auto pivot_step = [&](int c, auto qm_tag) {
         constexpr int QM = decltype(qm_tag)::value;        // live slots: columns c .. c+QM
+        // Per-pivot dependent chain (FP64 ops cost ~40 cycles each): shfl -> 1/d -> fma.  The next pivot column needs
+        // l_r l_{c+1} = (y_r y_{c+1}) / d, so it does not wait for rsqrt(d); the multipliers themselves (l = y rsqrt(d))
+        // are only consumed by the NEXT iteration's bulk update and by the stores, off the chain.
         const double d = __shfl_sync(full, y[0], c);
-        if (!(d > 0.0) && lane == 0) atomicCAS(info, 0, info_off + b0 + c + 1);
-        const double rd = rsqrt(d);
+        const double yn = __shfl_sync(full, y[0], (c + 1) & 31);        // element (c+1, c) before scaling
+        first_bad = (!(d > 0.0) && first_bad > c) ? c : first_bad;      // select, not a branch
+        const double id = rcp_nobranch(d);
+        const double rd = rsqrt_nobranch(d);
+        const double w = (lane > c) ? y[0] * yn : 0.0;
         // column c-1 applied to columns c+1 .. : multipliers of rows c+1.. are broadcast from shared memory (pointer +
         // immediate loads); results are written one slot down so that column c+1 becomes y[0] for the next pivot
         const double* lc = colbuf + ((c & 1) << 6) + c;      // lc[q] = l_{c+q, c-1}  (zero beyond row 31)
@@ -117,8 +192,7 @@ __device__ __forceinline__ void diag32_factor(double* __restrict__ S, int b0, do
         *sp = (lane == c) ? d * rd : l;
         if (lane == c) rdiag[c] = rd;
         colbuf[(((c + 1) & 1) << 6) + lane] = l;             // published for the next iteration's bulk update
-        const double l1 = __shfl_sync(full, l, (c + 1) & 31);
-        y[0] = t1 - l * l1;                // next pivot column, fully updated
+        y[0] = fma(-w, id, t1);            // next pivot column, fully updated
         lp = l;
         ++sp;
         __syncwarp();
@@ -127,6 +201,7 @@ __device__ __forceinline__ void diag32_factor(double* __restrict__ S, int b0, do
     for (int c = 0; c < 16; ++c) pivot_step(c, std::integral_constant<int, 31>{});
 #pragma unroll 1
     for (int c = 16; c < 32; ++c) pivot_step(c, std::integral_constant<int, 16>{});   // columns >= 32 do not exist
+    if (first_bad < 32 && lane == 0) atomicCAS(info, 0, info_off + b0 + first_bad + 1);
 }
 
 // One thread per row below the diagonal block: row <- row * L_kk^-T by a column sweep against L_kk in shared memory
@@ -202,15 +277,12 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
             if (tid < R) panel_sweep(S, b0, r1 + tid, rdiag + b0);
             bar256<BAR_ID>();
             LEAF_STAMP();
-            // trailing update: A22 -= P P^T (lower tiles)
-            for_tiles(R, R, tid, true, [&](int r0, int c0) {
-                double acc[4][4];
-                tile4x4<false, LDS_, LDS_, 1>(S + r1 * LDS_ + b0, S + r1 * LDS_ + b0, 32, r0, c0, acc);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) S[(r1 + r0 + i) * LDS_ + r1 + c0 + j] -= acc[i][j];
-            });
+            // trailing update: A22 -= P P^T (units touching the lower triangle), on the FP64 tensor pipe
+            {
+                double* C22 = S + r1 * LDS_ + r1;
+                smem_dmma<LDS_, LDS_, true, 2>(S + r1 * LDS_ + b0, S + r1 * LDS_ + b0, R / 16, R / 32, 32, tid,
+                                               [&](int r, int cc, double v) { C22[r * LDS_ + cc] -= v; });
+            }
             bar256<BAR_ID>();
             LEAF_STAMP();
         }
@@ -240,25 +312,15 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
 #pragma unroll 1
     for (int k = 2; k >= 0; --k) {
         const int r1 = 32 * (k + 1), R = LB - r1;
-        // T = L_col * W_kk           (B[c=j][q] = W_kk[q][j])
-        for_tiles(R, 32, tid, false, [&](int r0, int c0) {
-            double acc[4][4];
-            tile4x4<false, LDS_, 1, WLD>(S + r1 * LDS_ + 32 * k, Wd + k * 32 * WLD, 32, r0, c0, acc);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) T[(r0 + i) * WLD + c0 + j] = acc[i][j];
-        });
+        // T = L_col * W_kk            (R x 32, K = 32)
+        smem_dmma<LDS_, WLD, false, 0>(S + r1 * LDS_ + 32 * k, Wd + k * 32 * WLD, R / 16, 1, 32, tid,
+                                       [&](int r, int cc, double v) { T[r * WLD + cc] = v; });
         bar256<BAR_ID>();
-        // X = -W_trail * T           (W_trail lower => k <= r)
-        for_tiles(R, 32, tid, false, [&](int r0, int c0) {
-            double acc[4][4];
-            tile4x4<true, LDS_, 1, WLD>(S + r1 * LDS_ + r1, T, R, r0, c0, acc);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) S[(r1 + r0 + i) * LDS_ + 32 * k + c0 + j] = -acc[i][j];
-        });
+        // X = -W_trail * T            (W_trail lower triangular => k <= row)
+        {
+            double* X = S + r1 * LDS_ + 32 * k;
+            smem_dmma<LDS_, WLD, false, 1>(S + r1 * LDS_ + r1, T, R / 16, 1, R, tid, [&](int r, int cc, double v) { X[r * LDS_ + cc] = -v; });
+        }
         bar256<BAR_ID>();
         LEAF_STAMP();
     }
