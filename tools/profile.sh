@@ -15,6 +15,6 @@ timeout 900 ncu --set full --clock-control none --import-source on --kernel-name
 echo "lauum capture rc=$?"
 timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k regex:'6, .bool.1, .bool.1' -c 1 -o gpurun_out/gemm_syrk_$tag $CMD >> gpurun_out/ncu_full_$tag.log 2>&1
 echo "syrk capture rc=$?"
-true || timeout 600 ncu --set full --clock-control none --import-source on -k regex:potrf_dataflow -c 1 -o gpurun_out/potrf_$tag $CMD > gpurun_out/ncu_potrf_$tag.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:potrf_dataflow -c 1 -o gpurun_out/potrf_$tag $CMD > gpurun_out/ncu_potrf_$tag.log 2>&1
 echo "potrf capture rc=$?"
 ls -la gpurun_out/ | tail -12
