@@ -83,9 +83,21 @@ class GPnetClassifier(GPnetBase):
         return (self.fstar.T, self.V, self.predicted_probs)
 
     def gradLogPosterior(self, theta, *args):
-        raise NotImplementedError(
-            "GPnetClassifier.gradLogPosterior needs derivative kernels the reference never had (IndexError there, "
-            "SURVEY A-12); the classifier's optimize_params stays function-only like the reference's")
+        """RW Alg. 5.1 exactly as the reference writes it (GPnetClassifier.py:149-182), fed by the derivative kernels the
+        reference's own ``kernel`` no longer provides (it raises IndexError there, SURVEY A-12).  Returns ``-gradZ``.  Note that
+        this is the gradient of the true Laplace LML, not of the reference's ``logq`` (A-10), so ``optimize_params`` stays
+        function-only like the reference's."""
+        data, targets = args
+        th = self._theta_vec(theta)
+        ctx = self._engine.bind(self._positions(data), self._positions(self.test_nodes))
+        ctx._kernel_key = None
+        ctx._predict_token = None
+        st, out, iters, info = ctx.gpc_grad(self._kind(), th, self._labels(targets))
+        raise_domain(st)
+        if info > 0:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")
+        self.newton_iterations = iters
+        return out[1:].copy()
 
     def plot_latent(self, filename=False):
         pl = self._pyplot()

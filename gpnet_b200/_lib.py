@@ -54,6 +54,7 @@ SIGNATURES = {
                                  C.c_double, C.c_double, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p]),
     "gpn_gpc_predict": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_dbl_p,
                                   c_dbl_p, c_dbl_p, c_int_p]),
+    "gpn_gpc_grad": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_dbl_p, c_int_p, c_int_p]),
     "gpn_landscape": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dbl_p, C.c_int, C.c_int, C.c_int, c_dbl_p, C.c_int, c_dbl_p,
                                 C.c_int, c_dbl_p, C.c_long, C.c_long, C.c_long, C.c_int, c_dbl_p]),
 }
@@ -287,6 +288,18 @@ class Context:
             return st, None
         self._check(st, "gpn_gpc_predict")
         return 0, dict(f=f, a=a, logq=logq.value, iters=iters.value, info=info.value, fstar=fstar, V=V, pi_star=pi)
+
+    def gpc_grad(self, kind, theta, y):
+        th, yy = _f64(theta), _f64(y)
+        if len(yy) != self.n_train:
+            raise ValueError("len(y) != number of training nodes")
+        out = np.zeros(1 + len(th))
+        iters, info = C.c_int(0), C.c_int(0)
+        st = self.lib.gpn_gpc_grad(self.h, kind, _dp(th), len(th), _dp(yy), _dp(out), C.byref(iters), C.byref(info))
+        if st in (-100, -101):
+            return st, out, 0, 0
+        self._check(st, "gpn_gpc_grad")
+        return 0, out, iters.value, info.value
 
     # -- landscape slice ------------------------------------------------------------------------------
     def landscape(self, kind, classifier, theta, axidx, ax1, ax2, t, begin, end, stride, want_grad=False):

@@ -185,6 +185,44 @@ __global__ void pistar_kernel(int m, const double* __restrict__ fstar, const dou
     pistar[i] = acc + 0.5 * csum;
 }
 
+// ---- vector kernels of the classifier gradient (GPnetClassifier.py:156-182) ------------------------------------------
+__global__ void diag_extract_kernel(int n, const double* __restrict__ A, long ld, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = A[(long)i * ld + i];
+}
+// s2 = -0.5 (diag(K) - diag(C^T C)) * 2 hess (0.5 - p), hess = -w                                     (:163-168)
+__global__ void gpc_s2_kernel(int n, const double* __restrict__ kdiag, const double* __restrict__ cn, const double* __restrict__ w,
+                              const double* __restrict__ p, double* __restrict__ s2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) s2[i] = -0.5 * (kdiag[i] - cn[i]) * (2.0 * (-w[i]) * (0.5 - p[i]));
+}
+// out = x - y
+__global__ void vec_sub_kernel(int n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = x[i] - y[i];
+}
+__global__ void vec_fill_kernel(int n, double v, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+// out = sum_ij sw_i Binv_ij sw_j D_ij   (= tr(R D) for symmetric D), one block per row
+__global__ void gpc_trace_kernel(int n, const double* __restrict__ Binv, long ldb, const double* __restrict__ sw, const double* __restrict__ D,
+                                 long ldd, double* __restrict__ out) {
+    __shared__ double sh[32];
+    const int r = blockIdx.x;
+    double s = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) s += Binv[(long)r * ldb + c] * sw[c] * D[(long)r * ldd + c];
+    s *= sw[r];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(out, s);
+    }
+}
+
 inline int g1(long n) { return (int)((n + 255) / 256); }
 
 // register-resident DMMA.8x8x4 loop: the FP64 tensor issue-rate ceiling the roofline is reported against
@@ -516,7 +554,7 @@ int chain_bound_ctas(int n) {
 }
 
 // (d K / d theta_0)[tr,tr] pieces that are plain GEMM work and independent of the factorisation of K_y
-int gpr_grad_kernel_block(gpn_ctx* c, int kind, long ldn, const double** G, double* gs) {
+int gpr_grad_kernel_block(gpn_ctx* c, int kind, long ldn, const double** G, double* gs, bool full = false) {
     const int n = c->n_train, N = c->N;
     const int* tr = (const int*)c->train_idx.p;
     *G = nullptr;
@@ -526,7 +564,8 @@ int gpr_grad_kernel_block(gpn_ctx* c, int kind, long ldn, const double** G, doub
         // dK/dtheta0 = K^2 - K  => (K^2)[tr,tr] = K[tr,:] K[tr,:]^T  (SYRK n x n x N)
         GPN_TRY(ensure_nb(c, NB_ROWS1, n, c->ldN));
         GPN_TRY(gpn_k_gather_rows(c, kfull(c), c->ldN, tr, n, N, nbp(c, NB_ROWS1), c->ldN));
-        GPN_TRY(gpn_gemm(c, n, n, N, 1.0, nbp(c, NB_ROWS1), c->ldN, true, nbp(c, NB_ROWS1), c->ldN, true, 0.0, nbp(c, NB_G), ldn, GF_LOWER));
+        GPN_TRY(gpn_gemm(c, n, n, N, 1.0, nbp(c, NB_ROWS1), c->ldN, true, nbp(c, NB_ROWS1), c->ldN, true, 0.0, nbp(c, NB_G), ldn,
+                         GF_LOWER | (full ? GF_MIRROR : 0)));
         *G = nbp(c, NB_G); *gs = 1.0;
     } else if (kind == GPN_KERNEL_DIFFUSION) {
         // dK/dtheta0 = -beta L~ K = A K  => (A K)[tr,tr] = A[tr,:] K[tr,:]^T (symmetric: A and K commute)
@@ -534,7 +573,8 @@ int gpr_grad_kernel_block(gpn_ctx* c, int kind, long ldn, const double** G, doub
         GPN_TRY(ensure_nb(c, NB_ROWS2, n, c->ldN));
         GPN_TRY(gpn_k_gather_rows(c, mat(c, 0), c->ldN, tr, n, N, nbp(c, NB_ROWS1), c->ldN));
         GPN_TRY(gpn_k_gather_rows(c, kfull(c), c->ldN, tr, n, N, nbp(c, NB_ROWS2), c->ldN));
-        GPN_TRY(gpn_gemm(c, n, n, N, 1.0, nbp(c, NB_ROWS1), c->ldN, true, nbp(c, NB_ROWS2), c->ldN, true, 0.0, nbp(c, NB_G), ldn, GF_LOWER));
+        GPN_TRY(gpn_gemm(c, n, n, N, 1.0, nbp(c, NB_ROWS1), c->ldN, true, nbp(c, NB_ROWS2), c->ldN, true, 0.0, nbp(c, NB_G), ldn,
+                         GF_LOWER | (full ? GF_MIRROR : 0)));
         *G = nbp(c, NB_G); *gs = 1.0;
     } else {
         // dK/dtheta0 = a p B^(p-1); p = 1: B^0 = I; p <= 0: K = I, derivative 0
@@ -770,6 +810,104 @@ int gpc_train_block(gpn_ctx* c) {   // K = kernel(train, train) with noise on ev
     GPN_TRY(ensure_nb(c, NB_KY, ldn, ldn));
     const int* tr = (const int*)c->train_idx.p;
     return gpn_k_gather(c, kfull(c), c->ldN, tr, n, tr, n, c->theta_exp[c->P - 1], nbp(c, NB_KY), ldn);
+}
+
+// GPnetClassifier.gradLogPosterior (GPnetClassifier.py:149-182): RW Alg. 5.1 as written there, fed by the derivative
+// kernels of SURVEY Appendix C (the reference's own kernel() no longer returns them, quirk A-12).  out_h[0] = -logq,
+// out_h[1..P] = -gradZ.  Every expression is linear in dK_d, so the kernel-parameter part (d = 0) and the all-entries
+// noise part c 1 1^T (d = P-1) are accumulated separately; the rank-one part needs only vector sums.
+int gpc_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const double* y_h, double* out_h, int* iters_h, int* info_h) {
+    int st = kernel_build(c, kind, theta_h, P, 1);
+    if (st != 0) return st;
+    const int n = c->n_train;
+    const long ldn = pad128(n);
+    GPN_TRY(gpc_train_block(c));
+    const double* K = nbp(c, NB_KY);
+    double logq = 0.0;
+    GPN_TRY(gpc_newton(c, K, ldn, n, y_h, 0.1, 1e100, 1.0, 0, nullptr, nullptr, &logq, iters_h, info_h));   // :155
+    out_h[0] = -logq;
+    for (int j = 0; j < P; ++j) out_h[1 + j] = 0.0;
+    if (*info_h != 0) return 0;
+    const double noise = c->theta_exp[P - 1];
+    const int* tr = (const int*)c->train_idx.p;
+    NewtonState s;
+    s.n = n; s.ldn = ldn; s.K = K; s.ldk = ldn; s.have_wk = false;
+    // W, p from the converged f (:156-158, :163); B refactored (:159); Binv = W_B^T W_B (full)
+    newton_pre_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_F), vecp(c, V_Y), vecp(c, V_W), vecp(c, V_SW), vecp(c, V_P), vecp(c, V_B),
+                                                     vecp(c, V_G));
+    c->launches++;
+    GPN_TRY(factor_B(c, s));
+    GPN_TRY(ensure_nb(c, NB_KSS, ldn, ldn));
+    double* Binv = nbp(c, NB_KSS);
+    GPN_TRY(gpn_lauum_t(c, n, nbp(c, NB_WT), ldn, Binv, ldn, true));
+    // C = L^-1 sqrtW K = W_B (sw o K); only diag(C^T C) is needed (:162-166)
+    GPN_TRY(ensure_nb(c, NB_S, ldn, ldn));
+    GPN_TRY(ensure_nb(c, NB_V, ldn, ldn));
+    GPN_TRY(gpn_k_scale_rows(c, n, n, K, ldn, vecp(c, V_SW), nbp(c, NB_S), ldn));
+    GPN_TRY(gpn_gemm(c, n, n, n, 1.0, nbp(c, NB_WB), ldn, true, nbp(c, NB_S), ldn, false, 0.0, nbp(c, NB_V), ldn, GF_KHI_M));
+    GPN_TRY(gpn_k_colnorm2(c, n, n, nbp(c, NB_V), ldn, vecp(c, V_VN)));
+    diag_extract_kernel<<<g1(n), 256, 0, c->stream>>>(n, K, ldn, vecp(c, V_KSS));
+    gpc_s2_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_KSS), vecp(c, V_VN), vecp(c, V_W), vecp(c, V_P), vecp(c, V_VV));   // s2 -> V_VV
+    c->launches += 2;
+    // s3(b) = b - K (R b), R b = sw o (Binv (sw o b));  result dotted with s2 into dscal(slot)
+    auto s2_dot_s3 = [&](const double* b, int slot) -> int {
+        vec_mul_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_SW), b, vecp(c, V_RHS));
+        c->launches++;
+        GPN_TRY(gpn_k_gemv(c, n, n, Binv, ldn, vecp(c, V_RHS), vecp(c, V_Z2), GEMV_FULL));
+        vec_mul_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_SW), vecp(c, V_Z2), vecp(c, V_SOL));
+        c->launches++;
+        GPN_TRY(gpn_k_gemv(c, n, n, K, ldn, vecp(c, V_SOL), vecp(c, V_U), GEMV_FULL));
+        vec_sub_kernel<<<g1(n), 256, 0, c->stream>>>(n, b, vecp(c, V_U), vecp(c, V_PI));
+        c->launches++;
+        return gpn_k_dot(c, n, vecp(c, V_VV), vecp(c, V_PI), dscal(c, slot));
+    };
+    // ---- d = 0: D0 = dK/dtheta0 [tr,tr] (full symmetric) ----
+    const double* G = nullptr;
+    double gs = 0.0;
+    GPN_TRY(gpr_grad_kernel_block(c, kind, ldn, &G, &gs, true));
+    bool have_d0 = (G != nullptr);
+    if (have_d0) {
+        double* D0 = nbp(c, NB_G);
+        if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN) {      // D0 = (K^2)[tr,tr] - K[tr,tr]  (K without the noise)
+            GPN_TRY(ensure_nb(c, NB_KC, ldn, ldn));
+            GPN_TRY(gpn_k_gather(c, kfull(c), c->ldN, tr, n, tr, n, 0.0, nbp(c, NB_KC), ldn));
+            const double* X[2] = {D0, nbp(c, NB_KC)};
+            const long l2[2] = {ldn, ldn};
+            const double cf[2] = {1.0, -1.0};
+            GPN_TRY(gpn_k_lincomb(c, n, D0, ldn, 0.0, 2, X, l2, cf));
+        } else if (gs != 1.0) {
+            const double* X[1] = {D0};
+            const long l1[1] = {ldn};
+            const double cf[1] = {gs};
+            GPN_TRY(gpn_k_lincomb(c, n, D0, ldn, 0.0, 1, X, l1, cf));
+        }
+        GPN_TRY(gpn_k_gemv(c, n, n, D0, ldn, vecp(c, V_A), vecp(c, V_KB), GEMV_FULL));
+        GPN_TRY(gpn_k_dot(c, n, vecp(c, V_A), vecp(c, V_KB), dscal(c, Scal::TR0)));                 // a^T D0 a
+        GPN_CK(cudaMemsetAsync(dscal(c, Scal::TR1), 0, sizeof(double), c->stream));
+        gpc_trace_kernel<<<n, 256, 0, c->stream>>>(n, Binv, ldn, vecp(c, V_SW), D0, ldn, dscal(c, Scal::TR1));   // tr(R D0)
+        c->launches++;
+        GPN_TRY(gpn_k_gemv(c, n, n, D0, ldn, vecp(c, V_G), vecp(c, V_KB), GEMV_FULL));              // b = D0 ((t+1)/2 - p)
+        GPN_TRY(s2_dot_s3(vecp(c, V_KB), Scal::TR2));
+    }
+    // ---- d = P-1: D = c 1 1^T ----
+    GPN_TRY(gpn_k_sum(c, n, vecp(c, V_A), dscal(c, Scal::NORM0)));                                  // sum a
+    GPN_TRY(gpn_k_sum(c, n, vecp(c, V_G), dscal(c, Scal::NORM1)));                                  // sum ((t+1)/2 - p)
+    GPN_TRY(gpn_k_gemv(c, n, n, Binv, ldn, vecp(c, V_SW), vecp(c, V_Z), GEMV_FULL));
+    GPN_TRY(gpn_k_dot(c, n, vecp(c, V_SW), vecp(c, V_Z), dscal(c, Scal::NORM2)));                   // sw^T Binv sw = sum_ij R_ij
+    vec_fill_kernel<<<g1(n), 256, 0, c->stream>>>(n, 1.0, vecp(c, V_KB));
+    c->launches++;
+    GPN_TRY(s2_dot_s3(vecp(c, V_KB), Scal::NORM3));                                                 // s2 . s3(1)
+    double sc[Scal::NDBL];
+    int info[16];
+    GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
+    if (info[3] != 0) { *info_h = info[3]; return 0; }
+    double g0 = 0.0;
+    if (have_d0) g0 = 0.5 * sc[Scal::TR0] - 0.5 * sc[Scal::TR1] + sc[Scal::TR2];
+    const double sa = sc[Scal::NORM0], sg = sc[Scal::NORM1];
+    const double gn = 0.5 * noise * sa * sa - 0.5 * noise * sc[Scal::NORM2] + noise * sg * sc[Scal::NORM3];
+    out_h[1 + 0] += -g0;
+    out_h[1 + (P - 1)] += -gn;
+    return 0;
 }
 
 }   // namespace
@@ -1152,6 +1290,12 @@ int gpn_gpc_predict(gpn_ctx* c, int kind, const double* theta_h, int P, const do
     GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
     if (info[3] != 0) *info_h = info[3];
     return 0;
+}
+
+int gpn_gpc_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const double* y_h, double* out_h, int* iters_h, int* info_h) {
+    if (!c) return -1;
+    if (c->n_train <= 0) return -1;
+    return gpc_grad(c, kind, theta_h, P, y_h, out_h, iters_h, info_h);
 }
 
 int gpn_landscape(gpn_ctx* c, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1, const double* ax1_h, int n1,

@@ -112,6 +112,11 @@ int gpn_gpc_newton(gpn_ctx* ctx, int kind, const double* theta_h, int P, const d
 int gpn_gpc_predict(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* y_h, double* f_h, double* a_h,
                     double* logq_h, int* iters_h, double* fstar_h, double* V_h, double* pistar_h, int* info_h);
 
+/* GPnetClassifier.gradLogPosterior (:149-182, RW Alg. 5.1 as written there) with the derivative kernels of SURVEY App. C:
+ * out_h[0] = -logq (as logPosterior), out_h[1..P] = -gradZ. */
+int gpn_gpc_grad(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* y_h, double* out_h, int* iters_h,
+                 int* info_h);
+
 /* ---- landscape slice (GPnet.py:539-552) ---------------------------------------------------------------------- */
 /* For flat grid indices idx = idx_begin + q*idx_stride < idx_end: theta[ax0] = ax1_h[idx / n2], theta[ax1] =
  * ax2_h[idx % n2]; out_h[q*(1+P) ..] = (lml = +logp, dlogp/dtheta) (gradient only if want_grad).  classifier != 0

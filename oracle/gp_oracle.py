@@ -251,6 +251,33 @@ def gpc_predict(K, kstar, kss_diag, y, f):
     return fstar, V, probs
 
 
+def gpc_grad(K, dKs, y, f, a):
+    """GPnetClassifier.gradLogPosterior body after the kernel / NRiteration calls, GPnetClassifier.py:156-182 (RW Alg. 5.1
+    as written there; the reference cannot execute it today because its kernel() no longer returns derivative slices,
+    quirk A-12).  ``K``: train block incl. noise, ``dKs``: list of dK/dtheta_d blocks, ``f``/``a``: Newton outputs.
+    Returns ``-gradZ``."""
+    n = K.shape[0]
+    y = np.asarray(y, dtype=np.float64).reshape(n, 1)
+    f = np.asarray(f, dtype=np.float64).reshape(n, 1)
+    a = np.asarray(a, dtype=np.float64).reshape(n, 1)
+    s = np.where(f < 0, f, 0)
+    w = np.squeeze(np.exp(2 * s - f) / ((np.exp(s) + np.exp(s - f)) ** 2), axis=1)
+    sw = np.sqrt(w)
+    L = np.linalg.cholesky(np.eye(n) + sw[:, None] * K * sw[None, :])                      # :159
+    R = sw[:, None] * np.linalg.solve(L.T, np.linalg.solve(L, np.diag(sw)))                # :161
+    C = np.linalg.solve(L, sw[:, None] * K)                                                # :162
+    p = np.exp(s) / (np.exp(s) + np.exp(s - f))
+    hess = -np.exp(2 * s - f) / (np.exp(s) + np.exp(s - f)) ** 2
+    s2 = -0.5 * (np.diag(K) - np.sum(C * C, axis=0))[:, None] * (2 * hess * (0.5 - p))     # :165-168
+    gradZ = np.zeros(len(dKs))
+    for d, dK in enumerate(dKs):
+        s1 = 0.5 * float((a.T @ (dK @ a)).item()) - 0.5 * np.trace(R @ dK)                 # :174-176
+        b = dK @ ((y + 1) * 0.5 - p)                                                       # :177
+        s3 = b - K @ (R @ b)                                                               # :179
+        gradZ[d] = s1 + float((s2.T @ s3).item())
+    return -gradZ
+
+
 def pi_star_from(fstar, V):
     """5-erf averaged sigmoid, GPnetClassifier.py:221-231 (same expression order)."""
     m = len(V)
@@ -338,6 +365,26 @@ class OracleGP:
     # classifier -----------------------------------------------------------------------------
     def newton(self, theta, train, y, **kw):
         return gpc_newton(self.kernel(train, train, theta), y, **kw)
+
+    def classifier_grad(self, theta, train, y):
+        """(-logq, -gradZ): NRiteration + gradLogPosterior with the derivative kernels of SURVEY Appendix C."""
+        theta = np.atleast_1d(np.asarray(theta, dtype=np.float64))
+        P = len(theta)
+        Kfull = self.full(theta)
+        K = kernel_block(Kfull, train, train, theta)
+        r = np.array(sorted(train), dtype=np.int64)
+        dK0 = kernel_derivatives(self.Lnorm, Kfull, self.kerneltype, theta)[np.ix_(r, r)]
+        c = float(np.exp(theta[-1]))
+        dKs = []
+        for j in range(P):
+            D = np.zeros_like(K)
+            if j == 0:
+                D = D + dK0
+            if j == P - 1:
+                D = D + c
+            dKs.append(D)
+        f, logq, a, iters = gpc_newton(K, y)
+        return -logq, gpc_grad(K, dKs, y, f, a)
 
     def predict_classifier(self, theta, train, test, y):
         Kfull = self.full(theta)

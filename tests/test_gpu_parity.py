@@ -99,6 +99,44 @@ def test_classifier_parity(path):
     assert abs(float(np.squeeze(m.logp())) - g["logp"]) <= TOL * abs(g["logp"])
 
 
+@pytest.mark.parametrize("kt,theta", [("diffusion", np.log([0.6, 0.1])), ("regularized_laplacian", np.log([0.6, 0.1])),
+                                      ("pstep_walk", np.log([2.1, 2, 0.1])), ("pstep_walk", np.log([2.5, 1.5]))])
+def test_classifier_gradient_matches_oracle(kt, theta):
+    """GPnetClassifier.gradLogPosterior (RW Alg. 5.1 as written at GPnetClassifier.py:149-182; IndexError in the reference
+    itself, A-12): the device path against the oracle's line-by-line restatement fed by the same derivative kernels."""
+    import gpnet_b200
+    G, tr, te, y = cfg.ba_case(300, 150, 100)
+    ys = pd.Series(y[tr], index=tr)
+    m = gpnet_b200.GPnetClassifier(Graph=G, training_nodes=tr, test_nodes=te, theta=list(theta), relabel_nodes=True, kerneltype=kt,
+                                   training_values=ys)
+    g = m.gradLogPosterior(theta, tr, ys)
+    val, ref = go.OracleGP(G, kerneltype=kt, expm_mode="dense").classifier_grad(theta, tr, y[tr])
+    assert g.shape == (len(theta),)
+    assert nrel(g, ref) <= 1e-8
+    assert abs(float(np.squeeze(m.logPosterior(theta, tr, ys))) - val) <= TOL * abs(val)
+
+
+def test_large_n_diffusion_semigroup(gpu_ctx):
+    """C5 family (2-D grid, diffusion) at N = 16384 (2.1 GB per matrix; the full N = 32768 case is tools/c5_check.py):
+    exp(-b L~) exp(-b L~) = exp(-2b L~) on a column sample, product formed on the device through the C-ABI GEMM."""
+    import torch
+    a, b = 128, 128
+    N = a * b
+    indptr, indices, w = cfg.grid_csr_fast(a, b)
+    gpu_ctx.set_graph(indptr, indices, w)
+    cols = np.arange(0, N, N // 32, dtype=np.int32)[:32]
+    assert gpu_ctx.kernel_build(0, np.log([0.3, 0.01]), False) == 0
+    ptr, ld = gpu_ctx.kernel_ptr()
+    K1c = torch.from_numpy(np.ascontiguousarray(gpu_ctx.kernel_block(range(N), cols, 0.0))).cuda()
+    P = torch.zeros((N, 32), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    gpu_ctx.gemm(0, 0, N, 32, N, 1.0, ptr, ld, K1c.data_ptr(), 32, 0.0, P.data_ptr(), 32)
+    gpu_ctx.sync()
+    assert gpu_ctx.kernel_build(0, np.log([0.6, 0.01]), False) == 0
+    K2c = gpu_ctx.kernel_block(range(N), cols, 0.0)
+    assert np.max(np.abs(P.cpu().numpy() - K2c)) < 1e-12
+
+
 def test_notebook_known_answer_on_gpu(gpu_ctx):
     """The reference's only KAT (report_notebook.ipynb cell 49) through the CUDA Newton loop."""
     import torch
