@@ -93,6 +93,7 @@ struct gpn_ctx {
     DevBuf winv;                 // inverted diagonal blocks of the running Cholesky (N x 128)
     DevBuf flags;                // dataflow Cholesky: epoch-stamped tile-ready flags (T x T ints)
     int epoch = 0;
+    void* df_trace = nullptr;    // optional device buffer: 8 x int64 globaltimer stamps per dataflow-Cholesky task
     void* leaf_prof = nullptr;   // optional device buffer (32 x int64) receiving clock64 stamps of the leaf phases
     int potrf_mode = 0;          // 0: dataflow kernel (default), 1: recursive multi-launch (GPNET_B200_POTRF=recursive)
     DevBuf scal;                 // small device scalars (reductions, info)

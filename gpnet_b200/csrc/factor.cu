@@ -110,8 +110,9 @@ int gpn_potrf(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info,
 // DMMA path): T^T is kept instead of T, and each W21 block is stored both ways by the GEMM epilogue.
 int gpn_trtri(gpn_ctx* c, int n, const double* L, long ldl, const double* winv, double* W, double* WT, double* TT, long ldw) {
     if (n <= 0) return 0;
-    GPN_TRY(gpn_k_fill_zero(c, W, ldw, n, n));
-    GPN_TRY(gpn_k_fill_zero(c, WT, ldw, n, n));
+    // No zero fill of W / WT: every consumer restricts its k-range to the diagonal 128-block of the tile it reads (structure
+    // flags, GEMV_LOWER), the diagonal blocks are written completely (with their zero halves) right here, and the strictly
+    // upper (resp. lower) off-diagonal blocks are never read.
     const int m = (n + LB - 1) / LB;
     copy_diag_blocks_kernel<<<m, 256, 0, c->stream>>>(winv, W, WT, ldw, n);
     c->launches++;

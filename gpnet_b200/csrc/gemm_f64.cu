@@ -75,6 +75,8 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int r = tix - gid * per_group;
             tm = first_m + (r % gsz);
             tn = r / gsz;
+            // longest-first: with a lower-triangular A (k < m0+BM) the bottom tile rows carry the long k-loops
+            if ((g.flags & GF_KHI_M) && !(g.flags & (GF_KLO_M | GF_KLO_N))) tm = g.tiles_m - 1 - tm;
         }
     }
     const int m0 = tm * BM, n0 = tn * BN;

@@ -1084,6 +1084,9 @@ int gpn_fp64_peak(gpn_ctx* c, double seconds, double* tflops_h) {
 void gpn_debug_leaf_prof(gpn_ctx* c, void* dev_buf32) {
     if (c) c->leaf_prof = dev_buf32;
 }
+void gpn_debug_df_trace(gpn_ctx* c, void* dev_buf) {
+    if (c) c->df_trace = dev_buf;
+}
 
 void gpn_set_profile(gpn_ctx* c, int on) {
     if (!c) return;

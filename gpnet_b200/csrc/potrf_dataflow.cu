@@ -39,12 +39,49 @@ struct DfArgs {
     int epoch;
     int* info;
     int info_off;
+    long long* trace;     // optional: 8 x int64 globaltimer stamps per task (development aid)
 };
 
 __device__ __forceinline__ void wait_flag(const int* f, int epoch) {
     while (ld_acquire(f) != epoch) __nanosleep(32);
 }
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define DF_STAMP(slot) do { if (g.trace && tid == 0) g.trace[(long)q * 8 + (slot)] = gtime(); } while (0)
 __device__ __forceinline__ void sts64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
+// The epilogue reads the original tile A_ij (C = A_ij - acc) from global memory on the dependency chain: pull it into L2
+// a few k-steps earlier (128 rows x 1 KB; 256 threads x 4 lines of 128 B).
+__device__ __forceinline__ void prefetch_tile(const DfArgs& g, int i, int j, int tid) {
+    const long gr = (long)i * TB + (tid >> 1);
+    if (gr < g.n) {
+        const double* rowp = g.A + gr * g.lda + (long)j * TB + (tid & 1) * 64;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + l * 16));
+    }
+}
+
+// One k-step of a DIAGONAL tile for the warp at (WM_, WN_): only the 8x8 blocks touching the lower triangle are issued,
+// selected at compile time (no per-DMMA predicate arithmetic on the dependency chain's last k-block).
+template <int WM_, int WN_>
+__device__ __forceinline__ void diag_kstep(double (&acc)[8][4][2], uint32_t sa, uint32_t sb, int gq, int t) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        double af[8][2], bf[4][2];
+        load_frags<8, true>(af, sa, WM_ * 64, h, gq, t);
+        load_frags<4, true>(bf, sb, WN_ * 32, h, gq, t);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (32 * WN_ + 8 * b <= 64 * WM_ + 8 * a + 7) dmma884(acc[a][b], af[a][u], bf[b][u]);
+    }
+}
 
 __global__ void __launch_bounds__(384, 1)
 potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmW, const DfArgs g) {
@@ -149,10 +186,13 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
         for (int a = 0; a < 8; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-
+        DF_STAMP(0);
         const int niter = j * 8;
+        if (niter == 0) prefetch_tile(g, i, j, tid);
         const uint32_t mask = (i == j) ? diag_mask : 0xffffffffu;
+        const int npre = niter > 12 ? niter - 12 : 0;
         for (int n = 0; n < niter; ++n, ++it) {
+            if (n == npre) prefetch_tile(g, i, j, tid);      // shortly before the epilogue needs A_ij (see below)
             const int st = it % STAGES;
             mbar_wait(bar_full + st * 8, (it / STAGES) & 1);
             const uint32_t sa = smem0 + st * STAGE_BYTES, sb = sa + TILE_BYTES;
@@ -169,19 +209,15 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
 #pragma unroll
                             for (int b = 0; b < 4; ++b) dmma884(acc[a][b], af[a][u], bf[b][u]);
                 }
-            } else if (mask != 0) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    double af[8][2], bf[4][2];
-                    load_frags<8, true>(af, sa, wm * 64, h, gq, t);
-                    load_frags<4, true>(bf, sb, wn * 32, h, gq, t);
-#pragma unroll
-                    for (int u = 0; u < 2; ++u)
-#pragma unroll
-                        for (int a = 0; a < 8; ++a)
-#pragma unroll
-                            for (int b = 0; b < 4; ++b)
-                                if (mask & (1u << (a * 4 + b))) dmma884(acc[a][b], af[a][u], bf[b][u]);
+            } else {
+                switch (warp) {      // (wm, wn) = (w >> 2, w < 4 ? w : 7 - w); warps 2 and 3 own no lower-triangle block
+                    case 0: diag_kstep<0, 0>(acc, sa, sb, gq, t); break;
+                    case 1: diag_kstep<0, 1>(acc, sa, sb, gq, t); break;
+                    case 4: diag_kstep<1, 3>(acc, sa, sb, gq, t); break;
+                    case 5: diag_kstep<1, 2>(acc, sa, sb, gq, t); break;
+                    case 6: diag_kstep<1, 1>(acc, sa, sb, gq, t); break;
+                    case 7: diag_kstep<1, 0>(acc, sa, sb, gq, t); break;
+                    default: break;
                 }
             }
             __syncwarp();
@@ -189,6 +225,7 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
         }
         bar_consumers();                        // every consumer warp has finished reading the ring
         if (lane == 0) mbar_arrive(bar_mdone);
+        DF_STAMP(1);
 
         const long grow0 = (long)i * TB + wm * 64, gcol0 = (long)j * TB + wn * 32;
         if (i == j) {
@@ -211,6 +248,7 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
                     }
             }
             bar_consumers();
+            DF_STAMP(2);
             const int nv = min(TB, g.n - j * TB);
             leaf::potf2_inverse<1>(S, Wd, Tt, g.A + ((long)j * TB) * g.lda + (long)j * TB, g.lda, nv, g.winv + (long)j * TB * TB, g.info,
                                    g.info_off + j * TB, tid);
@@ -220,6 +258,7 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
                 fence_proxy_async();
                 st_release(g.flags + (long)j * T + j, g.epoch);
             }
+            DF_STAMP(4);
         } else {
             // ---- C = A_ij - acc -> K-major swizzled sub-tiles; L_ij = C W_j^T ----
 #pragma unroll
@@ -239,9 +278,11 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
                     }
             }
             bar_consumers();
+            DF_STAMP(2);
             for (int s = 0; s < 8; ++s, ++wit) {
                 const int ws = wit % WSTAGES;
                 mbar_wait(bar_wfull + ws * 8, (wit / WSTAGES) & 1);
+                if (s == 0) DF_STAMP(3);
                 const uint32_t sa = smem0 + s * TILE_BYTES, sb = smem0 + CREG_BYTES + ws * TILE_BYTES;
                 // W_j[n][k] == 0 for k > n: k-step s only reaches the 8-column blocks with 16 s <= 32 wn + 8 b + 7
                 if (16 * s <= 32 * wn + 31) {
@@ -263,6 +304,7 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_wempty + ws * 8);
             }
+            DF_STAMP(5);
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
                 const long gr = grow0 + a * 8 + pg;
@@ -279,6 +321,7 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
                 fence_proxy_async();
                 st_release(g.flags + (long)i * T + j, g.epoch);
             }
+            DF_STAMP(4);
         }
         fence_proxy_async();                    // generic smem traffic of this task before the next task's TMA writes
         if (lane == 0) mbar_arrive(bar_fdone);
@@ -313,7 +356,7 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
     }
     DfArgs a;
     a.A = A; a.lda = lda; a.n = n; a.T = T; a.ntasks = ntasks; a.winv = winv; a.flags = (int*)c->flags.p;
-    a.epoch = ++c->epoch; a.info = d_info; a.info_off = info_offset;
+    a.epoch = ++c->epoch; a.info = d_info; a.info_off = info_offset; a.trace = (long long*)c->df_trace;
     CUtensorMap tl, tw;
     GPN_TRY(encode_tiles(c, &tl, A, lda, n, n));
     GPN_TRY(encode_tiles(c, &tw, winv, TB, (long)T * TB, TB));

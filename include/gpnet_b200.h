@@ -45,6 +45,8 @@ void gpn_set_profile(gpn_ctx* ctx, int on);
 int gpn_profile_summary(gpn_ctx* ctx, double* out_h);
 /* development aid: device buffer of 32 int64 receiving clock64() stamps of the phases of the next leaf-kernel launch */
 void gpn_debug_leaf_prof(gpn_ctx* ctx, void* dev_buf32);
+/* development aid: device buffer receiving 8 int64 %globaltimer stamps per task of the next dataflow-Cholesky launches */
+void gpn_debug_df_trace(gpn_ctx* ctx, void* dev_buf);
 
 /* ---- graph and node sets (host -> device once; resident afterwards) -------------------------------------- */
 /* CSR adjacency in graph-position order (row i = i-th node of list(G)); weights_h may be NULL (all ones).

@@ -140,6 +140,40 @@ def stage_leaf(ctx):
         print(f"potrf {nn}: {ms*1e3:.1f} us  ({nn//128} tile columns -> {ms*1e3/(nn//128):.1f} us per column)", flush=True)
 
 
+def stage_chain(ctx):
+    """Per-task %globaltimer trace of the dataflow Cholesky: where the per-column dependency chain spends its time."""
+    for n in (2048, 8192):
+        T = n // 128
+        X = torch.randn(n, n, dtype=torch.float64, device=dev)
+        S = X @ X.T / n + torch.eye(n, dtype=torch.float64, device=dev)
+        Sb, ld = dmat(n, n, S)
+        ctx.potrf(n, Sb.data_ptr(), ld)
+        Sb[:, :n] = S
+        ntasks = T * (T + 1) // 2
+        tr = torch.zeros(ntasks * 8, dtype=torch.int64, device=dev)
+        ctx.lib.gpn_debug_df_trace(ctx.h, tr.data_ptr())
+        ctx.potrf(n, Sb.data_ptr(), ld)
+        ctx.lib.gpn_debug_df_trace(ctx.h, None)
+        t = tr.cpu().numpy().reshape(ntasks, 8).astype(np.float64) * 1e-3      # us
+        q0 = lambda j: j * T - j * (j - 1) // 2
+        rows = []
+        for j in range(T - 1):
+            dg, ts, dn = t[q0(j)], t[q0(j) + 1], t[q0(j + 1)]     # diag(j), trsm(j+1,j), diag(j+1)
+            rows.append([dg[4] - dg[2],          # leaf (S staged -> flag)
+                         dg[2] - dg[1],          # diag epilogue (A read, S staging)
+                         ts[3] - dg[4],          # flag(j,j) -> first W stage landed in the TRSM CTA
+                         ts[5] - ts[3],          # TRSM GEMM
+                         ts[4] - ts[5],          # TRSM store + fence + flag
+                         dn[1] - ts[4],          # flag(j+1,j) -> last k-block of diag(j+1) done
+                         dn[4] - dg[4]])         # column period
+        r = np.array(rows)
+        names = ["leaf", "diag-epilogue", "flag->W landed", "trsm gemm", "trsm store+flag", "flag->lastk done", "column period"]
+        print(f"n={n}: total {(t[:, 4].max() - t[:, 0].min()):.0f} us;  chain segments (us, median over columns; [first 5] .. [last 5]):")
+        for k, nm in enumerate(names):
+            print(f"   {nm:18s} median {np.median(r[:, k]):7.1f}   head {np.round(r[:5, k], 1)}  tail {np.round(r[-5:, k], 1)}")
+        sys.stdout.flush()
+
+
 def stage_potrf(ctx):
     torch.manual_seed(1)
     for n in (5, 100, 128, 129, 256, 900, 1024, 2048, 3000):
