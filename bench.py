@@ -13,7 +13,6 @@ import math
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -48,39 +47,50 @@ def algorithmic_flops(N, n):
     return float(N) ** 3 + float(n) ** 2 * N + float(n) ** 3
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): one streaming
+    `nvidia-smi -lms 50` process, started right before the region and stopped right after it."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
         self.index = index
-        self.samples = []
-        self.stop_flag = threading.Event()
+        self.proc = None
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)      # let the first sample arrive before the region starts
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        self.stop_flag.set()
-        self.join(timeout=6)
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        pw = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        samples = []
+        if self.proc is not None:
+            time.sleep(0.06)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            samples = [[x.strip() for x in line.split(",")] for line in out.strip().splitlines() if line.strip()]
+
+        def num(s):
+            try:
+                return float(s)
+            except ValueError:
+                return None
+        sm = [num(s[0]) for s in samples if len(s) >= 7 and num(s[0]) is not None]
+        mx = [num(s[1]) for s in samples if len(s) >= 7 and num(s[1]) is not None]
+        pw = [num(s[2]) for s in samples if len(s) >= 7 and num(s[2]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for s in samples if len(s) >= 7 for i in range(4) if s[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(self.samples), "reasons": reasons}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
 def cpu_port_eval(problem, N, reference_style):
@@ -144,7 +154,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native")
     ap.add_argument("--nodes", type=int, default=8192)
