@@ -105,8 +105,6 @@ struct gpn_ctx {
 int gpn_buf_ensure(gpn_ctx* c, DevBuf& b, size_t bytes);
 int gpn_winv_ensure(gpn_ctx* c, size_t bytes);
 
-static inline long gpn_round_ld(long n) { return (n + 15) / 16 * 16; }   // 128-byte rows: TMA-friendly, sector aligned
-
 // ---- internal device-level primitives (all stream-ordered on c->stream, device pointers) -----------------
 // C[M x N] = alpha * op(A) op(B) + beta * C.   a_kmajor: A stored [M][K] (row-major, K contiguous); else [K][M].
 // b_kmajor: B stored [N][K]; else [K][N].  Batched over `batch` problems with element strides sA/sB/sC.
@@ -132,7 +130,6 @@ int gpn_k_gather(gpn_ctx* c, const double* K, long ld, const int* rows, int nr, 
                  double* out, long ldo, int pad_r = -1, int pad_c = -1);
 int gpn_k_gather_rows(gpn_ctx* c, const double* K, long ld, const int* rows, int nr, int ncols, double* out, long ldo);
 int gpn_k_zero_upper(gpn_ctx* c, double* A, long ld, int n);
-int gpn_k_mirror_lower(gpn_ctx* c, double* A, long ld, int n);
 int gpn_k_lincomb(gpn_ctx* c, int n, double* out, long ldo, double diag, int nterms, const double* const* X, const long* ldx,
                   const double* coef);
 int gpn_k_onenorm(gpn_ctx* c, int n, const double* A, long ld, double* d_out /*device scalar*/);

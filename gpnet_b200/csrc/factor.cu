@@ -3,13 +3,13 @@
 // Replaces np.linalg.cholesky + the np.linalg.solve(L, .) chains of the reference (GPnetRegressor.py:123-126,141-144;
 // GPnetClassifier.py:110-121,208-211) and scipy.linalg.inv (GPnet.py:342).
 //
-//  * gpn_potrf   : recursive blocked Cholesky (lower, row-major, in place).  Leaves are 128x128 diagonal blocks
-//                  factored AND inverted by one CTA in shared memory (potf2_inv_kernel); everything else is GEMM:
-//                  TRSM is "multiply by the inverted diagonal block" (recursive), the trailing update is a
-//                  lower-tiles-only SYRK.  The inverted diagonal blocks are kept (winv) for the triangular inverse.
-//  * gpn_trtri_from_winv : W = L^-1 level by level; all pairs of one level run as ONE batched GEMM launch
-//                  (W21 = -W22 * (L21 * W11)), triangular structure skipped at tile granularity.
-//  * gpn_lauum   : W^T W as a single structure-aware GEMM (k >= max(m0,n0), lower tiles + mirrored store).
+//  * gpn_potrf   : n > 128: the single-kernel dataflow Cholesky (potrf_dataflow.cu).  n <= 128 (and the recursive multi-launch
+//                  fallback selected by GPNET_B200_POTRF=recursive, kept for A/B timing): leaves are 128x128 diagonal blocks
+//                  factored AND inverted by one CTA in shared memory (leaf.cuh); TRSM is "multiply by the inverted diagonal
+//                  block", the trailing update a lower-tiles-only SYRK.  The inverted diagonal blocks are kept (winv).
+//  * gpn_trtri   : W = L^-1 (and W^T) level by level; all pairs of one level run as ONE batched GEMM launch
+//                  (W21 = -W22 * (L21 * W11)), triangular structure skipped at tile granularity, K-major operands only.
+//  * gpn_lauum_t : W^T W as a single structure-aware GEMM (k >= max(m0,n0), lower tiles + mirrored store).
 #include "common.cuh"
 #include "leaf.cuh"
 

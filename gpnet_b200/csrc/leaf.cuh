@@ -1,11 +1,13 @@
 // 128x128 Cholesky leaf: factor AND invert one diagonal block in shared memory with 256 threads (8 warps).
 // Used by the stand-alone leaf kernel (factor.cu) and inside the dataflow Cholesky (potrf_dataflow.cu).
 //
-//  * 32x32 diagonal sub-blocks: ONE warp, rows in registers, column sweep with warp shuffles (no block barrier on
-//    the per-column critical chain), followed by the register-resident triangular inverse of the sub-block;
-//  * panel (L21 = A21 W11^T) and trailing update (A22 -= L21 L21^T) and the off-diagonal blocks of the inverse:
-//    4x4 register-tiled shared-memory GEMMs over all 8 warps.
-// Shared memory: S[128][129] (padded, conflict-free column access), Wd[4][32][33], T[96][33].
+//  * 32x32 diagonal sub-blocks: ONE warp, rows in registers, software-pipelined column sweep (no block barrier on the
+//    per-pivot dependency chain);
+//  * panel below a diagonal block: one thread per row, column sweep against L_kk in shared memory;
+//  * trailing updates and the off-diagonal blocks of the inverse: DMMA shared-memory GEMMs over all 8 warps;
+//  * inverses of the four diagonal blocks: row sweeps, one warp per block.
+// Shared memory: guard band, S[128][129] (padded, conflict-free column access), Wd[4][32][33], T[96][33], 1/diag, column
+// broadcast buffer.
 #pragma once
 #include <type_traits>
 
@@ -91,62 +93,6 @@ __device__ __forceinline__ void smem_dmma(const double* __restrict__ A, const do
             for (int j = 0; j < 4; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) epi(16 * mu + 8 * i + g, 32 * nu + 8 * j + 2 * t + e, acc[i][j][e]);
-    }
-}
-
-// acc[i][j] = sum_{k < klim(tile)} A[(r0+i)*SAR + k] * B[(c0+j)*SBC + k*SBK] for the 4x4 tile (r0, c0); strides are
-// compile-time so that every load address is pointer + immediate (a single warp issues integer ops at 1 per 2 cycles:
-// address arithmetic, not FP64, was the bottleneck of the first version).
-// KTRI: the A operand is lower triangular in (row, k) => k <= r0+3 suffices.
-template <bool KTRI, int SAR, int SBC, int SBK>
-__device__ __forceinline__ void tile4x4(const double* __restrict__ A, const double* __restrict__ B, int K, int r0, int c0,
-                                        double (&acc)[4][4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    const int klim = KTRI ? min(K, r0 + 4) : K;       // always a multiple of 4 here
-    const double* a0 = A + r0 * SAR;
-    const double* b0 = B + c0 * SBC;
-#pragma unroll 1
-    for (int k = 0; k < klim; k += 4, a0 += 4, b0 += 4 * SBK) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            double a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = a0[i * SAR + kk];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = b0[j * SBC + kk * SBK];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
-        }
-    }
-}
-
-// Loop over the 4x4 tiles of an R x Cn output (R multiple of 32, Cn multiple of 16): warp-level super tiles of
-// 32 rows x 16 cols, lane -> (tile row lane>>2, tile col lane&3).  f(r0, c0) is called for every tile this thread owns.
-template <typename F>
-__device__ __forceinline__ void for_tiles(int R, int Cn, int tid, bool lower_only, F f) {
-    const int warp = tid >> 5, lane = tid & 31;
-    const int superC = Cn >> 4, superR = R >> 5;
-    if (!lower_only) {
-        for (int st = warp; st < superR * superC; st += 8) {
-            const int sr = st / superC, sc = st - sr * superC;
-            f((sr * 8 + (lane >> 2)) * 4, (sc * 4 + (lane & 3)) * 4);
-        }
-    } else {
-        // super-tile row sr owns 2(sr+1) super tiles that touch the lower triangle: enumerate only those
-        const int total = superR * (superR + 1);
-        for (int st = warp; st < total; st += 8) {
-            int sr = 0;
-            while ((sr + 1) * (sr + 2) <= st) ++sr;
-            const int sc = st - sr * (sr + 1);
-            const int r0 = (sr * 8 + (lane >> 2)) * 4, c0 = (sc * 4 + (lane & 3)) * 4;
-            if (c0 > r0 + 3) continue;
-            f(r0, c0);
-        }
     }
 }
 
