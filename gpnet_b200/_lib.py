@@ -34,6 +34,7 @@ SIGNATURES = {
     "gpn_profile_summary": (C.c_int, [C.c_void_p, c_dbl_p]),
     "gpn_debug_leaf_prof": (None, [C.c_void_p, C.c_void_p]),
     "gpn_debug_df_trace": (None, [C.c_void_p, C.c_void_p]),
+    "gpn_debug_leaf_bench": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gpn_set_graph": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_dbl_p]),
     "gpn_set_nodes": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int, c_int_p]),
     "gpn_set_targets": (C.c_int, [C.c_void_p, c_dbl_p, C.c_int]),

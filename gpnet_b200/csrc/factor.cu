@@ -21,6 +21,11 @@ constexpr int LB = leaf::LB;
 // zeroed) and write inv(L) (identity-padded to 128x128, upper zero) to winv (ld 128).  Body: leaf.cuh.
 __global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ A, long lda, int nv, double* __restrict__ winv,
                                                             int* __restrict__ info, int info_off, long long* prof) {
+    // blockIdx.x > 0 only in the timing harness (gpn_debug_leaf_bench): every block factors its own copy so that the leaf is
+    // timed on a full grid (single-CTA launches of kernels larger than the instruction cache are not representative)
+    A += (long)blockIdx.x * LB * lda;
+    winv += (long)blockIdx.x * LB * LB;
+    if (blockIdx.x != 0) prof = nullptr;
     extern __shared__ double sm[];
     double* S = sm + leaf::GUARD;
     double* Wd = S + LB * leaf::LDS_;
@@ -54,6 +59,19 @@ int launch_leaf(gpn_ctx* c, double* A, long lda, int nv, double* winv, int* d_in
     GPN_CK(cudaGetLastError());
     return 0;
 }
+
+}   // namespace
+
+// Timing harness: `copies` independent 128x128 blocks stacked in A (lda = 128), one CTA each; block 0 records clock64 stamps.
+int gpn_leaf_bench(gpn_ctx* c, double* A, int copies, double* winv, int* d_info, long long* prof) {
+    GPN_CK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
+    potf2_inv_kernel<<<copies, 256, LEAF_SMEM, c->stream>>>(A, LB, LB, winv, d_info, 0, prof);
+    c->launches++;
+    GPN_CK(cudaGetLastError());
+    return 0;
+}
+
+namespace {
 
 inline int split_point(int n) {   // first-half size: a multiple of LB, at least half
     int blocks = (n + LB - 1) / LB;

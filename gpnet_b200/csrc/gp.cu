@@ -1084,6 +1084,12 @@ int gpn_fp64_peak(gpn_ctx* c, double seconds, double* tflops_h) {
 void gpn_debug_leaf_prof(gpn_ctx* c, void* dev_buf32) {
     if (c) c->leaf_prof = dev_buf32;
 }
+int gpn_debug_leaf_bench(gpn_ctx* c, void* A_dev, int copies, void* prof32_dev) {
+    if (!c) return -1;
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)copies * 128 * 128));
+    GPN_TRY(clear_info(c));
+    return gpn_leaf_bench(c, (double*)A_dev, copies, (double*)c->winv.p, iscal(c, 0), (long long*)prof32_dev);
+}
 void gpn_debug_df_trace(gpn_ctx* c, void* dev_buf) {
     if (c) c->df_trace = dev_buf;
 }

@@ -60,13 +60,17 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 // a warp needs about that many in flight), dealt round-robin to the 8 warps.  TRI = 1: A is lower triangular in (m, k)
 // (k-steps beyond the row blocks are skipped); TRI = 2: only units touching the lower triangle of a square C.
 // epi(row, col, value) receives the values a lane owns (C fragment: row g, cols 2t, 2t+1 of each 8x8 block).
+// Only the warps in `wmask` take part; skip_lead drops the leading 32x32 block (already updated ahead of the others).
 template <int SA, int SB, bool BT, int TRI, typename Epi>
 __device__ __forceinline__ void smem_dmma(const double* __restrict__ A, const double* __restrict__ B, int munits, int nunits, int K, int tid,
-                                          Epi epi) {
+                                          Epi epi, unsigned wmask = 0xffu, bool skip_lead = false) {
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    for (int u = warp; u < munits * nunits; u += 8) {
+    if (!((wmask >> warp) & 1u)) return;
+    const int nw = __popc(wmask), wrank = __popc(wmask & ((1u << warp) - 1u));
+    for (int u = wrank; u < munits * nunits; u += nw) {
         const int mu = u / nunits, nu = u - mu * nunits;
         if (TRI == 2 && 32 * nu > 16 * mu + 15) continue;
+        if (skip_lead && nu == 0 && mu < 2) continue;
         double acc[2][4][2];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
@@ -200,6 +204,26 @@ __device__ __forceinline__ void diag32_inverse(const double* __restrict__ S, int
     __syncwarp();
 }
 
+// Lookahead piece of the trailing update: only the NEXT diagonal block, D -= P P^T with P = its 32 rows of the freshly solved
+// panel (K = 32).  8x8 DMMA blocks of the lower triangle spread over the 8 warps.
+__device__ __forceinline__ void trail_diag(double* __restrict__ S, int b0, int tid) {
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int r1 = b0 + 32;
+    const double* P = S + r1 * LDS_ + b0;
+    double* D = S + r1 * LDS_ + r1;
+    for (int blk = warp; blk < 16; blk += 8) {
+        const int mb = blk >> 2, nb = blk & 3;
+        if (nb > mb) continue;
+        double acc[2] = {0.0, 0.0};
+        const double* ap = P + (8 * mb + g) * LDS_ + t;
+        const double* bp = P + (8 * nb + g) * LDS_ + t;
+#pragma unroll
+        for (int k0 = 0; k0 < 32; k0 += 4) dmma884(acc, ap[k0], bp[k0]);
+        D[(8 * mb + g) * LDS_ + 8 * nb + 2 * t] -= acc[0];
+        D[(8 * mb + g) * LDS_ + 8 * nb + 2 * t + 1] -= acc[1];
+    }
+}
+
 // S holds the lower triangle of an SPD 128x128 block (identity padded beyond the valid size by the caller).
 // On return S holds inv(L) (lower); L has been written to Lout (valid nv x nv region, strict upper zeroed) and
 // inv(L) to winv (128x128, ld 128, upper zero, identity padding).
@@ -211,27 +235,31 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
     int pidx = 0;
 #define LEAF_STAMP() do { if (prof && tid == 0) prof[pidx++] = clock64(); } while (0)
     LEAF_STAMP();
-    // ---------------- factorisation, 32-wide block columns ----------------
+    // ---------------- factorisation, 32-wide block columns, right looking with lookahead ----------------
+    // chain: D(0) -> [ panel(kb) -> next diagonal block update -> D(kb+1) ]; the rest of the trailing update of step kb runs on
+    // the six warps of SMSPs 1..3 while warp 0 (alone on SMSP 0: its dependent FP64 chain must not queue behind DMMAs)
+    // factors diagonal block kb+1.
     double* rdiag = T + 96 * WLD;
+    if (warp == 0) diag32_factor(S, 0, rdiag, rdiag + LB, info, info_off, lane);
+    bar256<BAR_ID>();
+    LEAF_STAMP();
 #pragma unroll 1
-    for (int kb = 0; kb < 4; ++kb) {
+    for (int kb = 0; kb < 3; ++kb) {
         const int b0 = 32 * kb, r1 = b0 + 32, R = LB - r1;
-        if (warp == 0) diag32_factor(S, b0, rdiag + b0, rdiag + LB, info, info_off, lane);
+        if (tid < R) panel_sweep(S, b0, r1 + tid, rdiag + b0);
         bar256<BAR_ID>();
         LEAF_STAMP();
-        if (R > 0) {
-            if (tid < R) panel_sweep(S, b0, r1 + tid, rdiag + b0);
-            bar256<BAR_ID>();
-            LEAF_STAMP();
-            // trailing update: A22 -= P P^T (units touching the lower triangle), on the FP64 tensor pipe
-            {
-                double* C22 = S + r1 * LDS_ + r1;
-                smem_dmma<LDS_, LDS_, true, 2>(S + r1 * LDS_ + b0, S + r1 * LDS_ + b0, R / 16, R / 32, 32, tid,
-                                               [&](int r, int cc, double v) { C22[r * LDS_ + cc] -= v; });
-            }
-            bar256<BAR_ID>();
-            LEAF_STAMP();
+        trail_diag(S, b0, tid);
+        bar256<BAR_ID>();
+        if (warp == 0) {
+            diag32_factor(S, r1, rdiag + r1, rdiag + LB, info, info_off, lane);
+        } else if (R > 32) {
+            double* C22 = S + r1 * LDS_ + r1;
+            smem_dmma<LDS_, LDS_, true, 2>(S + r1 * LDS_ + b0, S + r1 * LDS_ + b0, R / 16, R / 32, 32, tid,
+                                           [&](int r, int cc, double v) { C22[r * LDS_ + cc] -= v; }, 0xEEu, true);   // not warps 0, 4 (SMSP 0)
         }
+        bar256<BAR_ID>();
+        LEAF_STAMP();
     }
     // ---------------- write L back ----------------
     // lower triangle (+ the one pair straddling the diagonal); the strict upper triangle of a diagonal tile is never read

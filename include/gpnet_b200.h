@@ -45,6 +45,8 @@ void gpn_set_profile(gpn_ctx* ctx, int on);
 int gpn_profile_summary(gpn_ctx* ctx, double* out_h);
 /* development aid: device buffer of 32 int64 receiving clock64() stamps of the phases of the next leaf-kernel launch */
 void gpn_debug_leaf_prof(gpn_ctx* ctx, void* dev_buf32);
+/* development aid: run the 128x128 leaf on `copies` stacked blocks (lda 128), one CTA each; block 0 stamps its phases */
+int gpn_debug_leaf_bench(gpn_ctx* ctx, void* A_dev, int copies, void* prof32_dev);
 /* development aid: device buffer receiving 8 int64 %globaltimer stamps per task of the next dataflow-Cholesky launches */
 void gpn_debug_df_trace(gpn_ctx* ctx, void* dev_buf);
 

@@ -119,19 +119,16 @@ def stage_leaf(ctx):
     ctx.lib.gpn_potrf_f64.argtypes[4] = ctypes.c_void_p
     ms = ev(lambda: (run(), ctx.sync()))
     print(f"leaf potf2+inverse 128x128: {ms/50*1e3:.1f} us per launch (incl. zero_upper + launch overhead)", flush=True)
-    eye = torch.eye(n, dtype=torch.float64, device=dev)
-    blockdiag = torch.block_diag(*[S[:32, :32]] * 4)
-    for label, M in (("random SPD", S), ("identity", eye), ("block-diagonal (4 x same 32x32 block)", blockdiag), ("random SPD again", S)):
-        buf, _ = dmat(n, n, M)
+    for copies in (1, 148):
+        stack = S.repeat(copies, 1).contiguous()
         prof = torch.zeros(32, dtype=torch.int64, device=dev)
-        ctx.lib.gpn_debug_leaf_prof(ctx.h, prof.data_ptr())
-        ctx.lib.gpn_potrf_f64(ctx.h, n, buf.data_ptr(), 128, None)
+        torch.cuda.synchronize()
+        ctx.lib.gpn_debug_leaf_bench(ctx.h, stack.data_ptr(), copies, prof.data_ptr())
         ctx.sync()
-        ctx.lib.gpn_debug_leaf_prof(ctx.h, None)
         p = prof.cpu().numpy()
         stamps = [int(x) for x in p[:24] if x != 0]
-        print(f"leaf phase cycles [{label}] (load, then [diag32, panel, trailing] x kb, L write, diag inverses, inverse k=2,1,0, winv write):")
-        print("  load:", stamps[0] - int(p[31]), " phases:", [b - a for a, b in zip(stamps[:-1], stamps[1:])], " total:", stamps[-1] - int(p[31]), flush=True)
+        print(f"leaf phase cycles, grid {copies} (D0, then [panel, lookahead+D(kb+1)||trailing] x 3, L write, diag inverses, inverse k=2,1,0, winv write):")
+        print("   phases:", [b - a for a, b in zip(stamps[:-1], stamps[1:])], " total:", stamps[-1] - stamps[0], flush=True)
     for nn in (256, 512, 1024, 2048):
         X = torch.randn(nn, nn, dtype=torch.float64, device=dev)
         S = X @ X.T / nn + torch.eye(nn, dtype=torch.float64, device=dev)
