@@ -74,6 +74,7 @@ class GraphEngine:
         self.N = len(self.nodelist)
         self.device = device
         self._ctx = None
+        self._pos_cache = {}
 
     @property
     def ctx(self) -> Context:
@@ -96,10 +97,21 @@ class GraphEngine:
         return ctx
 
     def positions(self, nodes, relabelled: bool):
-        """graph positions of ``nodes``, de-duplicated and ascending (GPnet.py:305-323 set algebra, A-5)."""
-        if relabelled:
-            return sorted({int(x) for x in nodes})
-        return sorted({self.pos[x] for x in nodes})
+        """graph positions of ``nodes``, de-duplicated and ascending (GPnet.py:305-323 set algebra, A-5).  The optimiser and
+        landscape loops pass the same node list thousands of times: the mapping is memoised on the tuple of nodes."""
+        try:
+            key = (tuple(nodes), bool(relabelled))
+            hit = self._pos_cache.get(key)
+        except TypeError:            # unhashable node labels
+            key, hit = None, None
+        if hit is not None:
+            return hit
+        out = sorted({int(x) for x in nodes}) if relabelled else sorted({self.pos[x] for x in nodes})
+        if key is not None:
+            if len(self._pos_cache) > 8:
+                self._pos_cache.clear()
+            self._pos_cache[key] = out
+        return out
 
     def build_kernel(self, kerneltype: str, theta, want_grad=False):
         """Full N x N kernel resident on the device for these log-parameters (cached per theta)."""
