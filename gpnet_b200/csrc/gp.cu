@@ -549,7 +549,8 @@ enum VEC { V_TRES = 23, V_T = 0, V_Z, V_ALPHA, V_F, V_A, V_B, V_P, V_W, V_SW, V_
 // (~100 us): the busiest tile column has (T/2)^2 k-blocks of ~17 us.  The rest of the GPU is left to the side stream.
 int chain_bound_ctas(int n) {
     const int T = (n + 127) / 128;
-    const int need = (int)(0.25 * T * T * 17.0 / 90.0) + 8;
+    static const double scale = getenv("GPNET_B200_CHAIN_SCALE") ? atof(getenv("GPNET_B200_CHAIN_SCALE")) : 0.7;   // measured flat 0.5-1.0
+    const int need = (int)(scale * 0.25 * T * T * 17.0 / 90.0) + 8;
     return need < 16 ? 16 : need;
 }
 

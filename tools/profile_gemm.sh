@@ -4,7 +4,7 @@
 tag=${1:-r01}
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/bench_plain2_$tag.json 2> gpurun_out/bench_plain2_$tag.err || { echo "plain run failed"; exit 1; }
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'6, .bool.1, .bool.1' --launch-skip 8 -c 1 -o gpurun_out/gemm_lauum_$tag $CMD > gpurun_out/ncu_lauum_$tag.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'6, .bool.1, .bool.1' --launch-skip 8 -c 1 -f -o gpurun_out/gemm_lauum_$tag $CMD > gpurun_out/ncu_lauum_$tag.log 2>&1
 echo "lauum capture rc=$?"
-timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k regex:'6, .bool.1, .bool.1' --launch-skip 13 -c 1 -o gpurun_out/gemm_syrk_$tag $CMD > gpurun_out/ncu_syrk_$tag.log 2>&1
+timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k regex:'6, .bool.1, .bool.1' --launch-skip 13 -c 1 -f -o gpurun_out/gemm_syrk_$tag $CMD > gpurun_out/ncu_syrk_$tag.log 2>&1
 echo "syrk capture rc=$?"
