@@ -50,6 +50,7 @@ SIGNATURES = {
     "gpn_expm_info": (None, [C.c_void_p, c_int_p, c_int_p]),
     "gpn_kernel_block_h": (C.c_int, [C.c_void_p, c_int_p, C.c_int, c_int_p, C.c_int, C.c_double, c_dbl_p]),
     "gpn_gpr_logp_grad": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_int_p]),
+    "gpn_set_fast_paths": (None, [C.c_void_p, C.c_int]),
     "gpn_gpr_predict": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p]),
     "gpn_gpr_fetch": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p]),
     "gpn_gpc_newton": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, C.c_int, C.c_void_p, C.c_long, C.c_double,
@@ -241,6 +242,9 @@ class Context:
             return st, out, 0
         self._check(st, "gpn_gpr_logp_grad")
         return 0, out, info.value
+
+    def set_fast_paths(self, on: bool):
+        self.lib.gpn_set_fast_paths(self.h, int(bool(on)))
 
     def gpr_predict(self, kind, theta, t):
         th, tt = _f64(theta), _f64(t)

@@ -77,6 +77,15 @@ struct gpn_ctx {
     int n_train = 0, n_test = 0;
     DevBuf train_idx, test_idx, tvec;
 
+    // host copies (graph CSR, sorted training positions) and the "training nodes last" permuted graph of the
+    // regularized-Laplacian fast path (built lazily; see gpr_logp_grad_reglap_fast in gp.cu)
+    std::vector<int> h_indptr, h_indices, h_train;
+    std::vector<double> h_weights;
+    bool perm_valid = false;
+    bool train_unique = false;
+    int fast_reglap = 1;                 // GPNET_B200_REGLAP_FAST=0 disables the fast path (A/B timing, tests)
+    DevBuf p_indptr, p_indices, p_weights, p_dinv, iota;
+
     // full-kernel state
     int kind = -1;
     int P = 0;

@@ -595,8 +595,154 @@ int gpr_grad_kernel_block(gpn_ctx* c, int kind, long ldn, const double** G, doub
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Regularized-Laplacian fast path: never forms the full N x N inverse.
+//
+// logPosterior / its gradient only need K[tr,tr] and K[tr,:] of K = (I + beta L~)^-1.  With the training nodes numbered
+// LAST (a symmetric permutation of the graph, done once per node set), M = L L^T and W = L^-1 give
+//     K[tr,:] = W_tt^T [ W_to  W_tt ]          (W_tt = trailing block of W, W_to the block to its left)
+// so the N^3/3 flops of the full W^T W shrink to n^3 (K_to) + n^3/3 (K_tt), and without the gradient only the trailing
+// block of W is needed at all (n^3/3 instead of N^3/3 for the triangular inverse).  The block boundary is rounded down to a
+// multiple of 128 (o2) so that every operand stays aligned with the Cholesky's tiles; the up to 127 extra rows are computed
+// and ignored.  Values agree with the full-inverse path to rounding (different elimination order).
+int ensure_perm(gpn_ctx* c) {
+    if (c->perm_valid) return 0;
+    const int N = c->N, n = c->n_train;
+    std::vector<char> is_train(N, 0);
+    for (int v : c->h_train) is_train[v] = 1;
+    std::vector<int> perm(N), inv(N);
+    int a = 0, b = N - n;
+    for (int v = 0; v < N; ++v) {
+        const int p = is_train[v] ? b++ : a++;
+        perm[v] = p;
+        inv[p] = v;
+    }
+    std::vector<int> pptr(N + 1, 0), pidx(c->h_indices.size());
+    std::vector<double> pw(c->h_weights.size());
+    size_t e = 0;
+    for (int r = 0; r < N; ++r) {
+        const int v = inv[r];
+        for (int q = c->h_indptr[v]; q < c->h_indptr[v + 1]; ++q, ++e) {
+            pidx[e] = perm[c->h_indices[q]];
+            if (!pw.empty()) pw[e] = c->h_weights[q];
+        }
+        pptr[r + 1] = (int)e;
+    }
+    std::vector<int> iota(N);
+    for (int v = 0; v < N; ++v) iota[v] = v;
+    GPN_TRY(gpn_buf_ensure(c, c->p_indptr, sizeof(int) * (size_t)(N + 1)));
+    GPN_TRY(gpn_buf_ensure(c, c->p_indices, sizeof(int) * (pidx.size() + 1)));
+    GPN_TRY(gpn_buf_ensure(c, c->p_dinv, sizeof(double) * (size_t)(2 * N)));
+    GPN_TRY(gpn_buf_ensure(c, c->iota, sizeof(int) * (size_t)N));
+    GPN_TRY(upload(c, c->p_indptr.p, pptr.data(), sizeof(int) * (size_t)(N + 1)));
+    if (!pidx.empty()) GPN_TRY(upload(c, c->p_indices.p, pidx.data(), sizeof(int) * pidx.size()));
+    GPN_TRY(upload(c, c->iota.p, iota.data(), sizeof(int) * (size_t)N));
+    const double* wdev = nullptr;
+    if (!pw.empty()) {
+        GPN_TRY(gpn_buf_ensure(c, c->p_weights, sizeof(double) * pw.size()));
+        GPN_TRY(upload(c, c->p_weights.p, pw.data(), sizeof(double) * pw.size()));
+        wdev = (const double*)c->p_weights.p;
+    }
+    GPN_TRY(gpn_k_degree_dinv(c, N, (const int*)c->p_indptr.p, (const int*)c->p_indices.p, wdev, (double*)c->p_dinv.p));
+    c->perm_valid = true;
+    return 0;
+}
+
+int gpr_logp_grad_reglap_fast(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
+    const int N = c->N, n = c->n_train;
+    GPN_TRY(ensure_perm(c));
+    GPN_TRY(ensure_vecs(c));
+    c->have_full = false;                       // the resident full kernel is NOT formed on this path
+    c->kind = GPN_KERNEL_REGULARIZED_LAPLACIAN;
+    c->P = P;
+    for (int i = 0; i < P; ++i) c->theta_exp[i] = exp(theta_h[i]);
+    c->ldN = pad128(N);
+    GPN_TRY(clear_info(c));
+    const long ld = c->ldN, ldn = pad128(n);
+    const double beta = c->theta_exp[0], noise = c->theta_exp[P - 1];
+    const int o = N - n, o2 = (o / 128) * 128, d = o - o2, n2 = N - o2;
+    for (int i = 0; i < 4; ++i) GPN_TRY(ensure_mat(c, i));
+    double *M = mat(c, 0), *W = mat(c, 1), *TT = mat(c, 2), *WT = mat(c, 3);
+    if (t_h) GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
+    else GPN_CK(cudaMemcpyAsync(vecp(c, V_T), vecp(c, V_TRES), sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    // M = I + beta L~ on the permuted graph; L = chol(M)
+    GPN_TRY(gpn_k_fill_zero(c, M, ld, (int)ld, (int)ld));
+    GPN_TRY(gpn_k_laplacian_scatter(c, N, (const int*)c->p_indptr.p, (const int*)c->p_indices.p,
+                                    c->h_weights.empty() ? nullptr : (const double*)c->p_weights.p, (const double*)c->p_dinv.p, beta, 1.0, M, ld));
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(N) * 128));
+    GPN_TRY(gpn_potrf(c, N, M, ld, (double*)c->winv.p, iscal(c, 0)));
+    const long sub = (long)o2 * ld + o2;
+    GPN_TRY(ensure_nb(c, NB_ROWS1, n2, ld));
+    double* R = nbp(c, NB_ROWS1);                 // rows o2 .. N-1 of K (n2 x N)
+    if (want_grad) {
+        GPN_TRY(gpn_trtri(c, N, M, ld, (const double*)c->winv.p, W, WT, TT, ld));
+        // K[o2:, :o2] = W_tt^T W_to : A[i][k] = W_tt[k][i] = WT[o2+i][o2+k] (k >= i), B[j][k] = W_to[k][j] = WT[j][o2+k]
+        if (o2 > 0) GPN_TRY(gpn_gemm(c, n2, o2, n2, 1.0, WT + sub, ld, true, WT + o2, ld, true, 0.0, R, ld, GF_KLO_M));
+    } else {
+        // only the trailing block of W is needed
+        GPN_TRY(gpn_trtri(c, n2, M + sub, ld, (const double*)c->winv.p + (long)(o2 / 128) * 128 * 128, W + sub, WT + sub, TT + sub, ld));
+    }
+    // K[o2:, o2:] = W_tt^T W_tt (full symmetric block)
+    GPN_TRY(gpn_gemm(c, n2, n2, n2, 1.0, WT + sub, ld, true, WT + sub, ld, true, 0.0, R + o2, ld, GF_LOWER | GF_MIRROR | GF_KLO_M | GF_KLO_N));
+    // K_y = K[tr,tr] + c
+    GPN_TRY(ensure_nb(c, NB_KY, ldn, ldn));
+    GPN_TRY(ensure_nb(c, NB_W, ldn, ldn));
+    GPN_TRY(ensure_nb(c, NB_T, ldn, ldn));
+    GPN_TRY(ensure_nb(c, NB_WT, ldn, ldn));
+    const int* iota = (const int*)c->iota.p;
+    GPN_TRY(gpn_k_gather(c, R + o2, ld, iota + d, n, iota + d, n, noise, nbp(c, NB_KY), ldn));
+    const double* Rtr = R + (long)d * ld;         // the n training rows of K (n x N, K-major)
+    GprFactor f;
+    const double* G = nullptr;
+    bool forked = false;
+    int st;
+    if (want_grad) {
+        cudaStream_t main_stream = c->stream;
+        GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
+        c->potrf_grid_cap = chain_bound_ctas(n);
+        st = gpr_factor_ky(c, &f);
+        c->potrf_grid_cap = 0;
+        if (st != 0) return st;
+        GPN_CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        c->stream = c->stream2;
+        st = ensure_nb(c, NB_G, ldn, ldn);       // (K^2)[tr,tr] = K[tr,:] K[tr,:]^T
+        if (st == 0) st = gpn_gemm(c, n, n, N, 1.0, Rtr, ld, true, Rtr, ld, true, 0.0, nbp(c, NB_G), ldn, GF_LOWER);
+        c->stream = main_stream;
+        if (st != 0) return st;
+        GPN_CK(cudaEventRecord(c->ev_join, c->stream2));
+        G = nbp(c, NB_G);
+        forked = true;
+    } else {
+        GPN_TRY(gpr_factor_ky(c, &f));
+    }
+    GPN_TRY(gpn_k_gemv(c, n, n, f.W, f.ldn, vecp(c, V_T), vecp(c, V_Z), GEMV_LOWER));
+    GPN_TRY(gpn_k_dot(c, n, vecp(c, V_Z), vecp(c, V_Z), dscal(c, Scal::DOT)));
+    GPN_TRY(gpn_k_sumlogdiag(c, n, f.Ky, f.ldn, dscal(c, Scal::LOGDET)));
+    if (want_grad) {
+        GPN_TRY(gpn_k_gemv_t(c, n, n, f.W, f.ldn, vecp(c, V_Z), vecp(c, V_ALPHA), GEMV_LOWER));
+        GPN_TRY(gpn_lauum_t(c, n, f.WT, f.ldn, f.T, f.ldn, false));
+        if (forked) GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        // D0 = (K^2 - K)[tr,tr]: K[tr,tr] is read in place from the training rows (no noise in there)
+        GPN_TRY(gpn_k_grad_trace(c, n, f.T, f.ldn, G, f.ldn, Rtr + o2 + d, ld, 1.0, -1.0, 0.0, vecp(c, V_ALPHA), dscal(c, Scal::TR0)));
+    }
+    double sc[Scal::NDBL];
+    int info[16];
+    GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
+    if (info_h) *info_h = info[1] ? info[1] : info[0];
+    out_h[0] = 0.5 * sc[Scal::DOT] + sc[Scal::LOGDET] + 0.5 * n * LOG_2PI;
+    if (want_grad) {
+        for (int j = 0; j < P; ++j) out_h[1 + j] = 0.0;
+        const double sinv = sc[Scal::TR0], tr0 = sc[Scal::TR1], sa = sc[Scal::TR2];
+        out_h[1 + 0] += -0.5 * tr0;
+        out_h[1 + (P - 1)] += -0.5 * noise * (sa * sa - sinv);
+    }
+    return 0;
+}
+
 int gpr_logp_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
     if (c->n_train <= 0) return -1;
+    if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN && c->fast_reglap && c->train_unique && P >= 1 && P <= 8 && c->n_train < c->N)
+        return gpr_logp_grad_reglap_fast(c, theta_h, P, t_h, want_grad, out_h, info_h);
     int st = kernel_build(c, kind, theta_h, P, want_grad);
     if (st != 0) return st;
     GPN_TRY(ensure_vecs(c));
@@ -965,6 +1111,7 @@ gpn_ctx* gpn_create(int device, void* cuda_stream) {
         return nullptr;
     }
     if (const char* m = getenv("GPNET_B200_POTRF")) c->potrf_mode = (strcmp(m, "recursive") == 0) ? 1 : 0;
+    if (const char* m = getenv("GPNET_B200_REGLAP_FAST")) c->fast_reglap = atoi(m);
     if (cudaMalloc(&c->scal.p, 1024) != cudaSuccess || cudaMallocHost(&c->pinned, 4096) != cudaSuccess) {
         gpn_set_last_error(__FILE__, __LINE__, "initial allocations failed");
         delete c;
@@ -982,7 +1129,7 @@ void gpn_destroy(gpn_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->mat[9] = DevBuf();   // alias slot
     DevBuf* all[] = {&c->indptr, &c->indices, &c->weights, &c->dinv, &c->train_idx, &c->test_idx, &c->tvec, &c->winv, &c->scal, &c->partial,
-                     &c->flags};
+                     &c->flags, &c->p_indptr, &c->p_indices, &c->p_weights, &c->p_dinv, &c->iota};
     for (DevBuf* b : all)
         if (b->p) cudaFree(b->p);
     for (auto& b : c->mat)
@@ -1036,6 +1183,12 @@ int gpn_set_graph(gpn_ctx* c, int N, const int* indptr_h, const int* indices_h, 
     c->ldN = pad128(N);
     c->have_full = false;
     c->n_train = c->n_test = 0;
+    c->h_indptr.assign(indptr_h, indptr_h + N + 1);
+    c->h_indices.assign(indices_h, indices_h + nnz);
+    if (weights_h) c->h_weights.assign(weights_h, weights_h + nnz);
+    else c->h_weights.clear();
+    c->h_train.clear();
+    c->perm_valid = false;
     return gpn_k_degree_dinv(c, N, (const int*)c->indptr.p, (const int*)c->indices.p, (const double*)c->weights.p, (double*)c->dinv.p);
 }
 
@@ -1053,6 +1206,10 @@ int gpn_set_nodes(gpn_ctx* c, int n_train, const int* train_h, int n_test, const
     if (n_test) GPN_TRY(upload(c, c->test_idx.p, test_h, sizeof(int) * (size_t)n_test));
     c->n_train = n_train;
     c->n_test = n_test;
+    c->h_train.assign(train_h, train_h + n_train);
+    std::sort(c->h_train.begin(), c->h_train.end());
+    c->train_unique = std::adjacent_find(c->h_train.begin(), c->h_train.end()) == c->h_train.end();
+    c->perm_valid = false;
     return ensure_vecs(c);
 }
 
@@ -1090,6 +1247,9 @@ int gpn_debug_leaf_bench(gpn_ctx* c, void* A_dev, int copies, void* prof32_dev) 
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)copies * 128 * 128));
     GPN_TRY(clear_info(c));
     return gpn_leaf_bench(c, (double*)A_dev, copies, (double*)c->winv.p, iscal(c, 0), (long long*)prof32_dev);
+}
+void gpn_set_fast_paths(gpn_ctx* c, int on) {
+    if (c) c->fast_reglap = on ? 1 : 0;
 }
 void gpn_debug_df_trace(gpn_ctx* c, void* dev_buf) {
     if (c) c->df_trace = dev_buf;

@@ -105,6 +105,10 @@ int gpn_gpr_predict(gpn_ctx* ctx, int kind, const double* theta_h, int P, const 
 /* after gpn_gpr_predict: which = 0 k (n x n), 1 kstar (m x n), 2 L (n x n), 3 v (n x m), 4 kstarstar (m x m) */
 int gpn_gpr_fetch(gpn_ctx* ctx, int which, double* out_h);
 
+/* The regularized-Laplacian log-likelihood path numbers the training nodes last and never forms the full N x N inverse
+ * (only K[tr,:] is needed); on = 0 forces the full-kernel route (A/B comparisons, tests).  Default: on. */
+void gpn_set_fast_paths(gpn_ctx* ctx, int on);
+
 /* ---- GP classification, Laplace approximation (GPnetClassifier.py:90-147,184-240) ---------------------------- */
 /* Newton loop on K = kernel(train,train) (built from theta unless K_dev != NULL, in which case the n x n device
  * matrix is used as is -- the notebook KAT path).  variant 0 = GPnetClassifier.py:138-145 logq, 1 = the older
