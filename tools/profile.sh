@@ -8,7 +8,7 @@ $CMD > gpurun_out/bench_plain_$tag.json 2> gpurun_out/bench_plain_$tag.err || { 
 cat gpurun_out/bench_plain_$tag.json
 L=$(python -c "import json;print(json.loads(open('gpurun_out/bench_plain_$tag.json').read().strip().splitlines()[-1])['gpu_launches']//2)")
 echo "launches per step: $L"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3*L+2)) -c $L --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_launch_$tag.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^(?!dmma_peak)' -s $((3*L)) -c $L --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_launch_$tag.log 2>&1
 echo "launch list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:potrf_dataflow -c 1 -f -o gpurun_out/potrf_$tag $CMD > gpurun_out/ncu_potrf_$tag.log 2>&1
 echo "potrf capture rc=$?"
