@@ -257,31 +257,62 @@ def main():
     e2e_value = world * K / e2e_s
     assert abs(val - out[0]) <= 1e-12 * abs(val)
 
-    # ---- roofline of the dominant kernel (gemm_f64_kernel, 128x128 configuration): per-launch CUDA events ---------
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the context's stream over one extra (untimed) step ----
     roof = None
     cpu = None
+    routes = None
     if rank == 0:
         ctx.set_profile(True)
         ctx.gpr_logp_grad(kind, theta, None, True)
         prof = ctx.profile_summary()
         ctx.set_profile(False)
         algo = algorithmic_flops(N, n)
-        big_tf = prof["big_flops"] / (prof["big_ms"] * 1e-3) * 1e-12 if prof["big_ms"] > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_f64_kernel<2,4,6,*,*> (TMA + DMMA.8x8x4, 128x128x16 tiles)",
-                "achieved": big_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": big_tf / peak_tf if peak_tf else None,
+        cands = {
+            "gemm_f64_kernel<2,4,6,*,*> (TMA + DMMA.8x8x4, 128x128x16 tiles)": (prof["big_ms"], prof["big_flops"], prof["big_launches"]),
+            "potrf_dataflow_kernel (persistent tile-dataflow Cholesky, TMA + DMMA.8x8x4)": (prof["potrf_ms"], prof["potrf_flops"],
+                                                                                             prof["potrf_launches"]),
+        }
+        kname = max(cands, key=lambda k: cands[k][0])
+        k_ms, k_fl, k_cnt = cands[kname]
+        k_tf = k_fl / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": kname,
+                "achieved": k_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": k_tf / peak_tf if peak_tf else None,
                 "peak_source": "measured in this run: register-resident DMMA.8x8x4 loop (gpn_fp64_peak); MEASURED_PEAKS.json has no "
                                "FP64 entry; nominal B200 FP64 is 40 TFLOP/s (37.2 at 148 SM x 64 FMA/clk x 1.965 GHz)",
-                "flops_per_launch_avg": prof["big_flops"] / max(prof["big_launches"], 1),
-                "launch_ms_avg": prof["big_ms"] / max(prof["big_launches"], 1), "launches_per_step": prof["big_launches"],
-                "kernel_share_of_step": prof["gemm_ms"] / ms_step,
-                # utilisation is claimed from EXECUTED flops only (SURVEY 8d rule): the regularized-Laplacian fast path never
-                # forms the full inverse, so it executes fewer flops than the conventional count below
+                "flops_per_launch_avg": k_fl / max(k_cnt, 1), "launch_ms_avg": k_ms / max(k_cnt, 1), "launches_per_step": k_cnt,
+                "kernel_share_of_step": k_ms / ms_step,
+                "other_kernels": {k: {"ms_per_step": v[0], "tflops": v[1] / (v[0] * 1e-3) * 1e-12 if v[0] > 0 else None,
+                                      "launches": v[2], "share_of_step": v[0] / ms_step} for k, v in cands.items() if k != kname},
+                # utilisation is claimed from EXECUTED flops only (SURVEY 8d rule): the default route of this workload reads
+                # K_tt^-1 off the Cholesky factor and executes about half of the conventional count below
                 "step_executed_tflops": exec_flops / (ms_step * 1e-3) * 1e-12,
                 "step_executed_frac_of_measured_peak": exec_flops / (ms_step * 1e-3) * 1e-12 / peak_tf if peak_tf else None,
                 "step_executed_frac_of_nominal_40tf": exec_flops / (ms_step * 1e-3) * 1e-12 / 40.0,
                 "executed_gflop_per_step": exec_flops * 1e-9,
                 "conventional_gflop_per_step": algo * 1e-9,
                 "step_conventional_tflops": algo / (ms_step * 1e-3) * 1e-12, "traffic": None}
+        # the same evaluation through the two other exact routes (same outputs to rounding), device-timed like `value`
+        if world == 1:
+            routes = {}
+            names = {0: "full_kernel (K formed, gathered, K_y factored: the reference's order of operations)",
+                     1: "block (training nodes last, only K[tr,:] formed)", 2: "schur (default)"}
+            for level in (0, 1):
+                ctx.set_fast_paths(level)
+                for _ in range(2):
+                    o2 = ctx.gpr_logp_grad(kind, theta, None, True)[1]
+                ctx.reset_counters()
+                kk = max(4, K // 4)
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record(stream)
+                for _ in range(kk):
+                    ctx.gpr_logp_grad(kind, theta, None, True)
+                r1.record(stream)
+                torch.cuda.synchronize()
+                ms = r0.elapsed_time(r1) / kk
+                routes[names[level]] = {"value": 1e3 / ms, "ms_per_step": ms, "executed_gflop_per_step": ctx.flop_count() / kk * 1e-9,
+                                        "max_rel_diff_vs_default": float(np.max(np.abs(o2 - out) / np.abs(out)))}
+            ctx.set_fast_paths(2)
+            routes[names[2]] = {"value": value, "ms_per_step": ms_step, "executed_gflop_per_step": exec_flops * 1e-9}
         if world == 1 and not args.no_cpu_baseline:
             dt, cval = cpu_port_eval(problem, N, reference_style=False)
             cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": blas_threads(), "kind": "port",
@@ -297,6 +328,8 @@ def main():
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (n + P) + 4 * 0,
                                           "d2h_bytes_per_step": 8 * 32 + 4 * 16},
                 "gpu_launches": int(launches), "roofline": roof}
+        if routes is not None:
+            line["routes"] = routes
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

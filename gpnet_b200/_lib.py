@@ -174,10 +174,10 @@ class Context:
         self.lib.gpn_set_profile(self.h, int(bool(on)))
 
     def profile_summary(self):
-        out = np.zeros(6)
+        out = np.zeros(9)
         self._check(self.lib.gpn_profile_summary(self.h, _dp(out)), "gpn_profile_summary")
         return dict(gemm_ms=out[0], gemm_flops=out[1], gemm_launches=int(out[2]), big_ms=out[3], big_flops=out[4],
-                    big_launches=int(out[5]))
+                    big_launches=int(out[5]), potrf_ms=out[6], potrf_flops=out[7], potrf_launches=int(out[8]))
 
     # -- device-pointer primitives (pointers are ints, e.g. torch.Tensor.data_ptr()) --------------------
     def laplacian_dense(self, alpha, gamma, out_ptr, ld):
@@ -243,8 +243,9 @@ class Context:
         self._check(st, "gpn_gpr_logp_grad")
         return 0, out, info.value
 
-    def set_fast_paths(self, on: bool):
-        self.lib.gpn_set_fast_paths(self.h, int(bool(on)))
+    def set_fast_paths(self, level=True):
+        """Route of the regularized-Laplacian regressor likelihood: 0/False full kernel, 1 block path, 2/True Schur path."""
+        self.lib.gpn_set_fast_paths(self.h, 2 if level is True else int(level))
 
     def gpr_predict(self, kind, theta, t):
         th, tt = _f64(theta), _f64(t)

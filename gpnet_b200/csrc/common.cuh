@@ -52,6 +52,7 @@ struct ProfEvent {
     cudaEvent_t e0, e1;
     double flops;
     bool big;
+    int kind = 0;   // 0 GEMM launch, 2 dataflow Cholesky
 };
 
 struct gpn_ctx {
@@ -83,7 +84,7 @@ struct gpn_ctx {
     std::vector<double> h_weights;
     bool perm_valid = false;
     bool train_unique = false;
-    int fast_reglap = 1;                 // GPNET_B200_REGLAP_FAST=0 disables the fast path (A/B timing, tests)
+    int fast_reglap = 2;                 // regressor, regularized Laplacian: 0 full kernel, 1 block path, 2 Schur path (GPNET_B200_REGLAP_FAST)
     DevBuf p_indptr, p_indices, p_weights, p_dinv, iota;
 
     // full-kernel state
@@ -149,6 +150,10 @@ int gpn_k_gemv_t(gpn_ctx* c, int rows, int cols, const double* A, long lda, cons
 int gpn_k_dot(gpn_ctx* c, int n, const double* x, const double* y, double* d_out);
 int gpn_k_sum(gpn_ctx* c, int n, const double* x, double* d_out);
 int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out);
+int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v);
+int gpn_k_trap_pass(gpn_ctx* c, int rows, int cols, int off, const double* Wb, long ld, const double* ya, const double* yb, double* za,
+                    double* zb, double* d_fro);
+int gpn_k_multi_dot(gpn_ctx* c, int count, const double* const* x, const double* const* y, const int* n, double* d_out);
 int gpn_k_colnorm2(gpn_ctx* c, int rows, int cols, const double* V, long ld, double* out);
 int gpn_k_diag_gather(gpn_ctx* c, const double* K, long ld, const int* idx, int m, double addc, double* out);
 int gpn_k_grad_trace(gpn_ctx* c, int n, const double* Kinv, long ldi, const double* G, long ldg, const double* Ktt, long ldk,

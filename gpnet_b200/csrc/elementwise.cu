@@ -225,6 +225,52 @@ __global__ void sumlogdiag_kernel(int n, const double* __restrict__ A, long ld, 
     if (threadIdx.x == 0) *out = s;
 }
 
+// ---- Schur path of the regularized-Laplacian regressor: one pass over the bottom block-row Wb (rows x cols) of a lower-
+//      triangular inverse, row r being nonzero for col <= off + r:  za = Wb^T ya, zb = Wb^T yb (pre-zeroed; atomics over row
+//      blocks) and fro += sum Wb^2.  Each thread owns one column (coalesced rows).
+__global__ void trap_pass_kernel(int rows, int cols, int off, const double* __restrict__ Wb, long ld, const double* __restrict__ ya,
+                                 const double* __restrict__ yb, double* __restrict__ za, double* __restrict__ zb,
+                                 double* __restrict__ fro, int rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    double sa = 0.0, sb = 0.0, sf = 0.0;
+    if (c < cols) {
+        r0 = max(r0, c - off);
+#pragma unroll 8
+        for (int r = r0; r < r1; ++r) {
+            const double w = Wb[(long)r * ld + c];
+            sa += w * ya[r];
+            sb += w * yb[r];
+            sf += w * w;
+        }
+        if (r1 > r0) {
+            atomicAdd(&za[c], sa);
+            atomicAdd(&zb[c], sb);
+        }
+    }
+    sf = block_sum(sf);
+    if (threadIdx.x == 0 && sf != 0.0) atomicAdd(fro, sf);
+}
+// several dot products in one launch: block b computes out[b] = x_b . y_b
+struct DotBatch {
+    const double* x[8];
+    const double* y[8];
+    int n[8];
+};
+__global__ void multi_dot_kernel(DotBatch b, double* __restrict__ out) {
+    const double *x = b.x[blockIdx.x], *y = b.y[blockIdx.x];
+    const int n = b.n[blockIdx.x];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i] * y[i];
+    s = block_sum(s);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+__global__ void fill_vec_kernel(int n, double* y, double v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = v;
+}
+
 // ---- K9: column squared norms of V (rows x cols): out[c] = sum_r V[r][c]^2 -------------------------------------------
 __global__ void colnorm2_kernel(int rows, int cols, const double* __restrict__ V, long ld, double* __restrict__ out, int rows_per_block) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,6 +449,36 @@ int gpn_k_sum(gpn_ctx* c, int n, const double* x, double* d_out) {
 }
 int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out) {
     sumlogdiag_kernel<<<1, 1024, 0, c->stream>>>(n, A, ld, d_out);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v) {
+    if (n <= 0) return 0;
+    fill_vec_kernel<<<grid1(n), TPB, 0, c->stream>>>(n, y, v);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_trap_pass(gpn_ctx* c, int rows, int cols, int off, const double* Wb, long ld, const double* ya, const double* yb, double* za,
+                    double* zb, double* d_fro) {
+    // za and zb are contiguous (zb = za + cols rounded by the caller) or separate: zero both, and the scalar
+    zero_vec_kernel<<<grid1(cols), TPB, 0, c->stream>>>(cols, za);
+    LAUNCHED(c);
+    zero_vec_kernel<<<grid1(cols), TPB, 0, c->stream>>>(cols, zb);
+    LAUNCHED(c);
+    zero_vec_kernel<<<1, 32, 0, c->stream>>>(1, d_fro);
+    LAUNCHED(c);
+    if (rows <= 0 || cols <= 0) return 0;
+    const int rpb = 64;
+    dim3 grid(grid1(cols, 128), (rows + rpb - 1) / rpb);
+    trap_pass_kernel<<<grid, 128, 0, c->stream>>>(rows, cols, off, Wb, ld, ya, yb, za, zb, d_fro, rpb);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_multi_dot(gpn_ctx* c, int count, const double* const* x, const double* const* y, const int* n, double* d_out) {
+    if (count <= 0 || count > 8) return -1;
+    DotBatch b;
+    for (int i = 0; i < count; ++i) { b.x[i] = x[i]; b.y[i] = y[i]; b.n[i] = n[i]; }
+    multi_dot_kernel<<<count, 1024, 0, c->stream>>>(b, d_out);
     LAUNCHED(c);
     return 0;
 }

@@ -48,7 +48,7 @@ enum NB {
 static_assert(NB_COUNT <= 16, "nb[] too small");
 
 struct Scal {           // layout of c->scal (doubles), followed by ints
-    enum { DOT = 0, LOGDET, SUM, TR0, TR1, TR2, CONV, Q, LIK, AF, NORM0, NORM1, NORM2, NORM3, NDBL = 32 };
+    enum { DOT = 0, LOGDET, SUM, TR0, TR1, TR2, CONV, Q, LIK, AF, NORM0, NORM1, NORM2, NORM3, SCH0 /* 6 dots */, FRO = SCH0 + 6, NDBL = 32 };
 };
 
 double* dscal(gpn_ctx* c, int i) { return (double*)c->scal.p + i; }
@@ -739,10 +739,83 @@ int gpr_logp_grad_reglap_fast(gpn_ctx* c, const double* theta_h, int P, const do
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Regularized-Laplacian Schur path: no kernel block is formed at all.
+//
+// With the training nodes numbered last and M = I + beta L~ = L L^T, the trailing block of the factor IS the factor of the
+// inverse training block: K_tt^-1 = M_tt - M_to M_oo^-1 M_ot = L_tt L_tt^T.  K_y = K_tt + c 1 1^T (noise on every entry,
+// quirk A-3) is a rank-one update of it, so with r_1 = L_tt^T 1, r_t = L_tt^T t, s = r_1.r_1, a = r_1.r_t:
+//     K_y^-1 = S - c (S1)(S1)^T / (1 + c s),  S = L_tt L_tt^T;     t^T K_y^-1 t = r_t.r_t - c a^2 / (1 + c s)
+//     (1/2) log det K_y = -sum log diag(L_tt) + (1/2) log1p(c s)
+// i.e. -logp costs ONE Cholesky of M plus two triangular GEMVs.  The gradient needs the bottom block-row Wb = (L^-1)[tr,:]:
+//     D = dK_y/dtheta_0 = (K^2 - K)[tr,tr],  K[:,tr] x = Wb^T (W_tt x),  K_tt = W_tt^T W_tt,  W_tt L_tt = I
+//     x^T D x' = z_x.z_x' - y_x.y_x'   with  y_x = W_tt x, z_x = Wb^T y_x;   for x = S t: y = r_t;  for x = S 1: y = r_1
+//     tr(S D) = ||Wb||_F^2 - n,   tr(K_y^-1 D) = tr(S D) - c/(1 + c s) (S1)^T D (S1)
+// so after the triangular inverse one HBM pass over Wb (two transposed GEMVs + a Frobenius norm) finishes the job:
+// N^3/3 + N^3/3 flops instead of N^3 + n^2 N + n^3.  All scalar algebra happens on the host from nine reductions.
+int gpr_logp_grad_reglap_schur(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
+    const int N = c->N, n = c->n_train;
+    GPN_TRY(ensure_perm(c));
+    GPN_TRY(ensure_vecs(c));
+    c->have_full = false;
+    c->kind = GPN_KERNEL_REGULARIZED_LAPLACIAN;
+    c->P = P;
+    for (int i = 0; i < P; ++i) c->theta_exp[i] = exp(theta_h[i]);
+    c->ldN = pad128(N);
+    GPN_TRY(clear_info(c));
+    const long ld = c->ldN;
+    const double beta = c->theta_exp[0], noise = c->theta_exp[P - 1];
+    const int o = N - n;
+    for (int i = 0; i < (want_grad ? 4 : 1); ++i) GPN_TRY(ensure_mat(c, i));
+    double* M = mat(c, 0);
+    if (t_h) GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
+    else GPN_CK(cudaMemcpyAsync(vecp(c, V_T), vecp(c, V_TRES), sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    GPN_TRY(gpn_k_fill_zero(c, M, ld, (int)ld, (int)ld));
+    GPN_TRY(gpn_k_laplacian_scatter(c, N, (const int*)c->p_indptr.p, (const int*)c->p_indices.p,
+                                    c->h_weights.empty() ? nullptr : (const double*)c->p_weights.p, (const double*)c->p_dinv.p, beta, 1.0, M, ld));
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(N) * 128));
+    GPN_TRY(gpn_potrf(c, N, M, ld, (double*)c->winv.p, iscal(c, 0)));
+    const double* Ltt = M + (long)o * ld + o;
+    double *ones = vecp(c, V_U), *r1 = vecp(c, V_Z), *rt = vecp(c, V_Z2);
+    GPN_TRY(gpn_k_fill_vec(c, n, ones, 1.0));
+    GPN_TRY(gpn_k_gemv_t(c, n, n, Ltt, ld, ones, r1, GEMV_LOWER));
+    GPN_TRY(gpn_k_gemv_t(c, n, n, Ltt, ld, vecp(c, V_T), rt, GEMV_LOWER));
+    GPN_TRY(gpn_k_sumlogdiag(c, n, Ltt, ld, dscal(c, Scal::LOGDET)));
+    const double *dx[6] = {r1, r1, rt}, *dy[6] = {r1, rt, rt};
+    int dn[6] = {n, n, n, N, N, N};
+    if (want_grad) {
+        double *W = mat(c, 1), *TT = mat(c, 2), *WT = mat(c, 3);
+        GPN_TRY(gpn_trtri(c, N, M, ld, (const double*)c->winv.p, W, WT, TT, ld));
+        GPN_TRY(ensure_nb(c, NB_S, 2, ld));
+        double *z1 = nbp(c, NB_S), *zt = z1 + ld;
+        GPN_TRY(gpn_k_trap_pass(c, n, N, o, W + (long)o * ld, ld, r1, rt, z1, zt, dscal(c, Scal::FRO)));
+        dx[3] = z1; dy[3] = z1; dx[4] = z1; dy[4] = zt; dx[5] = zt; dy[5] = zt;
+    }
+    GPN_TRY(gpn_k_multi_dot(c, want_grad ? 6 : 3, dx, dy, dn, dscal(c, Scal::SCH0)));
+    double sc[Scal::NDBL];
+    int info[16];
+    GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
+    if (info_h) *info_h = info[0];
+    const double s = sc[Scal::SCH0], a = sc[Scal::SCH0 + 1], tSt = sc[Scal::SCH0 + 2];
+    const double den = 1.0 + noise * s, mu = noise * a / den;
+    out_h[0] = 0.5 * (tSt - mu * a) + (-sc[Scal::LOGDET] + 0.5 * log1p(noise * s)) + 0.5 * n * LOG_2PI;
+    if (want_grad) {
+        for (int j = 0; j < P; ++j) out_h[1 + j] = 0.0;
+        const double D11 = sc[Scal::SCH0 + 3] - s, D1t = sc[Scal::SCH0 + 4] - a, Dtt = sc[Scal::SCH0 + 5] - tSt;
+        const double aDa = Dtt - 2.0 * mu * D1t + mu * mu * D11;
+        const double trKD = (sc[Scal::FRO] - n) - noise / den * D11;
+        out_h[1 + 0] += -(0.5 * aDa - 0.5 * trKD);
+        const double sa = a / den, sinv = s / den;                               // 1^T alpha, 1^T K_y^-1 1
+        out_h[1 + (P - 1)] += -0.5 * noise * (sa * sa - sinv);
+    }
+    return 0;
+}
+
 int gpr_logp_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
     if (c->n_train <= 0) return -1;
     if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN && c->fast_reglap && c->train_unique && P >= 1 && P <= 8 && c->n_train < c->N)
-        return gpr_logp_grad_reglap_fast(c, theta_h, P, t_h, want_grad, out_h, info_h);
+        return c->fast_reglap >= 2 ? gpr_logp_grad_reglap_schur(c, theta_h, P, t_h, want_grad, out_h, info_h)
+                                   : gpr_logp_grad_reglap_fast(c, theta_h, P, t_h, want_grad, out_h, info_h);
     int st = kernel_build(c, kind, theta_h, P, want_grad);
     if (st != 0) return st;
     GPN_TRY(ensure_vecs(c));
@@ -1248,8 +1321,8 @@ int gpn_debug_leaf_bench(gpn_ctx* c, void* A_dev, int copies, void* prof32_dev) 
     GPN_TRY(clear_info(c));
     return gpn_leaf_bench(c, (double*)A_dev, copies, (double*)c->winv.p, iscal(c, 0), (long long*)prof32_dev);
 }
-void gpn_set_fast_paths(gpn_ctx* c, int on) {
-    if (c) c->fast_reglap = on ? 1 : 0;
+void gpn_set_fast_paths(gpn_ctx* c, int level) {
+    if (c) c->fast_reglap = level < 0 ? 0 : (level > 2 ? 2 : level);
 }
 void gpn_debug_df_trace(gpn_ctx* c, void* dev_buf) {
     if (c) c->df_trace = dev_buf;
@@ -1266,15 +1339,16 @@ void gpn_set_profile(gpn_ctx* c, int on) {
     c->prof_events.clear();
 }
 
-/* out_h[0] = summed duration (ms) of the GEMM launches recorded since gpn_set_profile(ctx,1), out_h[1] = their executed
- * flops, out_h[2] = number of launches, out_h[3] = same three restricted to the 128x128 configuration: ms, [4] flops, [5] count */
+/* out_h[0..2] = summed duration (ms), executed flops and count of the GEMM launches recorded since gpn_set_profile(ctx,1);
+ * out_h[3..5] = the same restricted to the 128x128 GEMM configuration; out_h[6..8] = the same for the dataflow Cholesky. */
 int gpn_profile_summary(gpn_ctx* c, double* out_h) {
     if (!c) return -1;
     GPN_CK(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < 6; ++i) out_h[i] = 0.0;
+    for (int i = 0; i < 9; ++i) out_h[i] = 0.0;
     for (auto& p : c->prof_events) {
         float ms = 0.f;
         GPN_CK(cudaEventElapsedTime(&ms, p.e0, p.e1));
+        if (p.kind == 2) { out_h[6] += ms; out_h[7] += p.flops; out_h[8] += 1; continue; }
         out_h[0] += ms; out_h[1] += p.flops; out_h[2] += 1;
         if (p.big) { out_h[3] += ms; out_h[4] += p.flops; out_h[5] += 1; }
     }

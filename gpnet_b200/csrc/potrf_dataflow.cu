@@ -368,11 +368,26 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
     int grid = ntasks < c->num_sms ? ntasks : c->num_sms;
     if (c->potrf_grid_cap > 0 && grid > c->potrf_grid_cap) grid = c->potrf_grid_cap;   // leave SMs to concurrent work
     void* args[] = {(void*)&tl, (void*)&tw, (void*)&a};
-    GPN_CK(cudaLaunchCooperativeKernel((const void*)potrf_dataflow_kernel, dim3(grid), dim3(384), args, DF_SMEM, c->stream));
-    c->launches++;
-    // executed flops: every task runs j k-blocks of 128^3 MACs (+ the in-CTA trsm / leaf)
+    // executed flops: an off-diagonal task runs j k-blocks of 128^3 MACs, a diagonal one only the 136 of 256 8x8 blocks that
+    // touch the lower triangle; the in-CTA trsm skips the zero k-steps of W_j (36 of 64); leaf = factor + inverse
     double kb = 0.0;
-    for (int j = 0; j < T; ++j) kb += (double)(T - j) * j + (T - j - 1);
-    c->flops += 2.0 * kb * TB * TB * TB;
+    for (int j = 0; j < T; ++j) kb += (double)(T - j - 1) * j + j * (136.0 / 256.0) + (T - j - 1) * (36.0 / 64.0) + 1.0 / 3.0;
+    const double fl = 2.0 * kb * TB * TB * TB;
+    ProfEvent pe;
+    if (c->profile) {
+        cudaEventCreate(&pe.e0);
+        cudaEventCreate(&pe.e1);
+        pe.flops = fl;
+        pe.big = false;
+        pe.kind = 2;
+        cudaEventRecord(pe.e0, c->stream);
+    }
+    GPN_CK(cudaLaunchCooperativeKernel((const void*)potrf_dataflow_kernel, dim3(grid), dim3(384), args, DF_SMEM, c->stream));
+    if (c->profile) {
+        cudaEventRecord(pe.e1, c->stream);
+        c->prof_events.push_back(pe);
+    }
+    c->launches++;
+    c->flops += fl;
     return 0;
 }

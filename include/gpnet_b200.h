@@ -38,8 +38,9 @@ double gpn_flop_count(gpn_ctx* ctx);
 void gpn_reset_counters(gpn_ctx* ctx);
 
 /* measurement hooks (bench.py): sustained FP64 tensor (DMMA.8x8x4) issue-rate ceiling of this GPU, measured for
- * about `seconds`; per-launch CUDA-event profiling of the GEMM kernel (out_h[0..2]: ms, executed flops, launches of
- * all GEMM launches since gpn_set_profile(ctx,1); out_h[3..5]: the same for the 128x128 configuration only). */
+ * about `seconds`; per-launch CUDA-event profiling of the flop-carrying kernels (out_h[0..2]: ms, executed flops, launches
+ * of all GEMM launches since gpn_set_profile(ctx,1); out_h[3..5]: the same for the 128x128 GEMM configuration only;
+ * out_h[6..8]: the same for the dataflow Cholesky kernel; out_h has 9 entries). */
 int gpn_fp64_peak(gpn_ctx* ctx, double seconds, double* tflops_h);
 void gpn_set_profile(gpn_ctx* ctx, int on);
 int gpn_profile_summary(gpn_ctx* ctx, double* out_h);
@@ -105,9 +106,12 @@ int gpn_gpr_predict(gpn_ctx* ctx, int kind, const double* theta_h, int P, const 
 /* after gpn_gpr_predict: which = 0 k (n x n), 1 kstar (m x n), 2 L (n x n), 3 v (n x m), 4 kstarstar (m x m) */
 int gpn_gpr_fetch(gpn_ctx* ctx, int which, double* out_h);
 
-/* The regularized-Laplacian log-likelihood path numbers the training nodes last and never forms the full N x N inverse
- * (only K[tr,:] is needed); on = 0 forces the full-kernel route (A/B comparisons, tests).  Default: on. */
-void gpn_set_fast_paths(gpn_ctx* ctx, int on);
+/* Route of gpn_gpr_logp_grad for the regularized-Laplacian kernel (all three agree to rounding):
+ *   0  full kernel: K = (I + beta L~)^-1 formed, block gathered, K_y factored (the reference's own order of operations);
+ *   1  block path: training nodes numbered last, only K[tr,:] formed from the triangular inverse;
+ *   2  Schur path (default): K_tt^-1 = L_tt L_tt^T is read off the Cholesky factor of I + beta L~, the all-entries noise
+ *      term is a rank-one update, and the gradient traces reduce to norms of the bottom block-row of L^-1. */
+void gpn_set_fast_paths(gpn_ctx* ctx, int level);
 
 /* ---- GP classification, Laplace approximation (GPnetClassifier.py:90-147,184-240) ---------------------------- */
 /* Newton loop on K = kernel(train,train) (built from theta unless K_dev != NULL, in which case the n x n device

@@ -233,8 +233,9 @@ def test_full_size_properties_c3_reglap(gpu_ctx):
 
 @pytest.mark.parametrize("shape", [(20, 13, 100), (37, 29, 300), (40, 40, 800), (32, 32, 1023)])
 def test_reglap_fast_path_equals_full_path(gpu_ctx, shape):
-    """The training-nodes-last path (no full inverse) against the full-kernel route on the same inputs, ragged block
-    boundaries included (N - n not a multiple of 128), with and without the gradient."""
+    """The training-nodes-last routes (1: only K[tr,:] formed; 2: Schur complement read off the Cholesky factor, no kernel
+    block formed) against the full-kernel route on the same inputs, ragged block boundaries included (N - n not a multiple
+    of 128), with and without the gradient."""
     a, b, n = shape
     N = a * b
     indptr, indices, w = cfg.grid_csr_fast(a, b)
@@ -245,15 +246,18 @@ def test_reglap_fast_path_equals_full_path(gpu_ctx, shape):
     th = np.log([0.7, 0.05])
     res = {}
     try:
-        for fast in (True, False):
-            gpu_ctx.set_fast_paths(fast)
-            res[fast] = (gpu_ctx.gpr_logp_grad(1, th, t, True), gpu_ctx.gpr_logp_grad(1, th, t, False))
+        for level in (2, 1, 0):
+            gpu_ctx.set_fast_paths(level)
+            res[level] = (gpu_ctx.gpr_logp_grad(1, th, t, True), gpu_ctx.gpr_logp_grad(1, th, t, False))
     finally:
         gpu_ctx.set_fast_paths(True)
-    (s1, g1, i1), (_, l1, _) = res[True]
-    (s0, g0, i0), (_, l0, _) = res[False]
-    assert s1 == 0 and s0 == 0 and i1 == 0 and i0 == 0
-    assert nrel(g1, g0) <= 1e-11 and abs(l1[0] - l0[0]) <= 1e-12 * abs(l0[0]) and abs(g1[0] - l1[0]) <= 1e-12 * abs(l1[0])
+    (s0, g0, i0), (_, l0, _) = res[0]
+    assert s0 == 0 and i0 == 0
+    for level in (1, 2):
+        (s1, g1, i1), (_, l1, _) = res[level]
+        assert s1 == 0 and i1 == 0
+        assert nrel(g1, g0) <= 1e-11, (level, g1, g0)
+        assert abs(l1[0] - l0[0]) <= 1e-12 * abs(l0[0]) and abs(g1[0] - l1[0]) <= 1e-12 * abs(l1[0])
 
 
 def test_diffusion_semigroup_property_n4096(gpu_ctx):
