@@ -60,6 +60,8 @@ SIGNATURES = {
     "gpn_gpc_grad": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_dbl_p, c_int_p, c_int_p]),
     "gpn_landscape": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dbl_p, C.c_int, C.c_int, C.c_int, c_dbl_p, C.c_int, c_dbl_p,
                                 C.c_int, c_dbl_p, C.c_long, C.c_long, C.c_long, C.c_int, c_dbl_p]),
+    "gpn_landscape_points": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dbl_p, C.c_int, C.c_int, C.c_int, c_dbl_p, C.c_int, c_dbl_p,
+                                       C.c_int, c_dbl_p, C.POINTER(C.c_long), C.c_long, C.c_int, c_dbl_p]),
 }
 
 _lib = None
@@ -321,4 +323,18 @@ class Context:
             if st in (-100, -101):
                 return st, out
             self._check(st, "gpn_landscape")
+        return 0, out
+
+    def landscape_points(self, kind, classifier, theta, axidx, ax1, ax2, t, indices, want_grad=False):
+        """(status, (len(indices), 1+P) array) for an explicit list of flat grid indices (i1*len(ax2) + i2)."""
+        th, a1, a2, tt = _f64(theta), _f64(ax1), _f64(ax2), _f64(t)
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        out = np.zeros((len(idx), 1 + len(th)), dtype=np.float64)
+        if len(idx):
+            st = self.lib.gpn_landscape_points(self.h, kind, int(classifier), _dp(th), len(th), int(axidx[0]), int(axidx[1]), _dp(a1),
+                                               len(a1), _dp(a2), len(a2), _dp(tt), idx.ctypes.data_as(C.POINTER(C.c_long)), len(idx),
+                                               int(want_grad), _dp(out))
+            if st in (-100, -101):
+                return st, out
+            self._check(st, "gpn_landscape_points")
         return 0, out

@@ -225,6 +225,36 @@ __global__ void sumlogdiag_kernel(int n, const double* __restrict__ A, long ld, 
     if (threadIdx.x == 0) *out = s;
 }
 
+// ---- noise-independent gradient reductions (landscape rows): with S lower-stored symmetric, D = g_scale*G + k_scale*Ktt,
+//      out[0] = sum_ij S_ij D_ij, out[1] = x1^T D x1, out[2] = x1^T D xt, out[3] = xt^T D xt  (out pre-zeroed) --------------
+__global__ void bilinear_trace_kernel(int n, const double* __restrict__ S, long lds, const double* __restrict__ G, long ldg,
+                                      const double* __restrict__ Ktt, long ldk, double g_scale, double k_scale,
+                                      const double* __restrict__ x1, const double* __restrict__ xt, double* __restrict__ out) {
+    const int r = blockIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const double a1 = x1[r], at = xt[r];
+    for (int c = threadIdx.x; c <= r; c += blockDim.x) {
+        const double w = (c == r) ? 1.0 : 2.0;
+        double d = 0.0;
+        if (G) d += g_scale * G[(long)r * ldg + c];
+        if (Ktt) d += k_scale * Ktt[(long)r * ldk + c];
+        const double b1 = x1[c], bt = xt[c];
+        s0 += w * S[(long)r * lds + c] * d;
+        s1 += w * a1 * b1 * d;
+        s2 += (c == r ? a1 * bt : a1 * bt + at * b1) * d;
+        s3 += w * at * bt * d;
+    }
+    s0 = block_sum(s0);
+    s1 = block_sum(s1);
+    s2 = block_sum(s2);
+    s3 = block_sum(s3);
+    if (threadIdx.x == 0) {
+        atomicAdd(&out[0], s0);
+        atomicAdd(&out[1], s1);
+        atomicAdd(&out[2], s2);
+        atomicAdd(&out[3], s3);
+    }
+}
 // ---- Schur path of the regularized-Laplacian regressor: one pass over the bottom block-row Wb (rows x cols) of a lower-
 //      triangular inverse, row r being nonzero for col <= off + r:  za = Wb^T ya, zb = Wb^T yb (pre-zeroed; atomics over row
 //      blocks) and fro += sum Wb^2.  Each thread owns one column (coalesced rows).
@@ -500,6 +530,14 @@ int gpn_k_grad_trace(gpn_ctx* c, int n, const double* Kinv, long ldi, const doub
     grad_trace_kernel<<<n, 256, 0, c->stream>>>(n, Kinv, ldi, G, ldg, Ktt, ldk, g_scale, k_scale, k_shift, alpha, d_out3);
     LAUNCHED(c);
     return gpn_k_sum(c, n, alpha, d_out3 + 2);
+}
+int gpn_k_bilinear_trace(gpn_ctx* c, int n, const double* S, long lds, const double* G, long ldg, const double* Ktt, long ldk, double g_scale,
+                         double k_scale, const double* x1, const double* xt, double* d_out4) {
+    zero_vec_kernel<<<1, 32, 0, c->stream>>>(4, d_out4);
+    LAUNCHED(c);
+    bilinear_trace_kernel<<<n, 256, 0, c->stream>>>(n, S, lds, G, ldg, Ktt, ldk, g_scale, k_scale, x1, xt, d_out4);
+    LAUNCHED(c);
+    return 0;
 }
 int gpn_k_form_B(gpn_ctx* c, int n, const double* K, long ldk, const double* sw, double* B, long ldb) {
     const int pad = (int)min((long)(n + 127) / 128 * 128, ldb);

@@ -48,7 +48,7 @@ enum NB {
 static_assert(NB_COUNT <= 16, "nb[] too small");
 
 struct Scal {           // layout of c->scal (doubles), followed by ints
-    enum { DOT = 0, LOGDET, SUM, TR0, TR1, TR2, CONV, Q, LIK, AF, NORM0, NORM1, NORM2, NORM3, SCH0 /* 6 dots */, FRO = SCH0 + 6, NDBL = 32 };
+    enum { DOT = 0, LOGDET, SUM, TR0, TR1, TR2, CONV, Q, LIK, AF, NORM0, NORM1, NORM2, NORM3, SCH0 /* up to 7 reductions */, FRO = SCH0 + 7, NDBL = 32 };
 };
 
 double* dscal(gpn_ctx* c, int i) { return (double*)c->scal.p + i; }
@@ -753,7 +753,29 @@ int gpr_logp_grad_reglap_fast(gpn_ctx* c, const double* theta_h, int P, const do
 //     tr(S D) = ||Wb||_F^2 - n,   tr(K_y^-1 D) = tr(S D) - c/(1 + c s) (S1)^T D (S1)
 // so after the triangular inverse one HBM pass over Wb (two transposed GEMVs + a Frobenius norm) finishes the job:
 // N^3/3 + N^3/3 flops instead of N^3 + n^2 N + n^3.  All scalar algebra happens on the host from nine reductions.
-int gpr_logp_grad_reglap_schur(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
+
+// Noise-independent reductions of one kernel: everything -logp and its gradient need for ANY noise level c, because
+// K_y = K_tt + c 1 1^T is a rank-one update of K_tt (S = K_tt^-1, D = dK_tt/dtheta_0).
+struct RowScalars {
+    int n = 0;
+    double half_logdet = 0.0;                    // (1/2) log det K_tt
+    double s = 0.0, a = 0.0, q = 0.0;            // 1^T S 1, 1^T S t, t^T S t
+    double trSD = 0.0, D11 = 0.0, D1t = 0.0, Dtt = 0.0;   // tr(S D), (S1)^T D (S1), (S1)^T D (St), (St)^T D (St)
+};
+// out[0] = -logp, out[1..P] = -dlogp/dtheta (GPnetRegressor.py:136-150 and the gradient of old_implementation/GPR.py:52-64)
+void row_eval(const RowScalars& r, double noise, int P, int want_grad, double* out) {
+    const double den = 1.0 + noise * r.s, mu = noise * r.a / den;
+    out[0] = 0.5 * (r.q - mu * r.a) + (r.half_logdet + 0.5 * log1p(noise * r.s)) + 0.5 * r.n * LOG_2PI;
+    if (!want_grad) return;
+    for (int j = 0; j < P; ++j) out[1 + j] = 0.0;
+    const double aDa = r.Dtt - 2.0 * mu * r.D1t + mu * mu * r.D11;          // alpha = S t - mu S 1
+    const double trKD = r.trSD - noise / den * r.D11;                       // K_y^-1 = S - c (S1)(S1)^T / (1 + c s)
+    out[1 + 0] += -(0.5 * aDa - 0.5 * trKD);
+    const double sa = r.a / den, sinv = r.s / den;                           // 1^T alpha, 1^T K_y^-1 1
+    out[1 + (P - 1)] += -0.5 * noise * (sa * sa - sinv);                     // D_last = c 1 1^T
+}
+
+int gpr_reglap_schur_scalars(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, RowScalars* rs, int* info_h) {
     const int N = c->N, n = c->n_train;
     GPN_TRY(ensure_perm(c));
     GPN_TRY(ensure_vecs(c));
@@ -764,7 +786,7 @@ int gpr_logp_grad_reglap_schur(gpn_ctx* c, const double* theta_h, int P, const d
     c->ldN = pad128(N);
     GPN_TRY(clear_info(c));
     const long ld = c->ldN;
-    const double beta = c->theta_exp[0], noise = c->theta_exp[P - 1];
+    const double beta = c->theta_exp[0];
     const int o = N - n;
     for (int i = 0; i < (want_grad ? 4 : 1); ++i) GPN_TRY(ensure_mat(c, i));
     double* M = mat(c, 0);
@@ -796,18 +818,69 @@ int gpr_logp_grad_reglap_schur(gpn_ctx* c, const double* theta_h, int P, const d
     int info[16];
     GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
     if (info_h) *info_h = info[0];
-    const double s = sc[Scal::SCH0], a = sc[Scal::SCH0 + 1], tSt = sc[Scal::SCH0 + 2];
-    const double den = 1.0 + noise * s, mu = noise * a / den;
-    out_h[0] = 0.5 * (tSt - mu * a) + (-sc[Scal::LOGDET] + 0.5 * log1p(noise * s)) + 0.5 * n * LOG_2PI;
+    rs->n = n;
+    rs->half_logdet = -sc[Scal::LOGDET];
+    rs->s = sc[Scal::SCH0]; rs->a = sc[Scal::SCH0 + 1]; rs->q = sc[Scal::SCH0 + 2];
     if (want_grad) {
-        for (int j = 0; j < P; ++j) out_h[1 + j] = 0.0;
-        const double D11 = sc[Scal::SCH0 + 3] - s, D1t = sc[Scal::SCH0 + 4] - a, Dtt = sc[Scal::SCH0 + 5] - tSt;
-        const double aDa = Dtt - 2.0 * mu * D1t + mu * mu * D11;
-        const double trKD = (sc[Scal::FRO] - n) - noise / den * D11;
-        out_h[1 + 0] += -(0.5 * aDa - 0.5 * trKD);
-        const double sa = a / den, sinv = s / den;                               // 1^T alpha, 1^T K_y^-1 1
-        out_h[1 + (P - 1)] += -0.5 * noise * (sa * sa - sinv);
+        rs->D11 = sc[Scal::SCH0 + 3] - rs->s; rs->D1t = sc[Scal::SCH0 + 4] - rs->a; rs->Dtt = sc[Scal::SCH0 + 5] - rs->q;
+        rs->trSD = sc[Scal::FRO] - n;
     }
+    return 0;
+}
+int gpr_logp_grad_reglap_schur(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
+    RowScalars rs;
+    GPN_TRY(gpr_reglap_schur_scalars(c, theta_h, P, t_h, want_grad, &rs, info_h));
+    row_eval(rs, c->theta_exp[P - 1], P, want_grad, out_h);
+    return 0;
+}
+
+// The same reductions for any kernel from the resident full kernel: L = chol(K_tt) (NO noise), W = L^-1, u = W 1, v = W t,
+// s = u.u, a = u.v, q = v.v; S1 = W^T u, St = W^T v, S = W^T W.  Used by the landscape driver, where every noise value of a
+// grid row shares them.  info > 0: K_tt itself is not positive definite (the caller falls back to factoring K_y per point).
+int gpr_row_scalars(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad, RowScalars* rs, int* info_h) {
+    if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN && c->fast_reglap >= 2 && c->train_unique && c->n_train < c->N)
+        return gpr_reglap_schur_scalars(c, theta_h, P, t_h, want_grad, rs, info_h);
+    int st = kernel_build(c, kind, theta_h, P, want_grad);
+    if (st != 0) return st;
+    GPN_TRY(ensure_vecs(c));
+    const int n = c->n_train;
+    const long ldn = pad128(n);
+    if (t_h) GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
+    else GPN_CK(cudaMemcpyAsync(vecp(c, V_T), vecp(c, V_TRES), sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    const bool reglap = kind == GPN_KERNEL_REGULARIZED_LAPLACIAN;
+    const double noise_saved = c->theta_exp[P - 1];
+    c->theta_exp[P - 1] = 0.0;                                   // gather K_tt without the noise term
+    st = gpr_gather_ky(c, want_grad && reglap);
+    c->theta_exp[P - 1] = noise_saved;
+    if (st != 0) return st;
+    GprFactor f;
+    GPN_TRY(gpr_factor_ky(c, &f));
+    double *ones = vecp(c, V_U), *u = vecp(c, V_Z), *v = vecp(c, V_Z2), *x1 = vecp(c, V_ALPHA), *xt = vecp(c, V_SOL);
+    GPN_TRY(gpn_k_fill_vec(c, n, ones, 1.0));
+    GPN_TRY(gpn_k_gemv(c, n, n, f.W, f.ldn, ones, u, GEMV_LOWER));
+    GPN_TRY(gpn_k_gemv(c, n, n, f.W, f.ldn, vecp(c, V_T), v, GEMV_LOWER));
+    GPN_TRY(gpn_k_sumlogdiag(c, n, f.Ky, f.ldn, dscal(c, Scal::LOGDET)));
+    const double *dx[3] = {u, u, v}, *dy[3] = {u, v, v};
+    const int dn[3] = {n, n, n};
+    GPN_TRY(gpn_k_multi_dot(c, 3, dx, dy, dn, dscal(c, Scal::SCH0)));
+    if (want_grad) {
+        const double* G = nullptr;
+        double gs = 0.0;
+        GPN_TRY(gpr_grad_kernel_block(c, kind, ldn, &G, &gs));
+        GPN_TRY(gpn_k_gemv_t(c, n, n, f.W, f.ldn, u, x1, GEMV_LOWER));
+        GPN_TRY(gpn_k_gemv_t(c, n, n, f.W, f.ldn, v, xt, GEMV_LOWER));
+        GPN_TRY(gpn_lauum_t(c, n, f.WT, f.ldn, f.T, f.ldn, false));            // S = W^T W (lower) -> NB_T
+        GPN_TRY(gpn_k_bilinear_trace(c, n, f.T, f.ldn, G, f.ldn, reglap ? nbp(c, NB_KC) : nullptr, f.ldn, gs, reglap ? -1.0 : 0.0, x1, xt,
+                                     dscal(c, Scal::SCH0 + 3)));
+    }
+    double sc[Scal::NDBL];
+    int info[16];
+    GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
+    if (info_h) *info_h = info[1] ? info[1] : info[0];
+    rs->n = n;
+    rs->half_logdet = sc[Scal::LOGDET];
+    rs->s = sc[Scal::SCH0]; rs->a = sc[Scal::SCH0 + 1]; rs->q = sc[Scal::SCH0 + 2];
+    if (want_grad) { rs->trSD = sc[Scal::SCH0 + 3]; rs->D11 = sc[Scal::SCH0 + 4]; rs->D1t = sc[Scal::SCH0 + 5]; rs->Dtt = sc[Scal::SCH0 + 6]; }
     return 0;
 }
 
@@ -1542,25 +1615,61 @@ int gpn_gpc_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const doubl
     return gpc_grad(c, kind, theta_h, P, y_h, out_h, iters_h, info_h);
 }
 
-int gpn_landscape(gpn_ctx* c, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1, const double* ax1_h, int n1,
-                  const double* ax2_h, int n2, const double* t_h, long idx_begin, long idx_end, long idx_stride, int want_grad,
-                  double* out_h) {
+int gpn_landscape_points(gpn_ctx* c, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1, const double* ax1_h, int n1,
+                         const double* ax2_h, int n2, const double* t_h, const long* idx_h, long count, int want_grad, double* out_h) {
     if (!c) return -1;
+    if (P < 1 || P > 8) return -5;
     if (ax0 < 0 || ax0 >= P) return -6;
     if (ax1 < 0 || ax1 >= P) return -7;
-    if (idx_stride <= 0) return -15;
-    double th[8];
+    if (count < 0) return -14;
     const int rec = 1 + P;
-    long q = 0;
-    for (long idx = idx_begin; idx < idx_end && idx < (long)n1 * n2; idx += idx_stride, ++q) {
+    // Points whose theta differs only in the noise entry (the LAST one, added to every kernel entry: quirk A-3) share the
+    // kernel; they are evaluated back to back so that it is built once per group.  The p-step kernel with P = 2 reads its
+    // order from the same entry (A-4), and P = 1 makes beta the noise: no sharing there.
+    const int last = P - 1;
+    const bool share = c->fast_reglap >= 1 && P >= 2 && !(kind == GPN_KERNEL_PSTEP_WALK && P == 2) && (ax0 == last || ax1 == last);
+    std::vector<long> order(count), key(count);
+    for (long q = 0; q < count; ++q) {
+        const long idx = idx_h[q];
+        if (idx < 0 || idx >= (long)n1 * n2) return -13;
+        order[q] = q;
+        if (!share) key[q] = q;
+        else if (ax1 == last) key[q] = (ax0 == last) ? 0 : idx / n2;        // the second axis is written last (GPnet.py:545-546)
+        else key[q] = idx % n2;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](long x, long y) { return key[x] < key[y]; });
+    double th[8];
+    RowScalars rs;
+    long cur_key = -1;
+    bool have_row = false, row_ok = false;
+    for (long k = 0; k < count; ++k) {
+        const long q = order[k], idx = idx_h[q];
         for (int j = 0; j < P; ++j) th[j] = theta_h[j];
         th[ax0] = ax1_h[idx / n2];          // GPnet.py:544-546 (ax0 written first, then ax1, as the reference)
         th[ax1] = ax2_h[idx % n2];
         double* o = out_h + q * rec;
         for (int j = 0; j < rec; ++j) o[j] = 0.0;
+        const bool fresh = !share || !have_row || key[q] != cur_key;
+        cur_key = key[q];
         int info = 0, st;
+        double tmp[9];
         if (!classifier) {
-            double tmp[9];
+            if (share) {
+                if (fresh) {
+                    st = gpr_row_scalars(c, kind, th, P, t_h, want_grad, &rs, &info);
+                    if (st != 0) return st;
+                    have_row = true;
+                    row_ok = info == 0 && std::isfinite(rs.half_logdet) && std::isfinite(rs.s);
+                }
+                if (row_ok) {
+                    row_eval(rs, exp(th[last]), P, want_grad, tmp);
+                    o[0] = -tmp[0];
+                    if (want_grad)
+                        for (int j = 0; j < P; ++j) o[1 + j] = -tmp[1 + j];
+                    continue;
+                }
+                have_row = false;           // K_tt not PD: factor K_y itself for this point (and rebuild the row state next time)
+            }
             st = gpr_logp_grad(c, kind, th, P, t_h, want_grad, tmp, &info);
             if (st != 0) return st;
             if (info > 0) {
@@ -1573,8 +1682,14 @@ int gpn_landscape(gpn_ctx* c, int kind, int classifier, const double* theta_h, i
         } else {
             double logq = 0.0;
             int iters = 0;
-            st = kernel_build(c, kind, th, P, 0);
-            if (st != 0) return st;
+            if (fresh || !c->have_full) {
+                st = kernel_build(c, kind, th, P, 0);
+                if (st != 0) return st;
+                have_row = true;
+            } else {
+                c->theta_exp[last] = exp(th[last]);     // same kernel, new noise
+                GPN_TRY(clear_info(c));
+            }
             GPN_TRY(gpc_train_block(c));
             st = gpc_newton(c, nbp(c, NB_KY), pad128(c->n_train), c->n_train, t_h, 0.1, 1e100, 1.0, 0, nullptr, nullptr, &logq, &iters,
                             &info);
@@ -1583,6 +1698,16 @@ int gpn_landscape(gpn_ctx* c, int kind, int classifier, const double* theta_h, i
         }
     }
     return 0;
+}
+
+int gpn_landscape(gpn_ctx* c, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1, const double* ax1_h, int n1,
+                  const double* ax2_h, int n2, const double* t_h, long idx_begin, long idx_end, long idx_stride, int want_grad,
+                  double* out_h) {
+    if (idx_stride <= 0) return -15;
+    std::vector<long> idx;
+    for (long i = idx_begin; i < idx_end && i < (long)n1 * n2; i += idx_stride) idx.push_back(i);
+    return gpn_landscape_points(c, kind, classifier, theta_h, P, ax0, ax1, ax1_h, n1, ax2_h, n2, t_h, idx.data(), (long)idx.size(), want_grad,
+                                out_h);
 }
 
 }   // extern "C"

@@ -20,19 +20,41 @@ def dist_info(group=None):
 
 
 def cyclic_slice(total: int, rank: int, world: int):
-    """Flat indices handled by ``rank``: rank, rank+world, ...  The grid's fast axis is the second one (noise),
-    so consecutive flat indices share beta; striding by ``world`` gives every rank the same mix of Pade
-    orders (cost depends on beta only)."""
+    """Flat indices handled by ``rank`` when no two grid points share a kernel: rank, rank+world, ...  (cost depends on
+    beta through the Pade order only, so striding gives every rank the same mix)."""
     return rank, total, world
 
 
-def allgather_rows(local: np.ndarray, total: int, rank: int, world: int, dist, group=None) -> np.ndarray:
-    """Reassemble ``total`` rows from per-rank cyclic shards (rank r holds rows r, r+world, ...)."""
+def kernel_group_keys(n1: int, n2: int, axidx, P: int, kerneltype: str) -> np.ndarray:
+    """Key of the kernel every flat grid index (i1*n2 + i2) needs: points that differ only in the noise entry
+    ``theta[P-1]`` (added to every kernel entry, quirk A-3) share it.  Mirrors ``gpn_landscape_points`` (csrc/gp.cu)."""
+    flat = np.arange(n1 * n2, dtype=np.int64)
+    last = P - 1
+    share = P >= 2 and not (kerneltype == "pstep_walk" and P == 2) and (axidx[0] == last or axidx[1] == last)
+    if not share:
+        return flat
+    if axidx[1] == last:
+        return np.zeros_like(flat) if axidx[0] == last else flat // n2
+    return flat % n2
+
+
+def shard_indices(keys: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Flat indices of ``rank``: whole kernel groups are dealt cyclically (group g -> rank g % world), so that a kernel
+    is built on exactly one GPU; with one point per group this is the plain cyclic split."""
+    uniq, inverse = np.unique(keys, return_inverse=True)
+    return np.nonzero(inverse % world == rank)[0].astype(np.int64)
+
+
+def allgather_rows(local: np.ndarray, total: int, rank: int, world: int, dist, group=None, shards=None) -> np.ndarray:
+    """Reassemble ``total`` rows from per-rank shards: ``shards[r]`` lists the row indices rank r holds (default: the cyclic
+    split r, r+world, ...).  One all-gather of equal-sized (padded) blocks."""
     width = local.shape[1]
     if world == 1 or dist is None:
         return local
     import torch
-    per = (total + world - 1) // world
+    if shards is None:
+        shards = [np.arange(r, total, world) for r in range(world)]
+    per = max(max(len(sh) for sh in shards), 1)
     backend = dist.get_backend(group)
     device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     send = torch.zeros((per, width), dtype=torch.float64, device=device)
@@ -42,9 +64,20 @@ def allgather_rows(local: np.ndarray, total: int, rank: int, world: int, dist, g
     recv = recv.cpu().numpy().reshape(world, per, width)
     out = np.empty((total, width), dtype=np.float64)
     for r in range(world):
-        cnt = len(range(r, total, world))
-        out[r::world] = recv[r, :cnt]
+        out[shards[r]] = recv[r, : len(shards[r])]
     return out
+
+
+def _bound_context(model):
+    ctx = model._engine.bind(model._positions(model.training_nodes), model._positions(model.test_nodes))
+    ctx._kernel_key = None
+    ctx._predict_token = None
+    return ctx
+
+
+def _targets(model):
+    t = model.training_values
+    return np.asarray(getattr(t, "values", t), dtype=np.float64).reshape(-1)
 
 
 def evaluate_slice(model, theta, axidx, ax1, ax2, begin, end, stride, want_grad=False):
@@ -53,25 +86,36 @@ def evaluate_slice(model, theta, axidx, ax1, ax2, begin, end, stride, want_grad=
     from .engine import raise_domain
     th = model._theta_vec(theta).copy()
     classifier = not hasattr(model, "logPosterior_and_grad")
-    t = model.training_values
-    t = np.asarray(getattr(t, "values", t), dtype=np.float64).reshape(-1)
-    ctx = model._engine.bind(model._positions(model.training_nodes), model._positions(model.test_nodes))
-    ctx._kernel_key = None
-    ctx._predict_token = None
-    st, out = ctx.landscape(KERNEL_IDS[model.kerneltype], classifier, th, axidx, ax1, ax2, t, begin, end, stride, want_grad)
+    st, out = _bound_context(model).landscape(KERNEL_IDS[model.kerneltype], classifier, th, axidx, ax1, ax2, _targets(model), begin, end,
+                                              stride, want_grad)
+    raise_domain(st)
+    return out
+
+
+def evaluate_points(model, theta, axidx, ax1, ax2, indices, want_grad=False):
+    """(len(indices), 1+P) array of (lml, dlml/dtheta) for an explicit list of flat grid indices."""
+    from ._lib import KERNEL_IDS
+    from .engine import raise_domain
+    th = model._theta_vec(theta).copy()
+    classifier = not hasattr(model, "logPosterior_and_grad")
+    st, out = _bound_context(model).landscape_points(KERNEL_IDS[model.kerneltype], classifier, th, axidx, ax1, ax2, _targets(model), indices,
+                                                     want_grad)
     raise_domain(st)
     return out
 
 
 def sharded_landscape(model, theta, axidx, ax1, ax2, want_grad=False, group=None) -> np.ndarray:
     """Full ``(len(ax1), len(ax2), 1+P)`` array on every rank: [..., 0] is the lml of GPnet.py:549,
-    [..., 1:] its gradient when ``want_grad``."""
+    [..., 1:] its gradient when ``want_grad``.  Kernel groups (grid points that differ only in the noise entry) stay
+    together on one rank; one all-gather of (1+P) doubles per point reassembles the grid."""
     rank, world, dist = dist_info(group)
     n1, n2 = len(ax1), len(ax2)
     total = n1 * n2
-    begin, end, stride = cyclic_slice(total, rank, world)
-    local = evaluate_slice(model, theta, axidx, ax1, ax2, begin, end, stride, want_grad)
-    full = allgather_rows(local, total, rank, world, dist, group)
+    P = len(model._theta_vec(theta))
+    keys = kernel_group_keys(n1, n2, axidx, P, model.kerneltype)
+    shards = [shard_indices(keys, r, world) for r in range(world)]
+    local = evaluate_points(model, theta, axidx, ax1, ax2, shards[rank], want_grad)
+    full = allgather_rows(local, total, rank, world, dist, group, shards)
     return full.reshape(n1, n2, -1)
 
 

@@ -129,10 +129,18 @@ int gpn_gpc_predict(gpn_ctx* ctx, int kind, const double* theta_h, int P, const 
 int gpn_gpc_grad(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* y_h, double* out_h, int* iters_h,
                  int* info_h);
 
-/* ---- landscape slice (GPnet.py:539-552) ---------------------------------------------------------------------- */
-/* For flat grid indices idx = idx_begin + q*idx_stride < idx_end: theta[ax0] = ax1_h[idx / n2], theta[ax1] =
- * ax2_h[idx % n2]; out_h[q*(1+P) ..] = (lml = +logp, dlogp/dtheta) (gradient only if want_grad).  classifier != 0
- * evaluates -logq... of the Laplace loop instead (y in t_h).  Used by the multi-GPU sharded landscape. */
+/* ---- landscape (GPnet.py:539-552) ------------------------------------------------------------------------------ */
+/* For the `count` flat grid indices idx_h[q] (idx = i1*n2 + i2): theta[ax0] = ax1_h[i1], theta[ax1] = ax2_h[i2] (in this
+ * order, as the reference writes them); out_h[q*(1+P) ..] = (lml = +logp, dlogp/dtheta) (gradient only if want_grad).
+ * classifier != 0 evaluates the Laplace loop's logq instead (y in t_h; no gradient).
+ * Points that differ only in the noise entry theta[P-1] share their kernel (the noise is added to every entry, quirk A-3):
+ * they are evaluated back to back with ONE kernel build, and for the regressor with ONE factorisation of K_tt -- K_y is a
+ * rank-one update of it, so every noise value of a grid row is host arithmetic on seven device reductions.
+ * gpn_set_fast_paths(ctx, 0) restores one independent evaluation per point.  Used by the multi-GPU sharded landscape. */
+int gpn_landscape_points(gpn_ctx* ctx, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1,
+                         const double* ax1_h, int n1, const double* ax2_h, int n2, const double* t_h, const long* idx_h,
+                         long count, int want_grad, double* out_h);
+/* The same for idx = idx_begin + q*idx_stride < idx_end. */
 int gpn_landscape(gpn_ctx* ctx, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1, const double* ax1_h,
                   int n1, const double* ax2_h, int n2, const double* t_h, long idx_begin, long idx_end, long idx_stride,
                   int want_grad, double* out_h);

@@ -260,6 +260,47 @@ def test_reglap_fast_path_equals_full_path(gpu_ctx, shape):
         assert abs(l1[0] - l0[0]) <= 1e-12 * abs(l0[0]) and abs(g1[0] - l1[0]) <= 1e-12 * abs(l1[0])
 
 
+@pytest.mark.parametrize("kind,theta,axidx", [(0, np.log([0.6, 0.01]), [0, 1]), (0, np.log([0.6, 0.01]), [1, 0]),
+                                              (1, np.log([0.6, 0.01]), [0, 1]), (2, np.log([2.3, 4, 0.01]), [0, 2]),
+                                              (2, np.log([2.3, 4]), [0, 1]), (1, np.log([0.6, 0.01]), [1, 1])])
+@pytest.mark.parametrize("classifier", [False, True])
+def test_landscape_kernel_reuse_equals_independent_points(gpu_ctx, kind, theta, axidx, classifier):
+    """gpn_landscape_points builds the kernel once per group of points that differ only in the noise entry (regressor: one
+    factorisation of K_tt, every noise value as a rank-one update): same grid as one independent evaluation per point
+    (fast paths off), in any index order, with the gradient."""
+    indptr, indices, w = cfg.grid_csr_fast(17, 19)
+    N = 17 * 19
+    gpu_ctx.set_graph(indptr, indices, w)
+    tr, te = cfg.split(N, 140, 60, seed=5)
+    gpu_ctx.set_nodes(tr, te)
+    rng = np.random.RandomState(2)
+    t = np.sign(rng.randn(140)) if classifier else np.sin(0.2 * np.arange(140))
+    lo0 = {0: np.log(0.05), 1: np.log(0.05), 2: np.log(2.0)}[kind]
+    hi0 = {0: np.log(0.95), 1: np.log(3.0), 2: np.log(3.0)}[kind]
+    axes = {0: np.linspace(lo0, hi0, 4), 1: np.linspace(np.log(1e-3), np.log(5.0), 5), 2: np.linspace(np.log(1e-3), np.log(5.0), 5)}
+    if kind == 2 and len(theta) == 2:
+        axes[1] = np.log(np.array([1.2, 2.0, 3.5, 4.1, 6.0]))        # the order p AND the noise (A-4): no sharing possible
+    a1, a2 = axes[axidx[0]], axes[axidx[1]]
+    idx = rng.permutation(len(a1) * len(a2))
+    res = {}
+    try:
+        for level in (2, 0):
+            gpu_ctx.set_fast_paths(level)
+            st, out = gpu_ctx.landscape_points(kind, classifier, theta, axidx, a1, a2, t, idx, want_grad=not classifier)
+            assert st == 0
+            res[level] = out
+    finally:
+        gpu_ctx.set_fast_paths(True)
+    assert np.all(np.isfinite(res[0]))
+    assert nrel(res[2][:, 0], res[0][:, 0]) <= 1e-11
+    if not classifier:
+        assert nrel(res[2][:, 1:], res[0][:, 1:]) <= 1e-10
+    # the strided form of the same call covers the same points
+    st, out = gpu_ctx.landscape(kind, classifier, theta, axidx, a1, a2, t, 1, len(idx), 3, want_grad=False)
+    ref = {int(i): v for i, v in zip(idx, res[0][:, 0])}
+    assert st == 0 and nrel(out[:, 0], np.array([ref[i] for i in range(1, len(idx), 3)])) <= 1e-11
+
+
 def test_diffusion_semigroup_property_n4096(gpu_ctx):
     """C4 size: exp(-b L~) exp(-b L~) = exp(-2b L~) on a column sample (Pade orders differ between the two sides)."""
     indptr, indices, w, pos, t = cfg.rgg_csr_fast(4096)

@@ -159,6 +159,28 @@ def test_cyclic_shards_cover_the_grid():
         assert np.all(seen == 1)
 
 
+def test_kernel_group_shards_cover_the_grid_and_keep_groups_together():
+    """Grid points that differ only in the noise entry share a kernel: whole groups go to one rank, every index to exactly
+    one rank; without sharing (p-step with P = 2, noise not on the grid) the split is the plain cyclic one."""
+    from gpnet_b200.sharded import kernel_group_keys, shard_indices
+    n1, n2 = 7, 5
+    for axidx, P, kt, ngroups in (([0, 1], 2, "diffusion", n1), ([1, 0], 2, "regularized_laplacian", n2), ([1, 1], 2, "diffusion", 1),
+                                  ([0, 1], 2, "pstep_walk", n1 * n2), ([0, 1], 3, "pstep_walk", n1 * n2), ([0, 2], 3, "pstep_walk", n1)):
+        keys = kernel_group_keys(n1, n2, axidx, P, kt)
+        assert len(np.unique(keys)) == ngroups
+        for world in (1, 2, 3, 8):
+            seen = np.zeros(n1 * n2, dtype=int)
+            owner = {}
+            for r in range(world):
+                idx = shard_indices(keys, r, world)
+                seen[idx] += 1
+                for k in np.unique(keys[idx]):
+                    assert owner.setdefault(int(k), r) == r
+            assert np.all(seen == 1)
+    keys = kernel_group_keys(4, 4, [0, 1], 2, "pstep_walk")
+    assert np.array_equal(shard_indices(keys, 1, 3), np.arange(1, 16, 3))
+
+
 WORKER = r"""
 import os, sys
 import numpy as np
@@ -175,6 +197,12 @@ local = np.stack([idx * 1.0, idx * 2.0 + 0.5, -idx * 1.0], axis=1)
 full = allgather_rows(local, total, rank, world, dist)
 exp = np.stack([np.arange(total) * 1.0, np.arange(total) * 2.0 + 0.5, -np.arange(total) * 1.0], axis=1)
 assert np.array_equal(full, exp), (rank, full[:5])
+from gpnet_b200.sharded import kernel_group_keys, shard_indices      # ragged shards: 5 kernel groups of 4 points on 2 ranks
+keys = kernel_group_keys(5, 4, [0, 1], 2, "diffusion")
+shards = [shard_indices(keys, r, world) for r in range(world)]
+mine = shards[rank]
+full = allgather_rows(np.stack([mine * 1.0, mine * 3.0], axis=1), 20, rank, world, dist, None, shards)
+assert np.array_equal(full, np.stack([np.arange(20) * 1.0, np.arange(20) * 3.0], axis=1)), (rank, full)
 
 class Fake:                                    # stands in for a model: value and gradient are functions of theta
     training_nodes = [0]; training_values = [0.0]
