@@ -262,20 +262,83 @@ class GPnetBase:
         )
         return self
 
-    # ---- plotting: presentation only (out of scope of the hot path); thin optional pass-through -------
+    # ---- plotting: presentation only (out of scope of the hot path); thin optional pass-through ------------------
+    # Without matplotlib (it is not part of this image) every plot_* method prints a note and returns, so demo drivers
+    # in the style of graph_test.py run to the end; with it they draw the same quantities as the reference's methods.
     def _pyplot(self):
         try:
             import matplotlib.pyplot as pl
-        except ImportError as exc:   # pragma: no cover
-            raise ImportError("matplotlib is required for the plot_* methods") from exc
+        except ImportError:
+            print("> matplotlib not available: plot skipped")
+            return None
         return pl
 
-    def plot_graph(self, filename=False):
-        pl = self._pyplot()
-        pl.figure(figsize=[15, 9])
-        pl.title("Graph")
-        nx.draw_networkx(self.Graph, self.plot_pos, with_labels=True, node_size=200)
-        for nodes, color in ((self.training_nodes, "r"), (self.test_nodes, "g"), (self.other_nodes, "b")):
-            nx.draw_networkx_nodes(self.Graph, self.plot_pos, nodelist=list(nodes), node_color=color)
+    @staticmethod
+    def _save(pl, filename):
         if isinstance(filename, str):
             pl.savefig(filename, bbox_inches="tight")
+
+    @staticmethod
+    def int_to_list(nodes):
+        """GPnet.py:566-570: a single node label becomes a one-element list."""
+        return [nodes] if isinstance(nodes, (int, np.integer)) else nodes
+
+    def plot_graph(self, filename=False):
+        """Training / test / other nodes in red / green / blue on the cached layout (GPnet.py:378-433)."""
+        pl = self._pyplot()
+        if pl is None:
+            return self
+        pl.figure(figsize=[15, 9])
+        pl.title("Graph")
+        for nodes, color, label in ((self.training_nodes, "r", "training nodes"), (self.test_nodes, "g", "test nodes"),
+                                    (self.other_nodes, "b", "other nodes")):
+            nx.draw_networkx_nodes(self.Graph, self.plot_pos, nodelist=list(nodes), node_color=color, node_size=200, label=label)
+        nx.draw_networkx_edges(self.Graph, self.plot_pos, alpha=0.2)
+        names = self.orig_labels_invdict if getattr(self, "relabel_nodes", False) and hasattr(self, "orig_labels_invdict") else None
+        nx.draw_networkx_labels(self.Graph, pos=self.plot_pos, labels=names, font_color="k")
+        pl.legend()
+        self._save(pl, filename)
+        return self
+
+    def _plot_draws(self, cov, mean, title, filename):
+        pl = self._pyplot()
+        if pl is None:
+            return
+        m = cov.shape[0]
+        chol = np.linalg.cholesky(cov + 1e-6 * np.eye(m))
+        draws = np.reshape(mean, (-1, 1)) + chol @ np.random.normal(size=(m, 5))
+        pl.figure()
+        pl.plot(self.test_nodes, draws)
+        pl.title(title)
+        pl.xlabel("nodes")
+        pl.ylabel("values")
+        self._save(pl, filename)
+
+    def plot_prior(self, filename=False):
+        """Five draws from the prior over the test nodes (GPnet.py:435-447)."""
+        self._plot_draws(np.asarray(self.kstarstar), 0.0, "5 draws from the prior", filename)
+
+    def plot_post(self, filename=False):
+        """Five draws from the posterior over the test nodes (GPnet.py:449-467)."""
+        v = np.asarray(self.v)               # L^-1 kstar^T
+        self._plot_draws(np.asarray(self.kstarstar) - v.T @ v, np.asarray(self.fstar), "5 draws from the posterior", filename)
+
+    def _plot_on_graph(self, title, train_colors, test_colors, filename):
+        """Shared body of plot_predict_graph (GPnetRegressor.py:284-336, GPnetClassifier.py:280-346): training nodes as
+        triangles, test nodes as squares, both coloured through self.cmap; other nodes grey."""
+        pl = self._pyplot()
+        if pl is None:
+            return self
+        pl.figure(figsize=[15, 9])
+        pl.title(title)
+        self.gen_cmap()
+        common = dict(node_size=200, cmap=self.cmap, vmin=self.vmin, vmax=self.vmax)
+        nx.draw_networkx_nodes(self.Graph, self.plot_pos, nodelist=list(self.training_nodes), node_color=train_colors, node_shape="v", **common)
+        nx.draw_networkx_nodes(self.Graph, self.plot_pos, nodelist=list(self.other_nodes), node_color="gray", node_size=200)
+        nx.draw_networkx_nodes(self.Graph, self.plot_pos, nodelist=list(self.test_nodes), node_color=test_colors, node_shape="s", **common)
+        nx.draw_networkx_edges(self.Graph, self.plot_pos, alpha=0.2)
+        sm = pl.cm.ScalarMappable(cmap=self.cmap, norm=pl.Normalize(vmin=self.vmin, vmax=self.vmax))
+        sm.set_array([])
+        pl.colorbar(sm, ax=pl.gca())
+        self._save(pl, filename)
+        return self

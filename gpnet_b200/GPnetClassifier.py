@@ -99,11 +99,47 @@ class GPnetClassifier(GPnetBase):
         self.newton_iterations = iters
         return out[1:].copy()
 
-    def plot_latent(self, filename=False):
+    # ---- plotting pass-through (presentation only) ---------------------------------------------------
+    def gen_cmap(self):
+        """Probabilities live in [0, 1] (GPnetClassifier.py:431-434)."""
+        self.vmin, self.vmax = 0, 1
         pl = self._pyplot()
+        self.cmap = pl.cm.seismic if pl is not None else None
+
+    def plot_latent(self, filename=False):
+        """Latent mean and its +-sqrt(V) band over the pivot distance (GPnetClassifier.py:366-391)."""
+        pl = self._pyplot()
+        if pl is None:
+            return self
         pl.figure(figsize=[15, 9])
         pl.plot(self.test_nodes, self.fstar, "b-")
         pl.gca().fill_between(self.test_nodes, self.fstar - self.s, self.fstar + self.s, color="#dddddd")
         pl.title("Latent Process Mean and Variance")
-        if isinstance(filename, str):
-            pl.savefig(filename, bbox_inches="tight")
+        self._save(pl, filename)
+        return self
+
+    plot_latent_old = plot_latent
+    plot_predict_2dold = plot_latent
+
+    def plot_predict_graph(self, filename=False):
+        if not self.is_trained:
+            print("need to train a model first, use GPnetClassifier.predict()")
+            return
+        y = (np.asarray([self.training_values[x] for x in self.training_nodes], dtype=np.float64) + 1.0) / 2.0
+        return self._plot_on_graph("Prediction plot", y, np.asarray(self.df["prob_1"][list(self.test_nodes)], dtype=np.float64), filename)
+
+    def plot_binary_prediction(self, filename=False):
+        """Predicted class and training labels against the pivot distance (GPnetClassifier.py:348-364)."""
+        pl = self._pyplot()
+        if pl is None:
+            return self
+        pl.figure(figsize=[15, 9])
+        frame = self.df.sort_values(by=["pvtdist"])
+        pl.plot(frame["pvtdist"].values, frame["predicted_class"].values, "bo", ms=8)
+        pl.plot(frame["pvtdist"].values, frame["train_vals"].values, "r+", ms=20)
+        pl.title("Binary Classification")
+        pl.xlabel("pivot distance")
+        pl.ylabel("classification label")
+        pl.legend(("test nodes", "training nodes"), loc="center right")
+        self._save(pl, filename)
+        return self

@@ -148,12 +148,33 @@ class GPnetRegressor(GPnetBase):
         return float(out[0]), out[1:].copy()
 
     # ---- plotting pass-through (presentation only) ---------------------------------------------------
-    def plot_predict_2d(self, filename=False):
+    def gen_cmap(self):
+        """Colour range over training values and predictions (GPnetRegressor.py:185-188)."""
+        tv = self._values(self.training_values)
+        self.vmin = min(float(np.min(tv)), float(np.min(self.fstar)))
+        self.vmax = max(float(np.max(tv)), float(np.max(self.fstar)))
         pl = self._pyplot()
+        self.cmap = pl.cm.inferno_r if pl is not None else None
+
+    def plot_predict_2d(self, filename=False):
+        """Training values, predictive mean and the +-s band over the node index (GPnetRegressor.py:237-282)."""
+        pl = self._pyplot()
+        if pl is None:
+            return self
         pl.figure(figsize=[15, 9])
         pl.plot(self.training_nodes, self._values(self.training_values), "r+", ms=20)
         pl.plot(self.test_nodes, self.fstar, "b-")
         pl.gca().fill_between(self.test_nodes, self.fstar - self.s, self.fstar + self.s, color="#dddddd")
         pl.title("Gaussian Process Mean and Variance")
-        if isinstance(filename, str):
-            pl.savefig(filename, bbox_inches="tight")
+        self._save(pl, filename)
+        return self
+
+    plot_predict_2d_old = plot_predict_2d
+
+    def plot_predict_graph(self, filename=False):
+        if not self.is_trained:
+            print("need to train a model first, use GPnetRegressor.predict()")
+            return
+        tv = self.training_values
+        colors = np.asarray([tv[x] for x in self.training_nodes], dtype=np.float64) if hasattr(tv, "__getitem__") else self._values(tv)
+        return self._plot_on_graph("Prediction plot", colors, np.asarray(self.fstar), filename)

@@ -151,6 +151,9 @@ int gpn_k_dot(gpn_ctx* c, int n, const double* x, const double* y, double* d_out
 int gpn_k_sum(gpn_ctx* c, int n, const double* x, double* d_out);
 int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out);
 int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v);
+int gpn_k_fill_zero_lower(gpn_ctx* c, double* A, long ld, int rows);
+int gpn_k_gemv_t2(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* x1, const double* x2, double* y1, double* y2,
+                  int mode);
 int gpn_k_bilinear_trace(gpn_ctx* c, int n, const double* S, long lds, const double* G, long ldg, const double* Ktt, long ldk, double g_scale,
                          double k_scale, const double* x1, const double* xt, double* d_out4);
 int gpn_k_trap_pass(gpn_ctx* c, int rows, int cols, int off, const double* Wb, long ld, const double* ya, const double* yb, double* za,

@@ -54,6 +54,14 @@ __global__ void fill_zero_kernel(double* __restrict__ A, long ld, int rows, int 
         reinterpret_cast<double2*>(A + r * ld)[v] = make_double2(0.0, 0.0);
     }
 }
+// (b') the same for the 128-wide tiles on and below the diagonal only (row r: columns [0, 128*(r/128 + 1))): consumers that
+//      read nothing above the diagonal tiles (dataflow Cholesky, triangular inverse) skip half of the write traffic
+__global__ void fill_zero_lower_kernel(double* __restrict__ A, long ld, int rows) {
+    const int r = blockIdx.y;
+    const int lim = min((r / 128 + 1) * 128, rows) / 2;      // double2 per row (rows is a multiple of 128)
+    double2* row = reinterpret_cast<double2*>(A + (long)r * ld);
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < lim; v += gridDim.x * blockDim.x) row[v] = make_double2(0.0, 0.0);
+}
 // (c) scatter of the nnz + diagonal: out[i][j] = alpha * (dinv_i * ((D-A)_ij * dinv_j)) (+ gamma on the diagonal),
 //     same operation order as networkx's  DH @ ((D - A) @ DH).  One warp per row.
 __global__ void laplacian_scatter_kernel(int N, const int* __restrict__ indptr, const int* __restrict__ indices,
@@ -199,6 +207,26 @@ __global__ void gemv_t_kernel(int rows, int cols, const double* __restrict__ A, 
     double s = 0.0;
     for (int r = r0; r < r1; ++r) s += A[(long)r * lda + c] * x[r];
     if (r1 > r0) atomicAdd(&y[c], s);
+}
+// two transposed GEMVs in one pass over A: y1 = A^T x1, y2 = A^T x2 (pre-zeroed; atomics over row blocks)
+__global__ void gemv_t2_kernel(int rows, int cols, const double* __restrict__ A, long lda, const double* __restrict__ x1,
+                               const double* __restrict__ x2, double* __restrict__ y1, double* __restrict__ y2, int mode,
+                               int rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    if (mode == GEMV_LOWER) r0 = max(r0, c);
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r) {
+        const double a = A[(long)r * lda + c];
+        s1 += a * x1[r];
+        s2 += a * x2[r];
+    }
+    if (r1 > r0) {
+        atomicAdd(&y1[c], s1);
+        atomicAdd(&y2[c], s2);
+    }
 }
 __global__ void zero_vec_kernel(int n, double* y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -382,6 +410,14 @@ int gpn_k_fill_zero(gpn_ctx* c, double* A, long ld, int rows, int cols) {
     LAUNCHED(c);
     return 0;
 }
+int gpn_k_fill_zero_lower(gpn_ctx* c, double* A, long ld, int rows) {
+    if (rows <= 0) return 0;
+    if (rows % 128 != 0) return gpn_k_fill_zero(c, A, ld, rows, rows);
+    dim3 grid(8, rows);
+    fill_zero_lower_kernel<<<grid, TPB, 0, c->stream>>>(A, ld, rows);
+    LAUNCHED(c);
+    return 0;
+}
 int gpn_k_laplacian_scatter(gpn_ctx* c, int N, const int* indptr, const int* indices, const double* w, const double* dinv,
                             double alpha, double gamma, double* out, long ld) {
     laplacian_scatter_kernel<<<grid1((long)N * 32), TPB, 0, c->stream>>>(N, indptr, indices, w, dinv, alpha, gamma, out, ld);
@@ -464,6 +500,20 @@ int gpn_k_gemv_t(gpn_ctx* c, int rows, int cols, const double* A, long lda, cons
     const int rpb = 128;
     dim3 grid(grid1(cols, 128), (rows + rpb - 1) / rpb);
     gemv_t_kernel<<<grid, 128, 0, c->stream>>>(rows, cols, A, lda, x, y, mode, rpb);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_gemv_t2(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* x1, const double* x2, double* y1, double* y2,
+                  int mode) {
+    if (cols <= 0) return 0;
+    zero_vec_kernel<<<grid1(cols), TPB, 0, c->stream>>>(cols, y1);
+    LAUNCHED(c);
+    zero_vec_kernel<<<grid1(cols), TPB, 0, c->stream>>>(cols, y2);
+    LAUNCHED(c);
+    if (rows <= 0) return 0;
+    const int rpb = 64;
+    dim3 grid(grid1(cols, 128), (rows + rpb - 1) / rpb);
+    gemv_t2_kernel<<<grid, 128, 0, c->stream>>>(rows, cols, A, lda, x1, x2, y1, y2, mode, rpb);
     LAUNCHED(c);
     return 0;
 }

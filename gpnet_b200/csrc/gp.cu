@@ -792,7 +792,7 @@ int gpr_reglap_schur_scalars(gpn_ctx* c, const double* theta_h, int P, const dou
     double* M = mat(c, 0);
     if (t_h) GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
     else GPN_CK(cudaMemcpyAsync(vecp(c, V_T), vecp(c, V_TRES), sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-    GPN_TRY(gpn_k_fill_zero(c, M, ld, (int)ld, (int)ld));
+    GPN_TRY(gpn_k_fill_zero_lower(c, M, ld, (int)ld));       // nothing on this route reads above the diagonal tiles
     GPN_TRY(gpn_k_laplacian_scatter(c, N, (const int*)c->p_indptr.p, (const int*)c->p_indices.p,
                                     c->h_weights.empty() ? nullptr : (const double*)c->p_weights.p, (const double*)c->p_dinv.p, beta, 1.0, M, ld));
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(N) * 128));
@@ -800,8 +800,7 @@ int gpr_reglap_schur_scalars(gpn_ctx* c, const double* theta_h, int P, const dou
     const double* Ltt = M + (long)o * ld + o;
     double *ones = vecp(c, V_U), *r1 = vecp(c, V_Z), *rt = vecp(c, V_Z2);
     GPN_TRY(gpn_k_fill_vec(c, n, ones, 1.0));
-    GPN_TRY(gpn_k_gemv_t(c, n, n, Ltt, ld, ones, r1, GEMV_LOWER));
-    GPN_TRY(gpn_k_gemv_t(c, n, n, Ltt, ld, vecp(c, V_T), rt, GEMV_LOWER));
+    GPN_TRY(gpn_k_gemv_t2(c, n, n, Ltt, ld, ones, vecp(c, V_T), r1, rt, GEMV_LOWER));
     GPN_TRY(gpn_k_sumlogdiag(c, n, Ltt, ld, dscal(c, Scal::LOGDET)));
     const double *dx[6] = {r1, r1, rt}, *dy[6] = {r1, rt, rt};
     int dn[6] = {n, n, n, N, N, N};

@@ -99,6 +99,52 @@ def test_classifier_parity(path):
     assert abs(float(np.squeeze(m.logp())) - g["logp"]) <= TOL * abs(g["logp"])
 
 
+def test_demo_driver_flow_through_module_aliases(capsys):
+    """A driver in the shape of the reference's graph_test.py (random node assignment from a seed, regressor on a lattice,
+    labels from the pivot distance, classifier on the same split, every plot_* call) runs unchanged through the module
+    aliases -- without matplotlib the plots print a note -- and its numbers match the oracle on the same split."""
+    import gpnet_b200
+    gpnet_b200.install_dropin()
+    from GPnetRegressor import GPnetRegressor
+    from GPnetClassifier import GPnetClassifier
+    G = nx.generators.lattice.grid_graph(dim=[15, 15], periodic=False)
+    theta = [np.log(2.3), np.log(4), np.log(0.01)]
+    gpr = GPnetRegressor(Graph=G, ntrain=125, ntest=100, theta=theta, seed=123, kerneltype="pstep_walk", relabel_nodes=True)
+    gpr.plot_graph()
+    assert gpr.predict() is gpr
+    gpr.plot_predict_2d()
+    gpr.plot_predict_graph()
+    gpr.plot_prior()
+    gpr.plot_post()
+    assert len(gpr.training_nodes) == 125 and len(gpr.test_nodes) == 100 and len(gpr.other_nodes) == 0
+    tr, te = sorted(gpr.training_nodes), sorted(gpr.test_nodes)
+    orc = go.OracleGP(gpr.Graph, kerneltype="pstep_walk")
+    tvals = np.asarray([gpr.training_values[x] for x in tr], dtype=np.float64)
+    ref = orc.predict_regressor(theta, tr, te, tvals)
+    assert nrel(gpr.fstar, ref["fstar"]) <= TOL and nrel(gpr.s, ref["s"]) <= TOL
+
+    labels = (np.sin(0.5 * gpr.pivot_distance(0)) > 0).replace({True: 1, False: -1})
+    train_labels = labels[gpr.training_nodes]
+    th_c = [np.log(2.1), np.log(2), np.log(0.1)]
+    gpc = GPnetClassifier(Graph=G, training_nodes=gpr.training_nodes, test_nodes=gpr.test_nodes, training_values=train_labels,
+                          theta=th_c, seed=321, kerneltype="pstep_walk", relabel_nodes=True)
+    fstar, V, probs = gpc.predict()
+    gpc.plot_graph()
+    gpc.plot_latent()
+    gpc.plot_predict_graph()
+    gpc.plot_binary_prediction()
+    y = np.asarray([train_labels[x] for x in tr], dtype=np.float64)
+    refc = orc.predict_classifier(th_c, tr, te, y)
+    assert gpc.newton_iterations == refc["iters"]
+    assert nrel(fstar, refc["fstar"]) <= TOL and nrel(probs, refc["probs"]) <= TOL
+    assert np.array_equal(np.asarray(gpc.df["predicted_class"][te], dtype=np.float64), refc["labels"])
+    out = capsys.readouterr().out
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        assert out.count("matplotlib not available: plot skipped") >= 9
+
+
 @pytest.mark.parametrize("kt,theta", [("diffusion", np.log([0.6, 0.1])), ("regularized_laplacian", np.log([0.6, 0.1])),
                                       ("pstep_walk", np.log([2.1, 2, 0.1])), ("pstep_walk", np.log([2.5, 1.5]))])
 def test_classifier_gradient_matches_oracle(kt, theta):
