@@ -40,6 +40,7 @@ struct DfArgs {
     int* info;
     int info_off;
     long long* trace;     // optional: 8 x int64 globaltimer stamps per task (development aid)
+    int leaf_exp;         // development aid (GPNET_B200_LEAF_EXP): switches off pieces of the leaf's off-chain work
 };
 
 __device__ __forceinline__ void wait_flag(const int* f, int epoch) {
@@ -52,17 +53,6 @@ __device__ __forceinline__ long long gtime() {
 }
 #define DF_STAMP(slot) do { if (g.trace && tid == 0) g.trace[(long)q * 8 + (slot)] = gtime(); } while (0)
 __device__ __forceinline__ void sts64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
-
-// The epilogue reads the original tile A_ij (C = A_ij - acc) from global memory on the dependency chain: pull it into L2
-// a few k-steps earlier (128 rows x 1 KB; 256 threads x 4 lines of 128 B).
-__device__ __forceinline__ void prefetch_tile(const DfArgs& g, int i, int j, int tid) {
-    const long gr = (long)i * TB + (tid >> 1);
-    if (gr < g.n) {
-        const double* rowp = g.A + gr * g.lda + (long)j * TB + (tid & 1) * 64;
-#pragma unroll
-        for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + l * 16));
-    }
-}
 
 // One k-step of a DIAGONAL tile for the warp at (WM_, WN_): only the 8x8 blocks touching the lower triangle are issued,
 // selected at compile time (no per-DMMA predicate arithmetic on the dependency chain's last k-block).
@@ -182,17 +172,28 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
         const int i = j + (q - q0);
 
         double acc[8][4][2];
+        // The accumulators start from -A_ij, so that after the k-loop they hold -(A_ij - sum L_ik L_jk^T) and the epilogue on
+        // the dependency chain needs no global loads: these 64 independent loads per lane are issued while the task is still
+        // waiting for its operands.  Rows / columns beyond n are identity padded (diagonal tile) or zero.
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+        for (int a = 0; a < 8; ++a) {
+            const int r = wm * 64 + a * 8 + pg;
+            const long gr = (long)i * TB + r;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int cc = wn * 32 + b * 8 + t + 4 * e;
+                    const long gc = (long)j * TB + cc;
+                    double v = (i == j && r == cc) ? -1.0 : 0.0;
+                    if (gr < g.n && gc < g.n) v = -g.A[gr * g.lda + gc];
+                    acc[a][b][e] = v;
+                }
+        }
         DF_STAMP(0);
         const int niter = j * 8;
-        if (niter == 0) prefetch_tile(g, i, j, tid);
         const uint32_t mask = (i == j) ? diag_mask : 0xffffffffu;
-        const int npre = niter > 12 ? niter - 12 : 0;
         for (int n = 0; n < niter; ++n, ++it) {
-            if (n == npre) prefetch_tile(g, i, j, tid);      // shortly before the epilogue needs A_ij (see below)
             const int st = it % STAGES;
             mbar_wait(bar_full + st * 8, (it / STAGES) & 1);
             const uint32_t sa = smem0 + st * STAGE_BYTES, sb = sa + TILE_BYTES;
@@ -229,29 +230,21 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
 
         const long grow0 = (long)i * TB + wm * 64, gcol0 = (long)j * TB + wn * 32;
         if (i == j) {
-            // ---- C = A_jj - acc -> S (identity padded); factor + invert in shared memory ----
+            // ---- C = -acc -> S (identity padded); factor + invert in shared memory ----
             if (tid < leaf::GUARD) reinterpret_cast<double*>(smem_gen)[tid] = 0.0;
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
                 const int r = wm * 64 + a * 8 + pg;
-                const long gr = (long)i * TB + r;
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int cc = wn * 32 + b * 8 + t + 4 * e;
-                        const long gc = (long)j * TB + cc;
-                        double v;
-                        if (gr < g.n && gc < g.n) v = g.A[gr * g.lda + gc] - acc[a][b][e];
-                        else v = (r == cc) ? 1.0 : 0.0;
-                        S[r * leaf::LDS_ + cc] = v;
-                    }
+                    for (int e = 0; e < 2; ++e) S[r * leaf::LDS_ + wn * 32 + b * 8 + t + 4 * e] = -acc[a][b][e];
             }
             bar_consumers();
             DF_STAMP(2);
             const int nv = min(TB, g.n - j * TB);
             leaf::potf2_inverse<1>(S, Wd, Tt, g.A + ((long)j * TB) * g.lda + (long)j * TB, g.lda, nv, g.winv + (long)j * TB * TB, g.info,
-                                   g.info_off + j * TB, tid);
+                                   g.info_off + j * TB, tid, nullptr, g.leaf_exp);
             __threadfence();
             bar_consumers();
             if (tid == 0) {
@@ -260,18 +253,16 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
             }
             DF_STAMP(4);
         } else {
-            // ---- C = A_ij - acc -> K-major swizzled sub-tiles; L_ij = C W_j^T ----
+            // ---- C = -acc -> K-major swizzled sub-tiles; L_ij = C W_j^T ----
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
                 const int r = wm * 64 + a * 8 + pg;
-                const long gr = (long)i * TB + r;
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int cc = wn * 32 + b * 8 + t + 4 * e;
-                        const long gc = (long)j * TB + cc;
-                        const double v = (gr < g.n) ? g.A[gr * g.lda + gc] - acc[a][b][e] : 0.0;
+                        const double v = -acc[a][b][e];
                         const int cw = cc & 15;
                         sts64(smem0 + (cc >> 4) * TILE_BYTES + r * 128 + ((((cw >> 1) ^ (r & 7)) << 4) | ((cw & 1) << 3)), v);
                         acc[a][b][e] = 0.0;
@@ -357,6 +348,8 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
     DfArgs a;
     a.A = A; a.lda = lda; a.n = n; a.T = T; a.ntasks = ntasks; a.winv = winv; a.flags = (int*)c->flags.p;
     a.epoch = ++c->epoch; a.info = d_info; a.info_off = info_offset; a.trace = (long long*)c->df_trace;
+    static const int leaf_exp = getenv("GPNET_B200_LEAF_EXP") ? atoi(getenv("GPNET_B200_LEAF_EXP")) : 0;
+    a.leaf_exp = leaf_exp;
     CUtensorMap tl, tw;
     GPN_TRY(encode_tiles(c, &tl, A, lda, n, n));
     GPN_TRY(encode_tiles(c, &tw, winv, TB, (long)T * TB, TB));
@@ -366,6 +359,7 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
         configured = true;
     }
     int grid = ntasks < c->num_sms ? ntasks : c->num_sms;
+    if (const char* e = getenv("GPNET_B200_POTRF_GRID")) { const int v = atoi(e); if (v > 0 && v < grid) grid = v; }   // experiments
     if (c->potrf_grid_cap > 0 && grid > c->potrf_grid_cap) grid = c->potrf_grid_cap;   // leave SMs to concurrent work
     void* args[] = {(void*)&tl, (void*)&tw, (void*)&a};
     // executed flops: an off-diagonal task runs j k-blocks of 128^3 MACs, a diagonal one only the 136 of 256 8x8 blocks that

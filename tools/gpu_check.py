@@ -126,9 +126,14 @@ def stage_leaf(ctx):
         ctx.lib.gpn_debug_leaf_bench(ctx.h, stack.data_ptr(), copies, prof.data_ptr())
         ctx.sync()
         p = prof.cpu().numpy()
-        stamps = [int(x) for x in p[:24] if x != 0]
-        print(f"leaf phase cycles, grid {copies} (D0, then [panel, lookahead+D(kb+1)||trailing] x 3, L write, diag inverses, inverse k=2,1,0, winv write):")
+        stamps = [int(x) for x in p[:12] if x != 0]
+        print(f"leaf phase cycles, grid {copies} (start, D0 + lockstep inverse, then [panel product + inverse row | next diagonal update + D(kb+1)] x 3, last inverse row, last write-back):")
         print("   phases:", [b - a for a, b in zip(stamps[:-1], stamps[1:])], " total:", stamps[-1] - stamps[0], flush=True)
+        if p[12] != 0:       # v2 diagnostics of phase (c), cycles after the barrier that starts it
+            for kb in range(3):
+                t0 = int(p[12 + kb])
+                print(f"   kb={kb}: factor warp done +{int(p[16+kb])-t0}, lockstep inverse done +{int(p[20+kb])-t0}, trailing update + T done "
+                      f"+{int(p[24+kb])-t0}, write-back (warp 4) done +{int(p[28+kb])-t0}; next-diagonal update before it: {t0 - stamps[2+2*kb]}", flush=True)
     for nn in (256, 512, 1024, 2048):
         X = torch.randn(nn, nn, dtype=torch.float64, device=dev)
         S = X @ X.T / nn + torch.eye(nn, dtype=torch.float64, device=dev)
@@ -169,6 +174,53 @@ def stage_chain(ctx):
         for k, nm in enumerate(names):
             print(f"   {nm:18s} median {np.median(r[:, k]):7.1f}   head {np.round(r[:5, k], 1)}  tail {np.round(r[-5:, k], 1)}")
         sys.stdout.flush()
+
+
+def stage_dfbreak(ctx):
+    """Where the CTA-time of the dataflow Cholesky goes (per-task %globaltimer trace, N = 8192, 148 CTAs): main loops,
+    epilogues (TRSM / leaf), waiting between tasks, idle after a CTA's last task."""
+    n = 8192
+    T = n // 128
+    X = torch.randn(n, n, dtype=torch.float64, device=dev)
+    S = X @ X.T / n + torch.eye(n, dtype=torch.float64, device=dev)
+    Sb, ld = dmat(n, n, S)
+    ctx.potrf(n, Sb.data_ptr(), ld)
+    Sb[:, :n] = S
+    ntasks = T * (T + 1) // 2
+    tr = torch.zeros(ntasks * 8, dtype=torch.int64, device=dev)
+    ctx.lib.gpn_debug_df_trace(ctx.h, tr.data_ptr())
+    ctx.potrf(n, Sb.data_ptr(), ld)
+    ctx.lib.gpn_debug_df_trace(ctx.h, None)
+    t = tr.cpu().numpy().reshape(ntasks, 8).astype(np.float64) * 1e-3      # us
+    G = 148
+    t0, t1 = t[:, 0].min(), t[:, 4].max()
+    tot = (t1 - t0) * G
+    main = epi = gap = tail = 0.0
+    jof = np.zeros(ntasks, dtype=int)
+    q = 0
+    for j in range(T):
+        jof[q:q + T - j] = j
+        q += T - j
+    ideal = 0.0
+    for cta in range(G):
+        prev = t0
+        for q in range(cta, ntasks, G):
+            gap += t[q, 0] - prev
+            main += t[q, 1] - t[q, 0]
+            epi += t[q, 4] - t[q, 1]
+            prev = t[q, 4]
+            ideal += jof[q] * 2 * 128 ** 3 / (37.0e12 / 148) * 1e6      # off-diagonal k-block at the per-SM DMMA ceiling
+        tail += t1 - prev
+    print(f"potrf {n}: {t1 - t0:.0f} us on {G} CTAs; CTA-time: main loops {100*main/tot:.1f} % (at the DMMA ceiling they would take "
+          f"{100*ideal/tot:.1f} %), epilogues {100*epi/tot:.1f} %, start-of-task gaps {100*gap/tot:.1f} %, idle after last task {100*tail/tot:.1f} %")
+    # the same per phase of the factorisation: thirds of the elapsed time
+    for lo, hi in ((0, 1 / 3), (1 / 3, 2 / 3), (2 / 3, 1)):
+        a, b = t0 + lo * (t1 - t0), t0 + hi * (t1 - t0)
+        busy = 0.0
+        for q in range(ntasks):
+            busy += max(0.0, min(t[q, 1], b) - max(t[q, 0], a))
+        print(f"   elapsed {lo:.2f}-{hi:.2f}: main-loop occupancy {100*busy/((b-a)*G):.1f} % of CTA-time")
+    sys.stdout.flush()
 
 
 def stage_potrf(ctx):
@@ -295,6 +347,26 @@ def stage_gpc(ctx):
         print(f"{os.path.basename(path)}: st {st} info {r['info']} iters {r['iters']}/{int(g['iters'])} logq {abs(r['logq']-g['logq'])/abs(g['logq']):.2e}"
               f" f {rel(r['f'], g['f']):.2e} a {rel(r['a'], g['a']):.2e} fstar {rel(r['fstar'], g['fstar']):.2e} V {rel(r['V'], g['V']):.2e}"
               f" probs {rel(probs, g['probs']):.2e} label-mismatch {int(np.sum(labels != g['labels']))} ({dt:.2f}s)", flush=True)
+
+
+def stage_potrftime(ctx):
+    """potrf timing only (for sweeps over GPNET_B200_POTRF_GRID and the like)."""
+    for n in (4096, 8192):
+        X = torch.randn(n, n, dtype=torch.float64, device=dev)
+        S = X @ X.T / n + torch.eye(n, dtype=torch.float64, device=dev)
+        Sb, ld = dmat(n, n)
+
+        def potrf():
+            Sb[:, :n] = S
+            ctx.potrf(n, Sb.data_ptr(), ld)
+
+        def copy_only():
+            Sb[:, :n] = S
+            ctx.sync()
+
+        t_p = ev(potrf, reps=5) - ev(copy_only, reps=5)
+        print(f"potrf {n}: {t_p:.3f} ms {n**3/3/t_p*1e-9:.2f} TFLOP/s", end="   ")
+    print(flush=True)
 
 
 if __name__ == "__main__":
