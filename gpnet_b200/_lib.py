@@ -246,8 +246,9 @@ class Context:
         return 0, out, info.value
 
     def set_fast_paths(self, level=True):
-        """Route of the regularized-Laplacian regressor likelihood: 0/False full kernel, 1 block path, 2/True Schur path."""
-        self.lib.gpn_set_fast_paths(self.h, 2 if level is True else int(level))
+        """Route of the regularized-Laplacian regressor likelihood: 0/False full kernel, 1 block route, 2 Schur route,
+        3/True Schur route with sparse coupling (default)."""
+        self.lib.gpn_set_fast_paths(self.h, 3 if level is True else int(level))
 
     def gpr_predict(self, kind, theta, t):
         th, tt = _f64(theta), _f64(t)

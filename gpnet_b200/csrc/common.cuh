@@ -84,8 +84,11 @@ struct gpn_ctx {
     std::vector<double> h_weights;
     bool perm_valid = false;
     bool train_unique = false;
-    int fast_reglap = 2;                 // regressor, regularized Laplacian: 0 full kernel, 1 block path, 2 Schur path (GPNET_B200_REGLAP_FAST)
+    int fast_reglap = 3;                 // regressor, regularized Laplacian: 0 full kernel, 1 block route, 2 Schur route, 3 Schur route with
+                                         // sparse coupling (GPNET_B200_REGLAP_FAST)
     DevBuf p_indptr, p_indices, p_weights, p_dinv, iota;
+    DevBuf to_indptr, to_idx, to_val;    // CSR of the (training rows) x (other columns) block of the permuted graph; values per theta
+    long long to_nnz = 0;
 
     // full-kernel state
     int kind = -1;
@@ -151,13 +154,18 @@ int gpn_k_dot(gpn_ctx* c, int n, const double* x, const double* y, double* d_out
 int gpn_k_sum(gpn_ctx* c, int n, const double* x, double* d_out);
 int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out);
 int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v);
+int gpn_k_csr_values(gpn_ctx* c, int rows, int row0, const int* indptr, const int* idx, const double* M, long ld, double* val);
+int gpn_k_spmm_rows(gpn_ctx* c, int rows, int cols, const int* indptr, const int* idx, const double* val, const double* Z, long ldz, double* X,
+                    long ldx);
+int gpn_k_schur_update(gpn_ctx* c, int n, const double* Mtt, long ldm, const int* indptr, const int* idx, const double* val, const double* X,
+                       long ldx, double* S, long lds);
 int gpn_k_fill_zero_lower(gpn_ctx* c, double* A, long ld, int rows);
 int gpn_k_gemv_t2(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* x1, const double* x2, double* y1, double* y2,
                   int mode);
 int gpn_k_bilinear_trace(gpn_ctx* c, int n, const double* S, long lds, const double* G, long ldg, const double* Ktt, long ldk, double g_scale,
                          double k_scale, const double* x1, const double* xt, double* d_out4);
 int gpn_k_trap_pass(gpn_ctx* c, int rows, int cols, int off, const double* Wb, long ld, const double* ya, const double* yb, double* za,
-                    double* zb, double* d_fro);
+                    double* zb, double* d_fro, bool zero_fro = true);
 int gpn_k_multi_dot(gpn_ctx* c, int count, const double* const* x, const double* const* y, const int* n, double* d_out);
 int gpn_k_colnorm2(gpn_ctx* c, int rows, int cols, const double* V, long ld, double* out);
 int gpn_k_diag_gather(gpn_ctx* c, const double* K, long ld, const int* idx, int m, double addc, double* out);

@@ -283,6 +283,58 @@ __global__ void bilinear_trace_kernel(int n, const double* __restrict__ S, long 
         atomicAdd(&out[3], s3);
     }
 }
+// ---- sparse coupling block of the permuted graph (training rows x other columns), CSR with row offsets into M ----------
+// val[e] = M[row0 + r][idx[e]]: the entries the scatter kernel wrote, so the sparse and the dense view hold identical numbers
+__global__ void csr_values_kernel(int rows, int row0, const int* __restrict__ indptr, const int* __restrict__ idx,
+                                  const double* __restrict__ M, long ld, double* __restrict__ val) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    for (int e = indptr[r] + lane; e < indptr[r + 1]; e += 32) val[e] = M[(long)(row0 + r) * ld + idx[e]];
+}
+// X[r][:] = sum_e val[e] * Z[idx[e]][:]   (sparse rows times a dense symmetric matrix; one double2 per thread, rows in grid.y)
+__global__ void spmm_rows_kernel(int cols, const int* __restrict__ indptr, const int* __restrict__ idx, const double* __restrict__ val,
+                                 const double* __restrict__ Z, long ldz, double* __restrict__ X, long ldx) {
+    const int r = blockIdx.y;
+    const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= cols) return;
+    const int e0 = indptr[r], e1 = indptr[r + 1];
+    double2 acc = make_double2(0.0, 0.0);
+    if (c + 1 < cols) {
+#pragma unroll 4
+        for (int e = e0; e < e1; ++e) {
+            const double v = val[e];
+            const double2 z = *reinterpret_cast<const double2*>(Z + (long)idx[e] * ldz + c);
+            acc.x = fma(v, z.x, acc.x);
+            acc.y = fma(v, z.y, acc.y);
+        }
+        *reinterpret_cast<double2*>(X + (long)r * ldx + c) = acc;
+    } else {
+        for (int e = e0; e < e1; ++e) acc.x = fma(val[e], Z[(long)idx[e] * ldz + c], acc.x);
+        X[(long)r * ldx + c] = acc.x;
+    }
+}
+// S[i][j] = Mtt[i][j] - sum_{e in row j} val[e] * X[i][idx[e]]  for j <= i  (lower triangle of the Schur complement
+// M_tt - M_to M_oo^-1 M_ot with X = M_to M_oo^-1; row i of X stays in L1 while the block sweeps j)
+__global__ void schur_update_kernel(int n, const double* __restrict__ Mtt, long ldm, const int* __restrict__ indptr,
+                                    const int* __restrict__ idx, const double* __restrict__ val, const double* __restrict__ X, long ldx,
+                                    double* __restrict__ S, long lds) {
+    const int i = blockIdx.x;
+    const double* xr = X + (long)i * ldx;
+    for (int j = threadIdx.x; j <= i; j += blockDim.x) {
+        double s0 = 0.0, s1 = 0.0;
+        int e = indptr[j];
+        const int e1 = indptr[j + 1];
+        for (; e + 1 < e1; e += 2) {
+            s0 = fma(val[e], xr[idx[e]], s0);
+            s1 = fma(val[e + 1], xr[idx[e + 1]], s1);
+        }
+        if (e < e1) s0 = fma(val[e], xr[idx[e]], s0);
+        S[(long)i * lds + j] = Mtt[(long)i * ldm + j] - (s0 + s1);
+    }
+    // the rest of the diagonal tile's row (strict upper part, never used by the factorisation) is left defined
+    const int jend = min(n, (i / 128 + 1) * 128);
+    for (int j = i + 1 + threadIdx.x; j < jend; j += blockDim.x) S[(long)i * lds + j] = 0.0;
+}
 // ---- Schur path of the regularized-Laplacian regressor: one pass over the bottom block-row Wb (rows x cols) of a lower-
 //      triangular inverse, row r being nonzero for col <= off + r:  za = Wb^T ya, zb = Wb^T yb (pre-zeroed; atomics over row
 //      blocks) and fro += sum Wb^2.  Each thread owns one column (coalesced rows).
@@ -538,15 +590,38 @@ int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v) {
     LAUNCHED(c);
     return 0;
 }
+int gpn_k_csr_values(gpn_ctx* c, int rows, int row0, const int* indptr, const int* idx, const double* M, long ld, double* val) {
+    if (rows <= 0) return 0;
+    csr_values_kernel<<<grid1((long)rows * 32), TPB, 0, c->stream>>>(rows, row0, indptr, idx, M, ld, val);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_spmm_rows(gpn_ctx* c, int rows, int cols, const int* indptr, const int* idx, const double* val, const double* Z, long ldz, double* X,
+                    long ldx) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid(grid1((cols + 1) / 2, 128), rows);
+    spmm_rows_kernel<<<grid, 128, 0, c->stream>>>(cols, indptr, idx, val, Z, ldz, X, ldx);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_schur_update(gpn_ctx* c, int n, const double* Mtt, long ldm, const int* indptr, const int* idx, const double* val, const double* X,
+                       long ldx, double* S, long lds) {
+    if (n <= 0) return 0;
+    schur_update_kernel<<<n, 256, 0, c->stream>>>(n, Mtt, ldm, indptr, idx, val, X, ldx, S, lds);
+    LAUNCHED(c);
+    return 0;
+}
 int gpn_k_trap_pass(gpn_ctx* c, int rows, int cols, int off, const double* Wb, long ld, const double* ya, const double* yb, double* za,
-                    double* zb, double* d_fro) {
+                    double* zb, double* d_fro, bool zero_fro) {
     // za and zb are contiguous (zb = za + cols rounded by the caller) or separate: zero both, and the scalar
     zero_vec_kernel<<<grid1(cols), TPB, 0, c->stream>>>(cols, za);
     LAUNCHED(c);
     zero_vec_kernel<<<grid1(cols), TPB, 0, c->stream>>>(cols, zb);
     LAUNCHED(c);
-    zero_vec_kernel<<<1, 32, 0, c->stream>>>(1, d_fro);
-    LAUNCHED(c);
+    if (zero_fro) {
+        zero_vec_kernel<<<1, 32, 0, c->stream>>>(1, d_fro);
+        LAUNCHED(c);
+    }
     if (rows <= 0 || cols <= 0) return 0;
     const int rpb = 64;
     dim3 grid(grid1(cols, 128), (rows + rpb - 1) / rpb);

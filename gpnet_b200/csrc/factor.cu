@@ -20,7 +20,7 @@ constexpr int LB = leaf::LB;
 // One CTA (256 threads): factor the nv x nv (nv <= 128) diagonal block at A (lower Cholesky, written back, strict upper
 // zeroed) and write inv(L) (identity-padded to 128x128, upper zero) to winv (ld 128).  Body: leaf.cuh.
 __global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ A, long lda, int nv, double* __restrict__ winv,
-                                                            int* __restrict__ info, int info_off, long long* prof, int exp) {
+                                                            int* __restrict__ info, int info_off, long long* prof) {
     // blockIdx.x > 0 only in the timing harness (gpn_debug_leaf_bench): every block factors its own copy so that the leaf is
     // timed on a full grid (single-CTA launches of kernels larger than the instruction cache are not representative)
     A += (long)blockIdx.x * LB * lda;
@@ -43,12 +43,10 @@ __global__ void __launch_bounds__(256, 1) potf2_inv_kernel(double* __restrict__ 
     }
     __syncthreads();
     if (prof && tid == 0) prof[31] = clock64();
-    leaf::potf2_inverse<0>(S, Wd, T, A, lda, nv, winv, info, info_off, tid, prof, exp);
+    leaf::potf2_inverse<0>(S, Wd, T, A, lda, nv, winv, info, info_off, tid, prof);
 }
 
 constexpr size_t LEAF_SMEM = leaf::SMEM_BYTES;
-// development aid: GPNET_B200_LEAF_EXP switches off pieces of the stand-alone leaf's off-chain work (timing experiments only)
-static int leaf_exp() { static const int v = getenv("GPNET_B200_LEAF_EXP") ? atoi(getenv("GPNET_B200_LEAF_EXP")) : 0; return v; }
 
 int launch_leaf(gpn_ctx* c, double* A, long lda, int nv, double* winv, int* d_info, int info_off) {
     static bool configured = false;
@@ -56,7 +54,7 @@ int launch_leaf(gpn_ctx* c, double* A, long lda, int nv, double* winv, int* d_in
         GPN_CK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
         configured = true;
     }
-    potf2_inv_kernel<<<1, 256, LEAF_SMEM, c->stream>>>(A, lda, nv, winv, d_info, info_off, (long long*)c->leaf_prof, leaf_exp());
+    potf2_inv_kernel<<<1, 256, LEAF_SMEM, c->stream>>>(A, lda, nv, winv, d_info, info_off, (long long*)c->leaf_prof);
     c->launches++;
     GPN_CK(cudaGetLastError());
     return 0;
@@ -67,7 +65,7 @@ int launch_leaf(gpn_ctx* c, double* A, long lda, int nv, double* winv, int* d_in
 // Timing harness: `copies` independent 128x128 blocks stacked in A (lda = 128), one CTA each; block 0 records clock64 stamps.
 int gpn_leaf_bench(gpn_ctx* c, double* A, int copies, double* winv, int* d_info, long long* prof) {
     GPN_CK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM));
-    potf2_inv_kernel<<<copies, 256, LEAF_SMEM, c->stream>>>(A, LB, LB, winv, d_info, 0, prof, leaf_exp());
+    potf2_inv_kernel<<<copies, 256, LEAF_SMEM, c->stream>>>(A, LB, LB, winv, d_info, 0, prof);
     c->launches++;
     GPN_CK(cudaGetLastError());
     return 0;

@@ -644,6 +644,20 @@ int ensure_perm(gpn_ctx* c) {
         wdev = (const double*)c->p_weights.p;
     }
     GPN_TRY(gpn_k_degree_dinv(c, N, (const int*)c->p_indptr.p, (const int*)c->p_indices.p, wdev, (double*)c->p_dinv.p));
+    // coupling block (training rows) x (other columns) of the permuted graph: what the sparse-coupling route multiplies with
+    const int o = N - n;
+    std::vector<int> tptr(n + 1, 0), tidx;
+    for (int r = 0; r < n; ++r) {
+        for (int q = pptr[o + r]; q < pptr[o + r + 1]; ++q)
+            if (pidx[q] < o) tidx.push_back(pidx[q]);
+        tptr[r + 1] = (int)tidx.size();
+    }
+    c->to_nnz = (long long)tidx.size();
+    GPN_TRY(gpn_buf_ensure(c, c->to_indptr, sizeof(int) * (size_t)(n + 1)));
+    GPN_TRY(gpn_buf_ensure(c, c->to_idx, sizeof(int) * (tidx.size() + 1)));
+    GPN_TRY(gpn_buf_ensure(c, c->to_val, sizeof(double) * (tidx.size() + 1)));
+    GPN_TRY(upload(c, c->to_indptr.p, tptr.data(), sizeof(int) * (size_t)(n + 1)));
+    if (!tidx.empty()) GPN_TRY(upload(c, c->to_idx.p, tidx.data(), sizeof(int) * tidx.size()));
     c->perm_valid = true;
     return 0;
 }
@@ -826,9 +840,79 @@ int gpr_reglap_schur_scalars(gpn_ctx* c, const double* theta_h, int P, const dou
     }
     return 0;
 }
+// Schur route with sparse coupling (gradient evaluations): the only link between the other nodes (o) and the training nodes (t)
+// in M = I + beta L~ is the SPARSE block M_to (graph edges between the two sets), so the elimination of the o-block does not
+// need the dense N x N factorisation:
+//     Z = M_oo^-1 (dense SPD inverse, o^3),   X = M_to Z (sparse x dense, memory bound),   S = M_tt - X M_ot = L_tt L_tt^T,
+//     W_tt = L_tt^-1,   W_to = -W_tt L_to W_oo = -W_tt M_to M_oo^-1 = -W_tt X            (one triangular n x o x n product)
+// and the reductions of the Schur route run over [W_to  W_tt] as before: o^3 + n^2 o + 2 n^3/3 flops instead of 2 N^3/3
+// (half at n = N/2).  S, L_tt and the reductions are the same quantities as on level 2, so results agree to rounding.
+int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const double* t_h, RowScalars* rs, int* info_h) {
+    const int N = c->N, n = c->n_train, o = N - n;
+    GPN_TRY(ensure_perm(c));
+    GPN_TRY(ensure_vecs(c));
+    c->have_full = false;
+    c->kind = GPN_KERNEL_REGULARIZED_LAPLACIAN;
+    c->P = P;
+    for (int i = 0; i < P; ++i) c->theta_exp[i] = exp(theta_h[i]);
+    c->ldN = pad128(N);
+    GPN_TRY(clear_info(c));
+    const long ld = c->ldN, ldn = pad128(n);
+    const double beta = c->theta_exp[0];
+    for (int i = 0; i < 4; ++i) GPN_TRY(ensure_mat(c, i));
+    double* M = mat(c, 0);
+    if (t_h) GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
+    else GPN_CK(cudaMemcpyAsync(vecp(c, V_T), vecp(c, V_TRES), sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    GPN_TRY(gpn_k_fill_zero_lower(c, M, ld, (int)ld));
+    GPN_TRY(gpn_k_laplacian_scatter(c, N, (const int*)c->p_indptr.p, (const int*)c->p_indices.p,
+                                    c->h_weights.empty() ? nullptr : (const double*)c->p_weights.p, (const double*)c->p_dinv.p, beta, 1.0, M, ld));
+    const int *tptr = (const int*)c->to_indptr.p, *tidx = (const int*)c->to_idx.p;
+    double* tval = (double*)c->to_val.p;
+    GPN_TRY(gpn_k_csr_values(c, n, o, tptr, tidx, M, ld, tval));
+    // Z = M_oo^-1 in place (full symmetric, leading o x o block of M); rows >= o of M keep M_to and the lower part of M_tt
+    GPN_TRY(spd_inverse(c, o, M, ld, mat(c, 1), mat(c, 2), mat(c, 3), M, 0));
+    GPN_TRY(ensure_nb(c, NB_ROWS1, n, ld));
+    double* X = nbp(c, NB_ROWS1);
+    GPN_TRY(gpn_k_spmm_rows(c, n, o, tptr, tidx, tval, M, ld, X, ld));
+    GPN_TRY(ensure_nb(c, NB_KY, ldn, ldn));
+    GPN_TRY(ensure_nb(c, NB_W, ldn, ldn));
+    GPN_TRY(ensure_nb(c, NB_T, ldn, ldn));
+    GPN_TRY(ensure_nb(c, NB_WT, ldn, ldn));
+    double* S = nbp(c, NB_KY);
+    GPN_TRY(gpn_k_schur_update(c, n, M + (long)o * ld + o, ld, tptr, tidx, tval, X, ld, S, ldn));
+    GprFactor f;
+    GPN_TRY(gpr_factor_ky(c, &f));                                                              // L_tt (in S), W_tt, W_tt^T
+    double *ones = vecp(c, V_U), *r1 = vecp(c, V_Z), *rt = vecp(c, V_Z2);
+    GPN_TRY(gpn_k_fill_vec(c, n, ones, 1.0));
+    GPN_TRY(gpn_k_gemv_t2(c, n, n, S, ldn, ones, vecp(c, V_T), r1, rt, GEMV_LOWER));
+    GPN_TRY(gpn_k_sumlogdiag(c, n, S, ldn, dscal(c, Scal::LOGDET)));
+    // P = W_tt X = -W_to  (W_tt lower triangular: only k < m0 + 128 contributes)
+    GPN_TRY(ensure_nb(c, NB_ROWS2, n, ld));
+    double* Pm = nbp(c, NB_ROWS2);
+    if (o > 0) GPN_TRY(gpn_gemm(c, n, o, n, 1.0, f.W, f.ldn, true, X, ld, false, 0.0, Pm, ld, GF_KHI_M));
+    GPN_TRY(ensure_nb(c, NB_S, 2, ld));
+    double *z1 = nbp(c, NB_S), *zt = z1 + ld;                    // z = Wb^T y laid out as [o | n]; the sign of the o part cancels in every dot
+    GPN_TRY(gpn_k_trap_pass(c, n, o, N, Pm, ld, r1, rt, z1, zt, dscal(c, Scal::FRO), true));
+    GPN_TRY(gpn_k_trap_pass(c, n, n, 0, f.W, f.ldn, r1, rt, z1 + o, zt + o, dscal(c, Scal::FRO), false));
+    const double *dx[6] = {r1, r1, rt, z1, z1, zt}, *dy[6] = {r1, rt, rt, z1, zt, zt};
+    const int dn[6] = {n, n, n, N, N, N};
+    GPN_TRY(gpn_k_multi_dot(c, 6, dx, dy, dn, dscal(c, Scal::SCH0)));
+    double sc[Scal::NDBL];
+    int info[16];
+    GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
+    if (info_h) *info_h = info[1] ? info[1] : info[0];
+    rs->n = n;
+    rs->half_logdet = -sc[Scal::LOGDET];
+    rs->s = sc[Scal::SCH0]; rs->a = sc[Scal::SCH0 + 1]; rs->q = sc[Scal::SCH0 + 2];
+    rs->D11 = sc[Scal::SCH0 + 3] - rs->s; rs->D1t = sc[Scal::SCH0 + 4] - rs->a; rs->Dtt = sc[Scal::SCH0 + 5] - rs->q;
+    rs->trSD = sc[Scal::FRO] - n;
+    return 0;
+}
+
 int gpr_logp_grad_reglap_schur(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
     RowScalars rs;
-    GPN_TRY(gpr_reglap_schur_scalars(c, theta_h, P, t_h, want_grad, &rs, info_h));
+    if (want_grad && c->fast_reglap >= 3) GPN_TRY(gpr_reglap_coupled_scalars(c, theta_h, P, t_h, &rs, info_h));
+    else GPN_TRY(gpr_reglap_schur_scalars(c, theta_h, P, t_h, want_grad, &rs, info_h));
     row_eval(rs, c->theta_exp[P - 1], P, want_grad, out_h);
     return 0;
 }
@@ -838,7 +922,8 @@ int gpr_logp_grad_reglap_schur(gpn_ctx* c, const double* theta_h, int P, const d
 // grid row shares them.  info > 0: K_tt itself is not positive definite (the caller falls back to factoring K_y per point).
 int gpr_row_scalars(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad, RowScalars* rs, int* info_h) {
     if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN && c->fast_reglap >= 2 && c->train_unique && c->n_train < c->N)
-        return gpr_reglap_schur_scalars(c, theta_h, P, t_h, want_grad, rs, info_h);
+        return (want_grad && c->fast_reglap >= 3) ? gpr_reglap_coupled_scalars(c, theta_h, P, t_h, rs, info_h)
+                                                  : gpr_reglap_schur_scalars(c, theta_h, P, t_h, want_grad, rs, info_h);
     int st = kernel_build(c, kind, theta_h, P, want_grad);
     if (st != 0) return st;
     GPN_TRY(ensure_vecs(c));
@@ -1274,7 +1359,7 @@ void gpn_destroy(gpn_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->mat[9] = DevBuf();   // alias slot
     DevBuf* all[] = {&c->indptr, &c->indices, &c->weights, &c->dinv, &c->train_idx, &c->test_idx, &c->tvec, &c->winv, &c->scal, &c->partial,
-                     &c->flags, &c->p_indptr, &c->p_indices, &c->p_weights, &c->p_dinv, &c->iota};
+                     &c->flags, &c->p_indptr, &c->p_indices, &c->p_weights, &c->p_dinv, &c->iota, &c->to_indptr, &c->to_idx, &c->to_val};
     for (DevBuf* b : all)
         if (b->p) cudaFree(b->p);
     for (auto& b : c->mat)
@@ -1394,7 +1479,7 @@ int gpn_debug_leaf_bench(gpn_ctx* c, void* A_dev, int copies, void* prof32_dev) 
     return gpn_leaf_bench(c, (double*)A_dev, copies, (double*)c->winv.p, iscal(c, 0), (long long*)prof32_dev);
 }
 void gpn_set_fast_paths(gpn_ctx* c, int level) {
-    if (c) c->fast_reglap = level < 0 ? 0 : (level > 2 ? 2 : level);
+    if (c) c->fast_reglap = level < 0 ? 0 : (level > 3 ? 3 : level);
 }
 void gpn_debug_df_trace(gpn_ctx* c, void* dev_buf) {
     if (c) c->df_trace = dev_buf;

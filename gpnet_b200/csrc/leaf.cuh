@@ -2,12 +2,12 @@
 // Used by the stand-alone leaf kernel (factor.cu) and inside the dataflow Cholesky (potrf_dataflow.cu).
 //
 //  * 32x32 diagonal sub-blocks: ONE warp, rows in registers, software-pipelined column sweep (no block barrier on the
-//    per-pivot dependency chain);
-//  * panel below a diagonal block: one thread per row, column sweep against L_kk in shared memory;
-//  * trailing updates and the off-diagonal blocks of the inverse: DMMA shared-memory GEMMs over all 8 warps;
-//  * inverses of the four diagonal blocks: row sweeps, one warp per block.
-// Shared memory: guard band, S[128][129] (padded, conflict-free column access), Wd[4][32][33], T[96][33], 1/diag, column
-// broadcast buffer.
+//    per-pivot dependency chain); a partner warp on another SMSP inverts the block in lockstep, one pivot step behind;
+//  * panel below a diagonal block, trailing updates, block rows of the inverse: DMMA shared-memory products;
+//  * global write-backs and everything that is not on the chain run next to the factorisation of the next diagonal block.
+// Shared memory: guard band, S[128][129] (padded, conflict-free column access; its unused strictly-upper 32-blocks hold the
+// off-diagonal blocks of the inverse), Wd[4][32][33] (diagonal blocks of the inverse), T (32 x 97 scratch), 1/diag, column
+// broadcast buffer, 32 step mbarriers.
 #pragma once
 #include <type_traits>
 
@@ -19,7 +19,7 @@ namespace leaf {
 constexpr int LB = 128;
 constexpr int LDS_ = LB + 1;
 constexpr int WLD = 33;
-constexpr int GUARD = 32;                   // doubles in front of S (diag32_inverse reads up to 31 doubles before a row start)
+constexpr int GUARD = 32;                   // doubles in front of S (kept zero; absorbs reads just before a row start)
 constexpr int TLD = 97;                     // row stride of T when it holds a 32 x 96 block row (v2)
 constexpr size_t SMEM_DOUBLES = GUARD + (size_t)LB * LDS_ + 4 * 32 * WLD + 96 * WLD + LB + 128 + 32;   // guard, S, Wd, T, 1/diag, column broadcast, 32 step mbarriers
 constexpr size_t SMEM_BYTES = SMEM_DOUBLES * sizeof(double);
@@ -157,56 +157,6 @@ __device__ __forceinline__ void diag32_factor(double* __restrict__ S, int b0, do
 #pragma unroll 1
     for (int c = 16; c < 32; ++c) pivot_step(c, std::integral_constant<int, 16>{});   // columns >= 32 do not exist
     if (first_bad < 32 && lane == 0) atomicCAS(info, 0, info_off + b0 + first_bad + 1);
-}
-
-// One thread per row below the diagonal block: row <- row * L_kk^-T by a column sweep against L_kk in shared memory
-// (broadcast reads), i.e. the panel solve without forming the inverse of the diagonal block.  Chain per column: mul -> fma.
-__device__ __forceinline__ void panel_sweep(double* __restrict__ S, int b0, int row, const double* __restrict__ rdiag) {
-    const double* lp = S + b0 * LDS_ + b0;      // &L_kk[c][c], advanced along the diagonal
-    double* Sr = S + row * LDS_ + b0;
-    double y[32];
-#pragma unroll
-    for (int q = 0; q < 32; ++q) y[q] = Sr[q];
-    auto step = [&](int c, auto qm_tag) {
-        constexpr int QM = decltype(qm_tag)::value;
-        const double x = y[0] * rdiag[c];
-        Sr[c] = x;
-        // y[q] is column c+q; L[c+q][c] = lp[q*LDS_]
-#pragma unroll
-        for (int q = 1; q <= QM; ++q) y[q - 1] = y[q] - x * lp[q * LDS_];
-        lp += LDS_ + 1;
-    };
-#pragma unroll 1
-    for (int c = 0; c < 16; ++c) step(c, std::integral_constant<int, 31>{});
-#pragma unroll 1
-    for (int c = 16; c < 32; ++c) step(c, std::integral_constant<int, 15>{});     // columns >= 32 do not exist
-}
-
-// One warp: W = L_kk^-1, lane r owns ROW r of W (x L_kk = e_r), columns swept from 31 down to 0 against the rows of
-// L_kk in shared memory (broadcast reads).  z[q] is the pending value of column c-q, so the current column is z[0]
-// (static register indices in a rolled loop); chain per column: mul -> fma.  Wrapped columns read the zero upper part.
-__device__ __forceinline__ void diag32_inverse(const double* __restrict__ S, int b0, double* __restrict__ Wb, const double* __restrict__ rdiag,
-                                               int lane) {
-    const double* lc = S + (b0 + 31) * LDS_ + b0 + 31;     // &L_kk[c][c], walked up the diagonal
-    double* wp = Wb + lane * WLD + 31;
-    double z[32];
-#pragma unroll
-    for (int q = 0; q < 32; ++q) z[q] = (lane == 31 - q) ? 1.0 : 0.0;
-    auto step = [&](int c, auto qm_tag) {
-        constexpr int QM = decltype(qm_tag)::value;
-        const double x = z[0] * rdiag[c];
-        *wp = x;                                      // zero for c > lane by construction
-        // z[q] is column c-q; L[c][c-q] = lc[-q]
-#pragma unroll
-        for (int q = 1; q <= QM; ++q) z[q - 1] = z[q] - x * lc[-q];
-        lc -= LDS_ + 1;
-        --wp;
-    };
-#pragma unroll 1
-    for (int c = 31; c >= 16; --c) step(c, std::integral_constant<int, 31>{});
-#pragma unroll 1
-    for (int c = 15; c >= 0; --c) step(c, std::integral_constant<int, 15>{});     // columns < 0 do not exist
-    __syncwarp();
 }
 
 // Lookahead piece of the trailing update: only the NEXT diagonal block, D -= P P^T with P = its 32 rows of the freshly solved
@@ -390,89 +340,10 @@ __device__ __forceinline__ void write_back_step(const double* __restrict__ S, co
 }
 
 // S holds the lower triangle of an SPD 128x128 block (identity padded beyond the valid size by the caller).
-// On return S holds inv(L) (lower); L has been written to Lout (valid nv x nv region, strict upper zeroed) and
-// inv(L) to winv (128x128, ld 128, upper zero, identity padding).
-template <int BAR_ID>
-__device__ __forceinline__ void potf2_inverse_v1(double* __restrict__ S, double* __restrict__ Wd, double* __restrict__ T,
-                                                 double* __restrict__ Lout, long ldl, int nv, double* __restrict__ winv, int* info,
-                                                 int info_off, int tid, long long* prof = nullptr) {
-    const int warp = tid >> 5, lane = tid & 31;
-    int pidx = 0;
-#define LEAF_STAMP() do { if (prof && tid == 0) prof[pidx++] = clock64(); } while (0)
-    LEAF_STAMP();
-    // ---------------- factorisation, 32-wide block columns, right looking with lookahead ----------------
-    // chain: D(0) -> [ panel(kb) -> next diagonal block update -> D(kb+1) ]; the rest of the trailing update of step kb runs on
-    // the six warps of SMSPs 1..3 while warp 0 (alone on SMSP 0: its dependent FP64 chain must not queue behind DMMAs)
-    // factors diagonal block kb+1.
-    double* rdiag = T + 96 * WLD;
-    if (warp == 0) diag32_factor(S, 0, rdiag, rdiag + LB, info, info_off, lane);
-    bar256<BAR_ID>();
-    LEAF_STAMP();
-#pragma unroll 1
-    for (int kb = 0; kb < 3; ++kb) {
-        const int b0 = 32 * kb, r1 = b0 + 32, R = LB - r1;
-        if (tid < R) panel_sweep(S, b0, r1 + tid, rdiag + b0);
-        bar256<BAR_ID>();
-        LEAF_STAMP();
-        trail_diag(S, b0, tid);
-        bar256<BAR_ID>();
-        if (warp == 0) {
-            diag32_factor(S, r1, rdiag + r1, rdiag + LB, info, info_off, lane);
-        } else if (R > 32) {
-            double* C22 = S + r1 * LDS_ + r1;
-            smem_dmma<LDS_, LDS_, true, 2>(S + r1 * LDS_ + b0, S + r1 * LDS_ + b0, R / 16, R / 32, 32, tid,
-                                           [&](int r, int cc, double v) { C22[r * LDS_ + cc] -= v; }, 0xEEu, true);   // not warps 0, 4 (SMSP 0)
-        }
-        bar256<BAR_ID>();
-        LEAF_STAMP();
-    }
-    // ---------------- write L back ----------------
-    // lower triangle (+ the one pair straddling the diagonal); the strict upper triangle of a diagonal tile is never read
-    // by the library (the public gpn_potrf_f64 zeroes it afterwards)
-    for (int idx = tid; idx < LB * LB / 2; idx += 256) {
-        const int r = idx >> 6, c = (idx & 63) * 2;
-        if (r < nv && c <= r) {
-            const double v0 = S[r * LDS_ + c], v1 = (c + 1 <= r) ? S[r * LDS_ + c + 1] : 0.0;
-            if (c + 1 < nv) *reinterpret_cast<double2*>(Lout + (long)r * ldl + c) = make_double2(v0, v1);
-            else Lout[(long)r * ldl + c] = v0;
-        }
-    }
-    bar256<BAR_ID>();
-    LEAF_STAMP();
-    // ---------------- inverse: the four diagonal blocks in parallel (one warp each), then block columns right to left ------
-    if (warp < 4) diag32_inverse(S, 32 * warp, Wd + warp * 32 * WLD, rdiag + 32 * warp, lane);
-    bar256<BAR_ID>();
-    LEAF_STAMP();
-    for (int idx = tid; idx < 4 * 32 * 32; idx += 256) {
-        const int b = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
-        S[(32 * b + r) * LDS_ + 32 * b + c] = Wd[b * 32 * WLD + r * WLD + c];
-    }
-    bar256<BAR_ID>();
-#pragma unroll 1
-    for (int k = 2; k >= 0; --k) {
-        const int r1 = 32 * (k + 1), R = LB - r1;
-        // T = L_col * W_kk            (R x 32, K = 32)
-        smem_dmma<LDS_, WLD, false, 0>(S + r1 * LDS_ + 32 * k, Wd + k * 32 * WLD, R / 16, 1, 32, tid,
-                                       [&](int r, int cc, double v) { T[r * WLD + cc] = v; });
-        bar256<BAR_ID>();
-        // X = -W_trail * T            (W_trail lower triangular => k <= row)
-        {
-            double* X = S + r1 * LDS_ + 32 * k;
-            smem_dmma<LDS_, WLD, false, 1>(S + r1 * LDS_ + r1, T, R / 16, 1, R, tid, [&](int r, int cc, double v) { X[r * LDS_ + cc] = -v; });
-        }
-        bar256<BAR_ID>();
-        LEAF_STAMP();
-    }
-    // lower triangle only: winv buffers are zero-initialised when they are allocated and the upper part is never written
-    for (int idx = tid; idx < LB * LB / 2; idx += 256) {
-        const int r = idx >> 6, c = (idx & 63) * 2;
-        if (c <= r) reinterpret_cast<double2*>(winv)[idx] = make_double2(S[r * LDS_ + c], (c + 1 <= r) ? S[r * LDS_ + c + 1] : 0.0);
-    }
-    LEAF_STAMP();
-#undef LEAF_STAMP
-}
-
-// Version 2 of the leaf: the same results, organised so that almost nothing but the 128 pivot steps is left on the critical path.
+// On return L has been written to Lout (valid nv x nv region, lower part) and inv(L) to winv (128x128, ld 128, lower part,
+// identity padding); S is scratch.
+//
+// Organised so that little but the 128 pivot steps is left on the critical path:
 //  * while warp 0 factors a 32x32 diagonal block, warp 1 (another SMSP) inverts it in lockstep (diag32_inverse_lockstep);
 //  * with W_kk at hand the panel below the block is ONE small DMMA product (panel * W_kk^T) instead of a 32-step sweep;
 //  * block row kb of the inverse, W(kb, :) = -W_kk (L(kb, :kb) W(:kb, :kb)), is finished right after W_kk: the product
@@ -480,9 +351,9 @@ __device__ __forceinline__ void potf2_inverse_v1(double* __restrict__ S, double*
 //    global write-backs of everything step kb - 1 finalised.
 // Chain: D0, then 3 x [panel product + next diagonal update, D(kb+1)], then the last -W_33 T and 32 rows of write-back.
 template <int BAR_ID>
-__device__ __forceinline__ void potf2_inverse_v2(double* __restrict__ S, double* __restrict__ Wd, double* __restrict__ T,
+__device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __restrict__ Wd, double* __restrict__ T,
                                                  double* __restrict__ Lout, long ldl, int nv, double* __restrict__ winv, int* info,
-                                                 int info_off, int tid, long long* prof = nullptr, int exp = 0) {
+                                                 int info_off, int tid, long long* prof = nullptr) {
     const int warp = tid >> 5, lane = tid & 31;
     int pidx = 0;
 #define LEAF_STAMP() do { if (prof && tid == 0) prof[pidx++] = clock64(); } while (0)
@@ -524,15 +395,15 @@ __device__ __forceinline__ void potf2_inverse_v2(double* __restrict__ S, double*
             diag32_inverse_lockstep(S, r1, Wd + (kb + 1) * 32 * WLD, rdiag + r1, bars, (kb + 1) & 1, lane);
             if (prof && lane == 0) prof[20 + kb] = clock64();
         } else if (warp == 4) {
-            if (!(exp & 2)) write_back_step(S, Wd, kb, Lout, ldl, nv, winv, tid, 0x10u, false);
+            write_back_step(S, Wd, kb, Lout, ldl, nv, winv, tid, 0x10u, false);
             if (prof && lane == 0) prof[28 + kb] = clock64();
         } else {
-            if (R > 32 && !(exp & 1)) {
+            if (R > 32) {
                 double* C22 = S + r1 * LDS_ + r1;
                 smem_dmma<LDS_, LDS_, true, 2>(S + r1 * LDS_ + b0, S + r1 * LDS_ + b0, R / 16, R / 32, 32, tid,
                                                [&](int r, int cc, double v) { C22[r * LDS_ + cc] -= v; }, OFFCHAIN, true);
             }
-            if (!(exp & 4)) inv_row_T(S, Wd, T, kb + 1, tid, OFFCHAIN);
+            inv_row_T(S, Wd, T, kb + 1, tid, OFFCHAIN);
             if (prof && tid == 64) prof[24 + kb] = clock64();
         }
         bar256<BAR_ID>();
@@ -543,20 +414,6 @@ __device__ __forceinline__ void potf2_inverse_v2(double* __restrict__ S, double*
     if (tid < 32) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + 8 * tid) : "memory");   // the region is reused (TMA ring)
     LEAF_STAMP();
 #undef LEAF_STAMP
-}
-
-#ifndef GPN_LEAF_VERSION
-#define GPN_LEAF_VERSION 2
-#endif
-template <int BAR_ID>
-__device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __restrict__ Wd, double* __restrict__ T,
-                                              double* __restrict__ Lout, long ldl, int nv, double* __restrict__ winv, int* info,
-                                              int info_off, int tid, long long* prof = nullptr, int exp = 0) {
-#if GPN_LEAF_VERSION == 1
-    potf2_inverse_v1<BAR_ID>(S, Wd, T, Lout, ldl, nv, winv, info, info_off, tid, prof);
-#else
-    potf2_inverse_v2<BAR_ID>(S, Wd, T, Lout, ldl, nv, winv, info, info_off, tid, prof, exp);
-#endif
 }
 
 }   // namespace leaf

@@ -40,7 +40,6 @@ struct DfArgs {
     int* info;
     int info_off;
     long long* trace;     // optional: 8 x int64 globaltimer stamps per task (development aid)
-    int leaf_exp;         // development aid (GPNET_B200_LEAF_EXP): switches off pieces of the leaf's off-chain work
 };
 
 __device__ __forceinline__ void wait_flag(const int* f, int epoch) {
@@ -244,7 +243,7 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
             DF_STAMP(2);
             const int nv = min(TB, g.n - j * TB);
             leaf::potf2_inverse<1>(S, Wd, Tt, g.A + ((long)j * TB) * g.lda + (long)j * TB, g.lda, nv, g.winv + (long)j * TB * TB, g.info,
-                                   g.info_off + j * TB, tid, nullptr, g.leaf_exp);
+                                   g.info_off + j * TB, tid);
             __threadfence();
             bar_consumers();
             if (tid == 0) {
@@ -348,8 +347,6 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
     DfArgs a;
     a.A = A; a.lda = lda; a.n = n; a.T = T; a.ntasks = ntasks; a.winv = winv; a.flags = (int*)c->flags.p;
     a.epoch = ++c->epoch; a.info = d_info; a.info_off = info_offset; a.trace = (long long*)c->df_trace;
-    static const int leaf_exp = getenv("GPNET_B200_LEAF_EXP") ? atoi(getenv("GPNET_B200_LEAF_EXP")) : 0;
-    a.leaf_exp = leaf_exp;
     CUtensorMap tl, tw;
     GPN_TRY(encode_tiles(c, &tl, A, lda, n, n));
     GPN_TRY(encode_tiles(c, &tw, winv, TB, (long)T * TB, TB));
@@ -359,7 +356,6 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
         configured = true;
     }
     int grid = ntasks < c->num_sms ? ntasks : c->num_sms;
-    if (const char* e = getenv("GPNET_B200_POTRF_GRID")) { const int v = atoi(e); if (v > 0 && v < grid) grid = v; }   // experiments
     if (c->potrf_grid_cap > 0 && grid > c->potrf_grid_cap) grid = c->potrf_grid_cap;   // leave SMs to concurrent work
     void* args[] = {(void*)&tl, (void*)&tw, (void*)&a};
     // executed flops: an off-diagonal task runs j k-blocks of 128^3 MACs, a diagonal one only the 136 of 256 8x8 blocks that
