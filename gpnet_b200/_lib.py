@@ -247,8 +247,8 @@ class Context:
 
     def set_fast_paths(self, level=True):
         """Route of the regularized-Laplacian regressor likelihood: 0/False full kernel, 1 block route, 2 Schur route,
-        3/True Schur route with sparse coupling (default)."""
-        self.lib.gpn_set_fast_paths(self.h, 3 if level is True else int(level))
+        3 Schur route with sparse coupling, 4/True the same with the triangular work appended to the Cholesky kernels (default)."""
+        self.lib.gpn_set_fast_paths(self.h, 4 if level is True else int(level))
 
     def gpr_predict(self, kind, theta, t):
         th, tt = _f64(theta), _f64(t)

@@ -84,8 +84,9 @@ struct gpn_ctx {
     std::vector<double> h_weights;
     bool perm_valid = false;
     bool train_unique = false;
-    int fast_reglap = 3;                 // regressor, regularized Laplacian: 0 full kernel, 1 block route, 2 Schur route, 3 Schur route with
-                                         // sparse coupling (GPNET_B200_REGLAP_FAST)
+    int fast_reglap = 4;                 // regressor, regularized Laplacian: 0 full kernel, 1 block route, 2 Schur route, 3 Schur route with
+                                         // sparse coupling, 4 the same with the triangular work appended to the
+                                         // two Cholesky kernels (GPNET_B200_REGLAP_FAST)
     DevBuf p_indptr, p_indices, p_weights, p_dinv, iota;
     DevBuf to_indptr, to_idx, to_val;    // CSR of the (training rows) x (other columns) block of the permuted graph; values per theta
     long long to_nnz = 0;
@@ -128,7 +129,8 @@ int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, lon
 // Cholesky (lower, in place, row-major), triangular inverse and SPD inverse.  info: device int (0 = ok).
 int gpn_potrf(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset = 0);
 int gpn_leaf_bench(gpn_ctx* c, double* A, int copies, double* winv, int* d_info, long long* prof);
-int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset);
+int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset, double* B = nullptr, long ldb = 0,
+                       int brows = 0, double* Wt = nullptr, long ldwt = 0);   // B <- B L^-T, Wt <- L^-T (upper tiles): see potrf_dataflow.cu
 // W = L^-1 (normal, lower) and WT = W^T (upper) from L and the inverted diagonal blocks; TT: n x n scratch.  All ld = ldw.
 int gpn_trtri(gpn_ctx* c, int n, const double* L, long ldl, const double* winv, double* W, double* WT, double* TT, long ldw);
 // out (lower [+ mirrored upper]) = W^T W computed from WT = W^T (both operands K-major)
@@ -154,6 +156,10 @@ int gpn_k_dot(gpn_ctx* c, int n, const double* x, const double* y, double* d_out
 int gpn_k_sum(gpn_ctx* c, int n, const double* x, double* d_out);
 int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out);
 int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v);
+int gpn_k_set_diag(gpn_ctx* c, double* A, long ld, int n, double v);
+int gpn_k_transpose(gpn_ctx* c, int rows, int cols, const double* A, long lda, double* B, long ldb);
+int gpn_k_rowdot_pass(gpn_ctx* c, int rows, int cols, const double* Y, long ld, const double* ya, const double* yb, double* za, double* zb,
+                      double* d_fro, bool upper_only, bool zero_fro);
 int gpn_k_csr_values(gpn_ctx* c, int rows, int row0, const int* indptr, const int* idx, const double* M, long ld, double* val);
 int gpn_k_spmm_rows(gpn_ctx* c, int rows, int cols, const int* indptr, const int* idx, const double* val, const double* Z, long ldz, double* X,
                     long ldx);

@@ -335,6 +335,49 @@ __global__ void schur_update_kernel(int n, const double* __restrict__ Mtt, long 
     const int jend = min(n, (i / 128 + 1) * 128);
     for (int j = i + 1 + threadIdx.x; j < jend; j += blockDim.x) S[(long)i * lds + j] = 0.0;
 }
+__global__ void set_diag_kernel(double* __restrict__ A, long ld, int n, double v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(long)i * ld + i] = v;
+}
+// B = A^T through a padded 32x32 shared tile (both sides coalesced)
+__global__ void transpose_kernel(int rows, int cols, const double* __restrict__ A, long lda, double* __restrict__ B, long ldb) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int r = r0 + k, c = c0 + threadIdx.x;
+        tile[k][threadIdx.x] = (r < rows && c < cols) ? A[(long)r * lda + c] : 0.0;
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int c = c0 + k, r = r0 + threadIdx.x;
+        if (c < cols && r < rows) B[(long)c * ldb + r] = tile[threadIdx.x][k];
+    }
+}
+// One pass over the rows of Y (rows x cols): za[r] = Y[r,:] . ya, zb[r] = Y[r,:] . yb, fro += sum Y^2; one warp per row.
+// upper_only: only columns >= r count (Y upper triangular, the rest of the buffer is undefined).
+__global__ void rowdot_pass_kernel(int rows, int cols, const double* __restrict__ Y, long ld, const double* __restrict__ ya,
+                                   const double* __restrict__ yb, double* __restrict__ za, double* __restrict__ zb,
+                                   double* __restrict__ fro, int upper_only) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    double sa = 0.0, sb = 0.0, sf = 0.0;
+    if (r < rows) {
+        const double* y = Y + (long)r * ld;
+        for (int c = (upper_only ? (r & ~31) : 0) + lane; c < cols; c += 32) {
+            const double v = (upper_only && c < r) ? 0.0 : y[c];
+            sa = fma(v, ya[c], sa);
+            sb = fma(v, yb[c], sb);
+            sf = fma(v, v, sf);
+        }
+        sa = warp_sum(sa);
+        sb = warp_sum(sb);
+        if (lane == 0) {
+            if (za) za[r] = sa;
+            if (zb) zb[r] = sb;
+        }
+    }
+    sf = block_sum(sf);
+    if (threadIdx.x == 0 && sf != 0.0) atomicAdd(fro, sf);
+}
 // ---- Schur path of the regularized-Laplacian regressor: one pass over the bottom block-row Wb (rows x cols) of a lower-
 //      triangular inverse, row r being nonzero for col <= off + r:  za = Wb^T ya, zb = Wb^T yb (pre-zeroed; atomics over row
 //      blocks) and fro += sum Wb^2.  Each thread owns one column (coalesced rows).
@@ -587,6 +630,30 @@ int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out)
 int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v) {
     if (n <= 0) return 0;
     fill_vec_kernel<<<grid1(n), TPB, 0, c->stream>>>(n, y, v);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_set_diag(gpn_ctx* c, double* A, long ld, int n, double v) {
+    if (n <= 0) return 0;
+    set_diag_kernel<<<grid1(n), TPB, 0, c->stream>>>(A, ld, n, v);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_transpose(gpn_ctx* c, int rows, int cols, const double* A, long lda, double* B, long ldb) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    transpose_kernel<<<grid, block, 0, c->stream>>>(rows, cols, A, lda, B, ldb);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_rowdot_pass(gpn_ctx* c, int rows, int cols, const double* Y, long ld, const double* ya, const double* yb, double* za, double* zb,
+                      double* d_fro, bool upper_only, bool zero_fro) {
+    if (zero_fro) {
+        zero_vec_kernel<<<1, 32, 0, c->stream>>>(1, d_fro);
+        LAUNCHED(c);
+    }
+    if (rows <= 0 || cols <= 0) return 0;
+    rowdot_pass_kernel<<<grid1((long)rows * 32), TPB, 0, c->stream>>>(rows, cols, Y, ld, ya, yb, za, zb, d_fro, upper_only ? 1 : 0);
     LAUNCHED(c);
     return 0;
 }

@@ -48,7 +48,7 @@ enum NB {
 static_assert(NB_COUNT <= 16, "nb[] too small");
 
 struct Scal {           // layout of c->scal (doubles), followed by ints
-    enum { DOT = 0, LOGDET, SUM, TR0, TR1, TR2, CONV, Q, LIK, AF, NORM0, NORM1, NORM2, NORM3, SCH0 /* up to 7 reductions */, FRO = SCH0 + 7, NDBL = 32 };
+    enum { DOT = 0, LOGDET, SUM, TR0, TR1, TR2, CONV, Q, LIK, AF, NORM0, NORM1, NORM2, NORM3, SCH0 /* up to 8 reductions */, FRO = SCH0 + 8, NDBL = 32 };
 };
 
 double* dscal(gpn_ctx* c, int i) { return (double*)c->scal.p + i; }
@@ -869,34 +869,61 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
     const int *tptr = (const int*)c->to_indptr.p, *tidx = (const int*)c->to_idx.p;
     double* tval = (double*)c->to_val.p;
     GPN_TRY(gpn_k_csr_values(c, n, o, tptr, tidx, M, ld, tval));
-    // Z = M_oo^-1 in place (full symmetric, leading o x o block of M); rows >= o of M keep M_to and the lower part of M_tt
-    GPN_TRY(spd_inverse(c, o, M, ld, mat(c, 1), mat(c, 2), mat(c, 3), M, 0));
     GPN_TRY(ensure_nb(c, NB_ROWS1, n, ld));
     double* X = nbp(c, NB_ROWS1);
-    GPN_TRY(gpn_k_spmm_rows(c, n, o, tptr, tidx, tval, M, ld, X, ld));
     GPN_TRY(ensure_nb(c, NB_KY, ldn, ldn));
-    GPN_TRY(ensure_nb(c, NB_W, ldn, ldn));
-    GPN_TRY(ensure_nb(c, NB_T, ldn, ldn));
     GPN_TRY(ensure_nb(c, NB_WT, ldn, ldn));
     double* S = nbp(c, NB_KY);
-    GPN_TRY(gpn_k_schur_update(c, n, M + (long)o * ld + o, ld, tptr, tidx, tval, X, ld, S, ldn));
-    GprFactor f;
-    GPN_TRY(gpr_factor_ky(c, &f));                                                              // L_tt (in S), W_tt, W_tt^T
     double *ones = vecp(c, V_U), *r1 = vecp(c, V_Z), *rt = vecp(c, V_Z2);
     GPN_TRY(gpn_k_fill_vec(c, n, ones, 1.0));
-    GPN_TRY(gpn_k_gemv_t2(c, n, n, S, ldn, ones, vecp(c, V_T), r1, rt, GEMV_LOWER));
-    GPN_TRY(gpn_k_sumlogdiag(c, n, S, ldn, dscal(c, Scal::LOGDET)));
-    // P = W_tt X = -W_to  (W_tt lower triangular: only k < m0 + 128 contributes)
-    GPN_TRY(ensure_nb(c, NB_ROWS2, n, ld));
-    double* Pm = nbp(c, NB_ROWS2);
-    if (o > 0) GPN_TRY(gpn_gemm(c, n, o, n, 1.0, f.W, f.ldn, true, X, ld, false, 0.0, Pm, ld, GF_KHI_M));
     GPN_TRY(ensure_nb(c, NB_S, 2, ld));
-    double *z1 = nbp(c, NB_S), *zt = z1 + ld;                    // z = Wb^T y laid out as [o | n]; the sign of the o part cancels in every dot
-    GPN_TRY(gpn_k_trap_pass(c, n, o, N, Pm, ld, r1, rt, z1, zt, dscal(c, Scal::FRO), true));
-    GPN_TRY(gpn_k_trap_pass(c, n, n, 0, f.W, f.ldn, r1, rt, z1 + o, zt + o, dscal(c, Scal::FRO), false));
-    const double *dx[6] = {r1, r1, rt, z1, z1, zt}, *dy[6] = {r1, rt, rt, z1, zt, zt};
-    const int dn[6] = {n, n, n, N, N, N};
-    GPN_TRY(gpn_k_multi_dot(c, 6, dx, dy, dn, dscal(c, Scal::SCH0)));
+    double *z1 = nbp(c, NB_S), *zt = z1 + ld;
+    const bool augmented = c->fast_reglap >= 4 && o >= 256 && n >= 256;
+    if (augmented) {
+        // Both factorisations are small enough to be bound by their per-column dependency chain, so the triangular work that
+        // follows them rides along in the same dataflow kernel as appended row blocks (potrf_dataflow.cu):
+        //   [M_oo; I]      -> L_oo and W_oo^T            then Z = W_oo^T W_oo
+        //   [S; X^T; I]    -> L_tt, Y = X^T L_tt^-T = (W_tt X)^T = -W_to^T, and W_tt^T
+        GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(std::max(n, o)) * 128));
+        GPN_TRY(gpn_potrf_dataflow(c, o, M, ld, (double*)c->winv.p, iscal(c, 0), 0, nullptr, 0, 0, mat(c, 2), ld));
+        GPN_TRY(gpn_lauum_t(c, o, mat(c, 2), ld, M, ld, true));                                   // Z, full symmetric, in place of M_oo
+        GPN_TRY(gpn_k_spmm_rows(c, n, o, tptr, tidx, tval, M, ld, X, ld));
+        const long po = pad128(o);
+        GPN_TRY(ensure_nb(c, NB_ROWS2, po, ldn));
+        double* Y = nbp(c, NB_ROWS2);                                                             // X^T (o x n), rows padded with zeros
+        if (po > o) GPN_TRY(gpn_k_fill_zero(c, Y + (po - 128) * ldn, ldn, 128, (int)ldn));
+        GPN_TRY(gpn_k_transpose(c, n, o, X, ld, Y, ldn));
+        GPN_TRY(gpn_k_schur_update(c, n, M + (long)o * ld + o, ld, tptr, tidx, tval, X, ld, S, ldn));
+        GPN_TRY(gpn_potrf_dataflow(c, n, S, ldn, (double*)c->winv.p, iscal(c, 1), 0, Y, ldn, o, nbp(c, NB_WT), ldn));
+        GPN_TRY(gpn_k_gemv_t2(c, n, n, S, ldn, ones, vecp(c, V_T), r1, rt, GEMV_LOWER));
+        GPN_TRY(gpn_k_sumlogdiag(c, n, S, ldn, dscal(c, Scal::LOGDET)));
+        // z = Wb^T y = [-Y y ; W_tt^T y] and W_tt^T L_tt^T x = x exactly: the training part of z is 1 resp. t, only Y is swept
+        GPN_TRY(gpn_k_rowdot_pass(c, o, n, Y, ldn, r1, rt, z1, zt, dscal(c, Scal::FRO), false, true));
+        GPN_TRY(gpn_k_rowdot_pass(c, n, n, nbp(c, NB_WT), ldn, r1, rt, nullptr, nullptr, dscal(c, Scal::FRO), true, false));
+        const double *dx[8] = {r1, r1, rt, z1, z1, zt, ones, vecp(c, V_T)}, *dy[8] = {r1, rt, rt, z1, zt, zt, vecp(c, V_T), vecp(c, V_T)};
+        const int dn[8] = {n, n, n, o, o, o, n, n};
+        GPN_TRY(gpn_k_multi_dot(c, 8, dx, dy, dn, dscal(c, Scal::SCH0)));
+    } else {
+        // Z = M_oo^-1 in place (full symmetric, leading o x o block of M); rows >= o of M keep M_to and the lower part of M_tt
+        GPN_TRY(spd_inverse(c, o, M, ld, mat(c, 1), mat(c, 2), mat(c, 3), M, 0));
+        GPN_TRY(gpn_k_spmm_rows(c, n, o, tptr, tidx, tval, M, ld, X, ld));
+        GPN_TRY(ensure_nb(c, NB_W, ldn, ldn));
+        GPN_TRY(ensure_nb(c, NB_T, ldn, ldn));
+        GPN_TRY(gpn_k_schur_update(c, n, M + (long)o * ld + o, ld, tptr, tidx, tval, X, ld, S, ldn));
+        GprFactor f;
+        GPN_TRY(gpr_factor_ky(c, &f));                                                              // L_tt (in S), W_tt, W_tt^T
+        GPN_TRY(gpn_k_gemv_t2(c, n, n, S, ldn, ones, vecp(c, V_T), r1, rt, GEMV_LOWER));
+        GPN_TRY(gpn_k_sumlogdiag(c, n, S, ldn, dscal(c, Scal::LOGDET)));
+        // P = W_tt X = -W_to  (W_tt lower triangular: only k < m0 + 128 contributes)
+        GPN_TRY(ensure_nb(c, NB_ROWS2, n, ld));
+        double* Pm = nbp(c, NB_ROWS2);
+        if (o > 0) GPN_TRY(gpn_gemm(c, n, o, n, 1.0, f.W, f.ldn, true, X, ld, false, 0.0, Pm, ld, GF_KHI_M));
+        GPN_TRY(gpn_k_trap_pass(c, n, o, N, Pm, ld, r1, rt, z1, zt, dscal(c, Scal::FRO), true));
+        GPN_TRY(gpn_k_trap_pass(c, n, n, 0, f.W, f.ldn, r1, rt, z1 + o, zt + o, dscal(c, Scal::FRO), false));
+        const double *dx[6] = {r1, r1, rt, z1, z1, zt}, *dy[6] = {r1, rt, rt, z1, zt, zt};
+        const int dn[6] = {n, n, n, N, N, N};
+        GPN_TRY(gpn_k_multi_dot(c, 6, dx, dy, dn, dscal(c, Scal::SCH0)));
+    }
     double sc[Scal::NDBL];
     int info[16];
     GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
@@ -905,6 +932,9 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
     rs->half_logdet = -sc[Scal::LOGDET];
     rs->s = sc[Scal::SCH0]; rs->a = sc[Scal::SCH0 + 1]; rs->q = sc[Scal::SCH0 + 2];
     rs->D11 = sc[Scal::SCH0 + 3] - rs->s; rs->D1t = sc[Scal::SCH0 + 4] - rs->a; rs->Dtt = sc[Scal::SCH0 + 5] - rs->q;
+    if (augmented) {        // the training part of z1 is the ones vector, that of zt is t
+        rs->D11 += n; rs->D1t += sc[Scal::SCH0 + 6]; rs->Dtt += sc[Scal::SCH0 + 7];
+    }
     rs->trSD = sc[Scal::FRO] - n;
     return 0;
 }
@@ -1479,7 +1509,7 @@ int gpn_debug_leaf_bench(gpn_ctx* c, void* A_dev, int copies, void* prof32_dev) 
     return gpn_leaf_bench(c, (double*)A_dev, copies, (double*)c->winv.p, iscal(c, 0), (long long*)prof32_dev);
 }
 void gpn_set_fast_paths(gpn_ctx* c, int level) {
-    if (c) c->fast_reglap = level < 0 ? 0 : (level > 3 ? 3 : level);
+    if (c) c->fast_reglap = level < 0 ? 0 : (level > 4 ? 4 : level);
 }
 void gpn_debug_df_trace(gpn_ctx* c, void* dev_buf) {
     if (c) c->df_trace = dev_buf;

@@ -12,6 +12,13 @@
 // deadlock-free, and several tile columns are in flight at once: the serial chain chol(j) -> trsm(j+1,j) -> chol(j+1)
 // overlaps the bulk updates of later columns.  Dependencies are epoch-stamped flags in global memory
 // (st.release / ld.acquire at gpu scope, fence.proxy.async before the TMA reads of tiles written by other SMs).
+//
+// Appended row blocks ("augmented" factorisation): below the square SPD block the task list may carry further tile rows whose
+// tiles obey the same recurrence with A_ij taken from another buffer,
+//     Y_ij = (B_ij - sum_{k<j} Y_ik L_jk^T) W_j^T        i.e.  Y = B L^-T  (a triangular solve with many right-hand sides),
+// and an identity block (B = I, tiles left of its diagonal are zero and skipped, k starts at the tile's own row) that yields
+// L^-T itself.  These tasks have no chain of their own: they fill the SMs that the per-column dependency chain of a small
+// Cholesky leaves idle, and they replace the separate triangular inverse / triangular product launches that would follow.
 #include "leaf.cuh"
 #include "tile_primitives.cuh"
 
@@ -30,10 +37,18 @@ constexpr size_t DF_SMEM = RING_BYTES + 256 + 1024;
 
 static_assert(leaf::SMEM_BYTES <= RING_BYTES, "leaf scratch must fit in the ring");
 
+struct DfSeg {          // one block of tile rows: [row0, row0 + rows) in tile units, stored at ptr with leading dimension ld
+    double* ptr;
+    long ld;
+    int row0, rows;
+};
 struct DfArgs {
     double* A;
     long lda;
     int n, T, ntasks;
+    int Trows;            // tile rows in total (T for a plain factorisation)
+    int id0;              // first tile row of the identity block (Trows if there is none)
+    DfSeg seg[2];         // appended blocks: seg[0] = general right-hand sides, seg[1] = identity block
     double* winv;
     int* flags;
     int epoch;
@@ -73,7 +88,8 @@ __device__ __forceinline__ void diag_kstep(double (&acc)[8][4][2], uint32_t sa, 
 }
 
 __global__ void __launch_bounds__(384, 1)
-potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmW, const DfArgs g) {
+potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmB1,
+                      const __grid_constant__ CUtensorMap tmB2, const DfArgs g) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
@@ -108,11 +124,16 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
         if (warp == 8 && lane == 0) {
             uint32_t it = 0, wit = 0;
             int task_idx = 0, j = 0, q0 = 0;
-            for (int q = blockIdx.x; q < g.ntasks; q += gridDim.x, ++task_idx) {
-                while (q >= q0 + (T - j)) { q0 += T - j; ++j; }
+            for (int q = blockIdx.x; q < g.ntasks; q += gridDim.x) {
+                while (q >= q0 + (g.Trows - j)) { q0 += g.Trows - j; ++j; }
                 const int i = j + (q - q0);
+                const int kstart = i >= g.id0 ? i - g.id0 : 0;                    // identity block: zero tiles left of its diagonal
+                if (j < kstart) continue;
+                // A-operand rows of this task: the square block or one of the appended blocks
+                const CUtensorMap* tmA = i < T ? &tmL : (i < g.id0 ? &tmB1 : &tmB2);
+                const int arow = (i < T ? i : (i < g.id0 ? i - g.seg[0].row0 : i - g.seg[1].row0)) * TB;
                 if (task_idx > 0) mbar_wait(bar_fdone, (task_idx - 1) & 1);      // consumers left the C region / leaf scratch
-                for (int kb = 0; kb < j; ++kb) {
+                for (int kb = kstart; kb < j; ++kb) {
                     wait_flag(g.flags + (long)i * T + kb, g.epoch);
                     if (i != j) wait_flag(g.flags + (long)j * T + kb, g.epoch);
                     fence_proxy_async();
@@ -123,7 +144,7 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
                         const uint32_t full = bar_full + st * 8;
                         mbar_expect_tx(full, STAGE_BYTES);
                         const uint32_t sa = smem0 + st * STAGE_BYTES;
-                        tma_load_3d(sa, &tmL, full, kb * TB + s * KSTEP, i * TB, 0);
+                        tma_load_3d(sa, tmA, full, kb * TB + s * KSTEP, arow, 0);
                         tma_load_3d(sa + TILE_BYTES, &tmL, full, kb * TB + s * KSTEP, j * TB, 0);
                     }
                 }
@@ -140,6 +161,7 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
                         tma_load_3d(smem0 + CREG_BYTES + ws * TILE_BYTES, &tmW, full, s * KSTEP, j * TB, 0);
                     }
                 }
+                ++task_idx;
             }
         }
         return;
@@ -165,10 +187,23 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
     double* Tt = Wd + 4 * 32 * leaf::WLD;
 
     uint32_t it = 0, wit = 0;
-    int task_idx = 0, j = 0, q0 = 0;
-    for (int q = blockIdx.x; q < g.ntasks; q += gridDim.x, ++task_idx) {
-        while (q >= q0 + (T - j)) { q0 += T - j; ++j; }
+    int task_idx = -1, j = 0, q0 = 0;
+    for (int q = blockIdx.x; q < g.ntasks; q += gridDim.x) {
+        while (q >= q0 + (g.Trows - j)) { q0 += g.Trows - j; ++j; }
         const int i = j + (q - q0);
+        const int kstart = i >= g.id0 ? i - g.id0 : 0;
+        if (j < kstart) continue;
+        ++task_idx;
+        // where this task's tile lives: the square block or an appended block (all of whose rows exist in memory)
+        double* tile_ptr;
+        long tile_ld;
+        long row_lim;                              // rows of the block that may be read / written
+        if (i < T) { tile_ptr = g.A + (long)i * TB * g.lda; tile_ld = g.lda; row_lim = (long)g.n - (long)i * TB; }
+        else {
+            const DfSeg& sg = g.seg[i < g.id0 ? 0 : 1];
+            tile_ptr = sg.ptr + (long)(i - sg.row0) * TB * sg.ld; tile_ld = sg.ld; row_lim = TB;
+        }
+        tile_ptr += (long)j * TB;
 
         double acc[8][4][2];
         // The accumulators start from -A_ij, so that after the k-loop they hold -(A_ij - sum L_ik L_jk^T) and the epilogue on
@@ -177,7 +212,6 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
             const int r = wm * 64 + a * 8 + pg;
-            const long gr = (long)i * TB + r;
 #pragma unroll
             for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -185,12 +219,12 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
                     const int cc = wn * 32 + b * 8 + t + 4 * e;
                     const long gc = (long)j * TB + cc;
                     double v = (i == j && r == cc) ? -1.0 : 0.0;
-                    if (gr < g.n && gc < g.n) v = -g.A[gr * g.lda + gc];
+                    if (r < row_lim && gc < g.n) v = -tile_ptr[(long)r * tile_ld + cc];
                     acc[a][b][e] = v;
                 }
         }
         DF_STAMP(0);
-        const int niter = j * 8;
+        const int niter = (j - kstart) * 8;
         const uint32_t mask = (i == j) ? diag_mask : 0xffffffffu;
         for (int n = 0; n < niter; ++n, ++it) {
             const int st = it % STAGES;
@@ -227,7 +261,6 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
         if (lane == 0) mbar_arrive(bar_mdone);
         DF_STAMP(1);
 
-        const long grow0 = (long)i * TB + wm * 64, gcol0 = (long)j * TB + wn * 32;
         if (i == j) {
             // ---- C = -acc -> S (identity padded); factor + invert in shared memory ----
             if (tid < leaf::GUARD) reinterpret_cast<double*>(smem_gen)[tid] = 0.0;
@@ -297,12 +330,12 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
             DF_STAMP(5);
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
-                const long gr = grow0 + a * 8 + pg;
-                if (gr < g.n) {
+                const int r = wm * 64 + a * 8 + pg;
+                if (r < row_lim) {
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) g.A[gr * g.lda + gcol0 + b * 8 + t + 4 * e] = acc[a][b][e];
+                        for (int e = 0; e < 2; ++e) tile_ptr[(long)r * tile_ld + wn * 32 + b * 8 + t + 4 * e] = acc[a][b][e];
                 }
             }
             __threadfence();
@@ -336,20 +369,38 @@ int encode_tiles(gpn_ctx* c, CUtensorMap* tm, const double* ptr, long ld, long r
 
 // Lower Cholesky of the n x n matrix A in place (tiles strictly above the diagonal are left untouched, the strict upper
 // triangle of the diagonal tiles is zeroed); inverted diagonal blocks go to winv (ceil(n/128) blocks of 128x128).
-int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset) {
+// Optional appended blocks (see the header comment): B (brows x n, overwritten by B L^-T; its rows beyond brows up to the
+// next multiple of 128 must exist and be zero) and Wt (pad128(n) x n, any content: overwritten by L^-T in its upper tiles,
+// i.e. the transposed inverse of the factor, lower tiles untouched).
+int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset, double* B, long ldb, int brows,
+                       double* Wt, long ldwt) {
     const int T = (n + TB - 1) / TB;
-    const int ntasks = T * (T + 1) / 2;
-    if (c->flags.cap < sizeof(int) * (size_t)T * T) {
-        GPN_TRY(gpn_buf_ensure(c, c->flags, sizeof(int) * (size_t)T * T));
+    const int R1 = B ? (brows + TB - 1) / TB : 0, R2 = Wt ? T : 0;
+    const int Trows = T + R1 + R2;
+    long nt = 0;
+    for (int j = 0; j < T; ++j) nt += Trows - j;
+    const int ntasks = (int)nt;
+    if (c->flags.cap < sizeof(int) * (size_t)Trows * T) {
+        GPN_TRY(gpn_buf_ensure(c, c->flags, sizeof(int) * (size_t)Trows * T));
         GPN_CK(cudaMemsetAsync(c->flags.p, 0, c->flags.cap, c->stream));
         c->epoch = 0;
     }
+    if (Wt) {   // identity block: I in the diagonal tiles (the zero tiles left of them are skipped, the ones to the right are read)
+        GPN_TRY(gpn_k_fill_zero(c, Wt, ldwt, T * TB, n));
+        GPN_TRY(gpn_k_set_diag(c, Wt, ldwt, T * TB < n ? T * TB : n, 1.0));
+    }
     DfArgs a;
     a.A = A; a.lda = lda; a.n = n; a.T = T; a.ntasks = ntasks; a.winv = winv; a.flags = (int*)c->flags.p;
+    a.Trows = Trows; a.id0 = T + R1;
+    a.seg[0] = DfSeg{B, ldb, T, R1};
+    a.seg[1] = DfSeg{Wt, ldwt, T + R1, R2};
     a.epoch = ++c->epoch; a.info = d_info; a.info_off = info_offset; a.trace = (long long*)c->df_trace;
-    CUtensorMap tl, tw;
+    CUtensorMap tl, tw, tb1, tb2;
     GPN_TRY(encode_tiles(c, &tl, A, lda, n, n));
     GPN_TRY(encode_tiles(c, &tw, winv, TB, (long)T * TB, TB));
+    tb1 = tl; tb2 = tl;
+    if (B) GPN_TRY(encode_tiles(c, &tb1, B, ldb, (long)R1 * TB, n));
+    if (Wt) GPN_TRY(encode_tiles(c, &tb2, Wt, ldwt, (long)T * TB, n));
     static bool configured = false;
     if (!configured) {
         GPN_CK(cudaFuncSetAttribute(potrf_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM));
@@ -357,11 +408,16 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
     }
     int grid = ntasks < c->num_sms ? ntasks : c->num_sms;
     if (c->potrf_grid_cap > 0 && grid > c->potrf_grid_cap) grid = c->potrf_grid_cap;   // leave SMs to concurrent work
-    void* args[] = {(void*)&tl, (void*)&tw, (void*)&a};
+    void* args[] = {(void*)&tl, (void*)&tw, (void*)&tb1, (void*)&tb2, (void*)&a};
     // executed flops: an off-diagonal task runs j k-blocks of 128^3 MACs, a diagonal one only the 136 of 256 8x8 blocks that
-    // touch the lower triangle; the in-CTA trsm skips the zero k-steps of W_j (36 of 64); leaf = factor + inverse
+    // touch the lower triangle; the in-CTA trsm skips the zero k-steps of W_j (36 of 64); leaf = factor + inverse; appended rows
+    // add their own tasks (identity block: k from the tile's own row)
     double kb = 0.0;
-    for (int j = 0; j < T; ++j) kb += (double)(T - j - 1) * j + j * (136.0 / 256.0) + (T - j - 1) * (36.0 / 64.0) + 1.0 / 3.0;
+    for (int j = 0; j < T; ++j) {
+        kb += (double)(T - j - 1) * j + j * (136.0 / 256.0) + (T - j - 1) * (36.0 / 64.0) + 1.0 / 3.0;
+        kb += (double)R1 * (j + 36.0 / 64.0);
+        if (R2) kb += 0.5 * j * (j + 1.0) + (j + 1) * (36.0 / 64.0);          // identity rows r <= j: (j - r) k-blocks each
+    }
     const double fl = 2.0 * kb * TB * TB * TB;
     ProfEvent pe;
     if (c->profile) {

@@ -111,8 +111,10 @@ int gpn_gpr_fetch(gpn_ctx* ctx, int which, double* out_h);
  *   1  block path: training nodes numbered last, only K[tr,:] formed from the triangular inverse;
  *   2  Schur route: K_tt^-1 = L_tt L_tt^T is read off the Cholesky factor of I + beta L~, the all-entries noise term is a
  *      rank-one update, and the gradient traces reduce to norms of the bottom block-row of L^-1;
- *   3  (default) the same, and for gradient evaluations the other nodes are eliminated through the SPARSE coupling block of
- *      I + beta L~: Z = M_oo^-1, X = M_to Z (sparse x dense), S = M_tt - X M_ot, W_to = -W_tt X. */
+ *   3  the same, and for gradient evaluations the other nodes are eliminated through the SPARSE coupling block of
+ *      I + beta L~: Z = M_oo^-1, X = M_to Z (sparse x dense), S = M_tt - X M_ot, W_to = -W_tt X;
+ *   4  (default) as 3, with the triangular inverse / triangular product that follow the two Cholesky factorisations carried
+ *      as appended row blocks of the dataflow Cholesky kernel itself ([M_oo; I] and [S; X^T; I]). */
 void gpn_set_fast_paths(gpn_ctx* ctx, int level);
 
 /* ---- GP classification, Laplace approximation (GPnetClassifier.py:90-147,184-240) ---------------------------- */
