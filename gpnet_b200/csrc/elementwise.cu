@@ -318,22 +318,27 @@ __global__ void spmm_rows_kernel(int cols, const int* __restrict__ indptr, const
 __global__ void schur_update_kernel(int n, const double* __restrict__ Mtt, long ldm, const int* __restrict__ indptr,
                                     const int* __restrict__ idx, const double* __restrict__ val, const double* __restrict__ X, long ldx,
                                     double* __restrict__ S, long lds) {
-    const int i = blockIdx.x;
-    const double* xr = X + (long)i * ldx;
-    for (int j = threadIdx.x; j <= i; j += blockDim.x) {
+    // two rows of S per block: every (value, column) pair of the sparse block is loaded once for both
+    const int i0 = 2 * blockIdx.x, i1 = min(i0 + 1, n - 1);
+    const double *x0 = X + (long)i0 * ldx, *x1 = X + (long)i1 * ldx;
+    for (int j = threadIdx.x; j <= i1; j += blockDim.x) {
         double s0 = 0.0, s1 = 0.0;
-        int e = indptr[j];
         const int e1 = indptr[j + 1];
-        for (; e + 1 < e1; e += 2) {
-            s0 = fma(val[e], xr[idx[e]], s0);
-            s1 = fma(val[e + 1], xr[idx[e + 1]], s1);
+        for (int e = indptr[j]; e < e1; ++e) {
+            const double v = val[e];
+            const int k = idx[e];
+            s0 = fma(v, x0[k], s0);
+            s1 = fma(v, x1[k], s1);
         }
-        if (e < e1) s0 = fma(val[e], xr[idx[e]], s0);
-        S[(long)i * lds + j] = Mtt[(long)i * ldm + j] - (s0 + s1);
+        if (j <= i0) S[(long)i0 * lds + j] = Mtt[(long)i0 * ldm + j] - s0;
+        if (i1 != i0) S[(long)i1 * lds + j] = Mtt[(long)i1 * ldm + j] - s1;
     }
-    // the rest of the diagonal tile's row (strict upper part, never used by the factorisation) is left defined
-    const int jend = min(n, (i / 128 + 1) * 128);
-    for (int j = i + 1 + threadIdx.x; j < jend; j += blockDim.x) S[(long)i * lds + j] = 0.0;
+    // the rest of each diagonal tile's row (strict upper part, never used by the factorisation) is left defined
+    for (int r = i0; r <= i1; ++r) {
+        const int jend = min(n, (r / 128 + 1) * 128);
+        for (int j = r + 1 + threadIdx.x; j < jend; j += blockDim.x) S[(long)r * lds + j] = 0.0;
+        if (i1 == i0) break;
+    }
 }
 __global__ void set_diag_kernel(double* __restrict__ A, long ld, int n, double v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -674,7 +679,7 @@ int gpn_k_spmm_rows(gpn_ctx* c, int rows, int cols, const int* indptr, const int
 int gpn_k_schur_update(gpn_ctx* c, int n, const double* Mtt, long ldm, const int* indptr, const int* idx, const double* val, const double* X,
                        long ldx, double* S, long lds) {
     if (n <= 0) return 0;
-    schur_update_kernel<<<n, 256, 0, c->stream>>>(n, Mtt, ldm, indptr, idx, val, X, ldx, S, lds);
+    schur_update_kernel<<<(n + 1) / 2, 256, 0, c->stream>>>(n, Mtt, ldm, indptr, idx, val, X, ldx, S, lds);
     LAUNCHED(c);
     return 0;
 }

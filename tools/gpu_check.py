@@ -349,6 +349,52 @@ def stage_gpc(ctx):
               f" probs {rel(probs, g['probs']):.2e} label-mismatch {int(np.sum(labels != g['labels']))} ({dt:.2f}s)", flush=True)
 
 
+def stage_augbreak(ctx):
+    """CTA-time breakdown of the augmented dataflow kernel [S; X^T; I] of the coupled regularized-Laplacian route
+    (N = 8192, n = 4096): per-task %globaltimer trace of the LAST dataflow launch of one logp+grad evaluation."""
+    import oracle.configs as cfg
+    N, n = 8192, 4096
+    indptr, indices, w, pos, t = cfg.rgg_csr_fast(N)
+    ctx.set_graph(indptr, indices, w)
+    tr, te = cfg.split(N, n, N - n)
+    ctx.set_nodes(tr, te)
+    th = np.log([0.6, 0.01])
+    ctx.gpr_logp_grad(1, th, t[tr], True)
+    T, Trows, id0 = n // 128, 3 * (n // 128), 2 * (n // 128)
+    tasks = [(i, j) for j in range(T) for i in range(j, Trows)]
+    ntasks = len(tasks)
+    trc = torch.zeros(ntasks * 8, dtype=torch.int64, device=dev)
+    ctx.lib.gpn_debug_df_trace(ctx.h, trc.data_ptr())
+    ctx.gpr_logp_grad(1, th, t[tr], True)
+    ctx.lib.gpn_debug_df_trace(ctx.h, None)
+    tt = trc.cpu().numpy().reshape(ntasks, 8).astype(np.float64) * 1e-3
+    live = np.array([not (i >= id0 and j < i - id0) for (i, j) in tasks])
+    G = 148
+    t0, t1 = tt[live, 0].min(), tt[live, 4].max()
+    tot = (t1 - t0) * G
+    main = epi = gap = tail = 0.0
+    for cta in range(G):
+        prev = t0
+        for q in range(cta, ntasks, G):
+            if not live[q]:
+                continue
+            gap += tt[q, 0] - prev
+            main += tt[q, 1] - tt[q, 0]
+            epi += tt[q, 4] - tt[q, 1]
+            prev = tt[q, 4]
+        tail += t1 - prev
+    print(f"[S; X^T; I] n={n}: {t1 - t0:.0f} us; CTA-time: main loops (incl. waiting for operands) {100*main/tot:.1f} %, epilogues {100*epi/tot:.1f} %, "
+          f"gaps {100*gap/tot:.1f} %, idle after last task {100*tail/tot:.1f} %")
+    kb = sum((j - (i - id0 if i >= id0 else 0)) for (i, j), l in zip(tasks, live) if l)
+    print(f"   k-blocks {kb}: at 17 us each on {G} CTAs: {kb*17/G:.0f} us")
+    for a in range(8):
+        lo, hi = t0 + a / 8 * (t1 - t0), t0 + (a + 1) / 8 * (t1 - t0)
+        busy = sum(max(0.0, min(tt[q, 1], hi) - max(tt[q, 0], lo)) for q in range(ntasks) if live[q])
+        dg = [j for (i, j), q in zip(tasks, range(ntasks)) if i == j and lo <= tt[q, 4] < hi]
+        print(f"   elapsed {a}/8: main-loop occupancy {100*busy/((hi-lo)*G):5.1f} %   diagonal tiles finished: {min(dg) if dg else '-'}..{max(dg) if dg else '-'}")
+    sys.stdout.flush()
+
+
 def stage_potrftime(ctx):
     """potrf timing only (for sweeps over GPNET_B200_POTRF_GRID and the like)."""
     for n in (4096, 8192):
