@@ -26,6 +26,26 @@ THETA = np.log([0.6, 0.01])      # C3 theta_0
 KERNEL = "regularized_laplacian"
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the original stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
+def workload_config(N, n, P, world):
+    """The same `config` object on both arms."""
+    return {"workload": f"C3: GPnetRegressor regularized_laplacian, random geometric graph N={N}, n={n}, P={P}, theta=log[0.6,0.01]; "
+                        f"one logp+grad per step per GPU (multi-start thetas across GPUs, (1+P)-double NCCL all-gather per step)",
+            "l2": "inputs larger than L2 (each N x N fp64 operand is 537 MB vs 126 MB L2)", "parallelism": f"replicas x{world}"}
+
+
 def c3_problem(N):
     """C3: nx.random_geometric_graph(N, r = sqrt(20/(pi N)), seed=0), 50/50 split, t = sin(4 pi x) cos(4 pi y)."""
     from gpnet_b200.engine import graph_csr
@@ -143,12 +163,12 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
             "warmup": args.warmup, "ms_per_step": t_step * 1e3 * (P + 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C3: GPnetRegressor regularized_laplacian, random geometric graph N={N}, n={N//2}, P=2"},
+            "config": workload_config(N, N // 2, P, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{len(times)} x one full-size logPosterior probe (N={N}); a logp+grad costs (P+1)=3 probes "
                                        "by finite differences as in the reference's optimize_params"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -160,6 +180,12 @@ def main():
     ap.add_argument("--nodes", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 themselves (NCCL's version banner, the
+    # drop-in classes' reference-style prints) are sent to stderr, and the line is written to the saved descriptor at the end
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -323,10 +349,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"C3: GPnetRegressor regularized_laplacian, random geometric graph N={N}, n={n}, P=2, "
-                                       f"theta=log[0.6,0.01]; one logp+grad per step per GPU (multi-start thetas across GPUs, "
-                                       f"(1+P)-double NCCL all-gather per step)",
-                           "l2": "inputs larger than L2 (each N x N fp64 operand is 537 MB vs 126 MB L2)", "parallelism": f"replicas x{world}"},
+                "config": workload_config(N, n, P, world),
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (n + P) + 4 * 0,
                                           "d2h_bytes_per_step": 8 * 32 + 4 * 16},
                 "gpu_launches": int(launches), "roofline": roof}
@@ -334,7 +357,7 @@ def main():
             line["routes"] = routes
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
