@@ -307,6 +307,29 @@ def test_reglap_fast_path_equals_full_path(gpu_ctx, shape):
         assert abs(l1[0] - l0[0]) <= 1e-12 * abs(l0[0]) and abs(g1[0] - l1[0]) <= 1e-12 * abs(l1[0])
 
 
+@pytest.mark.parametrize("beta,noise", [(0.01, 1e-6), (0.01, 100.0), (30.0, 1e-6), (30.0, 100.0), (0.99, 10.0)])
+def test_reglap_routes_agree_with_oracle_for_stiff_parameters(gpu_ctx, beta, noise):
+    """Every route of the regularized-Laplacian likelihood (full kernel ... Schur complement through the sparse coupling block
+    with augmented factorisations) against the numpy oracle at the ends of the parameter box and beyond (cond(I + beta L~) up
+    to 61, noise from 1e-6 to 100): the rank-one / Schur algebra must not lose digits where K_y is dominated by either term."""
+    G, tr, te, t = cfg.rgg_case(700, 300, 100)
+    indptr, indices, w, _ = go.graph_to_csr(G)
+    gpu_ctx.set_graph(indptr, indices, w)
+    gpu_ctx.set_nodes(tr, te)
+    th = np.log([beta, noise])
+    orc = go.OracleGP(G, kerneltype="regularized_laplacian")
+    ref_v, ref_g = orc.neg_logp_grad(th, tr, t[tr])
+    try:
+        for level in (0, 1, 2, 3, 4):
+            gpu_ctx.set_fast_paths(level)
+            st, out, info = gpu_ctx.gpr_logp_grad(1, th, t[tr], True)
+            assert st == 0 and info == 0
+            assert abs(out[0] - ref_v) <= TOL * abs(ref_v), (level, out[0], ref_v)
+            assert nrel(out[1:], ref_g) <= 1e-8, (level, out[1:], ref_g)
+    finally:
+        gpu_ctx.set_fast_paths(True)
+
+
 @pytest.mark.parametrize("kind,theta,axidx", [(0, np.log([0.6, 0.01]), [0, 1]), (0, np.log([0.6, 0.01]), [1, 0]),
                                               (1, np.log([0.6, 0.01]), [0, 1]), (2, np.log([2.3, 4, 0.01]), [0, 2]),
                                               (2, np.log([2.3, 4]), [0, 1]), (1, np.log([0.6, 0.01]), [1, 1])])
