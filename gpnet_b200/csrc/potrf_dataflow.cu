@@ -48,6 +48,9 @@ struct DfArgs {
     int n, T, ntasks;
     int Trows;            // tile rows in total (T for a plain factorisation)
     int id0;              // first tile row of the identity block (Trows if there is none)
+    int Gc;               // CTAs [0, Gc) own the square block's tasks (the dependency chain); all CTAs if nothing is appended
+    long nspd, napp, pc;  // tasks of the square block; appended tile slots (column-major, Trows - T per column); slots < pc
+                          // (the early columns) are dealt to the CTAs [Gc, grid) only, the rest to every CTA
     DfSeg seg[2];         // appended blocks: seg[0] = general right-hand sides, seg[1] = identity block
     double* winv;
     int* flags;
@@ -65,8 +68,52 @@ __device__ __forceinline__ long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define DF_STAMP(slot) do { if (g.trace && tid == 0) g.trace[(long)q * 8 + (slot)] = gtime(); } while (0)
+#define DF_STAMP(slot) do { if (g.trace && tid == 0) g.trace[((long)j * g.Trows + i) * 8 + (slot)] = gtime(); } while (0)
 __device__ __forceinline__ void sts64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
+// Static task schedule.  Global order: the square block's tiles column-major, then the appended tiles column-major; every
+// CTA walks its share in that order and every task only waits on tasks that precede it in it (appended tiles depend on the
+// square block and on earlier tiles of their own row, never the other way round), so the schedule cannot deadlock.
+//   * CTAs [0, Gc): the square block (its per-column dependency chain never queues behind a long appended task), afterwards
+//     their share of the late appended columns;
+//   * CTAs [Gc, grid): the appended tiles of the early columns (slots < pc), then their share of the late ones.
+struct TaskIter {
+    int phase = 0;
+    long q;
+    int j = 0;
+    long q0 = 0;
+};
+__device__ __forceinline__ bool next_task(const DfArgs& g, TaskIter& s, int& i, int& j) {
+    const int b = blockIdx.x, G = gridDim.x, R = g.Trows - g.T;
+    for (;;) {
+        long p;
+        if (s.phase == 0) {
+            if (b < g.Gc && s.q < g.nspd) {
+                while (s.q >= s.q0 + (g.T - s.j)) { s.q0 += g.T - s.j; ++s.j; }
+                i = s.j + (int)(s.q - s.q0);
+                j = s.j;
+                s.q += g.Gc;
+                return true;
+            }
+            if (b < g.Gc) { s.phase = 2; s.q = g.pc + b; }
+            else { s.phase = 1; s.q = b - g.Gc; }
+            continue;
+        }
+        if (s.phase == 1) {
+            if (s.q >= g.pc) { s.phase = 2; s.q = g.pc + b; continue; }
+            p = s.q;
+            s.q += G - g.Gc;
+        } else {
+            if (s.q >= g.napp) return false;
+            p = s.q;
+            s.q += G;
+        }
+        j = (int)(p / R);
+        i = g.T + (int)(p - (long)j * R);
+        if (i >= g.id0 && j < i - g.id0) continue;        // identity block: zero tiles left of its diagonal
+        return true;
+    }
+}
 
 // One k-step of a DIAGONAL tile for the warp at (WM_, WN_): only the 8x8 blocks touching the lower triangle are issued,
 // selected at compile time (no per-DMMA predicate arithmetic on the dependency chain's last k-block).
@@ -123,12 +170,11 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == 8 && lane == 0) {
             uint32_t it = 0, wit = 0;
-            int task_idx = 0, j = 0, q0 = 0;
-            for (int q = blockIdx.x; q < g.ntasks; q += gridDim.x) {
-                while (q >= q0 + (g.Trows - j)) { q0 += g.Trows - j; ++j; }
-                const int i = j + (q - q0);
-                const int kstart = i >= g.id0 ? i - g.id0 : 0;                    // identity block: zero tiles left of its diagonal
-                if (j < kstart) continue;
+            int task_idx = 0, i, j;
+            TaskIter ts;
+            ts.q = blockIdx.x;
+            while (next_task(g, ts, i, j)) {
+                const int kstart = i >= g.id0 ? i - g.id0 : 0;                    // identity block: k starts at the tile's own row
                 // A-operand rows of this task: the square block or one of the appended blocks
                 const CUtensorMap* tmA = i < T ? &tmL : (i < g.id0 ? &tmB1 : &tmB2);
                 const int arow = (i < T ? i : (i < g.id0 ? i - g.seg[0].row0 : i - g.seg[1].row0)) * TB;
@@ -187,13 +233,11 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
     double* Tt = Wd + 4 * 32 * leaf::WLD;
 
     uint32_t it = 0, wit = 0;
-    int task_idx = -1, j = 0, q0 = 0;
-    for (int q = blockIdx.x; q < g.ntasks; q += gridDim.x) {
-        while (q >= q0 + (g.Trows - j)) { q0 += g.Trows - j; ++j; }
-        const int i = j + (q - q0);
+    int i, j;
+    TaskIter ts;
+    ts.q = blockIdx.x;
+    while (next_task(g, ts, i, j)) {
         const int kstart = i >= g.id0 ? i - g.id0 : 0;
-        if (j < kstart) continue;
-        ++task_idx;
         // where this task's tile lives: the square block or an appended block (all of whose rows exist in memory)
         double* tile_ptr;
         long tile_ld;
@@ -408,6 +452,37 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
     }
     int grid = ntasks < c->num_sms ? ntasks : c->num_sms;
     if (c->potrf_grid_cap > 0 && grid > c->potrf_grid_cap) grid = c->potrf_grid_cap;   // leave SMs to concurrent work
+    // CTA groups (see next_task): with appended rows and enough tile columns for the chain to matter, a group of CTAs sized for
+    // the square block's flops keeps the dependency chain to itself; the other CTAs take the appended tiles of the columns the
+    // chain passes while it runs (about as many k-blocks as they can process in that time), everybody shares the rest.
+    const int R = Trows - T;
+    a.nspd = (long)T * (T + 1) / 2;
+    a.napp = (long)T * R;
+    a.Gc = grid;
+    a.pc = 0;
+    if (R > 0 && T >= 8 && grid >= 32) {
+        static const int gc_env = getenv("GPNET_B200_DF_CHAIN_CTAS") ? atoi(getenv("GPNET_B200_DF_CHAIN_CTAS")) : 0;
+        static const int jc_env = getenv("GPNET_B200_DF_SPLIT_COL") ? atoi(getenv("GPNET_B200_DF_SPLIT_COL")) : -1;
+        const double kb_us = 17.0, col_us = 66.0;                          // one k-block on one SM; one step of the chain
+        double spd_kb = 0.0;
+        for (int j = 0; j < T; ++j) spd_kb += (double)(T - j - 1) * j + 0.55 * j + 2.0 * (T - j);   // + epilogue / leaf equivalents
+        int gc = (int)(spd_kb * kb_us / (T * col_us) * 1.25) + 2;          // flops of the square block within the chain's duration
+        if (gc < 24) gc = 24;
+        if (gc > grid / 2) gc = grid / 2;
+        if (gc_env > 0 && gc_env < grid) gc = gc_env;
+        const double budget = (double)(grid - gc) * T * col_us / kb_us;    // k-blocks the followers process while the chain runs
+        int jc = 0;
+        double acc_kb = 0.0;
+        for (; jc < T; ++jc) {
+            double ck = (double)R1 * (jc + 1.2);                           // right-hand-side rows: jc k-blocks + epilogue
+            if (R2) ck += 0.5 * jc * (jc + 1.0) + 1.2 * (jc + 1);          // identity rows r <= jc: (jc - r) k-blocks each
+            if (acc_kb + ck > budget) break;
+            acc_kb += ck;
+        }
+        if (jc_env >= 0 && jc_env <= T) jc = jc_env;
+        a.Gc = gc;
+        a.pc = (long)jc * R;
+    }
     void* args[] = {(void*)&tl, (void*)&tw, (void*)&tb1, (void*)&tb2, (void*)&a};
     // executed flops: an off-diagonal task runs j k-blocks of 128^3 MACs, a diagonal one only the 136 of 256 8x8 blocks that
     // touch the lower triangle; the in-CTA trsm skips the zero k-steps of W_j (36 of 64); leaf = factor + inverse; appended rows

@@ -151,13 +151,13 @@ def stage_chain(ctx):
         Sb, ld = dmat(n, n, S)
         ctx.potrf(n, Sb.data_ptr(), ld)
         Sb[:, :n] = S
-        ntasks = T * (T + 1) // 2
+        ntasks = T * T                                  # trace slot of tile (i, j): j * T + i
         tr = torch.zeros(ntasks * 8, dtype=torch.int64, device=dev)
         ctx.lib.gpn_debug_df_trace(ctx.h, tr.data_ptr())
         ctx.potrf(n, Sb.data_ptr(), ld)
         ctx.lib.gpn_debug_df_trace(ctx.h, None)
         t = tr.cpu().numpy().reshape(ntasks, 8).astype(np.float64) * 1e-3      # us
-        q0 = lambda j: j * T - j * (j - 1) // 2
+        q0 = lambda j: j * T + j
         rows = []
         for j in range(T - 1):
             dg, ts, dn = t[q0(j)], t[q0(j) + 1], t[q0(j + 1)]     # diag(j), trsm(j+1,j), diag(j+1)
@@ -170,7 +170,8 @@ def stage_chain(ctx):
                          dn[4] - dg[4]])         # column period
         r = np.array(rows)
         names = ["leaf", "diag-epilogue", "flag->W landed", "trsm gemm", "trsm store+flag", "flag->lastk done", "column period"]
-        print(f"n={n}: total {(t[:, 4].max() - t[:, 0].min()):.0f} us;  chain segments (us, median over columns; [first 5] .. [last 5]):")
+        live = t[:, 4] > 0
+        print(f"n={n}: total {(t[live, 4].max() - t[live, 0].min()):.0f} us;  chain segments (us, median over columns; [first 5] .. [last 5]):")
         for k, nm in enumerate(names):
             print(f"   {nm:18s} median {np.median(r[:, k]):7.1f}   head {np.round(r[:5, k], 1)}  tail {np.round(r[-5:, k], 1)}")
         sys.stdout.flush()
@@ -186,21 +187,19 @@ def stage_dfbreak(ctx):
     Sb, ld = dmat(n, n, S)
     ctx.potrf(n, Sb.data_ptr(), ld)
     Sb[:, :n] = S
-    ntasks = T * (T + 1) // 2
-    tr = torch.zeros(ntasks * 8, dtype=torch.int64, device=dev)
+    tr = torch.zeros(T * T * 8, dtype=torch.int64, device=dev)
     ctx.lib.gpn_debug_df_trace(ctx.h, tr.data_ptr())
     ctx.potrf(n, Sb.data_ptr(), ld)
     ctx.lib.gpn_debug_df_trace(ctx.h, None)
-    t = tr.cpu().numpy().reshape(ntasks, 8).astype(np.float64) * 1e-3      # us
+    full = tr.cpu().numpy().reshape(T * T, 8).astype(np.float64) * 1e-3      # us; slot of tile (i, j): j * T + i
+    order = [j * T + i for j in range(T) for i in range(j, T)]                # the kernel's task order (dealt round-robin)
+    t = full[order]
+    ntasks = len(order)
     G = 148
     t0, t1 = t[:, 0].min(), t[:, 4].max()
     tot = (t1 - t0) * G
     main = epi = gap = tail = 0.0
-    jof = np.zeros(ntasks, dtype=int)
-    q = 0
-    for j in range(T):
-        jof[q:q + T - j] = j
-        q += T - j
+    jof = np.array([s // T for s in order])
     ideal = 0.0
     for cta in range(G):
         prev = t0
@@ -350,8 +349,9 @@ def stage_gpc(ctx):
 
 
 def stage_augbreak(ctx):
-    """CTA-time breakdown of the augmented dataflow kernel [S; X^T; I] of the coupled regularized-Laplacian route
-    (N = 8192, n = 4096): per-task %globaltimer trace of the LAST dataflow launch of one logp+grad evaluation."""
+    """CTA-time breakdown of the augmented dataflow kernels of the coupled regularized-Laplacian route (N = 8192, n = 4096):
+    per-task %globaltimer trace of the LAST dataflow launch ([S; X^T; I]) of one logp+grad evaluation.  Tasks are attributed
+    to CTAs by their SM-independent time stamps: the kernel runs G CTAs, each a chain of non-overlapping tasks."""
     import oracle.configs as cfg
     N, n = 8192, 4096
     indptr, indices, w, pos, t = cfg.rgg_csr_fast(N)
@@ -361,36 +361,25 @@ def stage_augbreak(ctx):
     th = np.log([0.6, 0.01])
     ctx.gpr_logp_grad(1, th, t[tr], True)
     T, Trows, id0 = n // 128, 3 * (n // 128), 2 * (n // 128)
-    tasks = [(i, j) for j in range(T) for i in range(j, Trows)]
-    ntasks = len(tasks)
-    trc = torch.zeros(ntasks * 8, dtype=torch.int64, device=dev)
+    trc = torch.zeros(T * Trows * 8, dtype=torch.int64, device=dev)
     ctx.lib.gpn_debug_df_trace(ctx.h, trc.data_ptr())
     ctx.gpr_logp_grad(1, th, t[tr], True)
     ctx.lib.gpn_debug_df_trace(ctx.h, None)
-    tt = trc.cpu().numpy().reshape(ntasks, 8).astype(np.float64) * 1e-3
-    live = np.array([not (i >= id0 and j < i - id0) for (i, j) in tasks])
+    tt = trc.cpu().numpy().reshape(T, Trows, 8).astype(np.float64) * 1e-3          # [j][i]
+    tasks = [(i, j) for j in range(T) for i in range(j, Trows) if not (i >= id0 and j < i - id0)]
     G = 148
-    t0, t1 = tt[live, 0].min(), tt[live, 4].max()
+    st = np.array([tt[j, i, 0] for (i, j) in tasks]); ml = np.array([tt[j, i, 1] for (i, j) in tasks]); en = np.array([tt[j, i, 4] for (i, j) in tasks])
+    t0, t1 = st.min(), en.max()
     tot = (t1 - t0) * G
-    main = epi = gap = tail = 0.0
-    for cta in range(G):
-        prev = t0
-        for q in range(cta, ntasks, G):
-            if not live[q]:
-                continue
-            gap += tt[q, 0] - prev
-            main += tt[q, 1] - tt[q, 0]
-            epi += tt[q, 4] - tt[q, 1]
-            prev = tt[q, 4]
-        tail += t1 - prev
+    main, epi = float(np.sum(ml - st)), float(np.sum(en - ml))
     print(f"[S; X^T; I] n={n}: {t1 - t0:.0f} us; CTA-time: main loops (incl. waiting for operands) {100*main/tot:.1f} %, epilogues {100*epi/tot:.1f} %, "
-          f"gaps {100*gap/tot:.1f} %, idle after last task {100*tail/tot:.1f} %")
-    kb = sum((j - (i - id0 if i >= id0 else 0)) for (i, j), l in zip(tasks, live) if l)
+          f"between / after tasks {100*(tot-main-epi)/tot:.1f} %")
+    kb = sum((j - (i - id0 if i >= id0 else 0)) for (i, j) in tasks)
     print(f"   k-blocks {kb}: at 17 us each on {G} CTAs: {kb*17/G:.0f} us")
     for a in range(8):
         lo, hi = t0 + a / 8 * (t1 - t0), t0 + (a + 1) / 8 * (t1 - t0)
-        busy = sum(max(0.0, min(tt[q, 1], hi) - max(tt[q, 0], lo)) for q in range(ntasks) if live[q])
-        dg = [j for (i, j), q in zip(tasks, range(ntasks)) if i == j and lo <= tt[q, 4] < hi]
+        busy = float(np.sum(np.clip(np.minimum(ml, hi) - np.maximum(st, lo), 0, None)))
+        dg = [j for (i, j), e in zip(tasks, en) if i == j and lo <= e < hi]
         print(f"   elapsed {a}/8: main-loop occupancy {100*busy/((hi-lo)*G):5.1f} %   diagonal tiles finished: {min(dg) if dg else '-'}..{max(dg) if dg else '-'}")
     sys.stdout.flush()
 
