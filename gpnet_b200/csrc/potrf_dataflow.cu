@@ -479,7 +479,8 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
             if (acc_kb + ck > budget) break;
             acc_kb += ck;
         }
-        if (jc_env >= 0 && jc_env <= T) jc = jc_env;
+        if (jc_env >= 0 && jc_env <= T) jc = jc_env;                       // (both overrides: tuning experiments; a sweep at C3 put
+                                                                           //  the model's choice within 1 % of the best setting)
         a.Gc = gc;
         a.pc = (long)jc * R;
     }
