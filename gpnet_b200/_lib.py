@@ -43,6 +43,10 @@ SIGNATURES = {
                                C.c_void_p, C.c_long, C.c_double, C.c_void_p, C.c_long]),
     "gpn_potrf_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, c_int_p]),
     "gpn_spd_inverse_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, c_int_p]),
+    "gpn_syrk_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_long, C.c_double, C.c_void_p, C.c_long]),
+    "gpn_posv_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long,
+                               C.POINTER(C.c_int)]),
+    "gpn_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gpn_gather_block_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double,
                                        C.c_void_p, C.c_long]),
     "gpn_kernel_build": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, C.c_int]),
@@ -86,6 +90,11 @@ def load_library(path: str = LIB_PATH):
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def workspace_bytes(N: int, n: int, m: int, kerneltype: str) -> int:
+    """Device memory a context needs for a model of this size (host arithmetic in the library, no GPU touched)."""
+    return int(load_library().gpn_workspace_bytes(int(N), int(n), int(m), KERNEL_IDS[kerneltype]))
 
 
 def _dp(a: np.ndarray):
@@ -188,6 +197,16 @@ class Context:
     def gemm(self, transa, transb, M, N, K, alpha, a_ptr, lda, b_ptr, ldb, beta, c_ptr, ldc):
         self._check(self.lib.gpn_gemm_f64(self.h, int(transa), int(transb), M, N, K, alpha, C.c_void_p(a_ptr), lda, C.c_void_p(b_ptr),
                                           ldb, beta, C.c_void_p(c_ptr), ldc), "gpn_gemm_f64")
+
+    def syrk(self, n, k, alpha, a_ptr, lda, beta, c_ptr, ldc):
+        self._check(self.lib.gpn_syrk_f64(self.h, n, k, alpha, C.c_void_p(a_ptr), lda, beta, C.c_void_p(c_ptr), ldc), "gpn_syrk_f64")
+
+    def posv(self, n, a_ptr, lda, b_ptr=None, ldb=0, brows=0, wt_ptr=None, ldw=0) -> int:
+        """Cholesky of A in place with B <- B L^-T and Winv_t <- L^-T in the same kernel; returns the LAPACK-style info."""
+        info = C.c_int(0)
+        self._check(self.lib.gpn_posv_f64(self.h, n, C.c_void_p(a_ptr), lda, C.c_void_p(b_ptr) if b_ptr else None, ldb, brows,
+                                          C.c_void_p(wt_ptr) if wt_ptr else None, ldw, C.byref(info)), "gpn_posv_f64")
+        return info.value
 
     def potrf(self, n, a_ptr, lda) -> int:
         info = C.c_int(0)

@@ -1577,6 +1577,41 @@ int gpn_potrf_f64(gpn_ctx* c, int n, double* A, long lda, int* info_h) {
     return 0;
 }
 
+int gpn_syrk_f64(gpn_ctx* c, int n, int k, double alpha, const double* A, long lda, double beta, double* C, long ldc) {
+    if (!c) return -1;
+    // C = alpha A A^T + beta C: lower tiles computed, mirrored into the upper ones (the result is the full symmetric matrix)
+    return gpn_gemm(c, n, n, k, alpha, A, lda, true, A, lda, true, beta, C, ldc, GF_LOWER | GF_MIRROR);
+}
+
+int gpn_posv_f64(gpn_ctx* c, int n, double* A, long lda, double* B, long ldb, int brows, double* Winv_t, long ldw, int* info_h) {
+    if (!c) return -1;
+    if (n <= 0) return -2;
+    if (B && brows <= 0) return -7;
+    GPN_TRY(clear_info(c));
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(n) * 128));
+    GPN_TRY(gpn_potrf_dataflow(c, n, A, lda, (double*)c->winv.p, iscal(c, 0), 0, B, ldb, brows, Winv_t, ldw));
+    GPN_TRY(gpn_k_zero_upper(c, A, lda, n));
+    if (!info_h) return 0;
+    int info[16];
+    GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
+    *info_h = info[0];
+    return 0;
+}
+
+long long gpn_workspace_bytes(int N, int n, int m, int kind) {
+    // what the context allocates on the device for one model of this size (see ensure_mat / ensure_nb in this file):
+    // N x N operands (padded to 128): 4 for the regularized Laplacian and the Cholesky-based inverses, 6 for the p-step powers,
+    // 10 for the Pade matrix exponential; block buffers K_y, W, T, W^T, G, a copy (n x n), two row panels (n x N), kstar
+    // (m x n), kstarstar, V (m x m), Newton scratch (3 n x n); inverted diagonal blocks; vectors
+    if (N <= 0 || n < 0 || m < 0) return -1;
+    const long long Np = pad128(N), np_ = pad128(n > 0 ? n : 1), mp = pad128(m > 0 ? m : 1);
+    const long long mats = kind == GPN_KERNEL_DIFFUSION ? 10 : (kind == GPN_KERNEL_PSTEP_WALK ? 6 : 4);
+    long long d = mats * Np * Np;
+    d += 6 * np_ * np_ + 2 * np_ * Np + mp * np_ + 2 * mp * mp + 3 * np_ * np_;
+    d += Np * 128 + 24 * (std::max(np_, mp) + 128) + 2 * Np;
+    return 8 * d;
+}
+
 int gpn_spd_inverse_f64(gpn_ctx* c, int n, double* A, long lda, double* out, long ldo, double* work, int* info_h) {
     if (!c) return -1;
     if (lda != ldo) return -6;

@@ -379,7 +379,10 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) tile_ptr[(long)r * tile_ld + wn * 32 + b * 8 + t + 4 * e] = acc[a][b][e];
+                        for (int e = 0; e < 2; ++e) {
+                            const int cc = wn * 32 + b * 8 + t + 4 * e;
+                            if ((long)j * TB + cc < g.n) tile_ptr[(long)r * tile_ld + cc] = acc[a][b][e];    // ragged last tile column
+                        }
                 }
             }
             __threadfence();

@@ -76,6 +76,20 @@ int gpn_potrf_f64(gpn_ctx* ctx, int n, double* A, long lda, int* info_h);
 /* out = inverse of the SPD matrix A (A is destroyed: it holds L afterwards); replaces scipy.linalg.inv (GPnet.py:342)
  * and the inv(K) of GPnetClassifier.py:126.  work: n*ld doubles of scratch. */
 int gpn_spd_inverse_f64(gpn_ctx* ctx, int n, double* A, long lda, double* out, long ldo, double* work, int* info_h);
+/* C = alpha*A*A^T + beta*C for the n x k row-major A, full symmetric result (lower tiles computed, mirrored): the SYRK
+ * behind (K^2)[tr,tr] and the expm / inverse products of symmetric operands. */
+int gpn_syrk_f64(gpn_ctx* ctx, int n, int k, double alpha, const double* A, long lda, double beta, double* C, long ldc);
+/* Cholesky with right-hand sides in ONE dataflow kernel (LAPACK posv-like): A = L L^T in place (strict upper zeroed) and,
+ * if B != NULL, B <- B L^-T for the brows x n row-major B (whose rows up to the next multiple of 128 must exist and be
+ * zero), and, if Winv_t != NULL, Winv_t <- L^-T (round128(n) x n buffer; its upper 128-tiles are written, the lower ones
+ * left alone).  Replaces np.linalg.cholesky followed by the np.linalg.solve(L, .) calls of GPnetRegressor.py:123-126,
+ * 141-144 and GPnetClassifier.py:110-119 in one launch; the appended rows fill the SMs the Cholesky's dependency chain
+ * leaves idle.  All leading dimensions even, bases 16-byte aligned. */
+int gpn_posv_f64(gpn_ctx* ctx, int n, double* A, long lda, double* B, long ldb, int brows, double* Winv_t, long ldw, int* info_h);
+/* Upper bound of the device memory (bytes) a context allocates for a model with N graph nodes, n training and m test nodes
+ * and the given kernel (host-only arithmetic, no context required): lets a caller size shards for the 180 GB of one B200
+ * (C5: N = 32768, n = m = 16384, diffusion -> 1.2e11; measured 1.06e11 for the regressor alone). */
+long long gpn_workspace_bytes(int N, int n, int m, int kind);
 /* out[i][j] = K[rows[i]][cols[j]] + addc  (GPnet.py:362-365: np.delete x2 + scalar noise on every entry) */
 int gpn_gather_block_add(gpn_ctx* ctx, const double* K, long ld, const int* rows, int nr, const int* cols, int nc,
                          double addc, double* out, long ldo);

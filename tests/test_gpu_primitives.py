@@ -88,6 +88,56 @@ def test_spd_inverse(gpu_ctx, n):
     assert torch.equal(Ob[:, :n], Ob[:, :n].T)                   # mirrored store => exactly symmetric
 
 
+@pytest.mark.parametrize("n,k", [(5, 3), (128, 64), (300, 1000), (1000, 257)])
+def test_syrk(gpu_ctx, n, k):
+    import torch
+    torch.manual_seed(n + k)
+    A = torch.randn(n, k, dtype=torch.float64, device="cuda:0")
+    C0 = torch.randn(n, n, dtype=torch.float64, device="cuda:0")
+    C0 = C0 + C0.T
+    Ab, lda = dmat(n, k, A)
+    Cb, ldc = dmat(n, n, C0)
+    gpu_ctx.syrk(n, k, 0.5, Ab.data_ptr(), lda, -2.0, Cb.data_ptr(), ldc)
+    gpu_ctx.sync()
+    ref = 0.5 * (A @ A.T) - 2.0 * C0
+    assert (Cb[:, :n] - ref).abs().max().item() / ref.abs().max().item() < FP_TOL
+    assert torch.equal(Cb[:, :n], Cb[:, :n].T)
+
+
+@pytest.mark.parametrize("n,brows,with_inv", [(100, 50, True), (128, 128, True), (700, 300, True), (1024, 2000, False), (1500, 129, True),
+                                              (2048, 0, True), (1111, 777, False)])
+def test_posv_factor_with_right_hand_sides_in_one_kernel(gpu_ctx, n, brows, with_inv):
+    """gpn_posv_f64: the dataflow Cholesky with appended row blocks -- A = L L^T, B <- B L^-T, Winv_t <- L^-T -- against
+    LAPACK (ragged sizes, no right-hand sides, no inverse, fewer tile columns than the CTA-group schedule needs)."""
+    import torch
+    torch.manual_seed(n + brows)
+    X = torch.randn(n, n, dtype=torch.float64, device="cuda:0")
+    S = X @ X.T / n + torch.eye(n, dtype=torch.float64, device="cuda:0")
+    B = torch.randn(brows, n, dtype=torch.float64, device="cuda:0")
+    Sb, ld = dmat(n, n, S)
+    pad = lambda r: (r + 127) // 128 * 128
+    Bb, ldb = dmat(max(pad(brows), 128), n)
+    Bb[:brows, :n] = B
+    Wb, ldw = dmat(pad(n), n)
+    Wb.fill_(7.0)                                                 # any content: the kernel zero-fills what it reads
+    info = gpu_ctx.posv(n, Sb.data_ptr(), ld, Bb.data_ptr() if brows else None, ldb, brows, Wb.data_ptr() if with_inv else None, ldw)
+    gpu_ctx.sync()
+    assert info == 0
+    L = torch.linalg.cholesky(S)
+    assert (Sb[:, :n] - L).abs().max().item() / L.abs().max().item() < FP_TOL
+    if brows:
+        ref = torch.linalg.solve_triangular(L, B.T, upper=False).T          # B L^-T
+        assert (Bb[:brows, :n] - ref).abs().max().item() / ref.abs().max().item() < 1e-11
+        assert Bb[brows:, :n].abs().max().item() == 0.0 if Bb.shape[0] > brows else True
+    if with_inv:
+        Winv_t = torch.linalg.inv(L).T
+        got = torch.triu(Wb[:n, :n])
+        assert (got - Winv_t).abs().max().item() / Winv_t.abs().max().item() < 1e-11
+        for r in range(0, n, 128):                                 # within the diagonal tiles the lower part is exactly zero
+            blk = Wb[r:min(r + 128, n), r:min(r + 128, n)]
+            assert torch.equal(torch.tril(blk, -1), torch.zeros_like(blk))
+
+
 def test_laplacian_and_gather_bit_exact(gpu_ctx):
     """Laplacian assembly reproduces networkx's operation order bit for bit (self-loop, isolated node, weights);
     the block gather reproduces np.delete x2 + scalar add (GPnet.py:362-365)."""

@@ -148,6 +148,19 @@ def test_cholesky_failure_maps_to_reference_behaviour(capsys):
     assert m.predict().is_trained and list(m.df["fstar"][m.test_nodes]) == [1.0] * 8
 
 
+def test_workspace_bytes_matches_the_measured_footprints():
+    """gpn_workspace_bytes is host arithmetic over the buffers a context can allocate (an upper bound: regressor and
+    classifier scratch together): C5 (N = 32768, n = m = 16384, diffusion) used 106 GB of HBM on the B200
+    (tools/c5_check.py), the headline configuration a few GB."""
+    from gpnet_b200._lib import workspace_bytes
+    c5 = workspace_bytes(32768, 16384, 16384, "diffusion")
+    assert 1.06e11 <= c5 < 1.25e11
+    c3 = workspace_bytes(8192, 4096, 4096, "regularized_laplacian")
+    assert 2.5e9 < c3 < 6e9
+    assert workspace_bytes(8192, 4096, 4096, "diffusion") > workspace_bytes(8192, 4096, 4096, "pstep_walk") > c3
+    assert workspace_bytes(0, 1, 1, "diffusion") == -1
+
+
 def test_cyclic_shards_cover_the_grid():
     from gpnet_b200.sharded import cyclic_slice
     total = 64 * 64
