@@ -381,6 +381,17 @@ def stage_augbreak(ctx):
         busy = float(np.sum(np.clip(np.minimum(ml, hi) - np.maximum(st, lo), 0, None)))
         dg = [j for (i, j), e in zip(tasks, en) if i == j and lo <= e < hi]
         print(f"   elapsed {a}/8: main-loop occupancy {100*busy/((hi-lo)*G):5.1f} %   diagonal tiles finished: {min(dg) if dg else '-'}..{max(dg) if dg else '-'}")
+    # the tail: tasks that end in the last eighth of the run
+    lo = t0 + 7 / 8 * (t1 - t0)
+    late = [(en[q] - t0, st[q] - t0, ml[q] - st[q], en[q] - ml[q], tasks[q]) for q in range(len(tasks)) if en[q] >= lo]
+    late.sort()
+    print(f"   {len(late)} tasks end in the last eighth; the last 12 (end, start, main loop, epilogue in us; tile (i, j); block):")
+    for e, s0, m, ep, (i, j) in late[-12:]:
+        print(f"      end {e:7.0f}  start {s0:7.0f}  main {m:6.0f}  epilogue {ep:5.0f}   ({i:3d},{j:3d})  {'square' if i < T else ('rhs' if i < id0 else 'identity')}")
+    bycol = {}
+    for e, s0, m, ep, (i, j) in late:
+        bycol[j] = bycol.get(j, 0) + 1
+    print("   tasks ending in the last eighth by tile column:", dict(sorted(bycol.items())))
     sys.stdout.flush()
 
 
