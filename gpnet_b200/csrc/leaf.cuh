@@ -385,26 +385,33 @@ __device__ __forceinline__ void potf2_inverse(double* __restrict__ S, double* __
         trail_diag(S, b0, tid);
         bar256<BAR_ID>();
         if (prof && tid == 0) prof[12 + kb] = clock64();
-        // ---- (c) chain: factor D(kb+1) + lockstep inverse.  Off the chain: the rest of the trailing update and T for block row
-        //      kb+1 of the inverse (warps 2, 3, 5, 6, 7); write-back of block column kb of L / block row kb of the inverse (warp 4:
-        //      memory traffic only next to the factor warp) ----
+        // ---- (c) chain: factor D(kb+1) + lockstep inverse.  Off the chain (warps 2, 3, 5, 6, 7; warp 4 only moves memory next
+        //      to the factor warp): what the NEXT step needs of the trailing matrix, left-looking -- block column kb+1 below its
+        //      diagonal block and diagonal block kb+2, each with all panels so far (K = 32 (kb+1)); the newest panel's
+        //      contribution to a diagonal block is always added by trail_diag --, T for block row kb+1 of the inverse, and the
+        //      write-back of block column kb of L / block row kb of the inverse shared by all six warps ----
         if (warp == 0) {
             diag32_factor(S, r1, rdiag + r1, rdiag + LB, info, info_off, lane, bars);
             if (prof && lane == 0) prof[16 + kb] = clock64();
         } else if (warp == 1) {
             diag32_inverse_lockstep(S, r1, Wd + (kb + 1) * 32 * WLD, rdiag + r1, bars, (kb + 1) & 1, lane);
             if (prof && lane == 0) prof[20 + kb] = clock64();
-        } else if (warp == 4) {
-            write_back_step(S, Wd, kb, Lout, ldl, nv, winv, tid, 0x10u, false);
-            if (prof && lane == 0) prof[28 + kb] = clock64();
         } else {
-            if (R > 32) {
-                double* C22 = S + r1 * LDS_ + r1;
-                smem_dmma<LDS_, LDS_, true, 2>(S + r1 * LDS_ + b0, S + r1 * LDS_ + b0, R / 16, R / 32, 32, tid,
-                                               [&](int r, int cc, double v) { C22[r * LDS_ + cc] -= v; }, OFFCHAIN, true);
+            if (warp != 4) {
+                if (R > 32) {
+                    const double* rows2 = S + (r1 + 32) * LDS_;           // rows below diagonal block kb+1, all panels 0..kb
+                    double* Cp = S + (r1 + 32) * LDS_ + r1;               // block column kb+1 below its diagonal block
+                    smem_dmma<LDS_, LDS_, true, 0>(rows2, S + r1 * LDS_, (R - 32) / 16, 1, r1, tid,
+                                                   [&](int r, int cc, double v) { Cp[r * LDS_ + cc] -= v; }, OFFCHAIN);
+                    double* Dn = S + (r1 + 32) * LDS_ + r1 + 32;          // diagonal block kb+2
+                    smem_dmma<LDS_, LDS_, true, 2>(rows2, rows2, 2, 1, r1, tid, [&](int r, int cc, double v) { Dn[r * LDS_ + cc] -= v; },
+                                                   kb == 0 ? 0xC0u : 0x60u);     // warps 6, 7 resp. 5, 6: the first product's least loaded
+                }
+                inv_row_T(S, Wd, T, kb + 1, tid, OFFCHAIN);
+                if (prof && tid == 64) prof[24 + kb] = clock64();
             }
-            inv_row_T(S, Wd, T, kb + 1, tid, OFFCHAIN);
-            if (prof && tid == 64) prof[24 + kb] = clock64();
+            write_back_step(S, Wd, kb, Lout, ldl, nv, winv, tid, OFFCHAIN | 0x10u, false);
+            if (prof && tid == 128) prof[28 + kb] = clock64();
         }
         bar256<BAR_ID>();
         LEAF_STAMP();
