@@ -330,6 +330,39 @@ def test_reglap_routes_agree_with_oracle_for_stiff_parameters(gpu_ctx, beta, noi
         gpu_ctx.set_fast_paths(True)
 
 
+def test_reglap_routes_on_a_weighted_graph_with_isolated_nodes_and_a_training_only_component(gpu_ctx):
+    """Edge cases of the Schur routes' graph handling: random edge weights (the sparse coupling block carries them), isolated
+    nodes on both sides (zero degree: their row of I + beta L~ is the identity), a component made of training nodes only (no
+    coupling at all) and training nodes without any other-node neighbour -- all five routes against the numpy oracle."""
+    rng = np.random.RandomState(7)
+    G = nx.random_geometric_graph(640, 0.09, seed=3)
+    G.add_nodes_from(range(640, 700))                              # 60 isolated nodes
+    for a in range(660, 680):                                      # a path component among some of them
+        G.add_edge(a, a + 1)
+    for (u, v) in G.edges():
+        G[u][v]["weight"] = float(rng.uniform(0.2, 3.0))
+    N = G.number_of_nodes()
+    perm = rng.permutation(640)
+    tr = sorted([int(x) for x in perm[:300]] + list(range(650, 685)))      # the path component and some isolated nodes are training nodes
+    te = sorted(int(x) for x in perm[300:360])
+    t = np.sin(0.05 * np.arange(len(tr))) + 0.1 * rng.randn(len(tr))
+    indptr, indices, w, _ = go.graph_to_csr(G)
+    gpu_ctx.set_graph(indptr, indices, w)
+    gpu_ctx.set_nodes(tr, te)
+    th = np.log([0.8, 0.05])
+    orc = go.OracleGP(G, kerneltype="regularized_laplacian")
+    ref_v, ref_g = orc.neg_logp_grad(th, tr, t)
+    try:
+        for level in (0, 1, 2, 3, 4):
+            gpu_ctx.set_fast_paths(level)
+            st, out, info = gpu_ctx.gpr_logp_grad(1, th, t, True)
+            assert st == 0 and info == 0
+            assert abs(out[0] - ref_v) <= TOL * abs(ref_v), (level, out[0], ref_v)
+            assert nrel(out[1:], ref_g) <= 1e-8, (level, out[1:], ref_g)
+    finally:
+        gpu_ctx.set_fast_paths(True)
+
+
 @pytest.mark.parametrize("kind,theta,axidx", [(0, np.log([0.6, 0.01]), [0, 1]), (0, np.log([0.6, 0.01]), [1, 0]),
                                               (1, np.log([0.6, 0.01]), [0, 1]), (2, np.log([2.3, 4, 0.01]), [0, 2]),
                                               (2, np.log([2.3, 4]), [0, 1]), (1, np.log([0.6, 0.01]), [1, 1])])
