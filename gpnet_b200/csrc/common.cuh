@@ -61,6 +61,7 @@ struct gpn_ctx {
     bool own_stream = false;
     cudaStream_t stream2 = nullptr;      // side stream: independent GEMM work overlapped with a latency-bound Cholesky
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    long flags_rows = 0;                 // layout of `flags`: [ready flags (flags_rows ints) | task counters]
     int potrf_grid_cap = 0;              // > 0: the next dataflow Cholesky may use at most this many CTAs
     int num_sms = 148;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;

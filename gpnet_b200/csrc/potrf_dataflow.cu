@@ -51,6 +51,10 @@ struct DfArgs {
     int Gc;               // CTAs [0, Gc) own the square block's tasks (the dependency chain); all CTAs if nothing is appended
     long nspd, napp, pc;  // tasks of the square block; appended tile slots (column-major, Trows - T per column); slots < pc
                           // (the early columns) are dealt to the CTAs [Gc, grid) only, the rest to every CTA
+    int* counters;        // three task counters (zeroed per launch): square block, early appended slots, late appended slots.
+                          // Tasks are GRABBED in list order by whichever CTA of the right group is free (atomicAdd), not dealt
+                          // round robin: the order -- and with it the deadlock argument -- is the same, the balance adapts to the
+                          // real task durations and to the moment a group finishes its own part
     DfSeg seg[2];         // appended blocks: seg[0] = general right-hand sides, seg[1] = identity block
     double* winv;
     int* flags;
@@ -79,34 +83,35 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v) { asm volatile("s
 //   * CTAs [Gc, grid): the appended tiles of the early columns (slots < pc), then their share of the late ones.
 struct TaskIter {
     int phase = 0;
-    long q;
-    int j = 0;
+    int j = 0;            // column tracking of the square block's list (only ever moves forward)
     long q0 = 0;
 };
+// Called by ONE thread per CTA (the producer); the result is handed to the consumer warps through shared memory.
 __device__ __forceinline__ bool next_task(const DfArgs& g, TaskIter& s, int& i, int& j) {
-    const int b = blockIdx.x, G = gridDim.x, R = g.Trows - g.T;
+    const int b = blockIdx.x, R = g.Trows - g.T;
     for (;;) {
         long p;
         if (s.phase == 0) {
-            if (b < g.Gc && s.q < g.nspd) {
-                while (s.q >= s.q0 + (g.T - s.j)) { s.q0 += g.T - s.j; ++s.j; }
-                i = s.j + (int)(s.q - s.q0);
-                j = s.j;
-                s.q += g.Gc;
-                return true;
+            if (b < g.Gc) {
+                const long q = atomicAdd(g.counters + 0, 1);
+                if (q < g.nspd) {
+                    while (q >= s.q0 + (g.T - s.j)) { s.q0 += g.T - s.j; ++s.j; }
+                    i = s.j + (int)(q - s.q0);
+                    j = s.j;
+                    return true;
+                }
+                s.phase = 2;
+            } else {
+                s.phase = 1;
             }
-            if (b < g.Gc) { s.phase = 2; s.q = g.pc + b; }
-            else { s.phase = 1; s.q = b - g.Gc; }
             continue;
         }
         if (s.phase == 1) {
-            if (s.q >= g.pc) { s.phase = 2; s.q = g.pc + b; continue; }
-            p = s.q;
-            s.q += G - g.Gc;
+            p = atomicAdd(g.counters + 1, 1);
+            if (p >= g.pc) { s.phase = 2; continue; }
         } else {
-            if (s.q >= g.napp) return false;
-            p = s.q;
-            s.q += G;
+            p = g.pc + atomicAdd(g.counters + 2, 1);
+            if (p >= g.napp) return false;
         }
         j = (int)(p / R);
         i = g.T + (int)(p - (long)j * R);
@@ -143,6 +148,8 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
     const uint32_t bar_full = smem0 + RING_BYTES, bar_empty = bar_full + STAGES * 8;
     const uint32_t bar_wfull = bar_empty + STAGES * 8, bar_wempty = bar_wfull + WSTAGES * 8;
     const uint32_t bar_mdone = bar_wempty + WSTAGES * 8, bar_fdone = bar_mdone + 8;
+    const uint32_t bar_task = bar_fdone + 8;                                   // two barriers: the producer has posted task t (slot t & 1)
+    volatile int2* task_slot = reinterpret_cast<volatile int2*>(smem_gen + RING_BYTES + 224);   // two (i, j) slots
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int T = g.T;
@@ -160,6 +167,8 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
         }
         mbar_init(bar_mdone, 8);
         mbar_init(bar_fdone, 8);
+        mbar_init(bar_task, 1);
+        mbar_init(bar_task + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -172,8 +181,13 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
             uint32_t it = 0, wit = 0;
             int task_idx = 0, i, j;
             TaskIter ts;
-            ts.q = blockIdx.x;
-            while (next_task(g, ts, i, j)) {
+            for (;;) {
+                const bool more = next_task(g, ts, i, j);
+                // slot t & 1 was last read for task t - 2, whose consumers are long past it (bar_fdone(t - 2) was waited for)
+                task_slot[task_idx & 1].x = more ? i : -1;
+                task_slot[task_idx & 1].y = j;
+                mbar_arrive(bar_task + (task_idx & 1) * 8);
+                if (!more) break;
                 const int kstart = i >= g.id0 ? i - g.id0 : 0;                    // identity block: k starts at the tile's own row
                 // A-operand rows of this task: the square block or one of the appended blocks
                 const CUtensorMap* tmA = i < T ? &tmL : (i < g.id0 ? &tmB1 : &tmB2);
@@ -233,10 +247,10 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
     double* Tt = Wd + 4 * 32 * leaf::WLD;
 
     uint32_t it = 0, wit = 0;
-    int i, j;
-    TaskIter ts;
-    ts.q = blockIdx.x;
-    while (next_task(g, ts, i, j)) {
+    for (int task_idx = 0;; ++task_idx) {
+        mbar_wait(bar_task + (task_idx & 1) * 8, (task_idx >> 1) & 1);
+        const int i = task_slot[task_idx & 1].x, j = task_slot[task_idx & 1].y;
+        if (i < 0) break;
         const int kstart = i >= g.id0 ? i - g.id0 : 0;
         // where this task's tile lives: the square block or an appended block (all of whose rows exist in memory)
         double* tile_ptr;
@@ -427,8 +441,9 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
     long nt = 0;
     for (int j = 0; j < T; ++j) nt += Trows - j;
     const int ntasks = (int)nt;
-    if (c->flags.cap < sizeof(int) * (size_t)Trows * T) {
-        GPN_TRY(gpn_buf_ensure(c, c->flags, sizeof(int) * (size_t)Trows * T));
+    if (c->flags.cap < sizeof(int) * ((size_t)Trows * T + 4) || c->flags_rows != (long)Trows * T) {     // ready flags + task counters
+        GPN_TRY(gpn_buf_ensure(c, c->flags, sizeof(int) * ((size_t)Trows * T + 4)));
+        c->flags_rows = (long)Trows * T;
         GPN_CK(cudaMemsetAsync(c->flags.p, 0, c->flags.cap, c->stream));
         c->epoch = 0;
     }
@@ -463,6 +478,8 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
     a.napp = (long)T * R;
     a.Gc = grid;
     a.pc = 0;
+    a.counters = (int*)c->flags.p + (size_t)Trows * T;
+    GPN_CK(cudaMemsetAsync(a.counters, 0, 4 * sizeof(int), c->stream));
     if (R > 0 && T >= 8 && grid >= 32) {
         static const int gc_env = getenv("GPNET_B200_DF_CHAIN_CTAS") ? atoi(getenv("GPNET_B200_DF_CHAIN_CTAS")) : 0;
         static const int jc_env = getenv("GPNET_B200_DF_SPLIT_COL") ? atoi(getenv("GPNET_B200_DF_SPLIT_COL")) : -1;
