@@ -49,12 +49,10 @@ struct DfArgs {
     int Trows;            // tile rows in total (T for a plain factorisation)
     int id0;              // first tile row of the identity block (Trows if there is none)
     int Gc;               // CTAs [0, Gc) own the square block's tasks (the dependency chain); all CTAs if nothing is appended
-    long nspd, napp, pc;  // tasks of the square block; appended tile slots (column-major, Trows - T per column); slots < pc
-                          // (the early columns) are dealt to the CTAs [Gc, grid) only, the rest to every CTA
-    int* counters;        // three task counters (zeroed per launch): square block, early appended slots, late appended slots.
-                          // Tasks are GRABBED in list order by whichever CTA of the right group is free (atomicAdd), not dealt
-                          // round robin: the order -- and with it the deadlock argument -- is the same, the balance adapts to the
-                          // real task durations and to the moment a group finishes its own part
+    long nspd, napp;      // tasks of the square block; appended tile slots (column-major, Trows - T per column)
+    int* counters;        // two task counters (zeroed per launch): square block, appended slots.  Tasks are GRABBED in list order
+                          // by whichever CTA is free (atomicAdd), not dealt round robin: the balance adapts to the real task
+                          // durations and to the moment the chain group runs out of square-block tasks
     DfSeg seg[2];         // appended blocks: seg[0] = general right-hand sides, seg[1] = identity block
     double* winv;
     int* flags;
@@ -75,12 +73,13 @@ __device__ __forceinline__ long long gtime() {
 #define DF_STAMP(slot) do { if (g.trace && tid == 0) g.trace[((long)j * g.Trows + i) * 8 + (slot)] = gtime(); } while (0)
 __device__ __forceinline__ void sts64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 
-// Static task schedule.  Global order: the square block's tiles column-major, then the appended tiles column-major; every
-// CTA walks its share in that order and every task only waits on tasks that precede it in it (appended tiles depend on the
-// square block and on earlier tiles of their own row, never the other way round), so the schedule cannot deadlock.
-//   * CTAs [0, Gc): the square block (its per-column dependency chain never queues behind a long appended task), afterwards
-//     their share of the late appended columns;
-//   * CTAs [Gc, grid): the appended tiles of the early columns (slots < pc), then their share of the late ones.
+// Task schedule.  Two lists, each in column-major order: the square block's tiles and the appended tiles.
+//   * CTAs [0, Gc) take square-block tasks until that list is exhausted (the per-column dependency chain never queues behind
+//     a long appended task), then appended tasks;
+//   * CTAs [Gc, grid) take appended tasks from the start.
+// Every task only waits on tasks that precede it in its own list or on square-block tasks (appended tiles depend on the
+// square block and on earlier tiles of their own row, never the other way round); the square-block list makes progress on
+// its own, so the schedule cannot deadlock.
 struct TaskIter {
     int phase = 0;
     int j = 0;            // column tracking of the square block's list (only ever moves forward)
@@ -88,11 +87,10 @@ struct TaskIter {
 };
 // Called by ONE thread per CTA (the producer); the result is handed to the consumer warps through shared memory.
 __device__ __forceinline__ bool next_task(const DfArgs& g, TaskIter& s, int& i, int& j) {
-    const int b = blockIdx.x, R = g.Trows - g.T;
+    const int R = g.Trows - g.T;
     for (;;) {
-        long p;
         if (s.phase == 0) {
-            if (b < g.Gc) {
+            if ((int)blockIdx.x < g.Gc) {
                 const long q = atomicAdd(g.counters + 0, 1);
                 if (q < g.nspd) {
                     while (q >= s.q0 + (g.T - s.j)) { s.q0 += g.T - s.j; ++s.j; }
@@ -100,19 +98,12 @@ __device__ __forceinline__ bool next_task(const DfArgs& g, TaskIter& s, int& i, 
                     j = s.j;
                     return true;
                 }
-                s.phase = 2;
-            } else {
-                s.phase = 1;
             }
+            s.phase = 1;
             continue;
         }
-        if (s.phase == 1) {
-            p = atomicAdd(g.counters + 1, 1);
-            if (p >= g.pc) { s.phase = 2; continue; }
-        } else {
-            p = g.pc + atomicAdd(g.counters + 2, 1);
-            if (p >= g.napp) return false;
-        }
+        const long p = atomicAdd(g.counters + 1, 1);
+        if (p >= g.napp) return false;
         j = (int)(p / R);
         i = g.T + (int)(p - (long)j * R);
         if (i >= g.id0 && j < i - g.id0) continue;        // identity block: zero tiles left of its diagonal
@@ -471,38 +462,24 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
     int grid = ntasks < c->num_sms ? ntasks : c->num_sms;
     if (c->potrf_grid_cap > 0 && grid > c->potrf_grid_cap) grid = c->potrf_grid_cap;   // leave SMs to concurrent work
     // CTA groups (see next_task): with appended rows and enough tile columns for the chain to matter, a group of CTAs sized for
-    // the square block's flops keeps the dependency chain to itself; the other CTAs take the appended tiles of the columns the
-    // chain passes while it runs (about as many k-blocks as they can process in that time), everybody shares the rest.
+    // the square block's work within the chain's duration (x 1.5: a sweep at C3 is flat between 72 and 96 of 148 CTAs) keeps
+    // the dependency chain to itself until the square block is done
     const int R = Trows - T;
     a.nspd = (long)T * (T + 1) / 2;
     a.napp = (long)T * R;
     a.Gc = grid;
-    a.pc = 0;
     a.counters = (int*)c->flags.p + (size_t)Trows * T;
     GPN_CK(cudaMemsetAsync(a.counters, 0, 4 * sizeof(int), c->stream));
     if (R > 0 && T >= 8 && grid >= 32) {
         static const int gc_env = getenv("GPNET_B200_DF_CHAIN_CTAS") ? atoi(getenv("GPNET_B200_DF_CHAIN_CTAS")) : 0;
-        static const int jc_env = getenv("GPNET_B200_DF_SPLIT_COL") ? atoi(getenv("GPNET_B200_DF_SPLIT_COL")) : -1;
-        const double kb_us = 17.0, col_us = 66.0;                          // one k-block on one SM; one step of the chain
+        const double kb_us = 17.0, col_us = 65.0;                          // one k-block on one SM; one step of the chain
         double spd_kb = 0.0;
         for (int j = 0; j < T; ++j) spd_kb += (double)(T - j - 1) * j + 0.55 * j + 2.0 * (T - j);   // + epilogue / leaf equivalents
-        int gc = (int)(spd_kb * kb_us / (T * col_us) * 1.25) + 2;          // flops of the square block within the chain's duration
+        int gc = (int)(spd_kb * kb_us / (T * col_us) * 1.5) + 2;
         if (gc < 24) gc = 24;
-        if (gc > grid / 2) gc = grid / 2;
+        if (gc > (2 * grid) / 3) gc = (2 * grid) / 3;
         if (gc_env > 0 && gc_env < grid) gc = gc_env;
-        const double budget = (double)(grid - gc) * T * col_us / kb_us;    // k-blocks the followers process while the chain runs
-        int jc = 0;
-        double acc_kb = 0.0;
-        for (; jc < T; ++jc) {
-            double ck = (double)R1 * (jc + 1.2);                           // right-hand-side rows: jc k-blocks + epilogue
-            if (R2) ck += 0.5 * jc * (jc + 1.0) + 1.2 * (jc + 1);          // identity rows r <= jc: (jc - r) k-blocks each
-            if (acc_kb + ck > budget) break;
-            acc_kb += ck;
-        }
-        if (jc_env >= 0 && jc_env <= T) jc = jc_env;                       // (both overrides: tuning experiments; a sweep at C3 put
-                                                                           //  the model's choice within 1 % of the best setting)
         a.Gc = gc;
-        a.pc = (long)jc * R;
     }
     void* args[] = {(void*)&tl, (void*)&tw, (void*)&tb1, (void*)&tb2, (void*)&a};
     // executed flops: an off-diagonal task runs j k-blocks of 128^3 MACs, a diagonal one only the 136 of 256 8x8 blocks that
