@@ -318,9 +318,9 @@ def main():
                 "conventional_gflop_per_step": algo * 1e-9,
                 "step_conventional_tflops": algo / (ms_step * 1e-3) * 1e-12,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of the two launches
-                # of this kernel in one step (profiles/r01_ncu_potrf_oo.txt: 0.343 GB, profiles/r01_ncu_potrf_tt.txt: 2.600 GB);
+                # of this kernel in one step (profiles/r01_ncu_potrf_oo.txt: 0.326 GB, profiles/r01_ncu_potrf_tt.txt: 3.033 GB);
                 # recorded, not re-measured here (numbers taken under a profiler are never bench values)
-                "traffic": 1.471e9 if kname.startswith("potrf_dataflow") and N == 8192 else None,
+                "traffic": 1.680e9 if kname.startswith("potrf_dataflow") and N == 8192 else None,
                 "traffic_unit": "bytes per launch (average of the step's two launches; ncu capture in profiles/)"}
         # the same evaluation through the two other exact routes (same outputs to rounding), device-timed like `value`
         if world == 1:
