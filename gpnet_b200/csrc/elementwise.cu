@@ -291,12 +291,16 @@ __global__ void csr_values_kernel(int rows, int row0, const int* __restrict__ in
     if (r >= rows) return;
     for (int e = indptr[r] + lane; e < indptr[r + 1]; e += 32) val[e] = M[(long)(row0 + r) * ld + idx[e]];
 }
-// X[r][:] = sum_e val[e] * Z[idx[e]][:]   (sparse rows times a dense symmetric matrix; one double2 per thread, rows in grid.y)
+// X[r][:] = sum_e val[e] * Z[idx[e]][:]   (sparse rows times a dense matrix; one double2 per thread, rows in grid.y);
+// with base != nullptr: X[r][c] = base[r][c] - sum ... for c <= r (lower triangle of the symmetric Schur complement
+// S = M_tt - M_to (M_oo^-1 M_ot), row by row; the rest of the diagonal tile's row is zeroed, tiles above it are not touched)
 __global__ void spmm_rows_kernel(int cols, const int* __restrict__ indptr, const int* __restrict__ idx, const double* __restrict__ val,
-                                 const double* __restrict__ Z, long ldz, double* __restrict__ X, long ldx) {
+                                 const double* __restrict__ Z, long ldz, double* __restrict__ X, long ldx, const double* __restrict__ base,
+                                 long ldb) {
     const int r = blockIdx.y;
     const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= cols) return;
+    if (base && c >= (r / 128 + 1) * 128) return;          // symmetric result: only the 128-tiles on and below the diagonal
     const int e0 = indptr[r], e1 = indptr[r + 1];
     double2 acc = make_double2(0.0, 0.0);
     if (c + 1 < cols) {
@@ -307,10 +311,14 @@ __global__ void spmm_rows_kernel(int cols, const int* __restrict__ indptr, const
             acc.x = fma(v, z.x, acc.x);
             acc.y = fma(v, z.y, acc.y);
         }
+        if (base) {                                         // entries above the diagonal (inside the diagonal tile) are left zero
+            acc.x = c <= r ? base[(long)r * ldb + c] - acc.x : 0.0;
+            acc.y = c + 1 <= r ? base[(long)r * ldb + c + 1] - acc.y : 0.0;
+        }
         *reinterpret_cast<double2*>(X + (long)r * ldx + c) = acc;
     } else {
         for (int e = e0; e < e1; ++e) acc.x = fma(val[e], Z[(long)idx[e] * ldz + c], acc.x);
-        X[(long)r * ldx + c] = acc.x;
+        X[(long)r * ldx + c] = base ? (c <= r ? base[(long)r * ldb + c] - acc.x : 0.0) : acc.x;
     }
 }
 // S[i][j] = Mtt[i][j] - sum_{e in row j} val[e] * X[i][idx[e]]  for j <= i  (lower triangle of the Schur complement
@@ -669,10 +677,10 @@ int gpn_k_csr_values(gpn_ctx* c, int rows, int row0, const int* indptr, const in
     return 0;
 }
 int gpn_k_spmm_rows(gpn_ctx* c, int rows, int cols, const int* indptr, const int* idx, const double* val, const double* Z, long ldz, double* X,
-                    long ldx) {
+                    long ldx, const double* base, long ldb) {
     if (rows <= 0 || cols <= 0) return 0;
     dim3 grid(grid1((cols + 1) / 2, 128), rows);
-    spmm_rows_kernel<<<grid, 128, 0, c->stream>>>(cols, indptr, idx, val, Z, ldz, X, ldx);
+    spmm_rows_kernel<<<grid, 128, 0, c->stream>>>(cols, indptr, idx, val, Z, ldz, X, ldx, base, ldb);
     LAUNCHED(c);
     return 0;
 }

@@ -893,7 +893,8 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
         double* Y = nbp(c, NB_ROWS2);                                                             // X^T (o x n), rows padded with zeros
         if (po > o) GPN_TRY(gpn_k_fill_zero(c, Y + (po - 128) * ldn, ldn, 128, (int)ldn));
         GPN_TRY(gpn_k_transpose(c, n, o, X, ld, Y, ldn));
-        GPN_TRY(gpn_k_schur_update(c, n, M + (long)o * ld + o, ld, tptr, tidx, tval, X, ld, S, ldn));
+        // S = M_tt - M_to (Z M_ot) = M_tt - M_to X^T, row by row: the sparse rows of M_to times the dense X^T (lower triangle)
+        GPN_TRY(gpn_k_spmm_rows(c, n, n, tptr, tidx, tval, Y, ldn, S, ldn, M + (long)o * ld + o, ld));
         GPN_TRY(gpn_potrf_dataflow(c, n, S, ldn, (double*)c->winv.p, iscal(c, 1), 0, Y, ldn, o, nbp(c, NB_WT), ldn));
         GPN_TRY(gpn_k_gemv_t2(c, n, n, S, ldn, ones, vecp(c, V_T), r1, rt, GEMV_LOWER));
         GPN_TRY(gpn_k_sumlogdiag(c, n, S, ldn, dscal(c, Scal::LOGDET)));
