@@ -157,7 +157,6 @@ int gpn_k_dot(gpn_ctx* c, int n, const double* x, const double* y, double* d_out
 int gpn_k_sum(gpn_ctx* c, int n, const double* x, double* d_out);
 int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out);
 int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v);
-int gpn_k_set_diag(gpn_ctx* c, double* A, long ld, int n, double v);
 int gpn_k_transpose(gpn_ctx* c, int rows, int cols, const double* A, long lda, double* B, long ldb);
 int gpn_k_rowdot_pass(gpn_ctx* c, int rows, int cols, const double* Y, long ld, const double* ya, const double* yb, double* za, double* zb,
                       double* d_fro, bool upper_only, bool zero_fro);

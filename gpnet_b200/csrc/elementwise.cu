@@ -348,10 +348,6 @@ __global__ void schur_update_kernel(int n, const double* __restrict__ Mtt, long 
         if (i1 == i0) break;
     }
 }
-__global__ void set_diag_kernel(double* __restrict__ A, long ld, int n, double v) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) A[(long)i * ld + i] = v;
-}
 // B = A^T through a padded 32x32 shared tile (both sides coalesced)
 __global__ void transpose_kernel(int rows, int cols, const double* __restrict__ A, long lda, double* __restrict__ B, long ldb) {
     __shared__ double tile[32][33];
@@ -643,12 +639,6 @@ int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out)
 int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v) {
     if (n <= 0) return 0;
     fill_vec_kernel<<<grid1(n), TPB, 0, c->stream>>>(n, y, v);
-    LAUNCHED(c);
-    return 0;
-}
-int gpn_k_set_diag(gpn_ctx* c, double* A, long ld, int n, double v) {
-    if (n <= 0) return 0;
-    set_diag_kernel<<<grid1(n), TPB, 0, c->stream>>>(A, ld, n, v);
     LAUNCHED(c);
     return 0;
 }

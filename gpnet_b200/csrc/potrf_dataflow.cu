@@ -268,7 +268,8 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
                     const int cc = wn * 32 + b * 8 + t + 4 * e;
                     const long gc = (long)j * TB + cc;
                     double v = (i == j && r == cc) ? -1.0 : 0.0;
-                    if (r < row_lim && gc < g.n) v = -tile_ptr[(long)r * tile_ld + cc];
+                    if (i >= g.id0) v = (j == i - g.id0 && r == cc) ? -1.0 : 0.0;        // identity block: nothing to read
+                    else if (r < row_lim && gc < g.n) v = -tile_ptr[(long)r * tile_ld + cc];
                     acc[a][b][e] = v;
                 }
         }
@@ -423,7 +424,7 @@ int encode_tiles(gpn_ctx* c, CUtensorMap* tm, const double* ptr, long ld, long r
 // triangle of the diagonal tiles is zeroed); inverted diagonal blocks go to winv (ceil(n/128) blocks of 128x128).
 // Optional appended blocks (see the header comment): B (brows x n, overwritten by B L^-T; its rows beyond brows up to the
 // next multiple of 128 must exist and be zero) and Wt (pad128(n) x n, any content: overwritten by L^-T in its upper tiles,
-// i.e. the transposed inverse of the factor, lower tiles untouched).
+// i.e. the transposed inverse of the factor, lower tiles untouched; its previous content is never read).
 int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset, double* B, long ldb, int brows,
                        double* Wt, long ldwt) {
     const int T = (n + TB - 1) / TB;
@@ -437,10 +438,6 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
         c->flags_rows = (long)Trows * T;
         GPN_CK(cudaMemsetAsync(c->flags.p, 0, c->flags.cap, c->stream));
         c->epoch = 0;
-    }
-    if (Wt) {   // identity block: I in the diagonal tiles (the zero tiles left of them are skipped, the ones to the right are read)
-        GPN_TRY(gpn_k_fill_zero(c, Wt, ldwt, T * TB, n));
-        GPN_TRY(gpn_k_set_diag(c, Wt, ldwt, T * TB < n ? T * TB : n, 1.0));
     }
     DfArgs a;
     a.A = A; a.lda = lda; a.n = n; a.T = T; a.ntasks = ntasks; a.winv = winv; a.flags = (int*)c->flags.p;
