@@ -157,12 +157,13 @@ int gpn_k_dot(gpn_ctx* c, int n, const double* x, const double* y, double* d_out
 int gpn_k_sum(gpn_ctx* c, int n, const double* x, double* d_out);
 int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out);
 int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v);
-int gpn_k_transpose(gpn_ctx* c, int rows, int cols, const double* A, long lda, double* B, long ldb);
 int gpn_k_rowdot_pass(gpn_ctx* c, int rows, int cols, const double* Y, long ld, const double* ya, const double* yb, double* za, double* zb,
                       double* d_fro, bool upper_only, bool zero_fro);
 int gpn_k_csr_values(gpn_ctx* c, int rows, int row0, const int* indptr, const int* idx, const double* M, long ld, double* val);
 int gpn_k_spmm_rows(gpn_ctx* c, int rows, int cols, const int* indptr, const int* idx, const double* val, const double* Z, long ldz, double* X,
                     long ldx, const double* base = nullptr, long ldb = 0);   // base: X = base - (sparse rows) Z
+int gpn_k_spmm_rows_t(gpn_ctx* c, int rows, int cols, const int* indptr, const int* idx, const double* val, const double* Z, long ldz,
+                      double* XT, long ldxt);   // XT = (sparse rows * Z)^T
 int gpn_k_schur_update(gpn_ctx* c, int n, const double* Mtt, long ldm, const int* indptr, const int* idx, const double* val, const double* X,
                        long ldx, double* S, long lds);
 int gpn_k_fill_zero_lower(gpn_ctx* c, double* A, long ld, int rows);

@@ -321,6 +321,40 @@ __global__ void spmm_rows_kernel(int cols, const int* __restrict__ indptr, const
         X[(long)r * ldx + c] = base ? (c <= r ? base[(long)r * ldb + c] - acc.x : 0.0) : acc.x;
     }
 }
+// XT = (sparse rows * Z)^T written directly: a block computes a 32-row x 64-column tile of X = M_to Z (every thread four rows
+// x one double2) and writes it out transposed through shared memory, both sides coalesced
+__global__ void spmm_rows_t_kernel(int rows, int cols, const int* __restrict__ indptr, const int* __restrict__ idx,
+                                   const double* __restrict__ val, const double* __restrict__ Z, long ldz, double* __restrict__ XT, long ldxt) {
+    __shared__ double tile[64][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 256 threads: 8 warps
+    const int r0 = blockIdx.y * 32, c = blockIdx.x * 64 + 2 * tx;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = r0 + ty + 8 * q;
+        double2 acc = make_double2(0.0, 0.0);
+        if (r < rows && c < cols) {
+            const int e0 = indptr[r], e1 = indptr[r + 1];
+            if (c + 1 < cols) {
+                for (int e = e0; e < e1; ++e) {
+                    const double v = val[e];
+                    const double2 z = *reinterpret_cast<const double2*>(Z + (long)idx[e] * ldz + c);
+                    acc.x = fma(v, z.x, acc.x);
+                    acc.y = fma(v, z.y, acc.y);
+                }
+            } else {
+                for (int e = e0; e < e1; ++e) acc.x = fma(val[e], Z[(long)idx[e] * ldz + c], acc.x);
+            }
+        }
+        tile[2 * tx][ty + 8 * q] = acc.x;
+        tile[2 * tx + 1][ty + 8 * q] = acc.y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int cc = ty + 8 * q, col = blockIdx.x * 64 + cc, r = r0 + tx;     // row `col` of XT, 32 consecutive entries
+        if (col < cols && r < rows) XT[(long)col * ldxt + r] = tile[cc][tx];
+    }
+}
 // S[i][j] = Mtt[i][j] - sum_{e in row j} val[e] * X[i][idx[e]]  for j <= i  (lower triangle of the Schur complement
 // M_tt - M_to M_oo^-1 M_ot with X = M_to M_oo^-1; row i of X stays in L1 while the block sweeps j)
 __global__ void schur_update_kernel(int n, const double* __restrict__ Mtt, long ldm, const int* __restrict__ indptr,
@@ -348,20 +382,6 @@ __global__ void schur_update_kernel(int n, const double* __restrict__ Mtt, long 
         if (i1 == i0) break;
     }
 }
-// B = A^T through a padded 32x32 shared tile (both sides coalesced)
-__global__ void transpose_kernel(int rows, int cols, const double* __restrict__ A, long lda, double* __restrict__ B, long ldb) {
-    __shared__ double tile[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
-        const int r = r0 + k, c = c0 + threadIdx.x;
-        tile[k][threadIdx.x] = (r < rows && c < cols) ? A[(long)r * lda + c] : 0.0;
-    }
-    __syncthreads();
-    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
-        const int c = c0 + k, r = r0 + threadIdx.x;
-        if (c < cols && r < rows) B[(long)c * ldb + r] = tile[threadIdx.x][k];
-    }
-}
 // One pass over the rows of Y (rows x cols): za[r] = Y[r,:] . ya, zb[r] = Y[r,:] . yb, fro += sum Y^2; one warp per row.
 // upper_only: only columns >= r count (Y upper triangular, the rest of the buffer is undefined).
 __global__ void rowdot_pass_kernel(int rows, int cols, const double* __restrict__ Y, long ld, const double* __restrict__ ya,
@@ -371,10 +391,22 @@ __global__ void rowdot_pass_kernel(int rows, int cols, const double* __restrict_
     double sa = 0.0, sb = 0.0, sf = 0.0;
     if (r < rows) {
         const double* y = Y + (long)r * ld;
-        for (int c = (upper_only ? (r & ~31) : 0) + lane; c < cols; c += 32) {
-            const double v = (upper_only && c < r) ? 0.0 : y[c];
-            sa = fma(v, ya[c], sa);
-            sb = fma(v, yb[c], sb);
+        const int c0 = upper_only ? (r & ~63) : 0;          // 16-byte aligned start (ld even, rows start aligned)
+        const int cend = cols & ~1;
+        // one double2 per lane and step, four steps in flight
+#pragma unroll 4
+        for (int c = c0 + 2 * lane; c < cend; c += 64) {
+            double2 v = *reinterpret_cast<const double2*>(y + c);
+            if (upper_only) { if (c < r) v.x = 0.0; if (c + 1 < r) v.y = 0.0; }
+            const double2 a2 = *reinterpret_cast<const double2*>(ya + c), b2 = *reinterpret_cast<const double2*>(yb + c);
+            sa = fma(v.x, a2.x, fma(v.y, a2.y, sa));
+            sb = fma(v.x, b2.x, fma(v.y, b2.y, sb));
+            sf = fma(v.x, v.x, fma(v.y, v.y, sf));
+        }
+        if ((cols & 1) && lane == 0) {
+            const double v = (upper_only && cols - 1 < r) ? 0.0 : y[cols - 1];
+            sa = fma(v, ya[cols - 1], sa);
+            sb = fma(v, yb[cols - 1], sb);
             sf = fma(v, v, sf);
         }
         sa = warp_sum(sa);
@@ -642,13 +674,6 @@ int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v) {
     LAUNCHED(c);
     return 0;
 }
-int gpn_k_transpose(gpn_ctx* c, int rows, int cols, const double* A, long lda, double* B, long ldb) {
-    if (rows <= 0 || cols <= 0) return 0;
-    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-    transpose_kernel<<<grid, block, 0, c->stream>>>(rows, cols, A, lda, B, ldb);
-    LAUNCHED(c);
-    return 0;
-}
 int gpn_k_rowdot_pass(gpn_ctx* c, int rows, int cols, const double* Y, long ld, const double* ya, const double* yb, double* za, double* zb,
                       double* d_fro, bool upper_only, bool zero_fro) {
     if (zero_fro) {
@@ -671,6 +696,14 @@ int gpn_k_spmm_rows(gpn_ctx* c, int rows, int cols, const int* indptr, const int
     if (rows <= 0 || cols <= 0) return 0;
     dim3 grid(grid1((cols + 1) / 2, 128), rows);
     spmm_rows_kernel<<<grid, 128, 0, c->stream>>>(cols, indptr, idx, val, Z, ldz, X, ldx, base, ldb);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_spmm_rows_t(gpn_ctx* c, int rows, int cols, const int* indptr, const int* idx, const double* val, const double* Z, long ldz,
+                      double* XT, long ldxt) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid((cols + 63) / 64, (rows + 31) / 32);
+    spmm_rows_t_kernel<<<grid, 256, 0, c->stream>>>(rows, cols, indptr, idx, val, Z, ldz, XT, ldxt);
     LAUNCHED(c);
     return 0;
 }

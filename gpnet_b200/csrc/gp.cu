@@ -887,12 +887,11 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
         GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(std::max(n, o)) * 128));
         GPN_TRY(gpn_potrf_dataflow(c, o, M, ld, (double*)c->winv.p, iscal(c, 0), 0, nullptr, 0, 0, mat(c, 2), ld));
         GPN_TRY(gpn_lauum_t(c, o, mat(c, 2), ld, M, ld, true));                                   // Z, full symmetric, in place of M_oo
-        GPN_TRY(gpn_k_spmm_rows(c, n, o, tptr, tidx, tval, M, ld, X, ld));
         const long po = pad128(o);
         GPN_TRY(ensure_nb(c, NB_ROWS2, po, ldn));
         double* Y = nbp(c, NB_ROWS2);                                                             // X^T (o x n), rows padded with zeros
         if (po > o) GPN_TRY(gpn_k_fill_zero(c, Y + (po - 128) * ldn, ldn, 128, (int)ldn));
-        GPN_TRY(gpn_k_transpose(c, n, o, X, ld, Y, ldn));
+        GPN_TRY(gpn_k_spmm_rows_t(c, n, o, tptr, tidx, tval, M, ld, Y, ldn));                    // X = M_to Z, written transposed
         // S = M_tt - M_to (Z M_ot) = M_tt - M_to X^T, row by row: the sparse rows of M_to times the dense X^T (lower triangle)
         GPN_TRY(gpn_k_spmm_rows(c, n, n, tptr, tidx, tval, Y, ldn, S, ldn, M + (long)o * ld + o, ld));
         GPN_TRY(gpn_potrf_dataflow(c, n, S, ldn, (double*)c->winv.p, iscal(c, 1), 0, Y, ldn, o, nbp(c, NB_WT), ldn));
