@@ -330,6 +330,36 @@ def test_reglap_routes_agree_with_oracle_for_stiff_parameters(gpu_ctx, beta, noi
         gpu_ctx.set_fast_paths(True)
 
 
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16])
+def test_reglap_routes_random_shapes_against_oracle(gpu_ctx, seed):
+    """Random geometric graphs of random size, training fraction, beta and noise (ragged blocks on both sides of the 256-row
+    threshold of the augmented factorisations): every route against the numpy oracle (tools/fuzz_routes.py is the long form)."""
+    rng = np.random.RandomState(seed)
+    N = int(rng.randint(300, 2200))
+    n = max(2, int(N * rng.uniform(0.12, 0.88)))
+    beta = float(np.exp(rng.uniform(np.log(0.01), np.log(5.0))))
+    noise = float(np.exp(rng.uniform(np.log(1e-4), np.log(10.0))))
+    G = nx.random_geometric_graph(N, np.sqrt(rng.uniform(6, 24) / (np.pi * N)), seed=int(rng.randint(1 << 30)))
+    perm = rng.permutation(N)
+    tr = sorted(int(x) for x in perm[:n])
+    te = sorted(int(x) for x in perm[n:n + min(N - n, 16)])
+    t = rng.randn(n)
+    indptr, indices, w, _ = go.graph_to_csr(G)
+    gpu_ctx.set_graph(indptr, indices, w)
+    gpu_ctx.set_nodes(tr, te)
+    th = np.log([beta, noise])
+    ref_v, ref_g = go.OracleGP(G, kerneltype="regularized_laplacian").neg_logp_grad(th, tr, t)
+    try:
+        for level in (0, 1, 2, 3, 4):
+            gpu_ctx.set_fast_paths(level)
+            st, out, info = gpu_ctx.gpr_logp_grad(1, th, t, True)
+            assert st == 0 and info == 0
+            assert abs(out[0] - ref_v) <= TOL * abs(ref_v), (level, N, n, out[0], ref_v)
+            assert nrel(out[1:], ref_g) <= 1e-8, (level, N, n, out[1:], ref_g)
+    finally:
+        gpu_ctx.set_fast_paths(True)
+
+
 def test_reglap_routes_on_a_weighted_graph_with_isolated_nodes_and_a_training_only_component(gpu_ctx):
     """Edge cases of the Schur routes' graph handling: random edge weights (the sparse coupling block carries them), isolated
     nodes on both sides (zero degree: their row of I + beta L~ is the identity), a component made of training nodes only (no
