@@ -48,7 +48,8 @@ int gpn_profile_summary(gpn_ctx* ctx, double* out_h);
 void gpn_debug_leaf_prof(gpn_ctx* ctx, void* dev_buf32);
 /* development aid: run the 128x128 leaf on `copies` stacked blocks (lda 128), one CTA each; block 0 stamps its phases */
 int gpn_debug_leaf_bench(gpn_ctx* ctx, void* A_dev, int copies, void* prof32_dev);
-/* development aid: device buffer receiving 8 int64 %globaltimer stamps per task of the next dataflow-Cholesky launches */
+/* development aid: device buffer receiving 8 int64 %globaltimer stamps per tile of the next dataflow-Cholesky launches
+ * (tile (i, j) at slot j * tile_rows + i; tools/gpu_check.py chain / dfbreak / augbreak read it); NULL switches it off */
 void gpn_debug_df_trace(gpn_ctx* ctx, void* dev_buf);
 
 /* ---- graph and node sets (host -> device once; resident afterwards) -------------------------------------- */
