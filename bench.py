@@ -3,9 +3,12 @@ Appendix D (GPnetRegressor, regularized-Laplacian kernel, random geometric graph
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nodes 8192]
 
-One "step" = one evaluation theta (host) -> (-logp, -dlogp/dtheta) (host): full kernel rebuilt from theta (no
-cross-evaluation caching, like the reference which rebuilds everything per call), block gather, Cholesky, alpha,
-log-det, K_y^-1, the P trace terms.  Prints ONE JSON line (see the task contract); rank 0 only.
+One "step" = one evaluation theta (host) -> (-logp, -dlogp/dtheta) (host), from scratch: nothing is carried over between
+evaluations (like the reference, which rebuilds everything per call); only the graph, the node sets and the targets are
+resident.  The default route reads the inverse training block off a Schur complement instead of forming the kernel
+(DESIGN.md section 4); `routes` in the JSON line times the reference's own order of operations (full kernel, block gather,
+Cholesky, alpha, log-det, K_y^-1, the P trace terms) and the intermediate routes beside it, and utilisation is always
+reported from EXECUTED flops.  Prints ONE JSON line (see the task contract); rank 0 only.
 """
 import argparse
 import json
