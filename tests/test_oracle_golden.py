@@ -106,3 +106,48 @@ def test_laplacian_matches_networkx_edge_cases():
 
 def test_neg_inf_on_cholesky_failure():
     assert go.gpr_neg_logp(-np.eye(3), np.ones(3)) == -np.inf
+
+
+@pytest.mark.parametrize("N,n,beta,c", [(420, 180, 0.6, 0.01), (333, 129, 0.9, 3.0), (300, 290, 0.05, 1e-3), (256, 1, 0.6, 0.01)])
+def test_schur_route_algebra_matches_the_oracle(N, n, beta, c):
+    """The algebra of the default regularized-Laplacian route of the CUDA path (csrc/gp.cu
+    gpr_reglap_coupled_scalars + row_eval), restated in numpy and checked against the oracle's Cholesky-of-K_y evaluation:
+    training nodes last, Z = M_oo^-1, X = M_to Z, S = M_tt - X M_ot = L L^T = K_tt^-1, the all-entries noise as a rank-one
+    update, and the gradient traces from Y = X^T L^-T and W = L^-1 (||Y||_F^2 + ||W||_F^2 - n = tr(S dK_tt/dtheta_0))."""
+    import scipy.linalg as sl
+    from oracle import configs as cfg
+    rng = np.random.RandomState(N + n)
+    indptr, indices, w = cfg.rgg_csr_fast(N)[:3]
+    Lt = go.normalized_laplacian(indptr, indices, w, N)
+    theta = np.log([beta, c])
+    tr = np.sort(rng.permutation(N)[:n])
+    t = rng.randn(n)
+    K = go.full_kernel(Lt, "regularized_laplacian", theta)
+    Ky = go.kernel_block(K, tr, tr, theta, 1.0)
+    dK0 = go.kernel_derivatives(Lt, K, "regularized_laplacian", theta)[np.ix_(tr, tr)]
+    ref = np.concatenate([[go.gpr_neg_logp(Ky, t)], go.gpr_neg_logp_grad(Ky, [dK0, c * np.ones((n, n))], t)])
+
+    oth = np.setdiff1d(np.arange(N), tr)
+    o = N - n
+    M = np.eye(N) + beta * Lt
+    Moo, Mto, Mtt = M[np.ix_(oth, oth)], M[np.ix_(tr, oth)], M[np.ix_(tr, tr)]
+    Z = np.linalg.inv(Moo)
+    X = Mto @ Z                                   # sparse x dense on the device
+    S = Mtt - X @ Mto.T                           # = K_tt^-1
+    L = np.linalg.cholesky(S)
+    r1, rt = L.T @ np.ones(n), L.T @ t
+    s, a, q = r1 @ r1, r1 @ rt, rt @ rt
+    den = 1.0 + c * s
+    mu = c * a / den
+    nlogp = 0.5 * (q - mu * a) + (-np.log(np.diag(L)).sum() + 0.5 * np.log1p(c * s)) + 0.5 * n * np.log(2 * np.pi)
+    W = sl.solve_triangular(L, np.eye(n), lower=True)
+    Y = sl.solve_triangular(L, X, lower=True).T   # X^T L^-T = -W_to^T
+    z1 = np.concatenate([Y @ r1, np.ones(n)])     # K[:, tr] (S 1): the training part is exactly 1
+    zt = np.concatenate([Y @ rt, t])              # K[:, tr] (S t): the training part is exactly t
+    assert np.allclose(Y @ r1, X.T @ np.ones(n), rtol=1e-10, atol=1e-12) and np.allclose(Y @ rt, X.T @ t, rtol=1e-10, atol=1e-12)
+    D11, D1t, Dtt = z1 @ z1 - s, z1 @ zt - a, zt @ zt - q
+    trSD = (Y * Y).sum() + (W * W).sum() - n
+    g0 = 0.5 * (Dtt - 2 * mu * D1t + mu * mu * D11) - 0.5 * (trSD - c / den * D11)
+    gl = 0.5 * c * ((a / den) ** 2 - s / den)
+    mine = np.array([nlogp, -g0, -gl])
+    assert np.max(np.abs(mine - ref) / np.abs(ref)) < 1e-10
