@@ -151,3 +151,44 @@ def test_schur_route_algebra_matches_the_oracle(N, n, beta, c):
     gl = 0.5 * c * ((a / den) ** 2 - s / den)
     mine = np.array([nlogp, -g0, -gl])
     assert np.max(np.abs(mine - ref) / np.abs(ref)) < 1e-10
+
+
+@pytest.mark.parametrize("kerneltype,theta0", [("diffusion", np.log(0.6)), ("pstep_walk", np.log(2.3))])
+def test_landscape_row_algebra_matches_the_oracle(kerneltype, theta0):
+    """What gpn_landscape_points does for grid points that differ only in the noise entry (csrc/gp.cu gpr_row_scalars +
+    row_eval): ONE factorisation of K_tt, every noise value c as the rank-one update K_y = K_tt + c 1 1^T -- restated in numpy
+    and checked against the oracle's independent evaluation of each point, value and gradient."""
+    import scipy.linalg as sl
+    from oracle import configs as cfg
+    N, n = 260, 110
+    rng = np.random.RandomState(3)
+    indptr, indices, w = cfg.rgg_csr_fast(N)[:3]
+    Lt = go.normalized_laplacian(indptr, indices, w, N)
+    tr = np.sort(rng.permutation(N)[:n])
+    t = rng.randn(n)
+    P = 3 if kerneltype == "pstep_walk" else 2
+    base = [theta0, np.log(4.0), 0.0] if P == 3 else [theta0, 0.0]
+    K = go.full_kernel(Lt, kerneltype, np.array(base))
+    Ktt = K[np.ix_(tr, tr)]
+    D = go.kernel_derivatives(Lt, K, kerneltype, np.array(base))[np.ix_(tr, tr)]
+    L = np.linalg.cholesky(Ktt)
+    Wi = sl.solve_triangular(L, np.eye(n), lower=True)
+    u, v = Wi @ np.ones(n), Wi @ t
+    s, a, q = u @ u, u @ v, v @ v
+    Sinv = Wi.T @ Wi
+    x1, xt = Wi.T @ u, Wi.T @ v
+    trSD, D11, D1t, Dtt = np.sum(Sinv * D), x1 @ D @ x1, x1 @ D @ xt, xt @ D @ xt
+    half_logdet = np.log(np.diag(L)).sum()
+    for c in (1e-4, 0.01, 0.7, 9.0):
+        th = np.array(base)
+        th[-1] = np.log(c)
+        Ky = go.kernel_block(K, tr, tr, th, 1.0)
+        dKs = [D] + [np.zeros((n, n))] * (P - 2) + [c * np.ones((n, n))]
+        ref = np.concatenate([[go.gpr_neg_logp(Ky, t)], go.gpr_neg_logp_grad(Ky, dKs, t)])
+        den = 1.0 + c * s
+        mu = c * a / den
+        val = 0.5 * (q - mu * a) + (half_logdet + 0.5 * np.log1p(c * s)) + 0.5 * n * np.log(2 * np.pi)
+        g0 = 0.5 * (Dtt - 2 * mu * D1t + mu * mu * D11) - 0.5 * (trSD - c / den * D11)
+        gl = 0.5 * c * ((a / den) ** 2 - s / den)
+        mine = np.concatenate([[val, -g0], np.zeros(P - 2), [-gl]])
+        assert np.max(np.abs(mine - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-9 or np.allclose(mine, ref, rtol=1e-9, atol=1e-12)
