@@ -166,7 +166,7 @@ int gpn_k_spmm_rows_t(gpn_ctx* c, int rows, int cols, const int* indptr, const i
                       double* XT, long ldxt);   // XT = (sparse rows * Z)^T
 int gpn_k_schur_update(gpn_ctx* c, int n, const double* Mtt, long ldm, const int* indptr, const int* idx, const double* val, const double* X,
                        long ldx, double* S, long lds);
-int gpn_k_fill_zero_lower(gpn_ctx* c, double* A, long ld, int rows);
+int gpn_k_fill_zero_lower(gpn_ctx* c, double* A, long ld, int rows, int skip_row0 = -1, int skip_cols = 0);
 int gpn_k_gemv_t2(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* x1, const double* x2, double* y1, double* y2,
                   int mode);
 int gpn_k_bilinear_trace(gpn_ctx* c, int n, const double* S, long lds, const double* G, long ldg, const double* Ktt, long ldk, double g_scale,

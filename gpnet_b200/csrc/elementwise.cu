@@ -56,11 +56,13 @@ __global__ void fill_zero_kernel(double* __restrict__ A, long ld, int rows, int 
 }
 // (b') the same for the 128-wide tiles on and below the diagonal only (row r: columns [0, 128*(r/128 + 1))): consumers that
 //      read nothing above the diagonal tiles (dataflow Cholesky, triangular inverse) skip half of the write traffic
-__global__ void fill_zero_lower_kernel(double* __restrict__ A, long ld, int rows) {
+//      rows >= skip_row0 start at column skip_cols (rounded down to even): a block below the diagonal nobody reads as zeros
+__global__ void fill_zero_lower_kernel(double* __restrict__ A, long ld, int rows, int skip_row0, int skip_cols) {
     const int r = blockIdx.y;
     const int lim = min((r / 128 + 1) * 128, rows) / 2;      // double2 per row (rows is a multiple of 128)
+    const int first = r >= skip_row0 ? skip_cols / 2 : 0;
     double2* row = reinterpret_cast<double2*>(A + (long)r * ld);
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < lim; v += gridDim.x * blockDim.x) row[v] = make_double2(0.0, 0.0);
+    for (int v = first + blockIdx.x * blockDim.x + threadIdx.x; v < lim; v += gridDim.x * blockDim.x) row[v] = make_double2(0.0, 0.0);
 }
 // (c) scatter of the nnz + diagonal: out[i][j] = alpha * (dinv_i * ((D-A)_ij * dinv_j)) (+ gamma on the diagonal),
 //     same operation order as networkx's  DH @ ((D - A) @ DH).  One warp per row.
@@ -546,11 +548,11 @@ int gpn_k_fill_zero(gpn_ctx* c, double* A, long ld, int rows, int cols) {
     LAUNCHED(c);
     return 0;
 }
-int gpn_k_fill_zero_lower(gpn_ctx* c, double* A, long ld, int rows) {
+int gpn_k_fill_zero_lower(gpn_ctx* c, double* A, long ld, int rows, int skip_row0, int skip_cols) {
     if (rows <= 0) return 0;
     if (rows % 128 != 0) return gpn_k_fill_zero(c, A, ld, rows, rows);
     dim3 grid(8, rows);
-    fill_zero_lower_kernel<<<grid, TPB, 0, c->stream>>>(A, ld, rows);
+    fill_zero_lower_kernel<<<grid, TPB, 0, c->stream>>>(A, ld, rows, skip_row0 < 0 ? rows : skip_row0, skip_cols);
     LAUNCHED(c);
     return 0;
 }

@@ -863,7 +863,7 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
     double* M = mat(c, 0);
     if (t_h) GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
     else GPN_CK(cudaMemcpyAsync(vecp(c, V_T), vecp(c, V_TRES), sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-    GPN_TRY(gpn_k_fill_zero_lower(c, M, ld, (int)ld));
+    GPN_TRY(gpn_k_fill_zero_lower(c, M, ld, (int)ld, o, o));   // M_oo and M_tt (lower tiles); of M_to only the scattered entries are read
     GPN_TRY(gpn_k_laplacian_scatter(c, N, (const int*)c->p_indptr.p, (const int*)c->p_indices.p,
                                     c->h_weights.empty() ? nullptr : (const double*)c->p_weights.p, (const double*)c->p_dinv.p, beta, 1.0, M, ld));
     const int *tptr = (const int*)c->to_indptr.p, *tidx = (const int*)c->to_idx.p;
