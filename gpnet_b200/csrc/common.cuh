@@ -89,6 +89,10 @@ struct gpn_ctx {
                                          // sparse coupling, 4 the same with the triangular work appended to the
                                          // two Cholesky kernels (GPNET_B200_REGLAP_FAST)
     DevBuf p_indptr, p_indices, p_weights, p_dinv, iota;
+    // level-set dissection of the other nodes (ensure_perm): they are numbered [A | B | Sep], no edge joins A and B
+    int dis_a = 0, dis_b = 0, dis_s = 0;   // block sizes (dis_s == 0: not dissected)
+    DevBuf sa_ptr, sa_idx, sa_val;         // CSR of the (Sep rows) x (A columns) block; values per theta
+    DevBuf sb_ptr, sb_idx, sb_idx_rel, sb_val;   // (Sep rows) x (B columns): absolute column ids and ids relative to B
     DevBuf to_indptr, to_idx, to_val;    // CSR of the (training rows) x (other columns) block of the permuted graph; values per theta
     long long to_nnz = 0;
 
@@ -108,6 +112,9 @@ struct gpn_ctx {
     DevBuf winv;                 // inverted diagonal blocks of the running Cholesky (N x 128)
     DevBuf flags;                // dataflow Cholesky: epoch-stamped tile-ready flags (T x T ints)
     int epoch = 0;
+    DevBuf flags2;               // the same for a second dataflow Cholesky running concurrently on the side stream (slot 1)
+    int epoch2 = 0;
+    long flags_rows2 = 0;
     void* df_trace = nullptr;    // optional device buffer: 8 x int64 globaltimer stamps per dataflow-Cholesky task
     void* leaf_prof = nullptr;   // optional device buffer (32 x int64) receiving clock64 stamps of the leaf phases
     int potrf_mode = 0;          // 0: dataflow kernel (default), 1: recursive multi-launch (GPNET_B200_POTRF=recursive)
@@ -131,7 +138,7 @@ int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, lon
 int gpn_potrf(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset = 0);
 int gpn_leaf_bench(gpn_ctx* c, double* A, int copies, double* winv, int* d_info, long long* prof);
 int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset, double* B = nullptr, long ldb = 0,
-                       int brows = 0, double* Wt = nullptr, long ldwt = 0);   // B <- B L^-T, Wt <- L^-T (upper tiles): see potrf_dataflow.cu
+                       int brows = 0, double* Wt = nullptr, long ldwt = 0, int slot = 0);   // B <- B L^-T, Wt <- L^-T (upper tiles): see potrf_dataflow.cu
 // W = L^-1 (normal, lower) and WT = W^T (upper) from L and the inverted diagonal blocks; TT: n x n scratch.  All ld = ldw.
 int gpn_trtri(gpn_ctx* c, int n, const double* L, long ldl, const double* winv, double* W, double* WT, double* TT, long ldw);
 // out (lower [+ mirrored upper]) = W^T W computed from WT = W^T (both operands K-major)

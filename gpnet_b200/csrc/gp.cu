@@ -605,17 +605,77 @@ int gpr_grad_kernel_block(gpn_ctx* c, int kind, long ldn, const double** G, doub
 // block of W is needed at all (n^3/3 instead of N^3/3 for the triangular inverse).  The block boundary is rounded down to a
 // multiple of 128 (o2) so that every operand stays aligned with the Cholesky's tiles; the up to 127 extra rows are computed
 // and ignored.  Values agree with the full-inverse path to rounding (different elimination order).
+// Level-set dissection of the subgraph induced on the other (non-training) nodes: BFS levels from a pseudo-peripheral node; a
+// middle level Sep separates the levels below it (A) from the levels above it (B) exactly, because edges only join equal or
+// adjacent levels.  With the others numbered [A | B | Sep], M_oo = I + beta L~_oo is block-arrow: M_AA and M_BB are independent
+// (two Cholesky chains of half the length, run concurrently) and Sep couples them through a rank-|Sep| correction.
+// *a = number of others, *b = *s = 0 when the dissection is not worth it (small blocks, fat separator, dense graphs).
+void dissect_others(const gpn_ctx* c, const std::vector<char>& is_train, std::vector<int>& order, int* a, int* b, int* s) {
+    const int N = c->N;
+    std::vector<int> others;
+    for (int v = 0; v < N; ++v)
+        if (!is_train[v]) others.push_back(v);
+    const int o = (int)others.size();
+    order = others;
+    *a = o; *b = 0; *s = 0;
+    if (o < 1536) return;
+    std::vector<int> lev(N), queue;
+    auto bfs = [&](int root) {
+        std::fill(lev.begin(), lev.end(), -1);
+        queue.clear();
+        queue.push_back(root);
+        lev[root] = 0;
+        for (size_t h = 0; h < queue.size(); ++h) {
+            const int u = queue[h];
+            for (int q = c->h_indptr[u]; q < c->h_indptr[u + 1]; ++q) {
+                const int v = c->h_indices[q];
+                if (!is_train[v] && lev[v] < 0) { lev[v] = lev[u] + 1; queue.push_back(v); }
+            }
+        }
+        return queue.back();                                   // a node of the last level
+    };
+    int root = others[0];
+    for (int sweep = 0; sweep < 2; ++sweep) root = bfs(root);  // pseudo-peripheral node
+    bfs(root);
+    const int reached = (int)queue.size();
+    int nlev = 0;
+    for (int v : queue) nlev = std::max(nlev, lev[v] + 1);
+    if (nlev < 5) return;
+    std::vector<int> cnt(nlev, 0);
+    for (int v : queue) cnt[lev[v]]++;
+    int mid = 0, cum = 0;
+    while (mid < nlev - 1 && cum + cnt[mid] < reached / 2) cum += cnt[mid++];
+    std::vector<int> A, B, S;
+    for (int v : others) {
+        if (lev[v] < 0 || lev[v] > mid) B.push_back(v);        // other components have no edge to A either
+        else if (lev[v] < mid) A.push_back(v);
+        else S.push_back(v);
+    }
+    if (A.size() & 1) { S.push_back(A.back()); A.pop_back(); } // block B starts at an even offset (16-byte aligned sub-matrix)
+    const int na = (int)A.size(), nb = (int)B.size(), ns = (int)S.size();
+    if (na < 512 || nb < 512 || ns < 1 || ns > std::min(na, nb) / 2) return;
+    order.clear();
+    order.insert(order.end(), A.begin(), A.end());
+    order.insert(order.end(), B.begin(), B.end());
+    order.insert(order.end(), S.begin(), S.end());
+    *a = na; *b = nb; *s = ns;
+}
+
 int ensure_perm(gpn_ctx* c) {
     if (c->perm_valid) return 0;
     const int N = c->N, n = c->n_train;
     std::vector<char> is_train(N, 0);
     for (int v : c->h_train) is_train[v] = 1;
     std::vector<int> perm(N), inv(N);
-    int a = 0, b = N - n;
-    for (int v = 0; v < N; ++v) {
-        const int p = is_train[v] ? b++ : a++;
-        perm[v] = p;
-        inv[p] = v;
+    // the other nodes first -- as [A | B | Sep] when a level-set dissection of their induced subgraph is worth it --, then the
+    // training nodes in their given (ascending) order
+    std::vector<int> others_order;
+    dissect_others(c, is_train, others_order, &c->dis_a, &c->dis_b, &c->dis_s);
+    {
+        int a = 0, b = N - n;
+        for (int v : others_order) { perm[v] = a; inv[a] = v; ++a; }
+        for (int v = 0; v < N; ++v)
+            if (is_train[v]) { perm[v] = b; inv[b] = v; ++b; }
     }
     std::vector<int> pptr(N + 1, 0), pidx(c->h_indices.size());
     std::vector<double> pw(c->h_weights.size());
@@ -658,6 +718,33 @@ int ensure_perm(gpn_ctx* c) {
     GPN_TRY(gpn_buf_ensure(c, c->to_val, sizeof(double) * (tidx.size() + 1)));
     GPN_TRY(upload(c, c->to_indptr.p, tptr.data(), sizeof(int) * (size_t)(n + 1)));
     if (!tidx.empty()) GPN_TRY(upload(c, c->to_idx.p, tidx.data(), sizeof(int) * tidx.size()));
+    if (c->dis_s > 0) {   // the two coupling blocks of the separator rows
+        const int da = c->dis_a, db = c->dis_b, ds = c->dis_s;
+        std::vector<int> aptr(ds + 1, 0), aidx, bptr(ds + 1, 0), bidx, bidr;
+        for (int r = 0; r < ds; ++r) {
+            for (int q = pptr[da + db + r]; q < pptr[da + db + r + 1]; ++q) {
+                const int k = pidx[q];
+                if (k < da) aidx.push_back(k);
+                else if (k < da + db) { bidx.push_back(k); bidr.push_back(k - da); }
+            }
+            aptr[r + 1] = (int)aidx.size();
+            bptr[r + 1] = (int)bidx.size();
+        }
+        GPN_TRY(gpn_buf_ensure(c, c->sa_ptr, sizeof(int) * (size_t)(ds + 1)));
+        GPN_TRY(gpn_buf_ensure(c, c->sb_ptr, sizeof(int) * (size_t)(ds + 1)));
+        GPN_TRY(gpn_buf_ensure(c, c->sa_idx, sizeof(int) * (aidx.size() + 1)));
+        GPN_TRY(gpn_buf_ensure(c, c->sb_idx, sizeof(int) * (bidx.size() + 1)));
+        GPN_TRY(gpn_buf_ensure(c, c->sb_idx_rel, sizeof(int) * (bidx.size() + 1)));
+        GPN_TRY(gpn_buf_ensure(c, c->sa_val, sizeof(double) * (aidx.size() + 1)));
+        GPN_TRY(gpn_buf_ensure(c, c->sb_val, sizeof(double) * (bidx.size() + 1)));
+        GPN_TRY(upload(c, c->sa_ptr.p, aptr.data(), sizeof(int) * (size_t)(ds + 1)));
+        GPN_TRY(upload(c, c->sb_ptr.p, bptr.data(), sizeof(int) * (size_t)(ds + 1)));
+        if (!aidx.empty()) GPN_TRY(upload(c, c->sa_idx.p, aidx.data(), sizeof(int) * aidx.size()));
+        if (!bidx.empty()) {
+            GPN_TRY(upload(c, c->sb_idx.p, bidx.data(), sizeof(int) * bidx.size()));
+            GPN_TRY(upload(c, c->sb_idx_rel.p, bidr.data(), sizeof(int) * bidr.size()));
+        }
+    }
     c->perm_valid = true;
     return 0;
 }
@@ -1389,7 +1476,8 @@ void gpn_destroy(gpn_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->mat[9] = DevBuf();   // alias slot
     DevBuf* all[] = {&c->indptr, &c->indices, &c->weights, &c->dinv, &c->train_idx, &c->test_idx, &c->tvec, &c->winv, &c->scal, &c->partial,
-                     &c->flags, &c->p_indptr, &c->p_indices, &c->p_weights, &c->p_dinv, &c->iota, &c->to_indptr, &c->to_idx, &c->to_val};
+                     &c->flags, &c->p_indptr, &c->p_indices, &c->p_weights, &c->p_dinv, &c->iota, &c->to_indptr, &c->to_idx, &c->to_val, &c->flags2, &c->sa_ptr, &c->sa_idx, &c->sa_val, &c->sb_ptr, &c->sb_idx,
+                     &c->sb_idx_rel, &c->sb_val};
     for (DevBuf* b : all)
         if (b->p) cudaFree(b->p);
     for (auto& b : c->mat)

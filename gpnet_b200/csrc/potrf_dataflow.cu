@@ -426,25 +426,29 @@ int encode_tiles(gpn_ctx* c, CUtensorMap* tm, const double* ptr, long ld, long r
 // next multiple of 128 must exist and be zero) and Wt (pad128(n) x n, any content: overwritten by L^-T in its upper tiles,
 // i.e. the transposed inverse of the factor, lower tiles untouched; its previous content is never read).
 int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset, double* B, long ldb, int brows,
-                       double* Wt, long ldwt) {
+                       double* Wt, long ldwt, int slot) {
+    // slot 1: own flag / counter buffer, for a factorisation that runs concurrently with another one (side stream)
+    DevBuf& fbuf = slot ? c->flags2 : c->flags;
+    int& fepoch = slot ? c->epoch2 : c->epoch;
+    long& frows = slot ? c->flags_rows2 : c->flags_rows;
     const int T = (n + TB - 1) / TB;
     const int R1 = B ? (brows + TB - 1) / TB : 0, R2 = Wt ? T : 0;
     const int Trows = T + R1 + R2;
     long nt = 0;
     for (int j = 0; j < T; ++j) nt += Trows - j;
     const int ntasks = (int)nt;
-    if (c->flags.cap < sizeof(int) * ((size_t)Trows * T + 4) || c->flags_rows != (long)Trows * T) {     // ready flags + task counters
-        GPN_TRY(gpn_buf_ensure(c, c->flags, sizeof(int) * ((size_t)Trows * T + 4)));
-        c->flags_rows = (long)Trows * T;
-        GPN_CK(cudaMemsetAsync(c->flags.p, 0, c->flags.cap, c->stream));
-        c->epoch = 0;
+    if (fbuf.cap < sizeof(int) * ((size_t)Trows * T + 4) || frows != (long)Trows * T) {     // ready flags + task counters
+        GPN_TRY(gpn_buf_ensure(c, fbuf, sizeof(int) * ((size_t)Trows * T + 4)));
+        frows = (long)Trows * T;
+        GPN_CK(cudaMemsetAsync(fbuf.p, 0, fbuf.cap, c->stream));
+        fepoch = 0;
     }
     DfArgs a;
-    a.A = A; a.lda = lda; a.n = n; a.T = T; a.ntasks = ntasks; a.winv = winv; a.flags = (int*)c->flags.p;
+    a.A = A; a.lda = lda; a.n = n; a.T = T; a.ntasks = ntasks; a.winv = winv; a.flags = (int*)fbuf.p;
     a.Trows = Trows; a.id0 = T + R1;
     a.seg[0] = DfSeg{B, ldb, T, R1};
     a.seg[1] = DfSeg{Wt, ldwt, T + R1, R2};
-    a.epoch = ++c->epoch; a.info = d_info; a.info_off = info_offset; a.trace = (long long*)c->df_trace;
+    a.epoch = ++fepoch; a.info = d_info; a.info_off = info_offset; a.trace = (long long*)c->df_trace;
     CUtensorMap tl, tw, tb1, tb2;
     GPN_TRY(encode_tiles(c, &tl, A, lda, n, n));
     GPN_TRY(encode_tiles(c, &tw, winv, TB, (long)T * TB, TB));
@@ -465,7 +469,7 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
     a.nspd = (long)T * (T + 1) / 2;
     a.napp = (long)T * R;
     a.Gc = grid;
-    a.counters = (int*)c->flags.p + (size_t)Trows * T;
+    a.counters = (int*)fbuf.p + (size_t)Trows * T;
     GPN_CK(cudaMemsetAsync(a.counters, 0, 4 * sizeof(int), c->stream));
     if (R > 0 && T >= 8 && grid >= 32) {
         static const int gc_env = getenv("GPNET_B200_DF_CHAIN_CTAS") ? atoi(getenv("GPNET_B200_DF_CHAIN_CTAS")) : 0;
