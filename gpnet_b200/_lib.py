@@ -266,8 +266,9 @@ class Context:
 
     def set_fast_paths(self, level=True):
         """Route of the regularized-Laplacian regressor likelihood: 0/False full kernel, 1 block route, 2 Schur route,
-        3 Schur route with sparse coupling, 4/True the same with the triangular work appended to the Cholesky kernels (default)."""
-        self.lib.gpn_set_fast_paths(self.h, 4 if level is True else int(level))
+        3 Schur route with sparse coupling, 4 the same with the triangular work appended to the Cholesky kernels, 5/True the
+        same with M_oo^-1 from two independent halves of a dissection of the other nodes (default)."""
+        self.lib.gpn_set_fast_paths(self.h, 5 if level is True else int(level))
 
     def gpr_predict(self, kind, theta, t):
         th, tt = _f64(theta), _f64(t)

@@ -85,9 +85,10 @@ struct gpn_ctx {
     std::vector<double> h_weights;
     bool perm_valid = false;
     bool train_unique = false;
-    int fast_reglap = 4;                 // regressor, regularized Laplacian: 0 full kernel, 1 block route, 2 Schur route, 3 Schur route with
+    int fast_reglap = 5;                 // regressor, regularized Laplacian: 0 full kernel, 1 block route, 2 Schur route, 3 Schur route with
                                          // sparse coupling, 4 the same with the triangular work appended to the
-                                         // two Cholesky kernels (GPNET_B200_REGLAP_FAST)
+                                         // two Cholesky kernels, 5 the same with M_oo^-1 from two independent halves
+                                         // of a dissection of the other nodes (GPNET_B200_REGLAP_FAST)
     DevBuf p_indptr, p_indices, p_weights, p_dinv, iota;
     // level-set dissection of the other nodes (ensure_perm): they are numbered [A | B | Sep], no edge joins A and B
     int dis_a = 0, dis_b = 0, dis_s = 0;   // block sizes (dis_s == 0: not dissected)
@@ -166,6 +167,7 @@ int gpn_k_sumlogdiag(gpn_ctx* c, int n, const double* A, long ld, double* d_out)
 int gpn_k_fill_vec(gpn_ctx* c, int n, double* y, double v);
 int gpn_k_rowdot_pass(gpn_ctx* c, int rows, int cols, const double* Y, long ld, const double* ya, const double* yb, double* za, double* zb,
                       double* d_fro, bool upper_only, bool zero_fro);
+int gpn_k_z_border(gpn_ctx* c, int D, int s, const double* V, long ldv, const double* Sigma, long ldsg, double* Z, long ldz);
 int gpn_k_csr_values(gpn_ctx* c, int rows, int row0, const int* indptr, const int* idx, const double* M, long ld, double* val);
 int gpn_k_spmm_rows(gpn_ctx* c, int rows, int cols, const int* indptr, const int* idx, const double* val, const double* Z, long ldz, double* X,
                     long ldx, const double* base = nullptr, long ldb = 0);   // base: X = base - (sparse rows) Z

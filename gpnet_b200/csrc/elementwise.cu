@@ -421,6 +421,19 @@ __global__ void rowdot_pass_kernel(int rows, int cols, const double* __restrict_
     sf = block_sum(sf);
     if (threadIdx.x == 0 && sf != 0.0) atomicAdd(fro, sf);
 }
+// Border of a block inverse: with D = a+b leading rows / columns and s separator rows behind them,
+//   Z[D + r][col] = Z[col][D + r] = -V[col][r]  (col < D),   Z[D + r][D + c] = Sigma[r][c]
+__global__ void z_border_kernel(int D, int s, const double* __restrict__ V, long ldv, const double* __restrict__ Sigma, long ldsg,
+                                double* __restrict__ Z, long ldz) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (col < D) {
+        const double v = -V[(long)col * ldv + r];
+        Z[(long)(D + r) * ldz + col] = v;
+        Z[(long)col * ldz + D + r] = v;
+    } else if (col < D + s) {
+        Z[(long)(D + r) * ldz + col] = Sigma[(long)r * ldsg + (col - D)];
+    }
+}
 // ---- Schur path of the regularized-Laplacian regressor: one pass over the bottom block-row Wb (rows x cols) of a lower-
 //      triangular inverse, row r being nonzero for col <= off + r:  za = Wb^T ya, zb = Wb^T yb (pre-zeroed; atomics over row
 //      blocks) and fro += sum Wb^2.  Each thread owns one column (coalesced rows).
@@ -684,6 +697,13 @@ int gpn_k_rowdot_pass(gpn_ctx* c, int rows, int cols, const double* Y, long ld, 
     }
     if (rows <= 0 || cols <= 0) return 0;
     rowdot_pass_kernel<<<grid1((long)rows * 32), TPB, 0, c->stream>>>(rows, cols, Y, ld, ya, yb, za, zb, d_fro, upper_only ? 1 : 0);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_z_border(gpn_ctx* c, int D, int s, const double* V, long ldv, const double* Sigma, long ldsg, double* Z, long ldz) {
+    if (s <= 0) return 0;
+    dim3 grid(grid1(D + s), s);
+    z_border_kernel<<<grid, TPB, 0, c->stream>>>(D, s, V, ldv, Sigma, ldsg, Z, ldz);
     LAUNCHED(c);
     return 0;
 }

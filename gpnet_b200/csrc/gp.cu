@@ -927,6 +927,68 @@ int gpr_reglap_schur_scalars(gpn_ctx* c, const double* theta_h, int P, const dou
     }
     return 0;
 }
+// Z = M_oo^-1 through the dissection of the other nodes (ensure_perm numbered them [A | B | Sep], no edge joins A and B):
+//   M_oo = [D C; C^T E],  D = blkdiag(M_AA, M_BB),  C = [M_AS; M_BS] (sparse),  E = M_SS
+//   Z_A = M_AA^-1 and Z_B = M_BB^-1: two INDEPENDENT augmented factorisations [M; I] (half the tile columns each: half the
+//   dependency chain) on the two streams, each on half of the SMs;  U = D^-1 C = [Z_A M_AS; Z_B M_BS] (sparse x dense),
+//   Sigma = (E - C^T U)^-1 (|Sep| x |Sep|),  V = U Sigma,
+//   Z = [D^-1 + V U^T, -V; -V^T, Sigma]                                   (a rank-|Sep| correction of blkdiag(Z_A, Z_B)).
+// a^3 + b^3 flops instead of o^3, and the chain of 32 tile columns at C3 becomes two concurrent chains of 16.
+// In: M holds I + beta L~ (lower tiles) with its (B, A) block zero.  Out: the full symmetric Z in its leading o x o block.
+int reglap_inverse_oo_dissected(gpn_ctx* c, double* M, long ld, int* info_slot_used) {
+    const int a = c->dis_a, b = c->dis_b, s = c->dis_s, D = a + b;
+    const long lds = pad128(s);
+    const int Ta = (a + 127) / 128, Tb = (b + 127) / 128;
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)(Ta + Tb + 2) * 128 * 128));
+    double* WT = mat(c, 2);
+    double* U = mat(c, 1);                                  // (a+b) x s, then V, S_sep, Sigma and the scratch of its inverse
+    double* V = U + (size_t)pad128(D) * lds;
+    double* Ssep = V + (size_t)pad128(D) * lds;
+    double* Sg = Ssep + lds * lds;
+    double *w1 = Sg + lds * lds, *w2 = w1 + lds * lds, *w3 = w2 + lds * lds;
+    if ((size_t)(2 * pad128(D) * lds + 6 * lds * lds) > (size_t)c->ldN * c->ldN) return -9;
+    // separator coupling values of this theta (the entries the scatter wrote)
+    GPN_TRY(gpn_k_csr_values(c, s, D, (const int*)c->sa_ptr.p, (const int*)c->sa_idx.p, M, ld, (double*)c->sa_val.p));
+    GPN_TRY(gpn_k_csr_values(c, s, D, (const int*)c->sb_ptr.p, (const int*)c->sb_idx.p, M, ld, (double*)c->sb_val.p));
+    // the two halves concurrently
+    cudaStream_t main_stream = c->stream;
+    double* MB = M + (long)a * ld + a;
+    GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
+    GPN_CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    c->potrf_grid_cap = c->num_sms / 2;
+    int st = gpn_potrf_dataflow(c, a, M, ld, (double*)c->winv.p, iscal(c, 0), 0, nullptr, 0, 0, WT, ld, 0);
+    if (st == 0) {
+        c->stream = c->stream2;
+        st = gpn_potrf_dataflow(c, b, MB, ld, (double*)c->winv.p + (size_t)Ta * 128 * 128, iscal(c, 2), 0, nullptr, 0, 0, WT + (long)a * ld + a, ld, 1);
+        if (st == 0) st = gpn_lauum_t(c, b, WT + (long)a * ld + a, ld, MB, ld, true);
+        c->stream = main_stream;
+    }
+    c->potrf_grid_cap = 0;
+    if (st != 0) return st;
+    GPN_CK(cudaEventRecord(c->ev_join, c->stream2));
+    GPN_TRY(gpn_lauum_t(c, a, WT, ld, M, ld, true));
+    GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    // U = [Z_A M_AS; Z_B M_BS] = ([M_SA Z_A, M_SB Z_B])^T, written transposed by the SpMM
+    GPN_TRY(gpn_k_spmm_rows_t(c, s, a, (const int*)c->sa_ptr.p, (const int*)c->sa_idx.p, (const double*)c->sa_val.p, M, ld, U, lds));
+    GPN_TRY(gpn_k_spmm_rows_t(c, s, b, (const int*)c->sb_ptr.p, (const int*)c->sb_idx_rel.p, (const double*)c->sb_val.p, MB, ld, U + (long)a * lds, lds));
+    // S_sep = M_SS - M_SA U_A - M_SB U_B  (lower triangle), Sigma = S_sep^-1
+    GPN_TRY(gpn_k_spmm_rows(c, s, s, (const int*)c->sa_ptr.p, (const int*)c->sa_idx.p, (const double*)c->sa_val.p, U, lds, Ssep, lds,
+                            M + (long)D * ld + D, ld));
+    GPN_TRY(gpn_k_spmm_rows(c, s, s, (const int*)c->sb_ptr.p, (const int*)c->sb_idx_rel.p, (const double*)c->sb_val.p, U + (long)a * lds, lds, Ssep, lds,
+                            Ssep, lds));
+    {   // spd_inverse works with one leading dimension for everything
+        GPN_TRY(gpn_potrf(c, s, Ssep, lds, (double*)c->winv.p, iscal(c, 3)));
+        GPN_TRY(gpn_trtri(c, s, Ssep, lds, (const double*)c->winv.p, w1, w2, w3, lds));
+        GPN_TRY(gpn_lauum_t(c, s, w2, lds, Sg, lds, true));
+    }
+    // V = U Sigma;  Z_DD = blkdiag(Z_A, Z_B) + V U^T;  borders
+    GPN_TRY(gpn_gemm(c, D, s, s, 1.0, U, lds, true, Sg, lds, true, 0.0, V, lds, 0));
+    GPN_TRY(gpn_gemm(c, D, D, s, 1.0, V, lds, true, U, lds, true, 1.0, M, ld, GF_LOWER | GF_MIRROR));
+    GPN_TRY(gpn_k_z_border(c, D, s, V, lds, Sg, lds, M, ld));
+    *info_slot_used = 3;
+    return 0;
+}
+
 // Schur route with sparse coupling (gradient evaluations): the only link between the other nodes (o) and the training nodes (t)
 // in M = I + beta L~ is the SPARSE block M_to (graph edges between the two sets), so the elimination of the o-block does not
 // need the dense N x N factorisation:
@@ -972,8 +1034,13 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
         //   [M_oo; I]      -> L_oo and W_oo^T            then Z = W_oo^T W_oo
         //   [S; X^T; I]    -> L_tt, Y = X^T L_tt^-T = (W_tt X)^T = -W_to^T, and W_tt^T
         GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(std::max(n, o)) * 128));
-        GPN_TRY(gpn_potrf_dataflow(c, o, M, ld, (double*)c->winv.p, iscal(c, 0), 0, nullptr, 0, 0, mat(c, 2), ld));
-        GPN_TRY(gpn_lauum_t(c, o, mat(c, 2), ld, M, ld, true));                                   // Z, full symmetric, in place of M_oo
+        if (c->fast_reglap >= 5 && c->dis_s > 0) {
+            int used = 0;
+            GPN_TRY(reglap_inverse_oo_dissected(c, M, ld, &used));                                // Z from two independent halves
+        } else {
+            GPN_TRY(gpn_potrf_dataflow(c, o, M, ld, (double*)c->winv.p, iscal(c, 0), 0, nullptr, 0, 0, mat(c, 2), ld));
+            GPN_TRY(gpn_lauum_t(c, o, mat(c, 2), ld, M, ld, true));                               // Z, full symmetric, in place of M_oo
+        }
         const long po = pad128(o);
         GPN_TRY(ensure_nb(c, NB_ROWS2, po, ldn));
         double* Y = nbp(c, NB_ROWS2);                                                             // X^T (o x n), rows padded with zeros
@@ -1014,7 +1081,7 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
     double sc[Scal::NDBL];
     int info[16];
     GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
-    if (info_h) *info_h = info[1] ? info[1] : info[0];
+    if (info_h) *info_h = info[1] ? info[1] : (info[0] ? info[0] : (info[2] ? info[2] : info[3]));
     rs->n = n;
     rs->half_logdet = -sc[Scal::LOGDET];
     rs->s = sc[Scal::SCH0]; rs->a = sc[Scal::SCH0 + 1]; rs->q = sc[Scal::SCH0 + 2];
@@ -1597,7 +1664,7 @@ int gpn_debug_leaf_bench(gpn_ctx* c, void* A_dev, int copies, void* prof32_dev) 
     return gpn_leaf_bench(c, (double*)A_dev, copies, (double*)c->winv.p, iscal(c, 0), (long long*)prof32_dev);
 }
 void gpn_set_fast_paths(gpn_ctx* c, int level) {
-    if (c) c->fast_reglap = level < 0 ? 0 : (level > 4 ? 4 : level);
+    if (c) c->fast_reglap = level < 0 ? 0 : (level > 5 ? 5 : level);
 }
 void gpn_debug_df_trace(gpn_ctx* c, void* dev_buf) {
     if (c) c->df_trace = dev_buf;

@@ -277,7 +277,7 @@ def test_full_size_properties_c3_reglap(gpu_ctx):
         assert abs(fd - out[1 + j]) <= 1e-6 * max(1.0, abs(fd))
 
 
-@pytest.mark.parametrize("shape", [(20, 13, 100), (37, 29, 300), (40, 40, 800), (32, 32, 1023), (48, 43, 1100), (64, 48, 1536)])
+@pytest.mark.parametrize("shape", [(20, 13, 100), (37, 29, 300), (40, 40, 800), (32, 32, 1023), (48, 43, 1100), (64, 48, 1536), (64, 64, 1700), (71, 67, 2100)])
 def test_reglap_fast_path_equals_full_path(gpu_ctx, shape):
     """The training-nodes-last routes (1: only K[tr,:] formed; 2: Schur complement read off the Cholesky factor, no kernel
     block formed; 3: other nodes eliminated through the sparse coupling block; 4: the same with the triangular work appended
@@ -293,14 +293,14 @@ def test_reglap_fast_path_equals_full_path(gpu_ctx, shape):
     th = np.log([0.7, 0.05])
     res = {}
     try:
-        for level in (4, 3, 2, 1, 0):
+        for level in (5, 4, 3, 2, 1, 0):
             gpu_ctx.set_fast_paths(level)
             res[level] = (gpu_ctx.gpr_logp_grad(1, th, t, True), gpu_ctx.gpr_logp_grad(1, th, t, False))
     finally:
         gpu_ctx.set_fast_paths(True)
     (s0, g0, i0), (_, l0, _) = res[0]
     assert s0 == 0 and i0 == 0
-    for level in (1, 2, 3, 4):
+    for level in (1, 2, 3, 4, 5):
         (s1, g1, i1), (_, l1, _) = res[level]
         assert s1 == 0 and i1 == 0
         assert nrel(g1, g0) <= 1e-11, (level, g1, g0)
@@ -320,7 +320,7 @@ def test_reglap_routes_agree_with_oracle_for_stiff_parameters(gpu_ctx, beta, noi
     orc = go.OracleGP(G, kerneltype="regularized_laplacian")
     ref_v, ref_g = orc.neg_logp_grad(th, tr, t[tr])
     try:
-        for level in (0, 1, 2, 3, 4):
+        for level in (0, 1, 2, 3, 4, 5):
             gpu_ctx.set_fast_paths(level)
             st, out, info = gpu_ctx.gpr_logp_grad(1, th, t[tr], True)
             assert st == 0 and info == 0
@@ -350,7 +350,7 @@ def test_reglap_routes_random_shapes_against_oracle(gpu_ctx, seed):
     th = np.log([beta, noise])
     ref_v, ref_g = go.OracleGP(G, kerneltype="regularized_laplacian").neg_logp_grad(th, tr, t)
     try:
-        for level in (0, 1, 2, 3, 4):
+        for level in (0, 1, 2, 3, 4, 5):
             gpu_ctx.set_fast_paths(level)
             st, out, info = gpu_ctx.gpr_logp_grad(1, th, t, True)
             assert st == 0 and info == 0
@@ -383,7 +383,7 @@ def test_reglap_routes_on_a_weighted_graph_with_isolated_nodes_and_a_training_on
     orc = go.OracleGP(G, kerneltype="regularized_laplacian")
     ref_v, ref_g = orc.neg_logp_grad(th, tr, t)
     try:
-        for level in (0, 1, 2, 3, 4):
+        for level in (0, 1, 2, 3, 4, 5):
             gpu_ctx.set_fast_paths(level)
             st, out, info = gpu_ctx.gpr_logp_grad(1, th, t, True)
             assert st == 0 and info == 0
@@ -417,7 +417,7 @@ def test_landscape_kernel_reuse_equals_independent_points(gpu_ctx, kind, theta, 
     idx = rng.permutation(len(a1) * len(a2))
     res = {}
     try:
-        for level in (4, 0):
+        for level in (5, 0):
             gpu_ctx.set_fast_paths(level)
             st, out = gpu_ctx.landscape_points(kind, classifier, theta, axidx, a1, a2, t, idx, want_grad=not classifier)
             assert st == 0
@@ -425,9 +425,9 @@ def test_landscape_kernel_reuse_equals_independent_points(gpu_ctx, kind, theta, 
     finally:
         gpu_ctx.set_fast_paths(True)
     assert np.all(np.isfinite(res[0]))
-    assert nrel(res[4][:, 0], res[0][:, 0]) <= 1e-11
+    assert nrel(res[5][:, 0], res[0][:, 0]) <= 1e-11
     if not classifier:
-        assert nrel(res[4][:, 1:], res[0][:, 1:]) <= 1e-10
+        assert nrel(res[5][:, 1:], res[0][:, 1:]) <= 1e-10
     # the strided form of the same call covers the same points
     st, out = gpu_ctx.landscape(kind, classifier, theta, axidx, a1, a2, t, 1, len(idx), 3, want_grad=False)
     ref = {int(i): v for i, v in zip(idx, res[0][:, 0])}

@@ -18,7 +18,7 @@ ctx = Context(0, ts.cuda_stream)
 rng = np.random.RandomState(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 worst = 0.0
 for case in range(int(sys.argv[2]) if len(sys.argv) > 2 else 16):
-    N = int(rng.randint(300, 2600))
+    N = int(rng.randint(300, 4200))
     frac = rng.uniform(0.12, 0.88)
     n = max(2, int(N * frac))
     beta = float(np.exp(rng.uniform(np.log(0.01), np.log(5.0))))
@@ -34,7 +34,7 @@ for case in range(int(sys.argv[2]) if len(sys.argv) > 2 else 16):
     th = np.log([beta, noise])
     ref_v, ref_g = go.OracleGP(G, kerneltype="regularized_laplacian").neg_logp_grad(th, tr, t)
     errs = []
-    for level in (0, 1, 2, 3, 4):
+    for level in (0, 1, 2, 3, 4, 5):
         ctx.set_fast_paths(level)
         st, out, info = ctx.gpr_logp_grad(1, th, t, True)
         assert st == 0 and info == 0, (case, level, st, info)
