@@ -321,10 +321,11 @@ def main():
                 "conventional_gflop_per_step": algo * 1e-9,
                 "step_conventional_tflops": algo / (ms_step * 1e-3) * 1e-12,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of the two launches
-                # of this kernel in one step (profiles/r01_ncu_potrf_oo.txt: 0.326 GB, profiles/r01_ncu_potrf_tt.txt: 3.033 GB);
+                # of this kernel in one step (profiles/r01_ncu_potrf_half.txt: 0.019 GB for each half-block launch,
+                # profiles/r01_ncu_potrf_tt.txt: 3.033 GB);
                 # recorded, not re-measured here (numbers taken under a profiler are never bench values)
-                "traffic": 1.680e9 if kname.startswith("potrf_dataflow") and N == 8192 else None,
-                "traffic_unit": "bytes per launch (average of the step's two launches; ncu capture in profiles/)"}
+                "traffic": 1.024e9 if kname.startswith("potrf_dataflow") and N == 8192 else None,
+                "traffic_unit": "bytes per launch (average of the step's three launches; ncu captures in profiles/)"}
         # the same evaluation through the two other exact routes (same outputs to rounding), device-timed like `value`
         if world == 1:
             routes = {}

@@ -128,8 +128,10 @@ int gpn_gpr_fetch(gpn_ctx* ctx, int which, double* out_h);
  *      rank-one update, and the gradient traces reduce to norms of the bottom block-row of L^-1;
  *   3  the same, and for gradient evaluations the other nodes are eliminated through the SPARSE coupling block of
  *      I + beta L~: Z = M_oo^-1, X = M_to Z (sparse x dense), S = M_tt - X M_ot, W_to = -W_tt X;
- *   4  (default) as 3, with the triangular inverse / triangular product that follow the two Cholesky factorisations carried
- *      as appended row blocks of the dataflow Cholesky kernel itself ([M_oo; I] and [S; X^T; I]). */
+ *   4  as 3, with the triangular inverse / triangular product that follow the two Cholesky factorisations carried as
+ *      appended row blocks of the dataflow Cholesky kernel itself ([M_oo; I] and [S; X^T; I]);
+ *   5  (default) as 4, with M_oo^-1 assembled from two independent halves of a level-set dissection of the other nodes (two
+ *      concurrent half-size factorisations and a rank-|separator| correction); falls back to 4 where no thin separator exists. */
 void gpn_set_fast_paths(gpn_ctx* ctx, int level);
 
 /* ---- GP classification, Laplace approximation (GPnetClassifier.py:90-147,184-240) ---------------------------- */
