@@ -989,6 +989,16 @@ int reglap_inverse_oo_dissected(gpn_ctx* c, double* M, long ld, int* info_slot_u
     return 0;
 }
 
+// Which evaluations take the sparse-coupling route: gradients from level 3 on; values alone only when the inverse of the
+// other-node block comes from the dissected halves (level 5): otherwise the dense Cholesky of M of the Schur route is as fast.
+bool coupled_route(gpn_ctx* c, int want_grad) {
+    if (want_grad) return c->fast_reglap >= 3;
+    const int o = c->N - c->n_train;
+    if (c->fast_reglap < 5 || o < 256 || c->n_train < 256) return false;
+    if (!c->perm_valid && ensure_perm(c) != 0) return false;
+    return c->dis_s > 0;
+}
+
 // Schur route with sparse coupling (gradient evaluations): the only link between the other nodes (o) and the training nodes (t)
 // in M = I + beta L~ is the SPARSE block M_to (graph edges between the two sets), so the elimination of the o-block does not
 // need the dense N x N factorisation:
@@ -996,7 +1006,7 @@ int reglap_inverse_oo_dissected(gpn_ctx* c, double* M, long ld, int* info_slot_u
 //     W_tt = L_tt^-1,   W_to = -W_tt L_to W_oo = -W_tt M_to M_oo^-1 = -W_tt X            (one triangular n x o x n product)
 // and the reductions of the Schur route run over [W_to  W_tt] as before: o^3 + n^2 o + 2 n^3/3 flops instead of 2 N^3/3
 // (half at n = N/2).  S, L_tt and the reductions are the same quantities as on level 2, so results agree to rounding.
-int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const double* t_h, RowScalars* rs, int* info_h) {
+int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, RowScalars* rs, int* info_h) {
     const int N = c->N, n = c->n_train, o = N - n;
     GPN_TRY(ensure_perm(c));
     GPN_TRY(ensure_vecs(c));
@@ -1048,6 +1058,23 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
         GPN_TRY(gpn_k_spmm_rows_t(c, n, o, tptr, tidx, tval, M, ld, Y, ldn));                    // X = M_to Z, written transposed
         // S = M_tt - M_to (Z M_ot) = M_tt - M_to X^T, row by row: the sparse rows of M_to times the dense X^T (lower triangle)
         GPN_TRY(gpn_k_spmm_rows(c, n, n, tptr, tidx, tval, Y, ldn, S, ldn, M + (long)o * ld + o, ld));
+        if (!want_grad) {
+            // -logp alone: L_tt = chol(S), two triangular GEMVs and the log-determinant; no right-hand sides, no inverse
+            GPN_TRY(gpn_potrf_dataflow(c, n, S, ldn, (double*)c->winv.p, iscal(c, 1), 0));
+            GPN_TRY(gpn_k_gemv_t2(c, n, n, S, ldn, ones, vecp(c, V_T), r1, rt, GEMV_LOWER));
+            GPN_TRY(gpn_k_sumlogdiag(c, n, S, ldn, dscal(c, Scal::LOGDET)));
+            const double *dx3[3] = {r1, r1, rt}, *dy3[3] = {r1, rt, rt};
+            const int dn3[3] = {n, n, n};
+            GPN_TRY(gpn_k_multi_dot(c, 3, dx3, dy3, dn3, dscal(c, Scal::SCH0)));
+            double sc0[Scal::NDBL];
+            int info0[16];
+            GPN_TRY(read_scalars(c, sc0, Scal::NDBL, info0, 16));
+            if (info_h) *info_h = info0[1] ? info0[1] : (info0[0] ? info0[0] : (info0[2] ? info0[2] : info0[3]));
+            rs->n = n;
+            rs->half_logdet = -sc0[Scal::LOGDET];
+            rs->s = sc0[Scal::SCH0]; rs->a = sc0[Scal::SCH0 + 1]; rs->q = sc0[Scal::SCH0 + 2];
+            return 0;
+        }
         GPN_TRY(gpn_potrf_dataflow(c, n, S, ldn, (double*)c->winv.p, iscal(c, 1), 0, Y, ldn, o, nbp(c, NB_WT), ldn));
         GPN_TRY(gpn_k_gemv_t2(c, n, n, S, ldn, ones, vecp(c, V_T), r1, rt, GEMV_LOWER));
         GPN_TRY(gpn_k_sumlogdiag(c, n, S, ldn, dscal(c, Scal::LOGDET)));
@@ -1095,7 +1122,7 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
 
 int gpr_logp_grad_reglap_schur(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
     RowScalars rs;
-    if (want_grad && c->fast_reglap >= 3) GPN_TRY(gpr_reglap_coupled_scalars(c, theta_h, P, t_h, &rs, info_h));
+    if (coupled_route(c, want_grad)) GPN_TRY(gpr_reglap_coupled_scalars(c, theta_h, P, t_h, want_grad, &rs, info_h));
     else GPN_TRY(gpr_reglap_schur_scalars(c, theta_h, P, t_h, want_grad, &rs, info_h));
     row_eval(rs, c->theta_exp[P - 1], P, want_grad, out_h);
     return 0;
@@ -1106,7 +1133,7 @@ int gpr_logp_grad_reglap_schur(gpn_ctx* c, const double* theta_h, int P, const d
 // grid row shares them.  info > 0: K_tt itself is not positive definite (the caller falls back to factoring K_y per point).
 int gpr_row_scalars(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad, RowScalars* rs, int* info_h) {
     if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN && c->fast_reglap >= 2 && c->train_unique && c->n_train < c->N)
-        return (want_grad && c->fast_reglap >= 3) ? gpr_reglap_coupled_scalars(c, theta_h, P, t_h, rs, info_h)
+        return coupled_route(c, want_grad) ? gpr_reglap_coupled_scalars(c, theta_h, P, t_h, want_grad, rs, info_h)
                                                   : gpr_reglap_schur_scalars(c, theta_h, P, t_h, want_grad, rs, info_h);
     int st = kernel_build(c, kind, theta_h, P, want_grad);
     if (st != 0) return st;
