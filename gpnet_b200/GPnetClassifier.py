@@ -10,7 +10,7 @@ import numpy as np
 import pandas as pd
 
 from ._lib import KERNEL_IDS
-from .engine import raise_domain
+from .engine import invalidate_predict, raise_domain
 from .GPnet import COEFS, LAMBDAS, GPnetBase, KERNEL_LIST  # noqa: F401  (re-exported like the reference module)
 
 
@@ -50,7 +50,7 @@ class GPnetClassifier(GPnetBase):
         th = self._theta_vec(theta)
         ctx = self._engine.bind(self._positions(data), self._positions(self.test_nodes))
         ctx._kernel_key = None
-        ctx._predict_token = None
+        invalidate_predict(ctx)
         st, r = ctx.gpc_newton(self._kind(), th, self._labels(targets), tol=tol, phif=phif, scale=scale, variant=0)
         raise_domain(st)
         if r["info"] > 0:
@@ -66,7 +66,7 @@ class GPnetClassifier(GPnetBase):
         th = self._theta_vec(self.theta)
         ctx = self._engine.bind(self._positions(self.training_nodes), self._positions(self.test_nodes))
         ctx._kernel_key = None
-        ctx._predict_token = None
+        invalidate_predict(ctx)
         st, r = ctx.gpc_predict(self._kind(), th, self._labels(self.training_values))
         raise_domain(st)
         if r["info"] > 0:
@@ -91,7 +91,7 @@ class GPnetClassifier(GPnetBase):
         th = self._theta_vec(theta)
         ctx = self._engine.bind(self._positions(data), self._positions(self.test_nodes))
         ctx._kernel_key = None
-        ctx._predict_token = None
+        invalidate_predict(ctx)
         st, out, iters, info = ctx.gpc_grad(self._kind(), th, self._labels(targets))
         raise_domain(st)
         if info > 0:

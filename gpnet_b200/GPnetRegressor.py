@@ -5,7 +5,9 @@ quirks: targets are mean-shifted in ``predict`` but not i
 ``logPosterior`` returns ``-inf`` when the Cholesky fails (A-8), PD gates print and return ``self`` (A-7,
 through the Cholesky info instead of ``eigvals``).  ``gradLogPosterior`` is the *correct* analytic gradient
 (the reference's own body is dead code, A-9) with the reference's sign convention (returns ``-grad``).
-Large attributes (``k``, ``kstar``, ``kstarstar``, ``L``, ``v``, ``V``) are fetched from the device on first access.
+Large attributes (``k``, ``kstar``, ``kstarstar``, ``L``, ``v``, ``V``) are fetched from the device on first access -- or, at the
+latest, right before another device call would reuse their buffers (``engine.invalidate_predict``), so that they stay
+readable for the life of the model like the reference's host arrays.
 """
 from __future__ import annotations
 
@@ -13,7 +15,7 @@ import numpy as np
 import pandas as pd
 
 from ._lib import KERNEL_IDS
-from .engine import raise_domain
+from .engine import PredictToken, invalidate_predict, raise_domain
 from .GPnet import GPnetBase, KERNEL_LIST, _is_false
 
 
@@ -70,17 +72,28 @@ class GPnetRegressor(GPnetBase):
         return np.asarray(t.values if isinstance(t, (pd.Series, pd.DataFrame)) else t, dtype=np.float64).reshape(-1)
 
     def _fetch(self, name):
-        ctx = self._engine.ctx
-        if self._predict_token is None or ctx._owner is not self._engine or ctx._predict_token is not self._predict_token:
-            raise AttributeError(f"'{name}' is only available right after predict() (device buffers were reused)")
         if name == "V":      # GPnetRegressor.py:127: kstarstar_diag - v^T v (m x m by broadcasting)
             v = self.v
             return self.kstarstar_diag - v.T @ v
+        ctx = self._engine.ctx
+        if self._predict_token is None or ctx._owner is not self._engine or ctx._predict_token is not self._predict_token:
+            raise AttributeError(f"'{name}' is only available after a successful predict()")
         return ctx.gpr_fetch(name)
 
     def _clear_lazy(self):
         for key in [k for k in self.__dict__ if k.startswith("_lazy_")]:
             del self.__dict__[key]
+
+    _DEVICE_ATTRS = ("k", "kstar", "kstarstar", "L", "v")
+
+    def _materialize(self):
+        """Copy every not-yet-fetched device-resident attribute of the last predict() to the host (``V`` is host arithmetic
+        on ``v`` and stays lazy).  Called by engine.invalidate_predict before the device buffers are reused."""
+        if self._predict_token is None or not getattr(self, "is_trained", False):
+            return
+        for name in self._DEVICE_ATTRS:
+            if self.__dict__.get("_lazy_" + name) is None:
+                self.__dict__["_lazy_" + name] = self._engine.ctx.gpr_fetch(name)
 
     # ---- GPnetRegressor.py:79-134 ----------------------------------------------------------------------
     def predict(self):
@@ -91,12 +104,14 @@ class GPnetRegressor(GPnetBase):
         self.t_mean = np.mean(self.training_values)
         self.t_shifted = self.training_values - self.t_mean
         th = self._theta_vec(self.theta)
+        self._clear_lazy()
+        self._predict_token = None          # this model's previous predict() is superseded, nothing to snapshot
         ctx = self._engine.bind(self._positions(self.training_nodes), self._positions(self.test_nodes))
         ctx._kernel_key = None
-        self._clear_lazy()
+        invalidate_predict(ctx)             # another model's predict() may own the buffers
         st, res = ctx.gpr_predict(self._kind(), th, t)
         raise_domain(st)
-        self._predict_token = object()
+        self._predict_token = PredictToken(self)
         ctx._predict_token = self._predict_token
         self.kstarstar_diag = res["kstarstar_diag"]
         if res["info_k"] > 0:
@@ -120,7 +135,7 @@ class GPnetRegressor(GPnetBase):
         th = self._theta_vec(theta)
         ctx = self._engine.bind(self._positions(data), self._positions(self.test_nodes) if not _is_false(self.test_nodes) else ())
         ctx._kernel_key = None          # the compound call rebuilds the resident kernel for this theta
-        ctx._predict_token = None       # ... and reuses the buffers predict() left behind
+        invalidate_predict(ctx)         # ... and reuses the buffers predict() left behind (their owner snapshots them first)
         st, out, info = ctx.gpr_logp_grad(self._kind(), th, self._values(t), want_grad)
         raise_domain(st)
         return out, info

@@ -46,6 +46,11 @@ SIGNATURES = {
     "gpn_syrk_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_long, C.c_double, C.c_void_p, C.c_long]),
     "gpn_posv_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long,
                                C.POINTER(C.c_int)]),
+    "gpn_trsm_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int]),
+    "gpn_potri_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long]),
+    "gpn_expm_sym_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, c_int_p, c_int_p]),
+    "gpn_matpow_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long]),
+    "gpn_last_route": (C.c_int, [C.c_void_p, c_int_p]),
     "gpn_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gpn_gather_block_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double,
                                        C.c_void_p, C.c_long]),
@@ -111,6 +116,13 @@ def _f64(x):
 
 def _i32(x):
     return np.ascontiguousarray(np.asarray(x, dtype=np.int32).reshape(-1))
+
+
+def _eth(theta):
+    """``np.exp(theta)`` -- the reference's own expression (GPnet.py:303) evaluated on the HOST.  The C-ABI takes the
+    exponentiated parameters so that ``int(np.exp(theta)[1])`` (the p-step order, quirk A-4) and the domain checks see
+    exactly numpy's values: numpy's exp and libm's exp differ by an ulp on some inputs (e.g. log 146, log 179)."""
+    return np.ascontiguousarray(np.exp(np.asarray(theta, dtype=np.float64).reshape(-1)))
 
 
 class Context:
@@ -208,6 +220,34 @@ class Context:
                                           C.c_void_p(wt_ptr) if wt_ptr else None, ldw, C.byref(info)), "gpn_posv_f64")
         return info.value
 
+    def trsm(self, n, l_ptr, ldl, b_ptr, ldb, brows):
+        """B <- B L^-T with the factor of the immediately preceding potrf()/posv()."""
+        self._check(self.lib.gpn_trsm_f64(self.h, n, C.c_void_p(l_ptr), ldl, C.c_void_p(b_ptr), ldb, brows), "gpn_trsm_f64")
+
+    def potri(self, n, l_ptr, ldl, out_ptr, ldo):
+        """out <- (L L^T)^-1 from the factor of the immediately preceding potrf()/posv()."""
+        self._check(self.lib.gpn_potri_f64(self.h, n, C.c_void_p(l_ptr), ldl, C.c_void_p(out_ptr), ldo), "gpn_potri_f64")
+
+    def expm_sym(self, N, a_ptr, lda, out_ptr, ldo):
+        """out <- expm(A), A symmetric negative semi-definite; returns (Pade order, squarings)."""
+        m, s = C.c_int(0), C.c_int(0)
+        self._kernel_key = None
+        self._check(self.lib.gpn_expm_sym_f64(self.h, N, C.c_void_p(a_ptr), lda, C.c_void_p(out_ptr), ldo, C.byref(m), C.byref(s)),
+                    "gpn_expm_sym_f64")
+        return m.value, s.value
+
+    def matpow(self, N, b_ptr, ldb, p, out_ptr, ldo, out_pm1_ptr=None, ldo1=0):
+        self._kernel_key = None
+        self._check(self.lib.gpn_matpow_f64(self.h, N, C.c_void_p(b_ptr), ldb, int(p), C.c_void_p(out_ptr), ldo,
+                                            C.c_void_p(out_pm1_ptr) if out_pm1_ptr else None, ldo1), "gpn_matpow_f64")
+
+    def last_route(self):
+        """(level, parts) of the last regressor likelihood evaluation: parts = [number of parts, separator size, sizes...]."""
+        parts = (C.c_int * 10)()
+        level = int(self.lib.gpn_last_route(self.h, parts))
+        k = parts[0]
+        return level, [int(x) for x in parts[: 2 + k]]
+
     def potrf(self, n, a_ptr, lda) -> int:
         info = C.c_int(0)
         self._check(self.lib.gpn_potrf_f64(self.h, n, C.c_void_p(a_ptr), lda, C.byref(info)), "gpn_potrf_f64")
@@ -225,7 +265,7 @@ class Context:
 
     # -- full kernel ---------------------------------------------------------------------------------
     def kernel_build(self, kind: int, theta, want_grad=False) -> int:
-        th = _f64(theta)
+        th = _eth(theta)
         st = self.lib.gpn_kernel_build(self.h, kind, _dp(th), len(th), int(want_grad))
         if st in (-100, -101):
             return st
@@ -245,13 +285,16 @@ class Context:
         r, c = _i32(rows), _i32(cols)
         out = np.empty((len(r), len(c)), dtype=np.float64)
         if out.size:
-            self._check(self.lib.gpn_kernel_block_h(self.h, _ip(r), len(r), _ip(c), len(c), float(addc), _dp(out)), "gpn_kernel_block_h")
+            st = self.lib.gpn_kernel_block_h(self.h, _ip(r), len(r), _ip(c), len(c), float(addc), _dp(out))
+            if st in (-2, -4):      # the reference's np.delete / fancy indexing raises IndexError for such labels
+                raise IndexError(f"node position out of bounds for a graph with {self.N} nodes")
+            self._check(st, "gpn_kernel_block_h")
         return out
 
     # -- regression ----------------------------------------------------------------------------------
     def gpr_logp_grad(self, kind, theta, t, want_grad):
         """t=None: use the resident targets of set_targets()."""
-        th = _f64(theta)
+        th = _eth(theta)
         tt = None if t is None else _f64(t)
         if tt is not None and len(tt) != self.n_train:
             raise ValueError("len(t) != number of training nodes")
@@ -271,7 +314,7 @@ class Context:
         self.lib.gpn_set_fast_paths(self.h, 5 if level is True else int(level))
 
     def gpr_predict(self, kind, theta, t):
-        th, tt = _f64(theta), _f64(t)
+        th, tt = _eth(theta), _f64(t)
         if len(tt) != self.n_train:
             raise ValueError("len(t) != number of training nodes")
         n, m = self.n_train, self.n_test
@@ -294,7 +337,7 @@ class Context:
 
     # -- classification ------------------------------------------------------------------------------
     def gpc_newton(self, kind, theta, y, tol=0.1, phif=1e100, scale=1.0, variant=0, K_ptr=None, ldk=0):
-        th, yy = _f64(theta), _f64(y)
+        th, yy = _eth(theta), _f64(y)
         n = len(yy)
         f, a = np.zeros(n), np.zeros(n)
         logq, iters, info = C.c_double(0), C.c_int(0), C.c_int(0)
@@ -306,7 +349,7 @@ class Context:
         return 0, dict(f=f, a=a, logq=logq.value, iters=iters.value, info=info.value)
 
     def gpc_predict(self, kind, theta, y):
-        th, yy = _f64(theta), _f64(y)
+        th, yy = _eth(theta), _f64(y)
         n, m = self.n_train, self.n_test
         if len(yy) != n:
             raise ValueError("len(y) != number of training nodes")
@@ -320,7 +363,7 @@ class Context:
         return 0, dict(f=f, a=a, logq=logq.value, iters=iters.value, info=info.value, fstar=fstar, V=V, pi_star=pi)
 
     def gpc_grad(self, kind, theta, y):
-        th, yy = _f64(theta), _f64(y)
+        th, yy = _eth(theta), _f64(y)
         if len(yy) != self.n_train:
             raise ValueError("len(y) != number of training nodes")
         out = np.zeros(1 + len(th))
@@ -333,7 +376,7 @@ class Context:
 
     # -- landscape slice ------------------------------------------------------------------------------
     def landscape(self, kind, classifier, theta, axidx, ax1, ax2, t, begin, end, stride, want_grad=False):
-        th, a1, a2, tt = _f64(theta), _f64(ax1), _f64(ax2), _f64(t)
+        th, a1, a2, tt = _eth(theta), _eth(ax1), _eth(ax2), _f64(t)
         total = len(a1) * len(a2)
         end = min(end, total)
         count = max(0, (end - begin + stride - 1) // stride)
@@ -348,7 +391,7 @@ class Context:
 
     def landscape_points(self, kind, classifier, theta, axidx, ax1, ax2, t, indices, want_grad=False):
         """(status, (len(indices), 1+P) array) for an explicit list of flat grid indices (i1*len(ax2) + i2)."""
-        th, a1, a2, tt = _f64(theta), _f64(ax1), _f64(ax2), _f64(t)
+        th, a1, a2, tt = _eth(theta), _eth(ax1), _eth(ax2), _f64(t)
         idx = np.ascontiguousarray(indices, dtype=np.int64)
         out = np.zeros((len(idx), 1 + len(th)), dtype=np.float64)
         if len(idx):

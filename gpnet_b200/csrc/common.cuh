@@ -30,6 +30,14 @@
 
 void gpn_set_last_error(const char* file, int line, const char* msg);
 
+// NVTX range per C-ABI call: header-only NVTX3, a no-op unless a profiler injects itself
+#include <nvtx3/nvToolsExt.h>
+struct GpnRange {
+    explicit GpnRange(const char* name) { nvtxRangePushA(name); }
+    ~GpnRange() { nvtxRangePop(); }
+};
+#define GPN_RANGE() GpnRange _gpn_range(__func__)
+
 // A growable device buffer owned by the context.
 struct DevBuf {
     void* p = nullptr;
@@ -85,6 +93,9 @@ struct gpn_ctx {
     std::vector<double> h_weights;
     bool perm_valid = false;
     bool train_unique = false;
+    int last_route = -1;                 // route the last regressor likelihood evaluation actually took (gpn_last_route)
+    const void* winv_for = nullptr;      // matrix whose inverted diagonal blocks `winv` holds (set by gpn_potrf_f64 / gpn_posv_f64
+    int winv_n = 0;                      // for gpn_trsm_f64 / gpn_potri_f64; any other factorisation clears it)
     int fast_reglap = 5;                 // regressor, regularized Laplacian: 0 full kernel, 1 block route, 2 Schur route, 3 Schur route with
                                          // sparse coupling, 4 the same with the triangular work appended to the
                                          // two Cholesky kernels, 5 the same with M_oo^-1 from two independent halves
@@ -137,6 +148,8 @@ int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, lon
 
 // Cholesky (lower, in place, row-major), triangular inverse and SPD inverse.  info: device int (0 = ok).
 int gpn_potrf(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset = 0);
+// X (m x k, ldx) <- X * L^-T for the factored k x k lower L (ldl) with its inverted diagonal blocks in winv
+int gpn_trsm(gpn_ctx* c, int m, int k, double* X, long ldx, const double* L, long ldl, const double* winv);
 int gpn_leaf_bench(gpn_ctx* c, double* A, int copies, double* winv, int* d_info, long long* prof);
 int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset, double* B = nullptr, long ldb = 0,
                        int brows = 0, double* Wt = nullptr, long ldwt = 0, int slot = 0);   // B <- B L^-T, Wt <- L^-T (upper tiles): see potrf_dataflow.cu

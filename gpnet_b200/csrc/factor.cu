@@ -118,7 +118,12 @@ __global__ void copy_diag_blocks_kernel(const double* __restrict__ winv, double*
 
 }   // namespace
 
+int gpn_trsm(gpn_ctx* c, int m, int k, double* X, long ldx, const double* L, long ldl, const double* winv) {
+    return trsm_rec(c, m, k, X, ldx, L, ldl, winv);
+}
+
 int gpn_potrf(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset) {
+    c->winv_for = nullptr;
     if (n <= 0) return 0;
     if (n > LB && c->potrf_mode == 0) return gpn_potrf_dataflow(c, n, A, lda, winv, d_info, info_offset);
     return potrf_rec(c, n, A, lda, winv, d_info, info_offset);

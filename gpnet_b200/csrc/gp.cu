@@ -346,13 +346,18 @@ int build_pstep(gpn_ctx* c, double a, int p, int want_grad) {
 // expm(-beta L~): scaling-and-squaring Pade (Al-Mohy & Higham 2009 order selection with exact 1-norms of the
 // even powers; the odd-power "ell" refinement of scipy is not needed for symmetric A), all
 // products symmetric, and Q X = P solved through the SPD inverse of Q (GPnet.py:340).
+int expm_of_mat0(gpn_ctx* c);
 int build_diffusion(gpn_ctx* c, double beta) {
     for (int i = 0; i < 8; ++i) GPN_TRY(ensure_mat(c, i));
+    GPN_TRY(laplacian_into(c, -beta, 0.0, mat(c, 0), c->ldN));
+    return expm_of_mat0(c);
+}
+// expm of the symmetric negative semi-definite N x N matrix in mat 0 (zero padded to ldN); result in mat[9]
+int expm_of_mat0(gpn_ctx* c) {
     const long ld = c->ldN;
     const int N = c->N;
     double *A = mat(c, 0), *A2 = mat(c, 1), *A4 = mat(c, 2), *A6 = mat(c, 3), *Z = mat(c, 4), *U = mat(c, 5), *V = mat(c, 6),
            *X8 = mat(c, 7);
-    GPN_TRY(laplacian_into(c, -beta, 0.0, A, ld));
     // Order selection with as few powers as possible (each power is an N^3 product): bounds ||A^(p+q)|| <= ||A^p|| ||A^q||
     // stand in for the powers that have not been formed yet, so the choice can only err towards a HIGHER order than
     // scipy's (which uses estimated norms), never a lower one.
@@ -472,7 +477,7 @@ int kernel_build(gpn_ctx* c, int kind, const double* theta_h, int P, int want_gr
     c->have_full = false;
     c->kind = kind;
     c->P = P;
-    for (int i = 0; i < P; ++i) c->theta_exp[i] = exp(theta_h[i]);     // GPnet.py:303
+    for (int i = 0; i < P; ++i) c->theta_exp[i] = theta_h[i];          // = np.exp(theta)[i] of GPnet.py:303, exponentiated by the HOST (A-4)
     c->ldN = pad128(c->N);
     GPN_TRY(clear_info(c));
     int st;
@@ -752,11 +757,12 @@ int ensure_perm(gpn_ctx* c) {
 int gpr_logp_grad_reglap_fast(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
     const int N = c->N, n = c->n_train;
     GPN_TRY(ensure_perm(c));
+    c->last_route = 1;
     GPN_TRY(ensure_vecs(c));
     c->have_full = false;                       // the resident full kernel is NOT formed on this path
     c->kind = GPN_KERNEL_REGULARIZED_LAPLACIAN;
     c->P = P;
-    for (int i = 0; i < P; ++i) c->theta_exp[i] = exp(theta_h[i]);
+    for (int i = 0; i < P; ++i) c->theta_exp[i] = theta_h[i];
     c->ldN = pad128(N);
     GPN_TRY(clear_info(c));
     const long ld = c->ldN, ldn = pad128(n);
@@ -879,11 +885,12 @@ void row_eval(const RowScalars& r, double noise, int P, int want_grad, double* o
 int gpr_reglap_schur_scalars(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, RowScalars* rs, int* info_h) {
     const int N = c->N, n = c->n_train;
     GPN_TRY(ensure_perm(c));
+    c->last_route = 2;
     GPN_TRY(ensure_vecs(c));
     c->have_full = false;
     c->kind = GPN_KERNEL_REGULARIZED_LAPLACIAN;
     c->P = P;
-    for (int i = 0; i < P; ++i) c->theta_exp[i] = exp(theta_h[i]);
+    for (int i = 0; i < P; ++i) c->theta_exp[i] = theta_h[i];
     c->ldN = pad128(N);
     GPN_TRY(clear_info(c));
     const long ld = c->ldN;
@@ -1013,7 +1020,7 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
     c->have_full = false;
     c->kind = GPN_KERNEL_REGULARIZED_LAPLACIAN;
     c->P = P;
-    for (int i = 0; i < P; ++i) c->theta_exp[i] = exp(theta_h[i]);
+    for (int i = 0; i < P; ++i) c->theta_exp[i] = theta_h[i];
     c->ldN = pad128(N);
     GPN_TRY(clear_info(c));
     const long ld = c->ldN, ldn = pad128(n);
@@ -1038,6 +1045,7 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
     GPN_TRY(ensure_nb(c, NB_S, 2, ld));
     double *z1 = nbp(c, NB_S), *zt = z1 + ld;
     const bool augmented = c->fast_reglap >= 4 && o >= 256 && n >= 256;
+    c->last_route = !augmented ? 3 : (c->fast_reglap >= 5 && c->dis_s > 0 ? 5 : 4);
     if (augmented) {
         // Both factorisations are small enough to be bound by their per-column dependency chain, so the triangular work that
         // follows them rides along in the same dataflow kernel as appended row blocks (potrf_dataflow.cu):
@@ -1186,6 +1194,7 @@ int gpr_logp_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const doub
                                    : gpr_logp_grad_reglap_fast(c, theta_h, P, t_h, want_grad, out_h, info_h);
     int st = kernel_build(c, kind, theta_h, P, want_grad);
     if (st != 0) return st;
+    c->last_route = 0;
     GPN_TRY(ensure_vecs(c));
     const int n = c->n_train;
     const long ldn = pad128(n);
@@ -1498,6 +1507,20 @@ int gpc_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const double* y
     return 0;
 }
 
+// the N x N scratch matrices belong to the bound graph's size: run `body` with the context temporarily sized for N
+template <class F>
+int with_matrix_size(gpn_ctx* c, int N, F body) {
+    const int N0 = c->N;
+    const long ld0 = c->ldN;
+    c->N = N;
+    c->ldN = pad128(N);
+    c->have_full = false;
+    const int st = body();
+    c->N = N0;
+    c->ldN = ld0;
+    return st;
+}
+
 }   // namespace
 
 // =====================================================================================================================
@@ -1508,6 +1531,7 @@ extern "C" {
 const char* gpn_last_error(void) { return g_last_error; }
 
 gpn_ctx* gpn_create(int device, void* cuda_stream) {
+    GPN_RANGE();
     if (cudaSetDevice(device) != cudaSuccess) {
         gpn_set_last_error(__FILE__, __LINE__, "cudaSetDevice failed (no CUDA device? this library has no CPU fallback)");
         return nullptr;
@@ -1587,6 +1611,7 @@ void gpn_destroy(gpn_ctx* c) {
 }
 
 int gpn_sync(gpn_ctx* c) {
+    GPN_RANGE();
     GPN_CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1598,6 +1623,7 @@ void gpn_reset_counters(gpn_ctx* c) {
 }
 
 int gpn_set_graph(gpn_ctx* c, int N, const int* indptr_h, const int* indices_h, const double* weights_h) {
+    GPN_RANGE();
     if (!c) return -1;
     if (N <= 0) return -2;
     if (!indptr_h) return -3;
@@ -1635,6 +1661,7 @@ int gpn_set_graph(gpn_ctx* c, int N, const int* indptr_h, const int* indices_h, 
 }
 
 int gpn_set_nodes(gpn_ctx* c, int n_train, const int* train_h, int n_test, const int* test_h) {
+    GPN_RANGE();
     if (!c) return -1;
     if (n_train < 0 || n_train > c->N) return -2;
     if (n_test < 0 || n_test > c->N) return -4;
@@ -1656,6 +1683,7 @@ int gpn_set_nodes(gpn_ctx* c, int n_train, const int* train_h, int n_test, const
 }
 
 int gpn_fp64_peak(gpn_ctx* c, double seconds, double* tflops_h) {
+    GPN_RANGE();
     if (!c) return -1;
     GPN_TRY(gpn_buf_ensure(c, c->partial, sizeof(double) * (size_t)c->num_sms * 512));
     cudaEvent_t e0, e1;
@@ -1685,6 +1713,7 @@ void gpn_debug_leaf_prof(gpn_ctx* c, void* dev_buf32) {
     if (c) c->leaf_prof = dev_buf32;
 }
 int gpn_debug_leaf_bench(gpn_ctx* c, void* A_dev, int copies, void* prof32_dev) {
+    GPN_RANGE();
     if (!c) return -1;
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)copies * 128 * 128));
     GPN_TRY(clear_info(c));
@@ -1711,6 +1740,7 @@ void gpn_set_profile(gpn_ctx* c, int on) {
 /* out_h[0..2] = summed duration (ms), executed flops and count of the GEMM launches recorded since gpn_set_profile(ctx,1);
  * out_h[3..5] = the same restricted to the 128x128 GEMM configuration; out_h[6..8] = the same for the dataflow Cholesky. */
 int gpn_profile_summary(gpn_ctx* c, double* out_h) {
+    GPN_RANGE();
     if (!c) return -1;
     GPN_CK(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < 9; ++i) out_h[i] = 0.0;
@@ -1725,6 +1755,7 @@ int gpn_profile_summary(gpn_ctx* c, double* out_h) {
 }
 
 int gpn_set_targets(gpn_ctx* c, const double* t_h, int n) {
+    GPN_RANGE();
     if (!c) return -1;
     if (n != c->n_train || n <= 0) return -3;
     GPN_TRY(ensure_vecs(c));
@@ -1732,6 +1763,7 @@ int gpn_set_targets(gpn_ctx* c, const double* t_h, int n) {
 }
 
 int gpn_laplacian_dense(gpn_ctx* c, double alpha, double gamma, double* out, long ld) {
+    GPN_RANGE();
     if (!c || c->N <= 0) return -1;
     if (ld < c->N || (ld & 1)) return -5;
     GPN_TRY(gpn_k_fill_zero(c, out, ld, c->N, c->N));
@@ -1742,16 +1774,20 @@ int gpn_laplacian_dense(gpn_ctx* c, double alpha, double gamma, double* out, lon
 
 int gpn_gemm_f64(gpn_ctx* c, int transa, int transb, int M, int N, int K, double alpha, const double* A, long lda, const double* B,
                  long ldb, double beta, double* C, long ldc) {
+    GPN_RANGE();
     if (!c) return -1;
     return gpn_gemm(c, M, N, K, alpha, A, lda, transa == 0, B, ldb, transb != 0, beta, C, ldc, 0);
 }
 
 int gpn_potrf_f64(gpn_ctx* c, int n, double* A, long lda, int* info_h) {
+    GPN_RANGE();
     if (!c) return -1;
     GPN_TRY(clear_info(c));
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(n) * 128));
     GPN_TRY(gpn_potrf(c, n, A, lda, (double*)c->winv.p, iscal(c, 0)));
     GPN_TRY(gpn_k_zero_upper(c, A, lda, n));
+    c->winv_for = A;             // gpn_trsm_f64 / gpn_potri_f64 may follow
+    c->winv_n = n;
     if (!info_h) return 0;       // asynchronous use: no read-back
     int info[16];
     GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
@@ -1760,12 +1796,14 @@ int gpn_potrf_f64(gpn_ctx* c, int n, double* A, long lda, int* info_h) {
 }
 
 int gpn_syrk_f64(gpn_ctx* c, int n, int k, double alpha, const double* A, long lda, double beta, double* C, long ldc) {
+    GPN_RANGE();
     if (!c) return -1;
     // C = alpha A A^T + beta C: lower tiles computed, mirrored into the upper ones (the result is the full symmetric matrix)
     return gpn_gemm(c, n, n, k, alpha, A, lda, true, A, lda, true, beta, C, ldc, GF_LOWER | GF_MIRROR);
 }
 
 int gpn_posv_f64(gpn_ctx* c, int n, double* A, long lda, double* B, long ldb, int brows, double* Winv_t, long ldw, int* info_h) {
+    GPN_RANGE();
     if (!c) return -1;
     if (n <= 0) return -2;
     if (B && brows <= 0) return -7;
@@ -1773,11 +1811,114 @@ int gpn_posv_f64(gpn_ctx* c, int n, double* A, long lda, double* B, long ldb, in
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(n) * 128));
     GPN_TRY(gpn_potrf_dataflow(c, n, A, lda, (double*)c->winv.p, iscal(c, 0), 0, B, ldb, brows, Winv_t, ldw));
     GPN_TRY(gpn_k_zero_upper(c, A, lda, n));
+    c->winv_for = A;
+    c->winv_n = n;
     if (!info_h) return 0;
     int info[16];
     GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
     *info_h = info[0];
     return 0;
+}
+
+/* B <- B L^-T for the brows x n row-major B and the factor L left in A by the gpn_potrf_f64 / gpn_posv_f64 call that
+ * immediately precedes on this context (the inverted diagonal blocks it produced are still resident). */
+int gpn_trsm_f64(gpn_ctx* c, int n, const double* L, long ldl, double* B, long ldb, int brows) {
+    GPN_RANGE();
+    if (!c) return -1;
+    if (n <= 0 || c->winv_for != (const void*)L || c->winv_n != n) return -2;
+    if (brows <= 0) return -7;
+    const void* keep = c->winv_for;
+    int st = gpn_trsm(c, brows, n, B, ldb, L, ldl, (const double*)c->winv.p);
+    c->winv_for = keep;
+    return st;
+}
+
+/* out = (L L^T)^-1 (full symmetric) from the factor L of the immediately preceding gpn_potrf_f64 / gpn_posv_f64 (LAPACK potri). */
+int gpn_potri_f64(gpn_ctx* c, int n, const double* L, long ldl, double* out, long ldo) {
+    GPN_RANGE();
+    if (!c) return -1;
+    if (n <= 0 || c->winv_for != (const void*)L || c->winv_n != n) return -2;
+    const long ldw = pad128(n);
+    GPN_TRY(ensure_nb(c, NB_W, ldw, ldw));
+    GPN_TRY(ensure_nb(c, NB_WT, ldw, ldw));
+    GPN_TRY(ensure_nb(c, NB_T, ldw, ldw));
+    GPN_TRY(gpn_trtri(c, n, L, ldl, (const double*)c->winv.p, nbp(c, NB_W), nbp(c, NB_WT), nbp(c, NB_T), ldw));
+    return gpn_lauum_t(c, n, nbp(c, NB_WT), ldw, out, ldo, true);
+}
+
+
+/* out = expm(A) for a symmetric negative semi-definite N x N device matrix A (scaling-and-squaring Pade, GPnet.py:340);
+ * m_used / s_used (host, may be NULL) receive the Pade order and the number of squarings. */
+int gpn_expm_sym_f64(gpn_ctx* c, int N, const double* A, long lda, double* out, long ldo, int* m_used, int* s_used) {
+    GPN_RANGE();
+    if (!c) return -1;
+    if (N <= 0) return -2;
+    const int st = with_matrix_size(c, N, [&]() -> int {
+        for (int i = 0; i < 8; ++i) GPN_TRY(ensure_mat(c, i));
+        GPN_TRY(clear_info(c));
+        GPN_TRY(gpn_k_fill_zero(c, mat(c, 0), c->ldN, (int)c->ldN, (int)c->ldN));
+        GPN_TRY(gpn_k_copy(c, N, N, A, lda, mat(c, 0), c->ldN));
+        GPN_TRY(expm_of_mat0(c));
+        GPN_TRY(gpn_k_copy(c, N, N, kfull(c), c->ldN, out, ldo));
+        return gpn_sync(c);
+    });
+    if (m_used) *m_used = c->expm_m;
+    if (s_used) *s_used = c->expm_s;
+    return st;
+}
+
+/* out = B^p for a symmetric N x N device matrix B (numpy's binary powering order, GPnet.py:346); out_pm1 (may be NULL)
+ * receives B^(p-1), the by-product the p-step derivative needs. */
+int gpn_matpow_f64(gpn_ctx* c, int N, const double* B, long ldb, int p, double* out, long ldo, double* out_pm1, long ldo1) {
+    GPN_RANGE();
+    if (!c) return -1;
+    if (N <= 0) return -2;
+    if (p < 0) return -5;
+    return with_matrix_size(c, N, [&]() -> int {
+        for (int i = 0; i < 7; ++i) GPN_TRY(ensure_mat(c, i));
+        const long ld = c->ldN;
+        GPN_TRY(gpn_k_fill_zero(c, mat(c, 0), ld, (int)ld, (int)ld));
+        GPN_TRY(gpn_k_copy(c, N, N, B, ldb, mat(c, 0), ld));
+        auto identity = [&](double* dst, long ldd) -> int {
+            GPN_TRY(gpn_k_fill_zero(c, mat(c, 5), ld, (int)ld, (int)ld));
+            const double* X[1] = {mat(c, 0)};
+            const long l1[1] = {ld};
+            const double cf[1] = {0.0};
+            GPN_TRY(gpn_k_lincomb(c, N, mat(c, 5), ld, 1.0, 1, X, l1, cf));
+            return gpn_k_copy(c, N, N, mat(c, 5), ld, dst, ldd);
+        };
+        const double* res = nullptr;
+        if (p == 0) {
+            GPN_TRY(identity(out, ldo));
+            if (out_pm1) return -8;                               // B^-1 is not a power
+            return gpn_sync(c);
+        }
+        if (out_pm1 && p >= 2) {
+            GPN_TRY(matpow(c, mat(c, 0), p - 1, mat(c, 1), mat(c, 2), mat(c, 3), mat(c, 6), &res));
+            if (res != mat(c, 4)) GPN_TRY(gpn_k_copy(c, N, N, res, ld, mat(c, 4), ld));
+            GPN_TRY(symm_mul(c, mat(c, 4), mat(c, 0), mat(c, 5)));
+            GPN_TRY(gpn_k_copy(c, N, N, mat(c, 4), ld, out_pm1, ldo1));
+            GPN_TRY(gpn_k_copy(c, N, N, mat(c, 5), ld, out, ldo));
+            return gpn_sync(c);
+        }
+        GPN_TRY(matpow(c, mat(c, 0), p, mat(c, 1), mat(c, 2), mat(c, 3), mat(c, 6), &res));
+        GPN_TRY(gpn_k_copy(c, N, N, res, ld, out, ldo));
+        if (out_pm1) GPN_TRY(identity(out_pm1, ldo1));           // p == 1: B^0
+        return gpn_sync(c);
+    });
+}
+
+/* Route the last gpn_gpr_logp_grad / landscape evaluation took (see gpn_set_fast_paths; -1: none yet).  parts_h (may be NULL,
+ * room for 10 ints): [number of parts of the node dissection used (0: none), separator size, part sizes...]. */
+int gpn_last_route(gpn_ctx* c, int* parts_h) {
+    if (!c) return -1;
+    if (parts_h) {
+        for (int i = 0; i < 10; ++i) parts_h[i] = 0;
+        if (c->last_route == 5) {
+            parts_h[0] = 2; parts_h[1] = c->dis_s; parts_h[2] = c->dis_a; parts_h[3] = c->dis_b;
+        }
+    }
+    return c->last_route;
 }
 
 long long gpn_workspace_bytes(int N, int n, int m, int kind) {
@@ -1795,6 +1936,7 @@ long long gpn_workspace_bytes(int N, int n, int m, int kind) {
 }
 
 int gpn_spd_inverse_f64(gpn_ctx* c, int n, double* A, long lda, double* out, long ldo, double* work, int* info_h) {
+    GPN_RANGE();
     if (!c) return -1;
     if (lda != ldo) return -6;
     GPN_TRY(clear_info(c));
@@ -1812,11 +1954,13 @@ int gpn_spd_inverse_f64(gpn_ctx* c, int n, double* A, long lda, double* out, lon
 
 int gpn_gather_block_add(gpn_ctx* c, const double* K, long ld, const int* rows, int nr, const int* cols, int nc, double addc,
                          double* out, long ldo) {
+    GPN_RANGE();
     if (!c) return -1;
     return gpn_k_gather(c, K, ld, rows, nr, cols, nc, addc, out, ldo, nr, nc);
 }
 
 int gpn_kernel_build(gpn_ctx* c, int kind, const double* theta_h, int P, int want_grad) {
+    GPN_RANGE();
     if (!c) return -1;
     return kernel_build(c, kind, theta_h, P, want_grad);
 }
@@ -1831,8 +1975,13 @@ void gpn_expm_info(gpn_ctx* c, int* m, int* s) {
 }
 
 int gpn_kernel_block_h(gpn_ctx* c, const int* rows_h, int nr, const int* cols_h, int nc, double addc, double* out_h) {
+    GPN_RANGE();
     if (!c || !c->have_full) return -1;
     if (nr <= 0 || nc <= 0) return 0;
+    for (int i = 0; i < nr; ++i)
+        if (rows_h[i] < 0 || rows_h[i] >= c->N) return -2;      // the reference's np.delete / indexing raises IndexError
+    for (int i = 0; i < nc; ++i)
+        if (cols_h[i] < 0 || cols_h[i] >= c->N) return -4;
     DevBuf& ib = c->partial;
     const long ldo = (nc + 1) & ~1L;
     GPN_TRY(gpn_buf_ensure(c, ib, sizeof(int) * (size_t)(nr + nc + 2)));
@@ -1847,17 +1996,20 @@ int gpn_kernel_block_h(gpn_ctx* c, const int* rows_h, int nr, const int* cols_h,
 }
 
 int gpn_gpr_logp_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
+    GPN_RANGE();
     if (!c) return -1;
     return gpr_logp_grad(c, kind, theta_h, P, t_h, want_grad, out_h, info_h);
 }
 
 int gpn_gpr_predict(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, double* alpha_h, double* fstar_h, double* s_h,
                     double* kss_diag_h, int* info_h) {
+    GPN_RANGE();
     if (!c) return -1;
     return gpr_predict(c, kind, theta_h, P, t_h, alpha_h, fstar_h, s_h, kss_diag_h, info_h);
 }
 
 int gpn_gpr_fetch(gpn_ctx* c, int which, double* out_h) {
+    GPN_RANGE();
     if (!c || !c->have_full) return -1;
     const int n = c->n_train, m = c->n_test;
     const long ldn = pad128(n), ldm = pad128(m);
@@ -1882,6 +2034,7 @@ int gpn_gpr_fetch(gpn_ctx* c, int which, double* out_h) {
 
 int gpn_gpc_newton(gpn_ctx* c, int kind, const double* theta_h, int P, const double* y_h, int n, const double* K_dev, long ldk, double tol,
                    double phif0, double scale, int variant, double* f_h, double* a_h, double* logq_h, int* iters_h, int* info_h) {
+    GPN_RANGE();
     if (!c) return -1;
     const double* K = K_dev;
     if (K == nullptr) {
@@ -1901,6 +2054,7 @@ int gpn_gpc_newton(gpn_ctx* c, int kind, const double* theta_h, int P, const dou
 
 int gpn_gpc_predict(gpn_ctx* c, int kind, const double* theta_h, int P, const double* y_h, double* f_h, double* a_h, double* logq_h,
                     int* iters_h, double* fstar_h, double* V_h, double* pistar_h, int* info_h) {
+    GPN_RANGE();
     if (!c) return -1;
     int st = kernel_build(c, kind, theta_h, P, 0);
     if (st != 0) return st;
@@ -1941,6 +2095,7 @@ int gpn_gpc_predict(gpn_ctx* c, int kind, const double* theta_h, int P, const do
 }
 
 int gpn_gpc_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const double* y_h, double* out_h, int* iters_h, int* info_h) {
+    GPN_RANGE();
     if (!c) return -1;
     if (c->n_train <= 0) return -1;
     return gpc_grad(c, kind, theta_h, P, y_h, out_h, iters_h, info_h);
@@ -1948,6 +2103,7 @@ int gpn_gpc_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const doubl
 
 int gpn_landscape_points(gpn_ctx* c, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1, const double* ax1_h, int n1,
                          const double* ax2_h, int n2, const double* t_h, const long* idx_h, long count, int want_grad, double* out_h) {
+    GPN_RANGE();
     if (!c) return -1;
     if (P < 1 || P > 8) return -5;
     if (ax0 < 0 || ax0 >= P) return -6;
@@ -1993,7 +2149,7 @@ int gpn_landscape_points(gpn_ctx* c, int kind, int classifier, const double* the
                     row_ok = info == 0 && std::isfinite(rs.half_logdet) && std::isfinite(rs.s);
                 }
                 if (row_ok) {
-                    row_eval(rs, exp(th[last]), P, want_grad, tmp);
+                    row_eval(rs, th[last], P, want_grad, tmp);
                     o[0] = -tmp[0];
                     if (want_grad)
                         for (int j = 0; j < P; ++j) o[1 + j] = -tmp[1 + j];
@@ -2018,7 +2174,7 @@ int gpn_landscape_points(gpn_ctx* c, int kind, int classifier, const double* the
                 if (st != 0) return st;
                 have_row = true;
             } else {
-                c->theta_exp[last] = exp(th[last]);     // same kernel, new noise
+                c->theta_exp[last] = th[last];          // same kernel, new noise
                 GPN_TRY(clear_info(c));
             }
             GPN_TRY(gpc_train_block(c));
@@ -2034,6 +2190,7 @@ int gpn_landscape_points(gpn_ctx* c, int kind, int classifier, const double* the
 int gpn_landscape(gpn_ctx* c, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1, const double* ax1_h, int n1,
                   const double* ax2_h, int n2, const double* t_h, long idx_begin, long idx_end, long idx_stride, int want_grad,
                   double* out_h) {
+    GPN_RANGE();
     if (idx_stride <= 0) return -15;
     std::vector<long> idx;
     for (long i = idx_begin; i < idx_end && i < (long)n1 * n2; i += idx_stride) idx.push_back(i);

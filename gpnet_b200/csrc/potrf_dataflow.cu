@@ -428,6 +428,7 @@ int encode_tiles(gpn_ctx* c, CUtensorMap* tm, const double* ptr, long ld, long r
 int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset, double* B, long ldb, int brows,
                        double* Wt, long ldwt, int slot) {
     // slot 1: own flag / counter buffer, for a factorisation that runs concurrently with another one (side stream)
+    c->winv_for = nullptr;
     DevBuf& fbuf = slot ? c->flags2 : c->flags;
     int& fepoch = slot ? c->epoch2 : c->epoch;
     long& frows = slot ? c->flags_rows2 : c->flags_rows;

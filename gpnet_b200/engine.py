@@ -44,7 +44,12 @@ def register_context(ctx: Context) -> Context:
 
 def graph_csr(G, weight="weight"):
     """CSR adjacency in ``list(G)`` order (what nx.normalized_laplacian_matrix(G) uses at GPnet.py:329);
-    a self-loop contributes once to its row, undirected edges appear in both rows."""
+    a self-loop contributes once to its row, undirected edges appear in both rows, parallel edges of a MultiGraph
+    are summed into one entry (as ``nx.to_scipy_sparse_array`` does).  Directed graphs raise the same
+    ``NetworkXNotImplemented`` the reference's ``nx.normalized_laplacian_matrix`` call raises for them."""
+    if G.is_directed():
+        import networkx as nx
+        raise nx.NetworkXNotImplemented("not implemented for directed type")
     nodelist = list(G)
     pos = {u: i for i, u in enumerate(nodelist)}
     N = len(nodelist)
@@ -60,10 +65,41 @@ def graph_csr(G, weight="weight"):
     wts = np.asarray(wts, dtype=np.float64)
     order = np.lexsort((dst, src))
     src, dst, wts = src[order], dst[order], wts[order]
+    if len(src) > 1:            # coalesce duplicate (i, j) entries: one CSR entry per matrix entry
+        first = np.ones(len(src), dtype=bool)
+        first[1:] = (src[1:] != src[:-1]) | (dst[1:] != dst[:-1])
+        if not first.all():
+            group = np.cumsum(first) - 1
+            wts = np.bincount(group, weights=wts)
+            src, dst = src[first], dst[first]
     indptr = np.zeros(N + 1, dtype=np.int64)
     np.add.at(indptr, src + 1, 1)
     indptr = np.cumsum(indptr)
     return indptr.astype(np.int32), dst.astype(np.int32), wts, nodelist, pos
+
+
+class PredictToken:
+    """Marks the device buffers a regressor's predict() left behind (k, kstar, L, v, kstarstar are fetched lazily)."""
+
+    def __init__(self, model):
+        import weakref
+        self.model = weakref.ref(model)
+
+
+def invalidate_predict(ctx):
+    """Call before ANY device call that may reuse the buffers of the last predict(): the model that owns them copies its
+    not-yet-fetched attributes to the host first, so they stay readable afterwards like the reference's host arrays
+    (GPnetRegressor.py:89-128 keeps k, kstar, kstarstar, L, v, V as ndarray attributes forever)."""
+    tok = ctx._predict_token
+    ctx._predict_token = None
+    if tok is not None:
+        model = tok.model()
+        if model is not None:
+            ctx._predict_token = tok          # the fetches below check it
+            try:
+                model._materialize()
+            finally:
+                ctx._predict_token = None
 
 
 class GraphEngine:
@@ -85,6 +121,7 @@ class GraphEngine:
     def bind(self, train_pos=None, test_pos=None) -> Context:
         ctx = self.ctx
         if ctx._owner is not self:
+            invalidate_predict(ctx)
             ctx.set_graph(self.indptr, self.indices, self.weights)
             ctx._owner = self
             ctx._nodes_key = None
@@ -92,6 +129,7 @@ class GraphEngine:
         if train_pos is not None:
             key = (tuple(train_pos), tuple(test_pos or ()))
             if ctx._nodes_key != key:
+                invalidate_predict(ctx)       # a pending predict() snapshot needs the node sets it was computed with
                 ctx.set_nodes(train_pos, test_pos or ())
                 ctx._nodes_key = key
         return ctx
@@ -107,6 +145,9 @@ class GraphEngine:
         if hit is not None:
             return hit
         out = sorted({int(x) for x in nodes}) if relabelled else sorted({self.pos[x] for x in nodes})
+        if out and (out[0] < 0 or out[-1] >= self.N):      # the reference's np.delete / fancy indexing raises IndexError
+            bad = out[0] if out[0] < 0 else out[-1]
+            raise IndexError(f"index {bad} is out of bounds for axis 0 with size {self.N}")
         if key is not None:
             if len(self._pos_cache) > 8:
                 self._pos_cache.clear()
@@ -121,7 +162,7 @@ class GraphEngine:
         if ctx._kernel_key == key:
             return ctx
         ctx._kernel_key = None
-        ctx._predict_token = None
+        invalidate_predict(ctx)
         st = ctx.kernel_build(KERNEL_IDS[kerneltype], th, want_grad)
         raise_domain(st)
         ctx._kernel_key = key

@@ -45,7 +45,39 @@ def shard_indices(keys: np.ndarray, rank: int, world: int) -> np.ndarray:
     return np.nonzero(inverse % world == rank)[0].astype(np.int64)
 
 
-def allgather_rows(local: np.ndarray, total: int, rank: int, world: int, dist, group=None, shards=None) -> np.ndarray:
+def _comm_device(dist, group, device_index=None):
+    """Device of the tensors a collective of this group needs: the GPU of the library context for NCCL, the host for gloo."""
+    import torch
+    if dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device() if device_index is None else int(device_index))
+    return torch.device("cpu")
+
+
+_ERR_CODES = {1: (AssertionError, "Lambda must be < 1"), 2: (AssertionError, "a must be >=2"),
+              3: (RuntimeError, "hyper-parameter evaluation failed on another rank")}
+
+
+def agree_on_error(err, world, dist, group=None, device_index=None):
+    """Every rank learns whether ANY rank failed (max-reduce of a small code) and raises the same kind of exception, instead of
+    the healthy ranks blocking forever in the all-gather that follows.  ``err``: the local exception or None."""
+    code = 0
+    if err is not None:
+        code = 3
+        if isinstance(err, AssertionError):
+            code = 2 if str(err).startswith("a must be") else 1
+    if world > 1 and dist is not None:
+        import torch
+        flag = torch.tensor([code], dtype=torch.int32, device=_comm_device(dist, group, device_index))
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        code = int(flag.item())
+    if err is not None:
+        raise err
+    if code:
+        exc, msg = _ERR_CODES[code]
+        raise exc(msg)
+
+
+def allgather_rows(local: np.ndarray, total: int, rank: int, world: int, dist, group=None, shards=None, device_index=None) -> np.ndarray:
     """Reassemble ``total`` rows from per-rank shards: ``shards[r]`` lists the row indices rank r holds (default: the cyclic
     split r, r+world, ...).  One all-gather of equal-sized (padded) blocks."""
     width = local.shape[1]
@@ -55,8 +87,7 @@ def allgather_rows(local: np.ndarray, total: int, rank: int, world: int, dist, g
     if shards is None:
         shards = [np.arange(r, total, world) for r in range(world)]
     per = max(max(len(sh) for sh in shards), 1)
-    backend = dist.get_backend(group)
-    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    device = _comm_device(dist, group, device_index)
     send = torch.zeros((per, width), dtype=torch.float64, device=device)
     send[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(device)
     recv = torch.empty((world * per, width), dtype=torch.float64, device=device)
@@ -69,9 +100,10 @@ def allgather_rows(local: np.ndarray, total: int, rank: int, world: int, dist, g
 
 
 def _bound_context(model):
+    from .engine import invalidate_predict
     ctx = model._engine.bind(model._positions(model.training_nodes), model._positions(model.test_nodes))
     ctx._kernel_key = None
-    ctx._predict_token = None
+    invalidate_predict(ctx)
     return ctx
 
 
@@ -114,8 +146,15 @@ def sharded_landscape(model, theta, axidx, ax1, ax2, want_grad=False, group=None
     P = len(model._theta_vec(theta))
     keys = kernel_group_keys(n1, n2, axidx, P, model.kerneltype)
     shards = [shard_indices(keys, r, world) for r in range(world)]
-    local = evaluate_points(model, theta, axidx, ax1, ax2, shards[rank], want_grad)
-    full = allgather_rows(local, total, rank, world, dist, group, shards)
+    err, local = None, np.zeros((len(shards[rank]), 1 + P))
+    try:
+        local = evaluate_points(model, theta, axidx, ax1, ax2, shards[rank], want_grad)
+    except Exception as e:      # e.g. a diffusion axis reaching exp(theta0) >= 1 on this rank's points only
+        err = e
+    dev = getattr(model._engine, "_ctx", None)
+    dev = dev.device if dev is not None else None
+    agree_on_error(err, world, dist, group, dev)
+    full = allgather_rows(local, total, rank, world, dist, group, shards, dev)
     return full.reshape(n1, n2, -1)
 
 

@@ -13,7 +13,12 @@
  *    sub-matrix column offset must be even and base pointers 16-byte aligned (TMA stride rule);
  *  - return value: 0 ok; >0 LAPACK-style info (order of the leading minor that is not positive definite);
  *    <0 bad argument (-i = i-th argument); <= -1000 CUDA/driver error (gpn_last_error() has the text);
- *  - never throws, never calls back into the host language.
+ *  - never throws, never calls back into the host language;
+ *  - hyper-parameters cross the boundary EXPONENTIATED: every `etheta_h` (and the landscape axes) holds np.exp(theta), the
+ *    vector the reference itself computes first (`theta = np.exp(theta)`, GPnet.py:303).  The host evaluates that expression
+ *    with numpy so that the p-step order int(np.exp(theta)[1]) (GPnet.py:347, quirk A-4) and the domain asserts
+ *    (GPnet.py:339,344) see exactly the reference's values: libm's exp differs from numpy's by an ulp on some inputs;
+ *  - every entry point that enqueues device work opens an NVTX range named after itself (visible to nsys / ncu --nvtx).
  */
 #ifndef GPNET_B200_H
 #define GPNET_B200_H
@@ -87,6 +92,20 @@ int gpn_syrk_f64(gpn_ctx* ctx, int n, int k, double alpha, const double* A, long
  * 141-144 and GPnetClassifier.py:110-119 in one launch; the appended rows fill the SMs the Cholesky's dependency chain
  * leaves idle.  All leading dimensions even, bases 16-byte aligned. */
 int gpn_posv_f64(gpn_ctx* ctx, int n, double* A, long lda, double* B, long ldb, int brows, double* Winv_t, long ldw, int* info_h);
+/* B <- B L^-T (brows x n, row-major) with the factor L that the gpn_potrf_f64 / gpn_posv_f64 call IMMEDIATELY preceding on
+ * this context left in place (its inverted diagonal blocks are still resident; -2 otherwise): the triangular solves
+ * np.linalg.solve(L, .) of GPnetRegressor.py:124,126,144 and GPnetClassifier.py:117-119,161-162,211 as a TRSM. */
+int gpn_trsm_f64(gpn_ctx* ctx, int n, const double* L, long ldl, double* B, long ldb, int brows);
+/* out = (L L^T)^-1, full symmetric, from the factor of the immediately preceding gpn_potrf_f64 / gpn_posv_f64 (LAPACK potri):
+ * the explicit K^-1 of the intended gradient (old_implementation/GPR.py:56) and the inv(K) of GPnetClassifier.py:126. */
+int gpn_potri_f64(gpn_ctx* ctx, int n, const double* L, long ldl, double* out, long ldo);
+/* out = expm(A) for a symmetric negative semi-definite N x N matrix (Pade 3/5/7/9/13 with scaling and squaring, all products
+ * on the DMMA GEMM): the scipy.linalg.expm of GPnet.py:340 as a primitive.  m_used_h / s_used_h (may be NULL): Pade order and
+ * number of squarings.  Synchronises.  Uses the context's N x N scratch (a resident full kernel is dropped). */
+int gpn_expm_sym_f64(gpn_ctx* ctx, int N, const double* A, long lda, double* out, long ldo, int* m_used_h, int* s_used_h);
+/* out = B^p for a symmetric N x N matrix in numpy's binary-powering order (np.linalg.matrix_power, GPnet.py:346); out_pm1
+ * (may be NULL) receives B^(p-1), the by-product of the p-step kernel's derivative.  Synchronises; scratch as above. */
+int gpn_matpow_f64(gpn_ctx* ctx, int N, const double* B, long ldb, int p, double* out, long ldo, double* out_pm1, long ldo1);
 /* Upper bound of the device memory (bytes) a context allocates for a model with N graph nodes, n training and m test nodes
  * and the given kernel (host-only arithmetic, no context required): lets a caller size shards for the 180 GB of one B200
  * (C5: N = 32768, n = m = 16384, diffusion -> 1.2e11; measured 1.06e11 for the regressor alone). */
@@ -96,15 +115,16 @@ int gpn_gather_block_add(gpn_ctx* ctx, const double* K, long ld, const int* rows
                          double addc, double* out, long ldo);
 
 /* ---- full kernel (GPnet.py:335-349) ------------------------------------------------------------------------ */
-/* Builds the N x N kernel for log-parameters theta_h[0..P) and keeps it resident.  Parameter-domain violations
- * return -100 (diffusion: exp(theta0) >= 1, GPnet.py:339) / -101 (p-step: exp(theta0) < 2, GPnet.py:344) so the
+/* Builds the N x N kernel for the parameters etheta_h[0..P) = np.exp(theta) and keeps it resident.  Parameter-domain
+ * violations return -100 (diffusion: exp(theta0) >= 1, GPnet.py:339) / -101 (p-step: exp(theta0) < 2, GPnet.py:344) so the
  * host can raise the reference's AssertionError.  want_grad keeps the derivative by-products. */
-int gpn_kernel_build(gpn_ctx* ctx, int kind, const double* theta_h, int P, int want_grad);
+int gpn_kernel_build(gpn_ctx* ctx, int kind, const double* etheta_h, int P, int want_grad);
 /* device pointer / leading dimension of the resident full kernel */
 const double* gpn_kernel_ptr(gpn_ctx* ctx, long* ld);
 /* Pade order and number of squarings used by the last diffusion build */
 void gpn_expm_info(gpn_ctx* ctx, int* m, int* s);
-/* K[rows][cols] + addc copied to the host (the return value of GPnetBase.kernel, GPnet.py:362-367) */
+/* K[rows][cols] + addc copied to the host (the return value of GPnetBase.kernel, GPnet.py:362-367); positions outside
+ * [0, N) return -2 (rows) / -4 (columns): the reference raises IndexError there */
 int gpn_kernel_block_h(gpn_ctx* ctx, const int* rows_h, int nr, const int* cols_h, int nc, double addc, double* out_h);
 
 /* ---- GP regression (GPnetRegressor.py:79-150) ---------------------------------------------------------------- */
@@ -112,11 +132,11 @@ int gpn_kernel_block_h(gpn_ctx* ctx, const int* rows_h, int nr, const int* cols_
  * -inf); with want_grad, out_h[1..P] = d(-logp)/d theta_j (analytic form of old_implementation/GPR.py:52-64).
  * Rebuilds the full kernel from theta (as the reference does on every call). t_h: n_train un-shifted targets
  * (NULL: the resident targets of gpn_set_targets). */
-int gpn_gpr_logp_grad(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* t_h, int want_grad,
+int gpn_gpr_logp_grad(gpn_ctx* ctx, int kind, const double* etheta_h, int P, const double* t_h, int want_grad,
                       double* out_h, int* info_h);
 /* GPnetRegressor.predict body (:86-128).  Outputs (host): alpha[n], fstar[m], s[m] (sqrt of the predictive
  * variance), kss_diag[m]; info_h[0]: Cholesky info of k, info_h[1]: info of kstarstar (the two PD gates, A-7). */
-int gpn_gpr_predict(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* t_h, double* alpha_h,
+int gpn_gpr_predict(gpn_ctx* ctx, int kind, const double* etheta_h, int P, const double* t_h, double* alpha_h,
                     double* fstar_h, double* s_h, double* kss_diag_h, int* info_h);
 /* after gpn_gpr_predict: which = 0 k (n x n), 1 kstar (m x n), 2 L (n x n), 3 v (n x m), 4 kstarstar (m x m) */
 int gpn_gpr_fetch(gpn_ctx* ctx, int which, double* out_h);
@@ -133,36 +153,40 @@ int gpn_gpr_fetch(gpn_ctx* ctx, int which, double* out_h);
  *   5  (default) as 4, with M_oo^-1 assembled from two independent halves of a level-set dissection of the other nodes (two
  *      concurrent half-size factorisations and a rank-|separator| correction); falls back to 4 where no thin separator exists. */
 void gpn_set_fast_paths(gpn_ctx* ctx, int level);
+/* Route the last regressor likelihood evaluation (gpn_gpr_logp_grad, landscape rows) actually took, after the fallbacks a
+ * level applies on its own (e.g. 5 -> 4 where the other nodes have no thin separator); -1 before the first evaluation.
+ * parts_h (may be NULL; room for 10 ints): [parts of the node dissection used (0: none), separator size, part sizes ...]. */
+int gpn_last_route(gpn_ctx* ctx, int* parts_h);
 
 /* ---- GP classification, Laplace approximation (GPnetClassifier.py:90-147,184-240) ---------------------------- */
 /* Newton loop on K = kernel(train,train) (built from theta unless K_dev != NULL, in which case the n x n device
  * matrix is used as is -- the notebook KAT path).  variant 0 = GPnetClassifier.py:138-145 logq, 1 = the older
  * expression of scripts/prova.py:197-200.  Outputs (host): f[n], a[n], logq, iterations. */
-int gpn_gpc_newton(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* y_h, int n, const double* K_dev,
+int gpn_gpc_newton(gpn_ctx* ctx, int kind, const double* etheta_h, int P, const double* y_h, int n, const double* K_dev,
                    long ldk, double tol, double phif0, double scale, int variant, double* f_h, double* a_h, double* logq_h,
                    int* iters_h, int* info_h);
 /* GPnetClassifier.predict (:184-233): Newton + fstar[m], V[m], pi_star[m] */
-int gpn_gpc_predict(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* y_h, double* f_h, double* a_h,
+int gpn_gpc_predict(gpn_ctx* ctx, int kind, const double* etheta_h, int P, const double* y_h, double* f_h, double* a_h,
                     double* logq_h, int* iters_h, double* fstar_h, double* V_h, double* pistar_h, int* info_h);
 
 /* GPnetClassifier.gradLogPosterior (:149-182, RW Alg. 5.1 as written there) with the derivative kernels of SURVEY App. C:
  * out_h[0] = -logq (as logPosterior), out_h[1..P] = -gradZ. */
-int gpn_gpc_grad(gpn_ctx* ctx, int kind, const double* theta_h, int P, const double* y_h, double* out_h, int* iters_h,
+int gpn_gpc_grad(gpn_ctx* ctx, int kind, const double* etheta_h, int P, const double* y_h, double* out_h, int* iters_h,
                  int* info_h);
 
 /* ---- landscape (GPnet.py:539-552) ------------------------------------------------------------------------------ */
-/* For the `count` flat grid indices idx_h[q] (idx = i1*n2 + i2): theta[ax0] = ax1_h[i1], theta[ax1] = ax2_h[i2] (in this
- * order, as the reference writes them); out_h[q*(1+P) ..] = (lml = +logp, dlogp/dtheta) (gradient only if want_grad).
+/* For the `count` flat grid indices idx_h[q] (idx = i1*n2 + i2): etheta[ax0] = ax1_h[i1], etheta[ax1] = ax2_h[i2] (in this
+ * order, as the reference writes them; the axes are exponentiated by the host like etheta_h); out_h[q*(1+P) ..] = (lml = +logp, dlogp/dtheta) (gradient only if want_grad).
  * classifier != 0 evaluates the Laplace loop's logq instead (y in t_h; no gradient).
  * Points that differ only in the noise entry theta[P-1] share their kernel (the noise is added to every entry, quirk A-3):
  * they are evaluated back to back with ONE kernel build, and for the regressor with ONE factorisation of K_tt -- K_y is a
  * rank-one update of it, so every noise value of a grid row is host arithmetic on seven device reductions.
  * gpn_set_fast_paths(ctx, 0) restores one independent evaluation per point.  Used by the multi-GPU sharded landscape. */
-int gpn_landscape_points(gpn_ctx* ctx, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1,
+int gpn_landscape_points(gpn_ctx* ctx, int kind, int classifier, const double* etheta_h, int P, int ax0, int ax1,
                          const double* ax1_h, int n1, const double* ax2_h, int n2, const double* t_h, const long* idx_h,
                          long count, int want_grad, double* out_h);
 /* The same for idx = idx_begin + q*idx_stride < idx_end. */
-int gpn_landscape(gpn_ctx* ctx, int kind, int classifier, const double* theta_h, int P, int ax0, int ax1, const double* ax1_h,
+int gpn_landscape(gpn_ctx* ctx, int kind, int classifier, const double* etheta_h, int P, int ax0, int ax1, const double* ax1_h,
                   int n1, const double* ax2_h, int n2, const double* t_h, long idx_begin, long idx_end, long idx_stride,
                   int want_grad, double* out_h);
 

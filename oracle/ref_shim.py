@@ -1,7 +1,13 @@
 """Run the UNMODIFIED reference classes (filippocastelli/GPnet, mounted read-only at /root/reference in
 the build container) under the three shims of SURVEY.md Appendix B.  TEST INFRASTRUCTURE ONLY
-(see oracle/__init__.py); used by oracle/make_golden.py to produce tests/golden/*.npz.  The reference
-does not exist on the GPU box, so nothing imported by -m gpu tests, smoke() or bench.py touches this.
+(see oracle/__init__.py); used by oracle/make_golden.py to produce tests/golden/*.npz and by
+``bench.py --impl reference`` to time the literal reference on the GPU box's host cores.
+
+/root/reference does not exist on the GPU box.  ``oracle/make_ref.py`` (run by ``__graft_entry__.build()`` in the
+build container) compiles the three reference modules of the hot path, unmodified and from where they lie, to
+bytecode under ``oracle/_ref/`` -- git-ignored build output, not gpurun-ignored, so it travels to the box like the
+built ``.so``.  ``find_reference()`` returns whichever of the two locations exists; the -m gpu tests and ``smoke()``
+never import this module.
 
 Shims (none edits a reference file):
  1. a stub ``matplotlib`` package (the reference imports pyplot/pylab/lines at module level,
@@ -21,7 +27,21 @@ import scipy.linalg
 import scipy.sparse
 import scipy.sparse.linalg
 
+import os
+
 REFERENCE_PATH = "/root/reference"
+VENDORED_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_MODULES = ("GPnet.py", "GPnetRegressor.py", "GPnetClassifier.py")
+
+
+def find_reference():
+    """Directory the reference modules import from: the read-only source mount (build container) or the compiled copy
+    oracle/_ref (GPU box); None when neither exists."""
+    if all(os.path.exists(os.path.join(REFERENCE_PATH, f)) for f in REFERENCE_MODULES):
+        return REFERENCE_PATH
+    if all(os.path.exists(os.path.join(VENDORED_PATH, f + "c")) for f in REFERENCE_MODULES):
+        return VENDORED_PATH
+    return None
 
 
 class _Inert:
@@ -72,8 +92,12 @@ class _ScipyLinalgProxy:
         return np.asarray(scipy.linalg.inv(np.asarray(A))).view(_ArrayWithToarray)
 
 
-def load_reference(path=REFERENCE_PATH):
+def load_reference(path=None):
     """Returns (GPnet module, GPnetRegressor class, GPnetClassifier class) of the shimmed reference."""
+    if path is None:
+        path = find_reference()
+    if path is None:
+        raise ImportError("the reference modules are neither at /root/reference nor under oracle/_ref")
     _install_matplotlib_stub()
     if path not in sys.path:
         sys.path.insert(0, path)

@@ -447,3 +447,144 @@ def test_diffusion_semigroup_property_n4096(gpu_ctx):
     K2c = gpu_ctx.kernel_block(range(4096), cols, 0.0)
     assert np.max(np.abs(K1 @ K1[:, cols] - K2c)) < 1e-12
     assert m1[0] in (5, 7, 9, 13) and m2[0] in (7, 9, 13)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Full-size parity against the oracle: the headline configuration itself, the default route AND the
+# reference's order of operations, with the route that actually ran asserted.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c3_case():
+    """C3 of SURVEY Appendix D at full size: nx.random_geometric_graph(8192, sqrt(20/(pi N)), seed=0), 4096/4096 split,
+    t = sin(4 pi x) cos(4 pi y), theta = log[0.6, 0.01]; oracle value + analytic gradient computed once (dense, ~10 s)."""
+    G, tr, te, t = cfg.rgg_case(8192, 4096, 4096)
+    assert nx.is_connected(G)
+    th = np.log([0.6, 0.01])
+    ref_v, ref_g = go.OracleGP(G, kerneltype="regularized_laplacian").neg_logp_grad(th, tr, t[tr])
+    return G, tr, te, t, th, ref_v, ref_g
+
+
+@pytest.mark.parametrize("level", [None, 5, 4, 2, 0])
+def test_c3_full_size_logp_and_gradient_against_oracle(c3_case, level):
+    """GPnetRegressor.logPosterior_and_grad at N = 8192 / n = 4096 (GPnetRegressor.py:136-150 + the gradient of
+    old_implementation/GPR.py:52-64) against OracleGP.neg_logp_grad: value to 1e-9, gradient to 1e-8, on the default route
+    (level None), the dissected / augmented Schur routes, and level 0 = the reference's own order of operations.  The route
+    that ran is read back (gpn_last_route) so that a silent fallback fails the test."""
+    import gpnet_b200
+    G, tr, te, t, th, ref_v, ref_g = c3_case
+    m = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=tr, test_nodes=te, theta=list(th), relabel_nodes=True,
+                                  kerneltype="regularized_laplacian", training_values=False)
+    tv = pd.Series(t[tr], index=tr)
+    m.set_training_values(tv)
+    ctx = m._engine.ctx
+    try:
+        if level is not None:
+            ctx.set_fast_paths(level)
+        val, grad = m.logPosterior_and_grad(th, tr, tv)
+        route, parts = ctx.last_route()
+        val_only = m.logPosterior(th, tr, tv)
+        route_v, _ = ctx.last_route()
+    finally:
+        ctx.set_fast_paths(True)
+    assert abs(val - ref_v) <= TOL * abs(ref_v), (level, val, ref_v)
+    assert nrel(grad, ref_g) <= 1e-8, (level, grad, ref_g)
+    assert abs(val_only - ref_v) <= TOL * abs(ref_v)
+    if level is None:
+        assert route >= 5 and parts[0] >= 2 and parts[1] > 0, (route, parts)      # the dissection really ran on the headline graph
+        assert route_v >= 5
+    else:
+        assert route == level, (route, level)
+        if level == 5:
+            assert parts[0] == 2 and min(parts[2:4]) >= 512 and 0 < parts[1] <= min(parts[2:4]) // 2
+
+
+@pytest.mark.parametrize("N,n,seed", [(4096, 1500, 1), (5000, 2500, 2), (6000, 2000, 3)])
+def test_dissected_route_against_oracle_on_graphs_with_many_other_nodes(gpu_ctx, N, n, seed):
+    """Random geometric graphs whose other-node block is large enough (o >= 2048) for the level-set dissection: every route
+    against the dense oracle, and the dissection must really have been taken on the default level."""
+    rng = np.random.RandomState(seed)
+    G = nx.random_geometric_graph(N, np.sqrt(18.0 / (np.pi * N)), seed=seed)
+    perm = rng.permutation(N)
+    tr = sorted(int(x) for x in perm[:n])
+    te = sorted(int(x) for x in perm[n:n + 32])
+    t = rng.randn(n)
+    indptr, indices, w, _ = go.graph_to_csr(G)
+    gpu_ctx.set_graph(indptr, indices, w)
+    gpu_ctx.set_nodes(tr, te)
+    th = np.log([0.8, 0.02])
+    ref_v, ref_g = go.OracleGP(G, kerneltype="regularized_laplacian").neg_logp_grad(th, tr, t)
+    try:
+        for level in (True, 5, 4, 0):
+            gpu_ctx.set_fast_paths(level)
+            st, out, info = gpu_ctx.gpr_logp_grad(1, th, t, True)
+            route, parts = gpu_ctx.last_route()
+            assert st == 0 and info == 0
+            assert abs(out[0] - ref_v) <= TOL * abs(ref_v), (level, out[0], ref_v)
+            assert nrel(out[1:], ref_g) <= 1e-8, (level, out[1:], ref_g)
+            if level is True or level == 5:
+                assert route >= 5 and parts[0] >= 2 and parts[1] > 0, (level, route, parts)
+            else:
+                assert route == level
+    finally:
+        gpu_ctx.set_fast_paths(True)
+
+
+def test_c4_landscape_points_against_dense_oracle():
+    """C4 (RGG N = 4096, n = 2048, diffusion): three points of the 64 x 64 landscape (Pade orders 5 / 7 / 9) through
+    GPnetRegressor.lml_landscape sub-grids against the dense oracle (GPnet.py:539-552)."""
+    import gpnet_b200
+    G, tr, te, t = cfg.rgg_case(4096, 2048, 0)
+    ax1 = np.linspace(np.log(0.01), np.log(0.99), 64)
+    ax2 = np.linspace(np.log(0.001), np.log(10.0), 64)
+    m = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=tr, test_nodes=[], theta=list(np.log([0.6, 0.01])), relabel_nodes=True,
+                                  kerneltype="diffusion", training_values=False)
+    tv = pd.Series(t[tr], index=tr)
+    m.set_training_values(tv)
+    orc = go.OracleGP(G, kerneltype="diffusion", expm_mode="dense")
+    orders = set()
+    for i1, i2 in ((20, 5), (45, 30), (63, 63)):
+        th = [0.0, 0.0]
+        lml = m.lml_landscape(th, [0, 1], ax1[i1:i1 + 1], ax2[i2:i2 + 1])
+        orders.add(m._engine.ctx.expm_info()[0])
+        ref = -orc.neg_logp([ax1[i1], ax2[i2]], tr, t[tr])
+        assert lml.shape == (1, 1) and abs(lml[0, 0] - ref) <= TOL * abs(ref), (i1, i2, lml, ref)
+        val, grad = m.logPosterior_and_grad([ax1[i1], ax2[i2]], tr, tv)
+        assert abs(-val - ref) <= TOL * abs(ref)
+    assert len(orders) >= 2          # the three points exercise different Pade orders
+
+
+def test_c5_family_grid_4096_against_dense_oracle():
+    """C5 family (2-D grid, diffusion, t = sin(0.05 d0)) at N = 4096 = 64 x 64, n = m = 2048: predict(), logp and the
+    analytic gradient against the dense oracle (the full N = 32768 case is tools/c5_check.py: identities only)."""
+    import gpnet_b200
+    G, tr, te, t = cfg.grid_case(64, 64, 2048, 2048, freq=0.05)
+    th = np.log([0.6, 0.01])
+    m = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=tr, test_nodes=te, theta=list(th), relabel_nodes=True,
+                                  kerneltype="diffusion", training_values=False)
+    tv = pd.Series(t[tr], index=tr)
+    m.set_training_values(tv)
+    orc = go.OracleGP(G, kerneltype="diffusion", expm_mode="dense")
+    pr = orc.predict_regressor(th, tr, te, t[tr])
+    assert m.predict() is m and m.is_trained
+    assert nrel(m.fstar, pr["fstar"]) <= TOL and nrel(m.s, pr["s"]) <= TOL and nrel(m.alpha, pr["alpha"]) <= TOL
+    ref_v, ref_g = orc.neg_logp_grad(th, tr, t[tr])
+    val, grad = m.logPosterior_and_grad(th, tr, tv)
+    assert abs(val - ref_v) <= TOL * abs(ref_v) and nrel(grad, ref_g) <= 1e-8
+    # ADVICE r1: the lazily fetched attributes survive the logPosterior call above (device buffers were reused)
+    assert nrel(m.kstar, pr["kstar"]) <= TOL and nrel(m.k, pr["k"]) <= TOL
+    L = m.L
+    assert nrel(L @ L.T, pr["k"]) <= TOL
+    assert m.v.shape == (2048, 2048)
+
+
+def test_kernel_with_labels_outside_the_graph_raises_index_error():
+    """GPnetBase.kernel with a label that is no graph position must not read out of bounds on the device."""
+    import gpnet_b200
+    G, tr, te, t = cfg.grid_case(8, 8, 20, 20)
+    m = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=tr, test_nodes=te, theta=list(np.log([0.5, 0.01])), relabel_nodes=True,
+                                  kerneltype="diffusion")
+    with pytest.raises(IndexError):
+        m.kernel([0, 1, 64], [0], m.theta)
+    with pytest.raises(IndexError):
+        m.kernel([0], [-3], m.theta)
+    assert m.kernel([0, 1], [2], m.theta).shape == (2, 1)

@@ -174,3 +174,91 @@ def test_empty_graph_rows_and_bad_arguments(gpu_ctx):
     gpu_ctx.laplacian_dense(1.0, 1.0, out.data_ptr(), ld)
     gpu_ctx.sync()
     assert np.array_equal(out[:, :3].cpu().numpy(), np.eye(3))
+
+
+@pytest.mark.parametrize("n,brows", [(100, 7), (256, 130), (700, 300), (1500, 64)])
+def test_trsm_and_potri_after_potrf(gpu_ctx, n, brows):
+    """gpn_trsm_f64 / gpn_potri_f64 reuse the factor (and the inverted diagonal blocks) of the potrf that precedes them: the
+    np.linalg.solve(L, .) chains of GPnetRegressor.py:124-126 and the explicit inverse of old_implementation/GPR.py:56."""
+    import torch
+    from gpnet_b200._lib import GpnetError
+    torch.manual_seed(n + brows)
+    X = torch.randn(n, n, dtype=torch.float64, device="cuda:0")
+    S = X @ X.T / n + torch.eye(n, dtype=torch.float64, device="cuda:0")
+    B = torch.randn(brows, n, dtype=torch.float64, device="cuda:0")
+    ld = (n + 127) // 128 * 128
+    Sb = torch.zeros(ld, ld, dtype=torch.float64, device="cuda:0")
+    Sb[:n, :n] = S
+    Bb = torch.zeros((brows + 127) // 128 * 128, ld, dtype=torch.float64, device="cuda:0")
+    Bb[:brows, :n] = B
+    out = torch.zeros(ld, ld, dtype=torch.float64, device="cuda:0")
+    torch.cuda.synchronize()
+    with pytest.raises(GpnetError):                       # no factor resident for this matrix yet
+        gpu_ctx.trsm(n, Sb.data_ptr(), ld, Bb.data_ptr(), ld, brows)
+    assert gpu_ctx.potrf(n, Sb.data_ptr(), ld) == 0
+    gpu_ctx.trsm(n, Sb.data_ptr(), ld, Bb.data_ptr(), ld, brows)
+    gpu_ctx.potri(n, Sb.data_ptr(), ld, out.data_ptr(), ld)
+    gpu_ctx.sync()
+    L = torch.linalg.cholesky(S)
+    ref = torch.linalg.solve_triangular(L, B.T, upper=False).T          # B L^-T
+    assert (Bb[:brows, :n] - ref).abs().max().item() / ref.abs().max().item() < FP_TOL
+    inv = torch.linalg.inv(S)
+    assert (out[:n, :n] - inv).abs().max().item() / inv.abs().max().item() < 1e-11
+    assert torch.equal(out[:n, :n], out[:n, :n].T)
+
+
+@pytest.mark.parametrize("N,scale", [(60, 0.01), (300, 0.3), (500, 0.9), (500, 6.0)])
+def test_expm_sym_matches_scipy(gpu_ctx, N, scale):
+    """gpn_expm_sym_f64 (the scipy.linalg.expm of GPnet.py:340 as a primitive) over all Pade orders incl. squaring."""
+    import scipy.linalg
+    import torch
+    G = nx.random_geometric_graph(N, 0.15, seed=N)
+    ip, ix, w, _ = go.graph_to_csr(G)
+    A = -scale * go.normalized_laplacian(ip, ix, w, N)
+    Ab, lda = dmat(N, N, torch.from_numpy(A).cuda())
+    Ob, ldo = dmat(N, N)
+    torch.cuda.synchronize()
+    m, s = gpu_ctx.expm_sym(N, Ab.data_ptr(), lda, Ob.data_ptr(), ldo)
+    ref = scipy.linalg.expm(A)
+    assert np.max(np.abs(Ob[:, :N].cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-12
+    assert m in (3, 5, 7, 9, 13) and (s > 0) == (scale >= 6.0)
+
+
+@pytest.mark.parametrize("N,p", [(50, 0), (50, 1), (200, 2), (200, 5), (333, 12)])
+def test_matpow_matches_numpy(gpu_ctx, N, p):
+    """gpn_matpow_f64 (np.linalg.matrix_power of GPnet.py:346) with the B^(p-1) by-product."""
+    import torch
+    G = nx.random_geometric_graph(N, 0.2, seed=N + p)
+    ip, ix, w, _ = go.graph_to_csr(G)
+    B = 2.2 * np.eye(N) - go.normalized_laplacian(ip, ix, w, N)
+    Bb, ldb = dmat(N, N, torch.from_numpy(B).cuda())
+    Ob, ldo = dmat(N, N)
+    O1, ld1 = dmat(N, N)
+    torch.cuda.synchronize()
+    gpu_ctx.matpow(N, Bb.data_ptr(), ldb, p, Ob.data_ptr(), ldo, O1.data_ptr() if p >= 1 else None, ld1)
+    ref = np.linalg.matrix_power(B, p)
+    assert np.max(np.abs(Ob[:, :N].cpu().numpy() - ref)) / np.max(np.abs(ref)) < 1e-13
+    if p >= 1:
+        ref1 = np.linalg.matrix_power(B, p - 1)
+        assert np.max(np.abs(O1[:, :N].cpu().numpy() - ref1)) / np.max(np.abs(ref1)) < 1e-13
+
+
+def test_pstep_order_uses_numpy_exp(gpu_ctx):
+    """Quirk A-4: p = int(np.exp(theta)[1]) with NUMPY's exp (np.exp(log 146) = 145.99999999999997 -> 145 on this stack,
+    where libm's exp gives 146.0): the host exponentiates, the library only truncates."""
+    N = 40
+    G = nx.path_graph(N)
+    ip, ix, w, _ = go.graph_to_csr(G)
+    gpu_ctx.set_graph(ip, ix, w)
+    for p_nominal in (146, 179, 5, 7):
+        th = np.log([2.0, float(p_nominal), 0.1])
+        p = int(np.exp(th)[1])
+        assert gpu_ctx.kernel_build(2, th, False) == 0
+        K = gpu_ctx.kernel_block(range(N), range(N), 0.0)
+        B = 2.0 * np.eye(N) - go.normalized_laplacian(ip, ix, w, N)
+        ref = np.linalg.matrix_power(B, p)
+        assert np.max(np.abs(K - ref)) / np.max(np.abs(ref)) < 1e-12, (p_nominal, p)
+    with pytest.raises(IndexError):
+        gpu_ctx.kernel_block([0, N], [0], 0.0)
+    with pytest.raises(IndexError):
+        gpu_ctx.kernel_block([0], [-1], 0.0)

@@ -46,6 +46,39 @@ def test_graph_csr_matches_networkx_adjacency():
     assert nodelist == list(G)
 
 
+def test_graph_csr_sums_parallel_edges_and_rejects_directed_graphs():
+    """One CSR entry per matrix entry: a MultiGraph's parallel edges are summed like nx.to_scipy_sparse_array does (the
+    Laplacian scatter kernel writes one value per entry); directed graphs raise what the reference's
+    nx.normalized_laplacian_matrix call raises for them (GPnet.py:329)."""
+    from gpnet_b200.engine import graph_csr
+    import scipy.sparse as sp
+    G = nx.MultiGraph()
+    G.add_nodes_from(range(5))
+    G.add_edge(0, 1, weight=0.5)
+    G.add_edge(0, 1, weight=2.0)
+    G.add_edge(1, 0)                       # default weight 1
+    G.add_edge(2, 3)
+    G.add_edge(3, 3, weight=1.5)
+    G.add_edge(3, 3, weight=0.25)
+    indptr, indices, w, nodelist, _ = graph_csr(G)
+    A = sp.csr_array((w, indices, indptr), shape=(5, 5))
+    assert A.nnz == len(indices) == 5       # (0,1) (1,0) (2,3) (3,2) (3,3)
+    assert np.array_equal(A.toarray(), nx.to_numpy_array(G, nodelist=nodelist))
+    assert np.allclose(nx.normalized_laplacian_matrix(G).toarray()[0, 1], -3.5 / np.sqrt(3.5 * 3.5))
+    with pytest.raises(nx.NetworkXNotImplemented):
+        graph_csr(nx.DiGraph([(0, 1), (1, 2)]))
+
+
+def test_positions_outside_the_graph_raise_index_error():
+    """relabelled graphs take int(label) as the position; labels outside [0, N) must not reach the device gather."""
+    m = _model()
+    with pytest.raises(IndexError):
+        m._positions([0, 1, 30])
+    with pytest.raises(IndexError):
+        m._positions([-1, 2])
+    assert m._positions([29, 0]) == [0, 29]
+
+
 def test_product_does_not_import_oracle():
     for fn in os.listdir(os.path.join(ROOT, "gpnet_b200")):
         if fn.endswith(".py"):
@@ -127,8 +160,18 @@ class _FakeCtx:
 
     def gpr_predict(self, kind, theta, t):
         n, m = self.n_train, self.n_test
+        self.generation = getattr(self, "generation", 0) + 1
         return 0, dict(alpha=np.zeros(n), fstar=np.ones(m), s=np.ones(m), kstarstar_diag=np.ones(m), info_k=self.info_k,
                        info_kss=self.info_kss)
+
+    def gpr_fetch(self, which):
+        n, m = self.n_train, self.n_test
+        shape = {"k": (n, n), "kstar": (m, n), "L": (n, n), "v": (n, m), "kstarstar": (m, m)}[which]
+        self.fetched = getattr(self, "fetched", []) + [which]
+        return np.full(shape, float(self.generation))
+
+    def kernel_build(self, kind, theta, want_grad=False):
+        return 0
 
 
 def test_cholesky_failure_maps_to_reference_behaviour(capsys):
@@ -146,6 +189,27 @@ def test_cholesky_failure_maps_to_reference_behaviour(capsys):
     assert "K** not positive definite, aborting..." in capsys.readouterr().out
     m._engine._ctx = _FakeCtx()
     assert m.predict().is_trained and list(m.df["fstar"][m.test_nodes]) == [1.0] * 8
+
+
+def test_predict_attributes_survive_later_device_calls():
+    """k, kstar, kstarstar, L, v, V are fetched lazily, but stay readable after logp() / kernel() / another model's
+    predict() reused the device buffers -- their owner snapshots them right before (the reference keeps them as host arrays,
+    GPnetRegressor.py:89-128, so gpr.predict(); gpr.logp(); gpr.plot_post() works there)."""
+    m = _model()
+    ctx = _FakeCtx()
+    m._engine._ctx = ctx
+    m.predict()
+    assert not getattr(ctx, "fetched", [])                      # nothing copied yet: lazy
+    assert m.k.shape == (10, 10) and ctx.fetched == ["k"]       # first read fetches one array
+    m.logp()                                                    # reuses the buffers: the rest is snapshotted first
+    assert sorted(ctx.fetched) == ["L", "k", "kstar", "kstarstar", "v"]
+    assert m.L.shape == (10, 10) and m.v.shape == (10, 8) and m.kstarstar.shape == (8, 8) and m.V.shape == (8, 8)
+    assert np.all(m.v == 1.0)
+    other = _model(seed=5)                                      # a second model on the same context
+    other._engine._ctx = ctx
+    m.predict()                                                 # generation 2
+    other.predict()                                             # must snapshot m's generation-2 arrays before running
+    assert np.all(m.kstar == 2.0) and np.all(other.kstar == 3.0)
 
 
 def test_workspace_bytes_matches_the_measured_footprints():
@@ -224,6 +288,14 @@ class Fake:                                    # stands in for a model: value an
 thetas = np.arange(14, dtype=float).reshape(7, 2)
 out = sharded_multistart(Fake(), thetas)
 assert np.allclose(out[:, 0], (thetas ** 2).sum(1)) and np.allclose(out[:, 1:], 2 * thetas)
+# a parameter-domain failure on ONE rank reaches every rank as the same exception (no rank is left waiting in the all-gather)
+from gpnet_b200.sharded import agree_on_error
+try:
+    agree_on_error(AssertionError("Lambda must be < 1") if rank == 1 else None, world, dist)
+    raise SystemExit("agree_on_error did not raise on rank %d" % rank)
+except AssertionError as e:
+    assert "Lambda must be < 1" in str(e)
+agree_on_error(None, world, dist)             # no failure anywhere: no exception
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
