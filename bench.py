@@ -333,8 +333,9 @@ def main():
                      1: "block (training nodes last, only K[tr,:] formed)", 2: "schur (dense N x N Cholesky + triangular inverse)",
                      3: "schur_sparse_coupling (separate triangular inverse / product launches)",
                      4: "schur_sparse_coupling_augmented (one factorisation of the other-node block)",
-                     5: "schur_sparse_coupling_augmented_dissected (default)"}
-            for level in (0, 1, 2, 3, 4):
+                     5: "schur_sparse_coupling_augmented_dissected (other nodes in two halves)",
+                     6: "whole_graph_dissection (default: no dense Schur complement, one augmented factorisation per part)"}
+            for level in (0, 1, 2, 3, 4, 5):
                 ctx.set_fast_paths(level)
                 for _ in range(2):
                     o2 = ctx.gpr_logp_grad(kind, theta, None, True)[1]
@@ -349,8 +350,8 @@ def main():
                 ms = r0.elapsed_time(r1) / kk
                 routes[names[level]] = {"value": 1e3 / ms, "ms_per_step": ms, "executed_gflop_per_step": ctx.flop_count() / kk * 1e-9,
                                         "max_rel_diff_vs_default": float(np.max(np.abs(o2 - out) / np.abs(out)))}
-            ctx.set_fast_paths(5)
-            routes[names[5]] = {"value": value, "ms_per_step": ms_step, "executed_gflop_per_step": exec_flops * 1e-9}
+            ctx.set_fast_paths(6)
+            routes[names[6]] = {"value": value, "ms_per_step": ms_step, "executed_gflop_per_step": exec_flops * 1e-9}
         if world == 1 and not args.no_cpu_baseline:
             dt, cval = cpu_port_eval(problem, N, reference_style=False)
             cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": blas_threads(), "kind": "port",

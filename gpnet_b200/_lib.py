@@ -51,6 +51,7 @@ SIGNATURES = {
     "gpn_expm_sym_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, c_int_p, c_int_p]),
     "gpn_matpow_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long]),
     "gpn_last_route": (C.c_int, [C.c_void_p, c_int_p]),
+    "gpn_set_dissection_parts": (None, [C.c_void_p, C.c_int]),
     "gpn_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gpn_gather_block_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double,
                                        C.c_void_p, C.c_long]),
@@ -309,9 +310,14 @@ class Context:
 
     def set_fast_paths(self, level=True):
         """Route of the regularized-Laplacian regressor likelihood: 0/False full kernel, 1 block route, 2 Schur route,
-        3 Schur route with sparse coupling, 4 the same with the triangular work appended to the Cholesky kernels, 5/True the
-        same with M_oo^-1 from two independent halves of a dissection of the other nodes (default)."""
-        self.lib.gpn_set_fast_paths(self.h, 5 if level is True else int(level))
+        3 Schur route with sparse coupling, 4 the same with the triangular work appended to the Cholesky kernels, 5 the
+        same with M_oo^-1 from two independent halves of a dissection of the other nodes, 6/True (default) no dense Schur
+        complement at all: K-way dissection of the whole graph, one augmented factorisation per part (falls back to 5, 4)."""
+        self.lib.gpn_set_fast_paths(self.h, 6 if level is True else int(level))
+
+    def set_dissection_parts(self, parts=0):
+        """Parts of the whole-graph dissection of route level 6 (0: from the graph size; 2..8: forced, small graphs allowed)."""
+        self.lib.gpn_set_dissection_parts(self.h, int(parts))
 
     def gpr_predict(self, kind, theta, t):
         th, tt = _eth(theta), _f64(t)

@@ -63,6 +63,26 @@ struct ProfEvent {
     int kind = 0;   // 0 GEMM launch, 2 dataflow Cholesky
 };
 
+// K-way level-set dissection of the WHOLE graph (level 6 of the regularized-Laplacian regressor likelihood, dissect.cu):
+// the nodes are numbered [P_1 | ... | P_K | Sep], no edge joins two different parts, every part is numbered [others | training]
+// and so is the separator.  M = I + beta L~ is then block-arrow, and the leading block of every M_kk (and of Sep) is the
+// corresponding block of M_oo: ONE factorisation per part serves both M and M_oo.
+struct Dissect6 {
+    bool built = false;          // the analysis below was run for the current graph / node set
+    bool usable = false;         // ... and found thin separators
+    int K = 0;                   // parts
+    int s = 0, so = 0;           // separator nodes, of which other (non-training) nodes (numbered first)
+    int ND = 0;                  // N - s: nodes in the parts
+    int off[9] = {0};            // first row of part k (even), off[K] = ND
+    int nk[8] = {0}, ok[8] = {0};   // nodes of part k, of which others (numbered first)
+    long long sep_nnz = 0;
+    DevBuf indptr, indices, weights, dinv;   // the permuted graph (CSR, D^-1/2 and degrees)
+    DevBuf trank;                // int[N]: rank of the permuted node among the training nodes (index into t), -1 for others
+    DevBuf sep_ptr, sep_idx, sep_w;          // CSR of the (Sep rows) x (part columns) block, columns ascending; sep_w = dinv_r (-w) dinv_c
+    DevBuf sep_pp;               // int[s x (K+1)]: entry range of part k inside row r is [sep_pp[r(K+1)+k], sep_pp[r(K+1)+k+1])
+    DevBuf work[12];             // G^T, G_o^T, U^T, U_o^T, T, T_o and their factors / inverses, vectors
+};
+
 struct gpn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -96,10 +116,12 @@ struct gpn_ctx {
     int last_route = -1;                 // route the last regressor likelihood evaluation actually took (gpn_last_route)
     const void* winv_for = nullptr;      // matrix whose inverted diagonal blocks `winv` holds (set by gpn_potrf_f64 / gpn_posv_f64
     int winv_n = 0;                      // for gpn_trsm_f64 / gpn_potri_f64; any other factorisation clears it)
-    int fast_reglap = 5;                 // regressor, regularized Laplacian: 0 full kernel, 1 block route, 2 Schur route, 3 Schur route with
+    int fast_reglap = 6;                 // regressor, regularized Laplacian: 0 full kernel, 1 block route, 2 Schur route, 3 Schur route with
                                          // sparse coupling, 4 the same with the triangular work appended to the
                                          // two Cholesky kernels, 5 the same with M_oo^-1 from two independent halves
-                                         // of a dissection of the other nodes (GPNET_B200_REGLAP_FAST)
+                                         // of a dissection of the other nodes, 6 no dense Schur complement at all: log-determinants,
+                                         // traces and solves of M and M_oo from one factorisation per part of a K-way dissection
+                                         // of the whole graph (GPNET_B200_REGLAP_FAST)
     DevBuf p_indptr, p_indices, p_weights, p_dinv, iota;
     // level-set dissection of the other nodes (ensure_perm): they are numbered [A | B | Sep], no edge joins A and B
     int dis_a = 0, dis_b = 0, dis_s = 0;   // block sizes (dis_s == 0: not dissected)
@@ -127,6 +149,14 @@ struct gpn_ctx {
     DevBuf flags2;               // the same for a second dataflow Cholesky running concurrently on the side stream (slot 1)
     int epoch2 = 0;
     long flags_rows2 = 0;
+    // slots 2..9: further concurrent factorisations (one per part of the whole-graph dissection), each on its own side stream
+    DevBuf flagsK[10];
+    int epochK[10] = {0};
+    long flags_rowsK[10] = {0};
+    cudaStream_t side[10] = {nullptr};
+    cudaEvent_t ev_side[10] = {nullptr};
+    Dissect6 d6;
+    int d6_parts = 0;                    // > 0: number of parts forced by gpn_set_dissection_parts (0: chosen from N)
     void* df_trace = nullptr;    // optional device buffer: 8 x int64 globaltimer stamps per dataflow-Cholesky task
     void* leaf_prof = nullptr;   // optional device buffer (32 x int64) receiving clock64 stamps of the leaf phases
     int potrf_mode = 0;          // 0: dataflow kernel (default), 1: recursive multi-launch (GPNET_B200_POTRF=recursive)
@@ -204,3 +234,15 @@ int gpn_k_form_B(gpn_ctx* c, int n, const double* K, long ldk, const double* sw,
 int gpn_k_scale_rows(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* s, double* out, long ldo);
 
 enum { GEMV_FULL = 0, GEMV_LOWER = 1 /* treat entries with col > row as zero */ };
+
+// whole-graph dissection route (dissect.cu)
+int gpn_d6_ensure(gpn_ctx* c);
+int gpn_d6_fill_zero(gpn_ctx* c, double* M, long ld);
+int gpn_d6_coupling(gpn_ctx* c, const double* t, double beta, double* b1, double* bt, double* d_out5);
+int gpn_d6_factor_reduce(gpn_ctx* c, const double* L, const double* WT, long ld, double* d_out4);
+int gpn_d6_sep_spmm(gpn_ctx* c, double beta, const double* WT, long ld, double* GT, double* GTo, long ldg);
+int gpn_d6_trace(gpn_ctx* c, int s, const double* A, long lda, const double* B, long ldb, const double* Lt, long ldl, double* d_out2);
+int gpn_d6_block_solve(gpn_ctx* c, const double* WT, long ld, const double* xa, const double* xb, double* va, double* vb, double* ua, double* ub);
+int gpn_d6_sep_gather(gpn_ctx* c, double beta, const double* ba, const double* bb, const double* ya, const double* yb, double* ra, double* rb);
+int gpn_d6_gemv2(gpn_ctx* c, int s, const double* A, long lda, const double* xa, const double* xb, double* ya, double* yb);
+int gpn_d6_sep_scatter(gpn_ctx* c, double beta, const double* ua, const double* ub, double* wa, double* wb);

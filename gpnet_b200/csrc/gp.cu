@@ -996,6 +996,202 @@ int reglap_inverse_oo_dissected(gpn_ctx* c, double* M, long ld, int* info_slot_u
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Level 6: whole-graph K-way dissection (dissect.cu has the derivation).  No dense Schur complement: log det S, the quadratic
+// forms and the gradient traces come from log det / tr(inverse) / two solves with M and M_oo, which K concurrent augmented
+// factorisations [M_kk; I] (one per part) and the small separator complements T, T_o deliver.
+// ---------------------------------------------------------------------------------------------------------------------
+int d6_side_stream(gpn_ctx* c, int k) {
+    if (!c->side[k]) {
+        GPN_CK(cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking));
+        GPN_CK(cudaEventCreateWithFlags(&c->ev_side[k], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, RowScalars* rs, int* info_h) {
+    Dissect6& q = c->d6;
+    const int N = c->N, n = c->n_train, K = q.K, s = q.s, so = q.so, ND = q.ND;
+    GPN_TRY(ensure_vecs(c));
+    c->have_full = false;
+    c->kind = GPN_KERNEL_REGULARIZED_LAPLACIAN;
+    c->P = P;
+    for (int i = 0; i < P; ++i) c->theta_exp[i] = theta_h[i];
+    c->ldN = pad128(N);
+    c->last_route = 6;
+    GPN_TRY(clear_info(c));
+    const long ld = c->ldN, ldg = pad128(ND), lds = pad128(s), ldso = pad128(std::max(so, 1));
+    const double beta = c->theta_exp[0];
+    GPN_TRY(ensure_mat(c, 0));
+    GPN_TRY(ensure_mat(c, 2));
+    double *M = mat(c, 0), *WT = mat(c, 2);
+    if (t_h) GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
+    else GPN_CK(cudaMemcpyAsync(vecp(c, V_T), vecp(c, V_TRES), sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    GPN_TRY(gpn_buf_ensure(c, q.work[0], sizeof(double) * (size_t)lds * ldg));         // G^T   (s x ND)
+    GPN_TRY(gpn_buf_ensure(c, q.work[1], sizeof(double) * (size_t)ldso * ldg));        // G_o^T (so x ND, training columns zero)
+    GPN_TRY(gpn_buf_ensure(c, q.work[4], sizeof(double) * (size_t)lds * lds * 4));     // T, W_T^T, T^-1, Q
+    GPN_TRY(gpn_buf_ensure(c, q.work[5], sizeof(double) * (size_t)ldso * ldso * 4));   // the same for the other-node block
+    GPN_TRY(gpn_buf_ensure(c, q.work[6], sizeof(double) * (size_t)ld * 16));           // vectors of length N
+    double *GT = (double*)q.work[0].p, *GTo = (double*)q.work[1].p;
+    double *Tb = (double*)q.work[4].p, *WTt = Tb + lds * lds, *Tinv = WTt + lds * lds, *Qm = Tinv + lds * lds;
+    double *Tob = (double*)q.work[5].p, *WTto = Tob + ldso * ldso, *Toinv = WTto + ldso * ldso, *Qo = Toinv + ldso * ldso;
+    auto vec = [&](int i) { return (double*)q.work[6].p + (long)i * ld; };
+    double *b1 = vec(0), *bt = vec(1), *v1 = vec(2), *vt = vec(3), *y1 = vec(4), *yt = vec(5), *w1 = vec(6), *wt = vec(7), *u1 = vec(8),
+           *ut = vec(9), *r1 = vec(10), *rt = vec(11), *us1 = vec(12), *ust = vec(13);
+    // scalar block of this route: [0..4] coupling sums, [5..8] factor reductions, [9,10] tr / log det of T, [11,12] of T_o, [13..18] dots
+    GPN_CK(cudaMemsetAsync(dscal(c, 0), 0, sizeof(double) * Scal::NDBL, c->stream));
+    // ---- assembly: M on the permuted graph (only the diagonal blocks and the separator block are read as dense) ----
+    GPN_TRY(gpn_d6_fill_zero(c, M, ld));
+    GPN_TRY(gpn_k_laplacian_scatter(c, N, (const int*)q.indptr.p, (const int*)q.indices.p, c->h_weights.empty() ? nullptr : (const double*)q.weights.p,
+                                    (const double*)q.dinv.p, beta, 1.0, M, ld));
+    GPN_TRY(gpn_d6_coupling(c, vecp(c, V_T), beta, b1, bt, dscal(c, 0)));
+    // ---- K concurrent augmented factorisations [M_kk; I] -> L_k (in place), W_k^T (upper tiles of WT) ----
+    int Tk[8], woff[9] = {0};
+    for (int k = 0; k < K; ++k) { Tk[k] = (q.nk[k] + 127) / 128; woff[k + 1] = woff[k] + Tk[k]; }
+    const int Ts = (s + 127) / 128, Tso = (std::max(so, 1) + 127) / 128;
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)(woff[K] + Ts + Tso + 2) * 128 * 128));
+    double* winv = (double*)c->winv.p;
+    {
+        double wsum = 0.0;
+        for (int k = 0; k < K; ++k) wsum += (double)q.nk[k] * q.nk[k] * q.nk[k];
+        int caps[8], used = 0;
+        for (int k = 0; k < K; ++k) { caps[k] = std::max(12, (int)(c->num_sms * ((double)q.nk[k] * q.nk[k] * q.nk[k] / wsum))); used += caps[k]; }
+        for (int k = 0; used > c->num_sms; k = (k + 1) % K)
+            if (caps[k] > 12) { --caps[k]; --used; }
+        cudaStream_t main_stream = c->stream;
+        GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
+        int st = 0;
+        for (int k = 0; k < K && st == 0; ++k) {
+            if (k > 0) {
+                st = d6_side_stream(c, k);
+                if (st != 0) break;
+                GPN_CK(cudaStreamWaitEvent(c->side[k], c->ev_fork, 0));
+                c->stream = c->side[k];
+            }
+            c->potrf_grid_cap = caps[k];
+            double* Mk = M + (long)q.off[k] * ld + q.off[k];
+            st = gpn_potrf_dataflow(c, q.nk[k], Mk, ld, winv + (size_t)woff[k] * 128 * 128, iscal(c, k), 0, nullptr, 0, 0,
+                                    WT + (long)q.off[k] * ld + q.off[k], ld, k);
+            if (k > 0 && st == 0) {
+                cudaError_t e = cudaEventRecord(c->ev_side[k], c->side[k]);
+                if (e != cudaSuccess) st = GPN_CUDA_ERR(e);
+            }
+            c->stream = main_stream;
+        }
+        c->potrf_grid_cap = 0;
+        if (st != 0) return st;
+        for (int k = 1; k < K; ++k) GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_side[k], 0));
+    }
+    GPN_TRY(gpn_d6_factor_reduce(c, M, WT, ld, dscal(c, 5)));
+    // ---- separator complements T = E - G^T G and T_o (other-node rows / columns only) ----
+    GPN_TRY(gpn_d6_sep_spmm(c, beta, WT, ld, GT, GTo, ldg));
+    const double* E = M + (long)ND * ld + ND;
+    GPN_TRY(gpn_k_copy(c, s, s, E, ld, Tb, lds));
+    GPN_TRY(gpn_gemm(c, s, s, ND, -1.0, GT, ldg, true, GT, ldg, true, 1.0, Tb, lds, GF_LOWER));
+    double* winvT = winv + (size_t)woff[K] * 128 * 128;
+    cudaStream_t main_stream = c->stream;
+    if (so > 0) {   // the other-node complement on a side stream, next to the full one
+        GPN_TRY(d6_side_stream(c, 1));
+        GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
+        GPN_CK(cudaStreamWaitEvent(c->side[1], c->ev_fork, 0));
+        c->stream = c->side[1];
+        int st = gpn_k_copy(c, so, so, E, ld, Tob, ldso);
+        if (st == 0) st = gpn_gemm(c, so, so, ND, -1.0, GTo, ldg, true, GTo, ldg, true, 1.0, Tob, ldso, GF_LOWER);
+        c->potrf_grid_cap = c->num_sms / 2;
+        if (st == 0) st = gpn_potrf_dataflow(c, so, Tob, ldso, winvT + (size_t)Ts * 128 * 128, iscal(c, 9), 0, nullptr, 0, 0, WTto, ldso, 1);
+        if (st == 0) st = gpn_lauum_t(c, so, WTto, ldso, Toinv, ldso, true);
+        c->stream = main_stream;
+        c->potrf_grid_cap = 0;
+        if (st != 0) return st;
+        GPN_CK(cudaEventRecord(c->ev_side[1], c->side[1]));
+    }
+    c->potrf_grid_cap = c->num_sms / 2;
+    {
+        int st = gpn_potrf_dataflow(c, s, Tb, lds, winvT, iscal(c, 8), 0, nullptr, 0, 0, WTt, lds, 0);
+        c->potrf_grid_cap = 0;
+        if (st != 0) return st;
+    }
+    if (want_grad) {
+        // U^T = G^T W per part (U = D^-1 C), Q = U^T U, tr(M^-1) = sum ||W_k||_F^2 + tr(T^-1 (I + Q))
+        GPN_TRY(gpn_buf_ensure(c, q.work[2], sizeof(double) * (size_t)lds * ldg));
+        GPN_TRY(gpn_buf_ensure(c, q.work[3], sizeof(double) * (size_t)ldso * ldg));
+        double *UT = (double*)q.work[2].p, *UTo = (double*)q.work[3].p;
+        GPN_TRY(gpn_lauum_t(c, s, WTt, lds, Tinv, lds, true));
+        for (int k = 0; k < K; ++k)
+            GPN_TRY(gpn_gemm(c, s, q.nk[k], q.nk[k], 1.0, GT + q.off[k], ldg, true, WT + (long)q.off[k] * ld + q.off[k], ld, true, 0.0,
+                             UT + q.off[k], ldg, GF_KLO_N));
+        GPN_TRY(gpn_gemm(c, s, s, ND, 1.0, UT, ldg, true, UT, ldg, true, 0.0, Qm, lds, GF_LOWER | GF_MIRROR));
+        GPN_TRY(gpn_d6_trace(c, s, Tinv, lds, Qm, lds, Tb, lds, dscal(c, 9)));
+        if (so > 0) {
+            GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
+            for (int k = 0; k < K; ++k)
+                if (q.ok[k] > 0)
+                    GPN_TRY(gpn_gemm(c, so, q.ok[k], q.ok[k], 1.0, GTo + q.off[k], ldg, true, WT + (long)q.off[k] * ld + q.off[k], ld, true, 0.0,
+                                     UTo + q.off[k], ldg, GF_KLO_N));
+            // U_o^T has content in the other-node columns only: the training columns of the buffer are never written, so the
+            // product runs per part over those columns
+            GPN_TRY(gpn_k_fill_zero(c, Qo, ldso, so, (int)ldso));
+            for (int k = 0; k < K; ++k)
+                if (q.ok[k] > 0)
+                    GPN_TRY(gpn_gemm(c, so, so, q.ok[k], 1.0, UTo + q.off[k], ldg, true, UTo + q.off[k], ldg, true, 1.0, Qo, ldso, GF_LOWER | GF_MIRROR));
+            GPN_TRY(gpn_d6_trace(c, so, Toinv, ldso, Qo, ldso, Tob, ldso, dscal(c, 11)));
+        }
+    } else {
+        GPN_TRY(gpn_d6_trace(c, s, nullptr, 0, nullptr, 0, Tb, lds, dscal(c, 9)));
+        if (so > 0) {
+            GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
+            GPN_TRY(gpn_d6_trace(c, so, nullptr, 0, nullptr, 0, Tob, ldso, dscal(c, 11)));
+        }
+    }
+    // ---- u_x = M_oo^-1 (M_ot x) for x = 1, t: block-arrow solve through the factors ----
+    GPN_CK(cudaMemsetAsync(u1, 0, sizeof(double) * 2 * ld, c->stream));                   // u1, ut (adjacent rows of the vector block)
+    if (so > 0) {
+        GPN_TRY(gpn_d6_block_solve(c, WT, ld, b1, bt, v1, vt, y1, yt));
+        GPN_TRY(gpn_d6_sep_gather(c, beta, b1, bt, y1, yt, r1, rt));
+        GPN_TRY(gpn_d6_gemv2(c, so, Toinv, ldso, r1, rt, us1, ust));
+        GPN_CK(cudaMemcpyAsync(w1, b1, sizeof(double) * ND, cudaMemcpyDeviceToDevice, c->stream));
+        GPN_CK(cudaMemcpyAsync(wt, bt, sizeof(double) * ND, cudaMemcpyDeviceToDevice, c->stream));
+        GPN_TRY(gpn_d6_sep_scatter(c, beta, us1, ust, w1, wt));
+        GPN_TRY(gpn_d6_block_solve(c, WT, ld, w1, wt, v1, vt, u1, ut));
+        GPN_CK(cudaMemcpyAsync(u1 + ND, us1, sizeof(double) * so, cudaMemcpyDeviceToDevice, c->stream));
+        GPN_CK(cudaMemcpyAsync(ut + ND, ust, sizeof(double) * so, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        GPN_TRY(gpn_d6_block_solve(c, WT, ld, b1, bt, v1, vt, u1, ut));
+    }
+    {
+        const double *dx[6] = {b1, b1, bt, u1, u1, ut}, *dy[6] = {u1, ut, ut, u1, ut, ut};
+        const int dn[6] = {N, N, N, N, N, N};
+        GPN_TRY(gpn_k_multi_dot(c, 6, dx, dy, dn, dscal(c, 13)));
+    }
+    double sc[Scal::NDBL];
+    int info[16];
+    GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
+    if (info_h) {
+        *info_h = 0;
+        for (int i = 0; i < 10 && *info_h == 0; ++i) *info_h = info[i];
+    }
+    rs->n = n;
+    rs->half_logdet = -((sc[7] + sc[10]) - (sc[8] + sc[12]));          // (1/2) log det K_tt = -(1/2) (log det M - log det M_oo)
+    rs->s = sc[0] - sc[13];
+    rs->a = sc[1] - sc[14];
+    rs->q = sc[2] - sc[15];
+    if (want_grad) {
+        const double trM = sc[5] + sc[9], trMoo = sc[6] + sc[11];
+        rs->trSD = trM - trMoo - n;
+        rs->D11 = sc[16] + n - rs->s;
+        rs->D1t = sc[17] + sc[3] - rs->a;
+        rs->Dtt = sc[18] + sc[4] - rs->q;
+    }
+    return 0;
+}
+
+// level 6 applies when the whole graph dissects into parts with thin separators; otherwise the caller takes level 5 / 4
+bool d6_route(gpn_ctx* c) {
+    if (c->fast_reglap < 6) return false;
+    if (gpn_d6_ensure(c) != 0) return false;
+    return c->d6.usable;
+}
+
 // Which evaluations take the sparse-coupling route: gradients from level 3 on; values alone only when the inverse of the
 // other-node block comes from the dissected halves (level 5): otherwise the dense Cholesky of M of the Schur route is as fast.
 bool coupled_route(gpn_ctx* c, int want_grad) {
@@ -1130,7 +1326,8 @@ int gpr_reglap_coupled_scalars(gpn_ctx* c, const double* theta_h, int P, const d
 
 int gpr_logp_grad_reglap_schur(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, double* out_h, int* info_h) {
     RowScalars rs;
-    if (coupled_route(c, want_grad)) GPN_TRY(gpr_reglap_coupled_scalars(c, theta_h, P, t_h, want_grad, &rs, info_h));
+    if (d6_route(c)) GPN_TRY(gpr_reglap_d6_scalars(c, theta_h, P, t_h, want_grad, &rs, info_h));
+    else if (coupled_route(c, want_grad)) GPN_TRY(gpr_reglap_coupled_scalars(c, theta_h, P, t_h, want_grad, &rs, info_h));
     else GPN_TRY(gpr_reglap_schur_scalars(c, theta_h, P, t_h, want_grad, &rs, info_h));
     row_eval(rs, c->theta_exp[P - 1], P, want_grad, out_h);
     return 0;
@@ -1140,9 +1337,11 @@ int gpr_logp_grad_reglap_schur(gpn_ctx* c, const double* theta_h, int P, const d
 // s = u.u, a = u.v, q = v.v; S1 = W^T u, St = W^T v, S = W^T W.  Used by the landscape driver, where every noise value of a
 // grid row shares them.  info > 0: K_tt itself is not positive definite (the caller falls back to factoring K_y per point).
 int gpr_row_scalars(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad, RowScalars* rs, int* info_h) {
-    if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN && c->fast_reglap >= 2 && c->train_unique && c->n_train < c->N)
+    if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN && c->fast_reglap >= 2 && c->train_unique && c->n_train < c->N) {
+        if (d6_route(c)) return gpr_reglap_d6_scalars(c, theta_h, P, t_h, want_grad, rs, info_h);
         return coupled_route(c, want_grad) ? gpr_reglap_coupled_scalars(c, theta_h, P, t_h, want_grad, rs, info_h)
                                                   : gpr_reglap_schur_scalars(c, theta_h, P, t_h, want_grad, rs, info_h);
+    }
     int st = kernel_build(c, kind, theta_h, P, want_grad);
     if (st != 0) return st;
     GPN_TRY(ensure_vecs(c));
@@ -1602,6 +1801,20 @@ void gpn_destroy(gpn_ctx* c) {
         if (b.p) cudaFree(b.p);
     for (auto& b : c->nb)
         if (b.p) cudaFree(b.p);
+    {
+        Dissect6& q = c->d6;
+        DevBuf* d6b[] = {&q.indptr, &q.indices, &q.weights, &q.dinv, &q.trank, &q.sep_ptr, &q.sep_idx, &q.sep_w, &q.sep_pp};
+        for (DevBuf* b : d6b)
+            if (b->p) cudaFree(b->p);
+        for (auto& b : q.work)
+            if (b.p) cudaFree(b.p);
+        for (auto& b : c->flagsK)
+            if (b.p) cudaFree(b.p);
+        for (int k = 0; k < 10; ++k) {
+            if (c->side[k]) { cudaStreamSynchronize(c->side[k]); cudaStreamDestroy(c->side[k]); }
+            if (c->ev_side[k]) cudaEventDestroy(c->ev_side[k]);
+        }
+    }
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1657,6 +1870,7 @@ int gpn_set_graph(gpn_ctx* c, int N, const int* indptr_h, const int* indices_h, 
     else c->h_weights.clear();
     c->h_train.clear();
     c->perm_valid = false;
+    c->d6.built = false;
     return gpn_k_degree_dinv(c, N, (const int*)c->indptr.p, (const int*)c->indices.p, (const double*)c->weights.p, (double*)c->dinv.p);
 }
 
@@ -1679,6 +1893,7 @@ int gpn_set_nodes(gpn_ctx* c, int n_train, const int* train_h, int n_test, const
     std::sort(c->h_train.begin(), c->h_train.end());
     c->train_unique = std::adjacent_find(c->h_train.begin(), c->h_train.end()) == c->h_train.end();
     c->perm_valid = false;
+    c->d6.built = false;
     return ensure_vecs(c);
 }
 
@@ -1720,7 +1935,12 @@ int gpn_debug_leaf_bench(gpn_ctx* c, void* A_dev, int copies, void* prof32_dev) 
     return gpn_leaf_bench(c, (double*)A_dev, copies, (double*)c->winv.p, iscal(c, 0), (long long*)prof32_dev);
 }
 void gpn_set_fast_paths(gpn_ctx* c, int level) {
-    if (c) c->fast_reglap = level < 0 ? 0 : (level > 5 ? 5 : level);
+    if (c) c->fast_reglap = level < 0 ? 0 : (level > 6 ? 6 : level);
+}
+void gpn_set_dissection_parts(gpn_ctx* c, int parts) {
+    if (!c) return;
+    c->d6_parts = parts < 0 ? 0 : (parts > 8 ? 8 : parts);
+    c->d6.built = false;
 }
 void gpn_debug_df_trace(gpn_ctx* c, void* dev_buf) {
     if (c) c->df_trace = dev_buf;
@@ -1916,6 +2136,9 @@ int gpn_last_route(gpn_ctx* c, int* parts_h) {
         for (int i = 0; i < 10; ++i) parts_h[i] = 0;
         if (c->last_route == 5) {
             parts_h[0] = 2; parts_h[1] = c->dis_s; parts_h[2] = c->dis_a; parts_h[3] = c->dis_b;
+        } else if (c->last_route == 6) {
+            parts_h[0] = c->d6.K; parts_h[1] = c->d6.s;
+            for (int k = 0; k < c->d6.K; ++k) parts_h[2 + k] = c->d6.nk[k];
         }
     }
     return c->last_route;

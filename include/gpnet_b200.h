@@ -141,7 +141,7 @@ int gpn_gpr_predict(gpn_ctx* ctx, int kind, const double* etheta_h, int P, const
 /* after gpn_gpr_predict: which = 0 k (n x n), 1 kstar (m x n), 2 L (n x n), 3 v (n x m), 4 kstarstar (m x m) */
 int gpn_gpr_fetch(gpn_ctx* ctx, int which, double* out_h);
 
-/* Route of gpn_gpr_logp_grad for the regularized-Laplacian kernel (all three agree to rounding):
+/* Route of gpn_gpr_logp_grad for the regularized-Laplacian kernel (all agree to rounding):
  *   0  full kernel: K = (I + beta L~)^-1 formed, block gathered, K_y factored (the reference's own order of operations);
  *   1  block path: training nodes numbered last, only K[tr,:] formed from the triangular inverse;
  *   2  Schur route: K_tt^-1 = L_tt L_tt^T is read off the Cholesky factor of I + beta L~, the all-entries noise term is a
@@ -150,9 +150,16 @@ int gpn_gpr_fetch(gpn_ctx* ctx, int which, double* out_h);
  *      I + beta L~: Z = M_oo^-1, X = M_to Z (sparse x dense), S = M_tt - X M_ot, W_to = -W_tt X;
  *   4  as 3, with the triangular inverse / triangular product that follow the two Cholesky factorisations carried as
  *      appended row blocks of the dataflow Cholesky kernel itself ([M_oo; I] and [S; X^T; I]);
- *   5  (default) as 4, with M_oo^-1 assembled from two independent halves of a level-set dissection of the other nodes (two
- *      concurrent half-size factorisations and a rank-|separator| correction); falls back to 4 where no thin separator exists. */
+ *   5  as 4, with M_oo^-1 assembled from two independent halves of a level-set dissection of the other nodes (two
+ *      concurrent half-size factorisations and a rank-|separator| correction); falls back to 4 where no thin separator exists;
+ *   6  (default) no dense Schur complement at all: log det S = log det M - log det M_oo, the quadratic forms through two
+ *      solves with M_oo, the gradient trace as tr(M^-1) - tr(M_oo^-1) - n, all from ONE augmented factorisation [M_kk; I] per
+ *      part of a K-way level-set dissection of the whole graph (K concurrent dataflow Cholesky kernels) plus the small
+ *      separator complements; falls back to 5 where the graph has no thin separators. */
 void gpn_set_fast_paths(gpn_ctx* ctx, int level);
+/* Number of parts of the whole-graph dissection of level 6: 0 (default) chooses it from the graph size (about 2048 nodes per
+ * part, at most 8) and requires N >= 2048; a value in 2..8 forces it and relaxes the size thresholds (tests, tuning). */
+void gpn_set_dissection_parts(gpn_ctx* ctx, int parts);
 /* Route the last regressor likelihood evaluation (gpn_gpr_logp_grad, landscape rows) actually took, after the fallbacks a
  * level applies on its own (e.g. 5 -> 4 where the other nodes have no thin separator); -1 before the first evaluation.
  * parts_h (may be NULL; room for 10 ints): [parts of the node dissection used (0: none), separator size, part sizes ...]. */

@@ -293,14 +293,19 @@ def test_reglap_fast_path_equals_full_path(gpu_ctx, shape):
     th = np.log([0.7, 0.05])
     res = {}
     try:
-        for level in (5, 4, 3, 2, 1, 0):
+        gpu_ctx.set_dissection_parts(2 + (N % 3))        # level 6 on small graphs: 2, 3 or 4 parts
+        for level in (6, 5, 4, 3, 2, 1, 0):
             gpu_ctx.set_fast_paths(level)
             res[level] = (gpu_ctx.gpr_logp_grad(1, th, t, True), gpu_ctx.gpr_logp_grad(1, th, t, False))
+            if level == 6 and N >= 600:
+                assert gpu_ctx.last_route()[0] == 6, (N, gpu_ctx.last_route())
     finally:
         gpu_ctx.set_fast_paths(True)
+        gpu_ctx.set_dissection_parts(0)
+        gpu_ctx.set_dissection_parts(0)
     (s0, g0, i0), (_, l0, _) = res[0]
     assert s0 == 0 and i0 == 0
-    for level in (1, 2, 3, 4, 5):
+    for level in (1, 2, 3, 4, 5, 6):
         (s1, g1, i1), (_, l1, _) = res[level]
         assert s1 == 0 and i1 == 0
         assert nrel(g1, g0) <= 1e-11, (level, g1, g0)
@@ -320,7 +325,8 @@ def test_reglap_routes_agree_with_oracle_for_stiff_parameters(gpu_ctx, beta, noi
     orc = go.OracleGP(G, kerneltype="regularized_laplacian")
     ref_v, ref_g = orc.neg_logp_grad(th, tr, t[tr])
     try:
-        for level in (0, 1, 2, 3, 4, 5):
+        gpu_ctx.set_dissection_parts(3)
+        for level in (0, 1, 2, 3, 4, 5, 6):
             gpu_ctx.set_fast_paths(level)
             st, out, info = gpu_ctx.gpr_logp_grad(1, th, t[tr], True)
             assert st == 0 and info == 0
@@ -328,6 +334,7 @@ def test_reglap_routes_agree_with_oracle_for_stiff_parameters(gpu_ctx, beta, noi
             assert nrel(out[1:], ref_g) <= 1e-8, (level, out[1:], ref_g)
     finally:
         gpu_ctx.set_fast_paths(True)
+        gpu_ctx.set_dissection_parts(0)
 
 
 @pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16])
@@ -350,7 +357,8 @@ def test_reglap_routes_random_shapes_against_oracle(gpu_ctx, seed):
     th = np.log([beta, noise])
     ref_v, ref_g = go.OracleGP(G, kerneltype="regularized_laplacian").neg_logp_grad(th, tr, t)
     try:
-        for level in (0, 1, 2, 3, 4, 5):
+        gpu_ctx.set_dissection_parts(3)
+        for level in (0, 1, 2, 3, 4, 5, 6):
             gpu_ctx.set_fast_paths(level)
             st, out, info = gpu_ctx.gpr_logp_grad(1, th, t, True)
             assert st == 0 and info == 0
@@ -358,6 +366,7 @@ def test_reglap_routes_random_shapes_against_oracle(gpu_ctx, seed):
             assert nrel(out[1:], ref_g) <= 1e-8, (level, N, n, out[1:], ref_g)
     finally:
         gpu_ctx.set_fast_paths(True)
+        gpu_ctx.set_dissection_parts(0)
 
 
 def test_reglap_routes_on_a_weighted_graph_with_isolated_nodes_and_a_training_only_component(gpu_ctx):
@@ -383,7 +392,8 @@ def test_reglap_routes_on_a_weighted_graph_with_isolated_nodes_and_a_training_on
     orc = go.OracleGP(G, kerneltype="regularized_laplacian")
     ref_v, ref_g = orc.neg_logp_grad(th, tr, t)
     try:
-        for level in (0, 1, 2, 3, 4, 5):
+        gpu_ctx.set_dissection_parts(3)
+        for level in (0, 1, 2, 3, 4, 5, 6):
             gpu_ctx.set_fast_paths(level)
             st, out, info = gpu_ctx.gpr_logp_grad(1, th, t, True)
             assert st == 0 and info == 0
@@ -391,6 +401,7 @@ def test_reglap_routes_on_a_weighted_graph_with_isolated_nodes_and_a_training_on
             assert nrel(out[1:], ref_g) <= 1e-8, (level, out[1:], ref_g)
     finally:
         gpu_ctx.set_fast_paths(True)
+        gpu_ctx.set_dissection_parts(0)
 
 
 @pytest.mark.parametrize("kind,theta,axidx", [(0, np.log([0.6, 0.01]), [0, 1]), (0, np.log([0.6, 0.01]), [1, 0]),
@@ -424,6 +435,7 @@ def test_landscape_kernel_reuse_equals_independent_points(gpu_ctx, kind, theta, 
             res[level] = out
     finally:
         gpu_ctx.set_fast_paths(True)
+        gpu_ctx.set_dissection_parts(0)
     assert np.all(np.isfinite(res[0]))
     assert nrel(res[5][:, 0], res[0][:, 0]) <= 1e-11
     if not classifier:
@@ -464,7 +476,7 @@ def c3_case():
     return G, tr, te, t, th, ref_v, ref_g
 
 
-@pytest.mark.parametrize("level", [None, 5, 4, 2, 0])
+@pytest.mark.parametrize("level", [None, 6, 5, 4, 2, 0])
 def test_c3_full_size_logp_and_gradient_against_oracle(c3_case, level):
     """GPnetRegressor.logPosterior_and_grad at N = 8192 / n = 4096 (GPnetRegressor.py:136-150 + the gradient of
     old_implementation/GPR.py:52-64) against OracleGP.neg_logp_grad: value to 1e-9, gradient to 1e-8, on the default route
@@ -496,6 +508,8 @@ def test_c3_full_size_logp_and_gradient_against_oracle(c3_case, level):
         assert route == level, (route, level)
         if level == 5:
             assert parts[0] == 2 and min(parts[2:4]) >= 512 and 0 < parts[1] <= min(parts[2:4]) // 2
+        if level == 6:
+            assert parts[0] == 4 and min(parts[2:6]) >= 1024 and sum(parts[1:6]) == 8192 and parts[1] < 1024
 
 
 @pytest.mark.parametrize("N,n,seed", [(4096, 1500, 1), (5000, 2500, 2), (6000, 2000, 3)])
@@ -514,19 +528,22 @@ def test_dissected_route_against_oracle_on_graphs_with_many_other_nodes(gpu_ctx,
     th = np.log([0.8, 0.02])
     ref_v, ref_g = go.OracleGP(G, kerneltype="regularized_laplacian").neg_logp_grad(th, tr, t)
     try:
-        for level in (True, 5, 4, 0):
+        for level in (True, 6, 5, 4, 0):
             gpu_ctx.set_fast_paths(level)
             st, out, info = gpu_ctx.gpr_logp_grad(1, th, t, True)
             route, parts = gpu_ctx.last_route()
+            st2, out2, info2 = gpu_ctx.gpr_logp_grad(1, th, t, False)
+            assert st2 == 0 and info2 == 0 and abs(out2[0] - ref_v) <= TOL * abs(ref_v), (level, out2[0], ref_v)
             assert st == 0 and info == 0
             assert abs(out[0] - ref_v) <= TOL * abs(ref_v), (level, out[0], ref_v)
             assert nrel(out[1:], ref_g) <= 1e-8, (level, out[1:], ref_g)
-            if level is True or level == 5:
-                assert route >= 5 and parts[0] >= 2 and parts[1] > 0, (level, route, parts)
+            if level is True or level >= 5:
+                assert route == (6 if level is True else level) and parts[0] >= 2 and parts[1] > 0, (level, route, parts)
             else:
                 assert route == level
     finally:
         gpu_ctx.set_fast_paths(True)
+        gpu_ctx.set_dissection_parts(0)
 
 
 def test_c4_landscape_points_against_dense_oracle():
