@@ -75,6 +75,9 @@ struct Dissect6 {
     int ND = 0;                  // N - s: nodes in the parts
     int off[9] = {0};            // first row of part k (even), off[K] = ND
     int nk[8] = {0}, ok[8] = {0};   // nodes of part k, of which others (numbered first)
+    int c0[8] = {0};             // first row of part k (multiple of 128) that has a neighbour in the separator: inside the other-node
+                                 // group and inside the training group the interior nodes are numbered before the boundary nodes,
+                                 // so G = W C is zero above row c0 of the part
     long long sep_nnz = 0;
     DevBuf indptr, indices, weights, dinv;   // the permuted graph (CSR, D^-1/2 and degrees)
     DevBuf trank;                // int[N]: rank of the permuted node among the training nodes (index into t), -1 for others
@@ -240,9 +243,12 @@ int gpn_d6_ensure(gpn_ctx* c);
 int gpn_d6_fill_zero(gpn_ctx* c, double* M, long ld);
 int gpn_d6_coupling(gpn_ctx* c, const double* t, double beta, double* b1, double* bt, double* d_out5);
 int gpn_d6_factor_reduce(gpn_ctx* c, const double* L, const double* WT, long ld, double* d_out4);
-int gpn_d6_sep_spmm(gpn_ctx* c, double beta, const double* WT, long ld, double* GT, double* GTo, long ldg);
-int gpn_d6_trace(gpn_ctx* c, int s, const double* A, long lda, const double* B, long ldb, const double* Lt, long ldl, double* d_out2);
+int gpn_d6_sep_spmm(gpn_ctx* c, int k, double beta, const double* WT, long ld, double* GT, double* GTo, long ldg);
+int gpn_d6_t_reduce(gpn_ctx* c, int s, const double* E, long lde, const double* Cb, long lds, int nb, double* T);
+int gpn_d6_sep_reduce(gpn_ctx* c, int s, const double* Lt, long ldl, const double* WTt, long ldw, const double* Y, long ldy, int rows,
+                      double* d_out2);
+int gpn_d6_tri_solve(gpn_ctx* c, int n, const double* WTf, long ld, const double* xa, const double* xb, double* va, double* vb, double* ua,
+                     double* ub);
 int gpn_d6_block_solve(gpn_ctx* c, const double* WT, long ld, const double* xa, const double* xb, double* va, double* vb, double* ua, double* ub);
 int gpn_d6_sep_gather(gpn_ctx* c, double beta, const double* ba, const double* bb, const double* ya, const double* yb, double* ra, double* rb);
-int gpn_d6_gemv2(gpn_ctx* c, int s, const double* A, long lda, const double* xa, const double* xb, double* ya, double* yb);
 int gpn_d6_sep_scatter(gpn_ctx* c, double beta, const double* ua, const double* ub, double* wa, double* wb);

@@ -143,15 +143,16 @@ __global__ void d6_factor_reduce_kernel(D6Desc d, const double* __restrict__ L, 
     }
 }
 
-// G^T = (W C)^T: row r of G^T is sum_e C[c_e, r] * (row c_e of W_k^T) over the entries of separator node r inside each part
-// (W_k^T upper triangular: row c contributes to columns j >= c only).  GTo = the same with other-node rows / columns only.
-__global__ void d6_sep_spmm_kernel(D6Desc d, const int* __restrict__ pp, const int* __restrict__ idx, const double* __restrict__ sw, double beta,
-                                   const double* __restrict__ WT, long ld, const int* __restrict__ trank, double* __restrict__ GT,
+// G^T = (W C)^T: row r of G^T is sum_e C[c_e, r] * (row c_e of W_k^T) over the entries of separator node r inside part k
+// (W_k^T upper triangular: row c contributes to columns j >= c only, and every c_e >= c0_k: the columns below c0_k are zero
+// and never stored).  GTo = the same with other-node rows / columns only.  One launch per part, so that it can follow the
+// part's factorisation on the part's own stream.
+__global__ void d6_sep_spmm_kernel(D6Desc d, int k, int c0, const int* __restrict__ pp, const int* __restrict__ idx, const double* __restrict__ sw,
+                                   double beta, const double* __restrict__ WT, long ld, const int* __restrict__ trank, double* __restrict__ GT,
                                    double* __restrict__ GTo, long ldg) {
     const int r = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= d.ND) return;
-    const int k = part_of(d, j);
+    const int j = d.off[k] + c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d.off[k + 1]) return;
     const int e0 = pp[r * (d.K + 1) + k], e1 = pp[r * (d.K + 1) + k + 1];
     double acc = 0.0;
     for (int e = e0; e < e1; ++e) {
@@ -162,17 +163,36 @@ __global__ void d6_sep_spmm_kernel(D6Desc d, const int* __restrict__ pp, const i
     if (r < d.so) GTo[(long)r * ldg + j] = trank[j] < 0 ? acc : 0.0;
 }
 
-// out[0] += sum_i A[i][i] + sum_ij A[i][j] B[i][j]   (tr(T^-1 (I + Q)) for symmetric T^-1, Q); out[1] += sum log diag(Lt)
-__global__ void d6_trace_kernel(int s, const double* __restrict__ A, long lda, const double* __restrict__ B, long ldb,
-                                const double* __restrict__ Lt, long ldl, double* __restrict__ out) {
-    const int r = blockIdx.x;
+// T = E - sum_b C_b on the lower 128-tiles (the split-K partial products G^T G were computed on their lower tiles only)
+__global__ void d6_t_reduce_kernel(int s, const double* __restrict__ E, long lde, const double* __restrict__ Cb, long lds, int nb,
+                                   double* __restrict__ T) {
+    const int r = blockIdx.y;
+    const int lim = min((r / 128 + 1) * 128, s);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < lim; c += gridDim.x * blockDim.x) {
+        const int rr = max(r, c), cc = min(r, c);          // partial products are valid on and below the diagonal (any tile size)
+        double acc = E[(long)rr * lde + cc];
+        for (int b = 0; b < nb; ++b) acc -= Cb[((long)b * lds + rr) * lds + cc];
+        T[(long)r * lds + c] = acc;
+    }
+}
+
+// After the augmented factorisation [T; I; U]: out[0] += ||W_T||_F^2 (upper triangle of WTt) + ||Y||_F^2 (Y = U L_T^-T, rows x s),
+// out[1] += sum log diag(L_T).  Blocks [0, s): rows of WTt; blocks [s, s + rows): rows of Y.
+__global__ void d6_sep_reduce_kernel(int s, const double* __restrict__ Lt, long ldl, const double* __restrict__ WTt, long ldw,
+                                     const double* __restrict__ Y, long ldy, int rows, double* __restrict__ out) {
+    const int b = blockIdx.x;
     double acc = 0.0;
-    if (B)
-        for (int c = threadIdx.x; c < s; c += blockDim.x) acc += A[(long)r * lda + c] * B[(long)r * ldb + c];
+    if (b < s) {
+        if (WTt)
+            for (int c = b + threadIdx.x; c < s; c += blockDim.x) { const double v = WTt[(long)b * ldw + c]; acc += v * v; }
+    } else {
+        const double* row = Y + (long)(b - s) * ldy;
+        for (int c = threadIdx.x; c < s; c += blockDim.x) { const double v = row[c]; acc += v * v; }
+    }
     acc = block_sum(acc);
     if (threadIdx.x == 0) {
-        if (A) atomicAdd(out + 0, acc + A[(long)r * lda + r]);
-        atomicAdd(out + 1, log(Lt[(long)r * ldl + r]));
+        if (acc != 0.0) atomicAdd(out + 0, acc);
+        if (b < s) atomicAdd(out + 1, log(Lt[(long)b * ldl + b]));
     }
 }
 
@@ -246,22 +266,6 @@ __global__ void d6_sep_gather_kernel(D6Desc d, const int* __restrict__ ptr, cons
     b = warp_sum(b);
     if (lane == 0) { ra[r] = ba[d.ND + r] - a; rb[r] = bb[d.ND + r] - b; }
 }
-// y = A x for a small dense s x s matrix, two right-hand sides (one warp per row)
-__global__ void d6_gemv2_kernel(int s, const double* __restrict__ A, long lda, const double* __restrict__ xa, const double* __restrict__ xb,
-                                double* __restrict__ ya, double* __restrict__ yb) {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (r >= s) return;
-    double a = 0.0, b = 0.0;
-    for (int c = lane; c < s; c += 32) {
-        const double v = A[(long)r * lda + c];
-        a += v * xa[c];
-        b += v * xb[c];
-    }
-    a = warp_sum(a);
-    b = warp_sum(b);
-    if (lane == 0) { ya[r] = a; yb[r] = b; }
-}
 // w = b_D - C_o u_S on the other-node rows of the parts: w starts as b, every separator row scatters its contribution
 __global__ void d6_sep_scatter_kernel(D6Desc d, const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ sw, double beta,
                                       const int* __restrict__ trank, const double* __restrict__ ua, const double* __restrict__ ub,
@@ -311,7 +315,7 @@ int gpn_d6_ensure(gpn_ctx* c) {
     const int N = c->N, n = c->n_train;
     static const int k_env = getenv("GPNET_B200_D6_PARTS") ? atoi(getenv("GPNET_B200_D6_PARTS")) : 0;
     const int forced = c->d6_parts > 0 ? c->d6_parts : k_env;      // forced: tests exercise the route on small graphs too
-    int K = forced > 0 ? forced : (N + 1024) / 2048;
+    int K = forced > 0 ? forced : (N + 820) / 1640;        // ~1600 nodes per part (a sweep at N = 8192 is flat between 5 and 6 parts)
     if (K > 8) K = 8;
     const int min_nodes = forced > 0 ? 64 : 2048, min_part = forced > 0 ? 8 : 256;
     if (K < 2 || N < min_nodes || n <= 0 || n >= N) return 0;
@@ -391,6 +395,24 @@ int gpn_d6_ensure(gpn_ctx* c) {
     }
     std::sort(so_nodes.begin(), so_nodes.end());
     std::sort(st_nodes.begin(), st_nodes.end());
+    {   // inside each group: interior nodes first, then the nodes with a neighbour in the separator (ascending ids in both)
+        std::vector<char> in_sep(N, 0), bnd(N, 0);
+        for (int v : so_nodes) in_sep[v] = 1;
+        for (int v : st_nodes) in_sep[v] = 1;
+        for (int v = 0; v < N; ++v)
+            for (int e = c->h_indptr[v]; e < c->h_indptr[v + 1] && !bnd[v]; ++e) bnd[v] = in_sep[c->h_indices[e]];
+        for (int k = 0; k < K; ++k) {
+            std::stable_partition(po[k].begin(), po[k].end(), [&](int v) { return !bnd[v]; });
+            std::stable_partition(pt[k].begin(), pt[k].end(), [&](int v) { return !bnd[v]; });
+            int first = (int)(po[k].size() + pt[k].size());
+            for (size_t i = 0; i < po[k].size(); ++i)
+                if (bnd[po[k][i]]) { first = (int)i; break; }
+            if (first == (int)(po[k].size() + pt[k].size()))
+                for (size_t i = 0; i < pt[k].size(); ++i)
+                    if (bnd[pt[k][i]]) { first = (int)(po[k].size() + i); break; }
+            q.c0[k] = first / 128 * 128;
+        }
+    }
     const int s = (int)(so_nodes.size() + st_nodes.size());
     int minpart = N;
     for (int k = 0; k < K; ++k) minpart = std::min(minpart, (int)(po[k].size() + pt[k].size()));
@@ -492,20 +514,44 @@ int gpn_d6_factor_reduce(gpn_ctx* c, const double* L, const double* WT, long ld,
     GPN_CK(cudaGetLastError());
     return 0;
 }
-int gpn_d6_sep_spmm(gpn_ctx* c, double beta, const double* WT, long ld, double* GT, double* GTo, long ldg) {
+int gpn_d6_sep_spmm(gpn_ctx* c, int k, double beta, const double* WT, long ld, double* GT, double* GTo, long ldg) {
     const Dissect6& q = c->d6;
-    d6_sep_spmm_kernel<<<dim3((q.ND + TPB - 1) / TPB, q.s), TPB, 0, c->stream>>>(make_desc(q), (const int*)q.sep_pp.p, (const int*)q.sep_idx.p,
-                                                                                 (const double*)q.sep_w.p, beta, WT, ld, (const int*)q.trank.p, GT,
-                                                                                 GTo, ldg);
+    const int cols = q.nk[k] - q.c0[k];
+    if (cols <= 0) return 0;
+    d6_sep_spmm_kernel<<<dim3((cols + TPB - 1) / TPB, q.s), TPB, 0, c->stream>>>(make_desc(q), k, q.c0[k], (const int*)q.sep_pp.p,
+                                                                               (const int*)q.sep_idx.p, (const double*)q.sep_w.p, beta, WT, ld,
+                                                                               (const int*)q.trank.p, GT, GTo, ldg);
     c->launches++;
     GPN_CK(cudaGetLastError());
     return 0;
 }
-// d_out[0] += tr(A) + sum A o B (skipped when A == nullptr), d_out[1] += sum log diag(Lt); the caller zeroes d_out
-int gpn_d6_trace(gpn_ctx* c, int s, const double* A, long lda, const double* B, long ldb, const double* Lt, long ldl, double* d_out2) {
+int gpn_d6_t_reduce(gpn_ctx* c, int s, const double* E, long lde, const double* Cb, long lds, int nb, double* T) {
     if (s <= 0) return 0;
-    d6_trace_kernel<<<s, TPB, 0, c->stream>>>(s, A, lda, B, ldb, Lt, ldl, d_out2);
+    d6_t_reduce_kernel<<<dim3(2, s), TPB, 0, c->stream>>>(s, E, lde, Cb, lds, nb, T);
     c->launches++;
+    GPN_CK(cudaGetLastError());
+    return 0;
+}
+// d_out2[0] += ||W_T||_F^2 + ||Y||_F^2 (either may be NULL / rows == 0), d_out2[1] += sum log diag(Lt); the caller zeroes d_out2
+int gpn_d6_sep_reduce(gpn_ctx* c, int s, const double* Lt, long ldl, const double* WTt, long ldw, const double* Y, long ldy, int rows,
+                      double* d_out2) {
+    if (s <= 0) return 0;
+    if (!Y) rows = 0;
+    d6_sep_reduce_kernel<<<s + rows, TPB, 0, c->stream>>>(s, Lt, ldl, WTt, ldw, Y, ldy, rows, d_out2);
+    c->launches++;
+    GPN_CK(cudaGetLastError());
+    return 0;
+}
+// u = (L L^T)^-1 x for ONE dense n x n factor given as WTf = L^-T (upper): u = W^T (W x), two right-hand sides; v = scratch
+int gpn_d6_tri_solve(gpn_ctx* c, int n, const double* WTf, long ld, const double* xa, const double* xb, double* va, double* vb, double* ua,
+                     double* ub) {
+    if (n <= 0) return 0;
+    D6Desc d = {};
+    d.K = 1; d.ND = n; d.nk[0] = n; d.ok[0] = n; d.off[0] = 0;
+    for (int k = 1; k < 9; ++k) d.off[k] = n;
+    d6_w_mul_kernel<<<dim3((n + 31) / 32, 1), dim3(32, 8), 0, c->stream>>>(d, WTf, ld, xa, xb, va, vb);
+    d6_wt_mul_kernel<<<(n * 32 + TPB - 1) / TPB, TPB, 0, c->stream>>>(d, WTf, ld, va, vb, ua, ub);
+    c->launches += 2;
     GPN_CK(cudaGetLastError());
     return 0;
 }
@@ -525,13 +571,6 @@ int gpn_d6_sep_gather(gpn_ctx* c, double beta, const double* ba, const double* b
     if (q.so <= 0) return 0;
     d6_sep_gather_kernel<<<(q.so * 32 + TPB - 1) / TPB, TPB, 0, c->stream>>>(make_desc(q), (const int*)q.sep_ptr.p, (const int*)q.sep_idx.p,
                                                                             (const double*)q.sep_w.p, beta, (const int*)q.trank.p, ba, bb, ya, yb, ra, rb);
-    c->launches++;
-    GPN_CK(cudaGetLastError());
-    return 0;
-}
-int gpn_d6_gemv2(gpn_ctx* c, int s, const double* A, long lda, const double* xa, const double* xb, double* ya, double* yb) {
-    if (s <= 0) return 0;
-    d6_gemv2_kernel<<<(s * 32 + TPB - 1) / TPB, TPB, 0, c->stream>>>(s, A, lda, xa, xb, ya, yb);
     c->launches++;
     GPN_CK(cudaGetLastError());
     return 0;

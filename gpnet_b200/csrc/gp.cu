@@ -1020,24 +1020,49 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
     c->ldN = pad128(N);
     c->last_route = 6;
     GPN_TRY(clear_info(c));
-    const long ld = c->ldN, ldg = pad128(ND), lds = pad128(s), ldso = pad128(std::max(so, 1));
+    const long ld = c->ldN, ldg = pad128(ND), lds = pad128(s), ldso = pad128(std::max(so, 1)), rowsU = pad128(ND);
+    const int nb = K;                                           // partial products G_k^T G_k, one per part
     const double beta = c->theta_exp[0];
     GPN_TRY(ensure_mat(c, 0));
     GPN_TRY(ensure_mat(c, 2));
     double *M = mat(c, 0), *WT = mat(c, 2);
     if (t_h) GPN_TRY(upload(c, vecp(c, V_T), t_h, sizeof(double) * n));
     else GPN_CK(cudaMemcpyAsync(vecp(c, V_T), vecp(c, V_TRES), sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-    GPN_TRY(gpn_buf_ensure(c, q.work[0], sizeof(double) * (size_t)lds * ldg));         // G^T   (s x ND)
-    GPN_TRY(gpn_buf_ensure(c, q.work[1], sizeof(double) * (size_t)ldso * ldg));        // G_o^T (so x ND, training columns zero)
-    GPN_TRY(gpn_buf_ensure(c, q.work[4], sizeof(double) * (size_t)lds * lds * 4));     // T, W_T^T, T^-1, Q
-    GPN_TRY(gpn_buf_ensure(c, q.work[5], sizeof(double) * (size_t)ldso * ldso * 4));   // the same for the other-node block
-    GPN_TRY(gpn_buf_ensure(c, q.work[6], sizeof(double) * (size_t)ld * 16));           // vectors of length N
+    GPN_TRY(gpn_buf_ensure(c, q.work[0], sizeof(double) * (size_t)lds * ldg));             // G^T   (s x ND; only columns >= c0 of each part are used)
+    GPN_TRY(gpn_buf_ensure(c, q.work[1], sizeof(double) * (size_t)ldso * ldg));            // G_o^T (so x ND, training columns zero)
+    GPN_TRY(gpn_buf_ensure(c, q.work[4], sizeof(double) * (size_t)lds * lds * 2));         // T, W_T^T
+    GPN_TRY(gpn_buf_ensure(c, q.work[5], sizeof(double) * (size_t)ldso * ldso * 2));       // T_o, W_To^T
+    GPN_TRY(gpn_buf_ensure(c, q.work[6], sizeof(double) * (size_t)ld * 16));               // vectors of length N
+    GPN_TRY(gpn_buf_ensure(c, q.work[7], sizeof(double) * (size_t)nb * lds * lds));        // split-K partial products of G^T G
+    GPN_TRY(gpn_buf_ensure(c, q.work[8], sizeof(double) * (size_t)nb * ldso * ldso));
     double *GT = (double*)q.work[0].p, *GTo = (double*)q.work[1].p;
-    double *Tb = (double*)q.work[4].p, *WTt = Tb + lds * lds, *Tinv = WTt + lds * lds, *Qm = Tinv + lds * lds;
-    double *Tob = (double*)q.work[5].p, *WTto = Tob + ldso * ldso, *Toinv = WTto + ldso * ldso, *Qo = Toinv + ldso * ldso;
+    double *Tb = (double*)q.work[4].p, *WTt = Tb + lds * lds;
+    double *Tob = (double*)q.work[5].p, *WTto = Tob + ldso * ldso;
+    double *U = nullptr, *Uo = nullptr;
+    if (want_grad) {   // U = D^-1 C (ND x s) and its other-node counterpart (rows of training nodes stay zero)
+        const size_t ub = sizeof(double) * (size_t)rowsU * lds, uob = sizeof(double) * (size_t)rowsU * ldso;
+        const bool fresh = q.work[2].cap < ub;
+        GPN_TRY(gpn_buf_ensure(c, q.work[2], ub));
+        GPN_TRY(gpn_buf_ensure(c, q.work[3], uob));
+        U = (double*)q.work[2].p;
+        Uo = (double*)q.work[3].p;
+        if (fresh) GPN_CK(cudaMemsetAsync(U, 0, q.work[2].cap, c->stream));                // rows [ND, rowsU) must read as zero
+        GPN_CK(cudaMemsetAsync(Uo, 0, uob, c->stream));
+    }
     auto vec = [&](int i) { return (double*)q.work[6].p + (long)i * ld; };
     double *b1 = vec(0), *bt = vec(1), *v1 = vec(2), *vt = vec(3), *y1 = vec(4), *yt = vec(5), *w1 = vec(6), *wt = vec(7), *u1 = vec(8),
            *ut = vec(9), *r1 = vec(10), *rt = vec(11), *us1 = vec(12), *ust = vec(13);
+    // development aid (GPNET_B200_D6_TIMING=1): CUDA-event time of every phase on the main stream, printed to stderr
+    static const bool timing = getenv("GPNET_B200_D6_TIMING") != nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    auto mark = [&](const char* name) {
+        if (!timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, c->stream);
+        marks.push_back({name, e});
+    };
+    mark("start");
     // scalar block of this route: [0..4] coupling sums, [5..8] factor reductions, [9,10] tr / log det of T, [11,12] of T_o, [13..18] dots
     GPN_CK(cudaMemsetAsync(dscal(c, 0), 0, sizeof(double) * Scal::NDBL, c->stream));
     // ---- assembly: M on the permuted graph (only the diagonal blocks and the separator block are read as dense) ----
@@ -1045,12 +1070,14 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
     GPN_TRY(gpn_k_laplacian_scatter(c, N, (const int*)q.indptr.p, (const int*)q.indices.p, c->h_weights.empty() ? nullptr : (const double*)q.weights.p,
                                     (const double*)q.dinv.p, beta, 1.0, M, ld));
     GPN_TRY(gpn_d6_coupling(c, vecp(c, V_T), beta, b1, bt, dscal(c, 0)));
-    // ---- K concurrent augmented factorisations [M_kk; I] -> L_k (in place), W_k^T (upper tiles of WT) ----
+    mark("assembly");
+    // ---- one stream per part: [M_kk; I] -> L_k, W_k^T;  G_k^T = (W_k C_k)^T;  U_k = W_k^T G_k (gradient only) ----
     int Tk[8], woff[9] = {0};
     for (int k = 0; k < K; ++k) { Tk[k] = (q.nk[k] + 127) / 128; woff[k + 1] = woff[k] + Tk[k]; }
     const int Ts = (s + 127) / 128, Tso = (std::max(so, 1) + 127) / 128;
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)(woff[K] + Ts + Tso + 2) * 128 * 128));
     double* winv = (double*)c->winv.p;
+    cudaStream_t main_stream = c->stream;
     {
         double wsum = 0.0;
         for (int k = 0; k < K; ++k) wsum += (double)q.nk[k] * q.nk[k] * q.nk[k];
@@ -1058,7 +1085,6 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
         for (int k = 0; k < K; ++k) { caps[k] = std::max(12, (int)(c->num_sms * ((double)q.nk[k] * q.nk[k] * q.nk[k] / wsum))); used += caps[k]; }
         for (int k = 0; used > c->num_sms; k = (k + 1) % K)
             if (caps[k] > 12) { --caps[k]; --used; }
-        cudaStream_t main_stream = c->stream;
         GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
         int st = 0;
         for (int k = 0; k < K && st == 0; ++k) {
@@ -1069,9 +1095,35 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
                 c->stream = c->side[k];
             }
             c->potrf_grid_cap = caps[k];
-            double* Mk = M + (long)q.off[k] * ld + q.off[k];
-            st = gpn_potrf_dataflow(c, q.nk[k], Mk, ld, winv + (size_t)woff[k] * 128 * 128, iscal(c, k), 0, nullptr, 0, 0,
-                                    WT + (long)q.off[k] * ld + q.off[k], ld, k);
+            double *Mk = M + (long)q.off[k] * ld + q.off[k], *WTk = WT + (long)q.off[k] * ld + q.off[k];
+            st = gpn_potrf_dataflow(c, q.nk[k], Mk, ld, winv + (size_t)woff[k] * 128 * 128, iscal(c, k), 0, nullptr, 0, 0, WTk, ld, k);
+            c->potrf_grid_cap = 0;
+            if (st == 0) st = gpn_d6_sep_spmm(c, k, beta, WT, ld, GT, GTo, ldg);
+            // G_k is zero above row c0 of the part (interior nodes come first): every product below starts there
+            const int c0 = q.c0[k], kr = q.nk[k] - c0, c0o = std::min(c0, q.ok[k]), kro = q.ok[k] - c0o;
+            const double* GTk = GT + q.off[k] + c0;
+            double *Cb = (double*)q.work[7].p + (size_t)k * lds * lds, *Cbo = (double*)q.work[8].p + (size_t)k * ldso * ldso;
+            if (st == 0) {
+                if (kr > 0) st = gpn_gemm(c, s, s, kr, 1.0, GTk, ldg, true, GTk, ldg, true, 0.0, Cb, lds, GF_LOWER);
+                else st = gpn_k_fill_zero(c, Cb, lds, s, (int)lds);
+            }
+            if (st == 0 && so > 0) {
+                if (kro > 0) st = gpn_gemm(c, so, so, kro, 1.0, GTo + q.off[k] + c0o, ldg, true, GTo + q.off[k] + c0o, ldg, true, 0.0, Cbo, ldso, GF_LOWER);
+                else st = gpn_k_fill_zero(c, Cbo, ldso, so, (int)ldso);
+            }
+            if (st == 0 && want_grad && kr > 0) {
+                // U_k[m][r] = sum_{j >= max(m, c0)} WT_k[m][j] G^T[r][j]: rows above c0 see the full range, the rest is triangular
+                double* Uk = U + (long)q.off[k] * lds;
+                if (c0 > 0) st = gpn_gemm(c, c0, s, kr, 1.0, WTk + c0, ld, true, GTk, ldg, true, 0.0, Uk, lds, 0);
+                if (st == 0) st = gpn_gemm(c, kr, s, kr, 1.0, WTk + (long)c0 * ld + c0, ld, true, GTk, ldg, true, 0.0, Uk + (long)c0 * lds, lds, GF_KLO_M);
+                if (st == 0 && so > 0 && kro > 0) {
+                    double* Uok = Uo + (long)q.off[k] * ldso;
+                    const double* GTok = GTo + q.off[k] + c0o;
+                    if (c0o > 0) st = gpn_gemm(c, c0o, so, kro, 1.0, WTk + c0o, ld, true, GTok, ldg, true, 0.0, Uok, ldso, 0);
+                    if (st == 0) st = gpn_gemm(c, kro, so, kro, 1.0, WTk + (long)c0o * ld + c0o, ld, true, GTok, ldg, true, 0.0, Uok + (long)c0o * ldso, ldso,
+                                               GF_KLO_M);
+                }
+            }
             if (k > 0 && st == 0) {
                 cudaError_t e = cudaEventRecord(c->ev_side[k], c->side[k]);
                 if (e != cudaSuccess) st = GPN_CUDA_ERR(e);
@@ -1082,90 +1134,73 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
         if (st != 0) return st;
         for (int k = 1; k < K; ++k) GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_side[k], 0));
     }
+    mark("parts: factor, G, U");
     GPN_TRY(gpn_d6_factor_reduce(c, M, WT, ld, dscal(c, 5)));
-    // ---- separator complements T = E - G^T G and T_o (other-node rows / columns only) ----
-    GPN_TRY(gpn_d6_sep_spmm(c, beta, WT, ld, GT, GTo, ldg));
+    // ---- separator complements T = E - sum_k G_k^T G_k (partial products from the part streams) and T_o; their augmented
+    //      factorisations [T; I; U] give L_T, W_T^T and Y = U L_T^-T:  tr(T^-1 (I + U^T U)) = ||W_T||_F^2 + ||Y||_F^2 ----
     const double* E = M + (long)ND * ld + ND;
-    GPN_TRY(gpn_k_copy(c, s, s, E, ld, Tb, lds));
-    GPN_TRY(gpn_gemm(c, s, s, ND, -1.0, GT, ldg, true, GT, ldg, true, 1.0, Tb, lds, GF_LOWER));
     double* winvT = winv + (size_t)woff[K] * 128 * 128;
-    cudaStream_t main_stream = c->stream;
     if (so > 0) {   // the other-node complement on a side stream, next to the full one
         GPN_TRY(d6_side_stream(c, 1));
         GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
         GPN_CK(cudaStreamWaitEvent(c->side[1], c->ev_fork, 0));
         c->stream = c->side[1];
-        int st = gpn_k_copy(c, so, so, E, ld, Tob, ldso);
-        if (st == 0) st = gpn_gemm(c, so, so, ND, -1.0, GTo, ldg, true, GTo, ldg, true, 1.0, Tob, ldso, GF_LOWER);
-        c->potrf_grid_cap = c->num_sms / 2;
-        if (st == 0) st = gpn_potrf_dataflow(c, so, Tob, ldso, winvT + (size_t)Ts * 128 * 128, iscal(c, 9), 0, nullptr, 0, 0, WTto, ldso, 1);
-        if (st == 0) st = gpn_lauum_t(c, so, WTto, ldso, Toinv, ldso, true);
+        int st = gpn_d6_t_reduce(c, so, E, ld, (const double*)q.work[8].p, ldso, nb, Tob);
+        c->potrf_grid_cap = c->num_sms / 3;
+        if (st == 0) st = gpn_potrf_dataflow(c, so, Tob, ldso, winvT + (size_t)Ts * 128 * 128, iscal(c, 9), 0, want_grad ? Uo : nullptr, ldso,
+                                             want_grad ? ND : 0, WTto, ldso, 1);
+        c->potrf_grid_cap = 0;
+        if (st == 0) st = gpn_d6_sep_reduce(c, so, Tob, ldso, want_grad ? WTto : nullptr, ldso, want_grad ? Uo : nullptr, ldso, ND, dscal(c, 11));
+        // u_x = M_oo^-1 (M_ot x) for x = 1, t: block-arrow solve through the factors
+        if (st == 0) st = gpn_d6_block_solve(c, WT, ld, b1, bt, v1, vt, y1, yt);
+        if (st == 0) st = gpn_d6_sep_gather(c, beta, b1, bt, y1, yt, r1, rt);
+        if (st == 0) st = gpn_d6_tri_solve(c, so, WTto, ldso, r1, rt, v1, vt, us1, ust);
         c->stream = main_stream;
-        c->potrf_grid_cap = 0;
         if (st != 0) return st;
+        GPN_CK(cudaMemcpyAsync(w1, b1, sizeof(double) * ND, cudaMemcpyDeviceToDevice, c->side[1]));
+        GPN_CK(cudaMemcpyAsync(wt, bt, sizeof(double) * ND, cudaMemcpyDeviceToDevice, c->side[1]));
+        GPN_CK(cudaMemsetAsync(u1, 0, sizeof(double) * 2 * ld, c->side[1]));               // u1, ut are adjacent
+        c->stream = c->side[1];
+        st = gpn_d6_sep_scatter(c, beta, us1, ust, w1, wt);
+        if (st == 0) st = gpn_d6_block_solve(c, WT, ld, w1, wt, v1, vt, u1, ut);
+        c->stream = main_stream;
+        if (st != 0) return st;
+        GPN_CK(cudaMemcpyAsync(u1 + ND, us1, sizeof(double) * so, cudaMemcpyDeviceToDevice, c->side[1]));
+        GPN_CK(cudaMemcpyAsync(ut + ND, ust, sizeof(double) * so, cudaMemcpyDeviceToDevice, c->side[1]));
         GPN_CK(cudaEventRecord(c->ev_side[1], c->side[1]));
-    }
-    c->potrf_grid_cap = c->num_sms / 2;
-    {
-        int st = gpn_potrf_dataflow(c, s, Tb, lds, winvT, iscal(c, 8), 0, nullptr, 0, 0, WTt, lds, 0);
-        c->potrf_grid_cap = 0;
-        if (st != 0) return st;
-    }
-    if (want_grad) {
-        // U^T = G^T W per part (U = D^-1 C), Q = U^T U, tr(M^-1) = sum ||W_k||_F^2 + tr(T^-1 (I + Q))
-        GPN_TRY(gpn_buf_ensure(c, q.work[2], sizeof(double) * (size_t)lds * ldg));
-        GPN_TRY(gpn_buf_ensure(c, q.work[3], sizeof(double) * (size_t)ldso * ldg));
-        double *UT = (double*)q.work[2].p, *UTo = (double*)q.work[3].p;
-        GPN_TRY(gpn_lauum_t(c, s, WTt, lds, Tinv, lds, true));
-        for (int k = 0; k < K; ++k)
-            GPN_TRY(gpn_gemm(c, s, q.nk[k], q.nk[k], 1.0, GT + q.off[k], ldg, true, WT + (long)q.off[k] * ld + q.off[k], ld, true, 0.0,
-                             UT + q.off[k], ldg, GF_KLO_N));
-        GPN_TRY(gpn_gemm(c, s, s, ND, 1.0, UT, ldg, true, UT, ldg, true, 0.0, Qm, lds, GF_LOWER | GF_MIRROR));
-        GPN_TRY(gpn_d6_trace(c, s, Tinv, lds, Qm, lds, Tb, lds, dscal(c, 9)));
-        if (so > 0) {
-            GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
-            for (int k = 0; k < K; ++k)
-                if (q.ok[k] > 0)
-                    GPN_TRY(gpn_gemm(c, so, q.ok[k], q.ok[k], 1.0, GTo + q.off[k], ldg, true, WT + (long)q.off[k] * ld + q.off[k], ld, true, 0.0,
-                                     UTo + q.off[k], ldg, GF_KLO_N));
-            // U_o^T has content in the other-node columns only: the training columns of the buffer are never written, so the
-            // product runs per part over those columns
-            GPN_TRY(gpn_k_fill_zero(c, Qo, ldso, so, (int)ldso));
-            for (int k = 0; k < K; ++k)
-                if (q.ok[k] > 0)
-                    GPN_TRY(gpn_gemm(c, so, so, q.ok[k], 1.0, UTo + q.off[k], ldg, true, UTo + q.off[k], ldg, true, 1.0, Qo, ldso, GF_LOWER | GF_MIRROR));
-            GPN_TRY(gpn_d6_trace(c, so, Toinv, ldso, Qo, ldso, Tob, ldso, dscal(c, 11)));
-        }
     } else {
-        GPN_TRY(gpn_d6_trace(c, s, nullptr, 0, nullptr, 0, Tb, lds, dscal(c, 9)));
-        if (so > 0) {
-            GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
-            GPN_TRY(gpn_d6_trace(c, so, nullptr, 0, nullptr, 0, Tob, ldso, dscal(c, 11)));
-        }
-    }
-    // ---- u_x = M_oo^-1 (M_ot x) for x = 1, t: block-arrow solve through the factors ----
-    GPN_CK(cudaMemsetAsync(u1, 0, sizeof(double) * 2 * ld, c->stream));                   // u1, ut (adjacent rows of the vector block)
-    if (so > 0) {
-        GPN_TRY(gpn_d6_block_solve(c, WT, ld, b1, bt, v1, vt, y1, yt));
-        GPN_TRY(gpn_d6_sep_gather(c, beta, b1, bt, y1, yt, r1, rt));
-        GPN_TRY(gpn_d6_gemv2(c, so, Toinv, ldso, r1, rt, us1, ust));
-        GPN_CK(cudaMemcpyAsync(w1, b1, sizeof(double) * ND, cudaMemcpyDeviceToDevice, c->stream));
-        GPN_CK(cudaMemcpyAsync(wt, bt, sizeof(double) * ND, cudaMemcpyDeviceToDevice, c->stream));
-        GPN_TRY(gpn_d6_sep_scatter(c, beta, us1, ust, w1, wt));
-        GPN_TRY(gpn_d6_block_solve(c, WT, ld, w1, wt, v1, vt, u1, ut));
-        GPN_CK(cudaMemcpyAsync(u1 + ND, us1, sizeof(double) * so, cudaMemcpyDeviceToDevice, c->stream));
-        GPN_CK(cudaMemcpyAsync(ut + ND, ust, sizeof(double) * so, cudaMemcpyDeviceToDevice, c->stream));
-    } else {
+        GPN_CK(cudaMemsetAsync(u1, 0, sizeof(double) * 2 * ld, c->stream));
         GPN_TRY(gpn_d6_block_solve(c, WT, ld, b1, bt, v1, vt, u1, ut));
     }
+    {
+        GPN_TRY(gpn_d6_t_reduce(c, s, E, ld, (const double*)q.work[7].p, lds, nb, Tb));
+        mark("T");
+        c->potrf_grid_cap = so > 0 ? c->num_sms - c->num_sms / 3 : 0;
+        int st = gpn_potrf_dataflow(c, s, Tb, lds, winvT, iscal(c, 8), 0, want_grad ? U : nullptr, lds, want_grad ? ND : 0,
+                                    want_grad ? WTt : nullptr, lds, 0);
+        c->potrf_grid_cap = 0;
+        if (st != 0) return st;
+        mark("[T; I; U]");
+        GPN_TRY(gpn_d6_sep_reduce(c, s, Tb, lds, want_grad ? WTt : nullptr, lds, want_grad ? U : nullptr, lds, ND, dscal(c, 9)));
+    }
+    if (so > 0) GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
     {
         const double *dx[6] = {b1, b1, bt, u1, u1, ut}, *dy[6] = {u1, ut, ut, u1, ut, ut};
         const int dn[6] = {N, N, N, N, N, N};
         GPN_TRY(gpn_k_multi_dot(c, 6, dx, dy, dn, dscal(c, 13)));
     }
+    mark("reductions, join, dots");
     double sc[Scal::NDBL];
     int info[16];
     GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
+    if (timing) {
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            fprintf(stderr, "d6 %-26s %8.3f ms\n", marks[i].first, ms);
+        }
+        for (auto& m : marks) cudaEventDestroy(m.second);
+    }
     if (info_h) {
         *info_h = 0;
         for (int i = 0; i < 10 && *info_h == 0; ++i) *info_h = info[i];
