@@ -1,21 +1,32 @@
 """Headline benchmark: GP logp+grad evaluations per second at N = 8192 graph nodes (fp64), config C3 of SURVEY.md
 Appendix D (GPnetRegressor, regularized-Laplacian kernel, random geometric graph, n = 4096 training nodes, P = 2).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nodes 8192]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c4] [--evals-per-step B]
 
-One "step" = one evaluation theta (host) -> (-logp, -dlogp/dtheta) (host), from scratch: nothing is carried over between
-evaluations (like the reference, which rebuilds everything per call); only the graph, the node sets and the targets are
-resident.  The default route reads the inverse training block off a Schur complement instead of forming the kernel
-(DESIGN.md section 4); `routes` in the JSON line times the reference's own order of operations (full kernel, block gather,
-Cholesky, alpha, log-det, K_y^-1, the P trace terms) and the intermediate routes beside it, and utilisation is always
-reported from EXECUTED flops.  Prints ONE JSON line (see the task contract); rank 0 only.
+One "step" = one batch of B multi-start evaluations theta (host) -> (-logp, -dlogp/dtheta) (host), each from scratch: nothing
+is carried over between evaluations (like the reference, which rebuilds everything per call); only the graph, the node sets
+and the targets are resident.  `value` = evaluations per second over all ranks (weak scaling: every GPU runs its own batch;
+the (1+P)-double results are all-gathered once, after the K steps, inside the timed region).  The default route never forms
+the kernel; `routes` times the reference's own order of operations (full kernel, block gather, Cholesky,
+alpha, log-det, K_y^-1, the P trace terms) beside it, and utilisation is always reported from EXECUTED flops.
+
+`--workload c4` makes the 64 x 64 diffusion landscape at N = 4096 (config C4, GPnet.py:539-552; strong scaling over the ranks,
+kernel groups dealt longest-first, ONE all-gather) the headline; in the default run it is reported under `extras.c4_landscape`
+at every N so that the driver's scaling runs carry it.  Prints ONE JSON line; rank 0 only.
 """
+import os
+import sys
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # the CPU arm runs single-process on ALL host cores: torchrun exports OMP_NUM_THREADS=1, undo that before numpy loads its BLAS
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(_k, None)
+
 import argparse
+import contextlib
 import json
 import math
-import os
 import subprocess
-import sys
 import time
 
 import numpy as np
@@ -27,7 +38,6 @@ METRIC = "GP logp+grad evals/sec at N=8192 nodes (fp64)"
 UNIT = "evals/s"
 THETA = np.log([0.6, 0.01])      # C3 theta_0
 KERNEL = "regularized_laplacian"
-
 
 _JSON_FD = None
 
@@ -42,10 +52,17 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
-def workload_config(N, n, P, world):
+def workload_config(workload, N, n, P, world, B):
     """The same `config` object on both arms."""
+    if workload == "c4":
+        return {"workload": f"C4: GPnetRegressor diffusion, 64x64 logp landscape (theta0 x noise) on a random geometric graph N={N}, n={n}; "
+                            "one whole landscape per step, grid sharded over the GPUs by kernel group, ONE all-gather of (1+P) doubles per point",
+                "l2": "inputs larger than L2 (each N x N fp64 operand is 134 MB vs 126 MB L2; ten are live per kernel build)",
+                "parallelism": f"grid sharded x{world}"}
     return {"workload": f"C3: GPnetRegressor regularized_laplacian, random geometric graph N={N}, n={n}, P={P}, theta=log[0.6,0.01]; "
-                        f"one logp+grad per step per GPU (multi-start thetas across GPUs, (1+P)-double NCCL all-gather per step)",
+                        f"one step = {B} multi-start logp+grad evaluations per GPU, each from scratch; (1+P)-double results all-gathered "
+                        "once after the K steps (inside the timed region)",
+            "evals_per_step": B,
             "l2": "inputs larger than L2 (each N x N fp64 operand is 537 MB vs 126 MB L2)", "parallelism": f"replicas x{world}"}
 
 
@@ -63,6 +80,12 @@ def c3_problem(N):
     pos = np.array([G.nodes[i]["pos"] for i in range(N)])
     t = np.sin(4 * np.pi * pos[:, 0]) * np.cos(4 * np.pi * pos[:, 1])
     return G, (indptr, indices, w), train, test, t
+
+
+def multistart_thetas(rank, B):
+    """B log-parameter vectors around the C3 theta_0 (multi-start / line-search probes of an optimiser), distinct per rank."""
+    d = np.array([1.0, -1.0])
+    return [THETA + (0.01 * rank + 0.004 * (b - B / 2) / max(B, 1)) * d for b in range(B)]
 
 
 def algorithmic_flops(N, n):
@@ -116,72 +139,194 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
-def cpu_port_eval(problem, N, reference_style):
-    """CPU legs (the ONLY place bench.py executes oracle/).  reference_style=True: one logPosterior the way the
-    reference computes it (scipy.linalg.inv + cholesky + two general solves, GPnet.py:342 + GPnetRegressor.py:139-150);
-    False: the best-effort dense restatement with the analytic gradient (one full logp+grad)."""
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs (the ONLY place bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------------------------------
+def pin_blas_threads():
+    """All host cores for the BLAS/LAPACK pools, also under torchrun (which exports OMP_NUM_THREADS=1).  Returns the count."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=cores)
+        return max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
+    except Exception:
+        return cores
+
+
+def cpu_port_eval(problem, N):
+    """Best-effort dense numpy/scipy restatement with the analytic gradient: ONE full logp+grad (cpu_baseline, kind "port")."""
     from oracle import gp_oracle as go
     _, csr, train, test, t = problem
     orc = go.OracleGP(csr=csr, kerneltype=KERNEL, expm_mode="dense")
-    tt = t[train]
     t0 = time.perf_counter()
-    if reference_style:
-        val = orc.neg_logp(THETA, train, tt)
-    else:
-        val, _ = orc.neg_logp_grad(THETA, train, tt)
+    val, _ = orc.neg_logp_grad(THETA, train, t[train])
     return time.perf_counter() - t0, val
 
 
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        return max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
-    except Exception:
-        return os.cpu_count()
+class ReferenceModel:
+    """The reference's own GPnetRegressor (unmodified, under the shims of oracle/ref_shim.py) when its modules are available
+    (oracle/_ref on the GPU box, /root/reference in the build container); else the numpy port with the reference's call
+    pattern.  logp+grad costs (P+1) logPosterior calls there: optimize_params passes no jac, scipy takes forward differences
+    (GPnet.py:264-271)."""
+
+    def __init__(self, problem, N):
+        import pandas as pd
+        G, csr, train, test, t = problem
+        self.train, self.tv = train, t[train]
+        self.kind = "port"
+        self.model = None
+        try:
+            from oracle import ref_shim
+            path = ref_shim.find_reference()
+            if path is not None:
+                import io
+                _, REG, _ = ref_shim.load_reference(path)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    self.model = REG(Graph=G, training_nodes=list(train), test_nodes=list(test), theta=list(THETA), relabel_nodes=True,
+                                     kerneltype=KERNEL, training_values=False)
+                self.series = pd.Series(self.tv, index=train)
+                self.model.set_training_values(self.series.copy())
+                self.kind = "reference"
+        except Exception as e:      # stay runnable: the port restates the same call pattern
+            print("reference modules not usable (%s: %s); timing the numpy port" % (type(e).__name__, e), file=sys.stderr)
+            self.model = None
+        if self.model is None:
+            from oracle import gp_oracle as go
+            self.orc = go.OracleGP(csr=csr, kerneltype=KERNEL, expm_mode="dense")
+
+    def log_posterior(self, theta):
+        if self.model is not None:
+            return float(self.model.logPosterior(np.array(theta), self.train, self.series))      # GPnetRegressor.py:136-150
+        return float(self.orc.neg_logp(theta, self.train, self.tv))
+
+    def logp_and_fd_grad(self, theta):
+        """What one gradient evaluation costs the reference's optimiser: f(x) and P forward-difference probes."""
+        h = 1.4901161193847656e-08      # scipy's default 2-point step sqrt(eps)
+        f0 = self.log_posterior(theta)
+        g = np.zeros(len(theta))
+        for j in range(len(theta)):
+            tp = np.array(theta, dtype=float)
+            tp[j] += h
+            g[j] = (self.log_posterior(tp) - f0) / h
+        return f0, g
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path (the oracle port with the reference's call pattern; the pure-Python
-    reference cannot travel to the GPU box) on all host cores.  The reference's optimiser gets gradients by finite
-    differences: (P+1) logPosterior calls per logp+grad (GPnet.py:264-271 passes no jac).  Each step times ONE such
-    logPosterior probe at full size; value = 1 / ((P+1) * t_step)."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, single process (rank 0 alone
+    under torchrun; the CPU arm does not scale with the number of GPUs, so `value` is the same at every N).  Every step runs ONE
+    full-size logp+grad = all (P+1) logPosterior probes; nothing is extrapolated."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = pin_blas_threads()
     N = args.nodes
     problem = c3_problem(N)
     P = len(THETA)
-    budget = 200.0
-    times = []
+    ref = ReferenceModel(problem, N)
+    W, K = args.warmup, args.steps
+    thetas = multistart_thetas(0, max(W + K, 1))
+    times, val = [], None
+    budget = 1500.0                  # safety net: report the steps actually run if the box is much slower than expected
     t_begin = time.perf_counter()
-    for i in range(args.warmup + args.steps):
-        dt, _ = cpu_port_eval(problem, N, reference_style=True)
-        if i >= args.warmup:
-            times.append(dt)
-        if time.perf_counter() - t_begin > budget and len(times) >= 1:
+    for i in range(W + K):
+        t0 = time.perf_counter()
+        val, _ = ref.logp_and_fd_grad(thetas[i % len(thetas)])
+        if i >= W:
+            times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget and times:
             break
     t_step = float(np.mean(times))
-    value = 1.0 / ((P + 1) * t_step)
-    cores = blas_threads()
+    value = 1.0 / t_step
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-            "warmup": args.warmup, "ms_per_step": t_step * 1e3 * (P + 1), "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(N, N // 2, P, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{len(times)} x one full-size logPosterior probe (N={N}); a logp+grad costs (P+1)=3 probes "
-                                       "by finite differences as in the reference's optimize_params"},
+            "config": workload_config("c3", N, N // 2, P, args.gpus, args.evals_per_step),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": ref.kind,
+                             "sample": f"{len(times)} steps of ONE full-size logp+grad (N={N}, n={N // 2}) = (P+1)={P + 1} logPosterior "
+                                       "calls each (forward differences, as the reference's optimize_params gets its gradient); the "
+                                       "unmodified GPnetRegressor under oracle/ref_shim.py" if ref.kind == "reference" else
+                                       f"{len(times)} steps of (P+1) logPosterior calls of the numpy port (reference modules not found)",
+                             "single_process": True},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def recorded_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture committed under profiles/
+    (profiles/r02_traffic.json is written by tools/ncu_summary.py from that capture); None when no capture is recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
+            rec = json.load(fh)
+        for k, v in rec.items():
+            if k != "source" and k in kernel_substr:
+                return v, rec.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
+def c4_problem(N=4096):
+    from oracle import configs as cfg      # canonical synthetic inputs only (pure host code, no numerics)
+    G, train, _, t = cfg.rgg_case(N, N // 2, 0)
+    ax1 = np.linspace(np.log(0.01), np.log(0.99), 64)
+    ax2 = np.linspace(np.log(0.001), np.log(10.0), 64)
+    return G, train, t, ax1, ax2
+
+
+def run_c4(ctx, stream, world, rank, local, reps, barrier):
+    """The 64 x 64 diffusion landscape of config C4 through the public API (GPnetRegressor.lml_landscape, GPnet.py:539-552):
+    host buffers in, host array out, grid sharded over the ranks, one all-gather.  Returns (seconds per landscape max over
+    ranks, lml array, device-event ms per landscape)."""
+    import pandas as pd
+    import torch
+    import torch.distributed as dist
+    import gpnet_b200
+    from gpnet_b200.engine import register_context
+    G, train, t, ax1, ax2 = c4_problem()
+    with contextlib.redirect_stdout(sys.stderr):
+        model = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=train, test_nodes=[], theta=list(np.log([0.6, 0.01])), relabel_nodes=True,
+                                          kerneltype="diffusion", training_values=False)
+    model.set_training_values(pd.Series(t[train], index=train))
+    register_context(ctx)
+    model._engine.device = local
+    best, best_ev, lml = None, None, None
+    with contextlib.redirect_stdout(sys.stderr):
+        for rep in range(reps + 1):            # first repetition = warm-up (allocations, graph upload)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(stream)
+            lml = model.lml_landscape([0.0, 0.0], [0, 1], ax1, ax2)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            ev = e0.elapsed_time(e1)
+            if world > 1:
+                tm = torch.tensor([dt, ev], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                dt, ev = float(tm[0].item()), float(tm[1].item())
+            if rep > 0 and (best is None or dt < best):
+                best, best_ev = dt, ev
+    return best, lml, best_ev
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4"])
+    ap.add_argument("--evals-per-step", type=int, default=48)
     ap.add_argument("--nodes", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 themselves (NCCL's version banner, the
     # drop-in classes' reference-style prints) are sent to stderr, and the line is written to the saved descriptor at the end
@@ -206,37 +351,42 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W = max(args.warmup, 3)
     K = args.steps
-    N = args.nodes
-    n = N // 2
-    problem = c3_problem(N)
-    G, csr, train, test, t = problem
-    P = len(THETA)
-    kind = KERNEL_IDS[KERNEL]
+    B = max(args.evals_per_step, 1)
 
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = Context(local, stream.cuda_stream)
-    ctx.set_graph(*csr)
-    ctx.set_nodes(train, test)
-    ctx.set_targets(t[train])
-    # multi-start: every rank evaluates its own theta (weak scaling: per-GPU work fixed), results all-gathered
-    theta = THETA + 0.01 * rank * np.array([1.0, -1.0])
-    gathered = torch.zeros((world, 1 + P), dtype=torch.float64, device="cuda") if world > 1 else None
-
-    def step():
-        st, out, info = ctx.gpr_logp_grad(kind, theta, None, True)
-        assert st == 0 and info == 0, (st, info)
-        if world > 1:     # the path's real exchange step: (1+P) doubles per rank
-            dist.all_gather_into_tensor(gathered, torch.from_numpy(out).to("cuda", non_blocking=True).reshape(1, -1))
-        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W):
-        out = step()
+    if args.workload == "c4":
+        return main_c4(args, ctx, stream, world, rank, local, W, K, barrier)
+
+    N = args.nodes
+    n = N // 2
+    problem = c3_problem(N)
+    G, csr, train, test, t = problem
+    P = len(THETA)
+    kind = KERNEL_IDS[KERNEL]
+    ctx.set_graph(*csr)
+    ctx.set_nodes(train, test)
+    ctx.set_targets(t[train])
+    thetas = multistart_thetas(rank, B)
+    results = np.zeros((K, B, 1 + P))
+    gathered = torch.zeros((world, K * B * (1 + P)), dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def step(k):
+        for b in range(B):
+            st, out, info = ctx.gpr_logp_grad(kind, thetas[b], None, True)
+            assert st == 0 and info == 0, (st, info)
+            results[k % K, b] = out
+
+    for k in range(W):
+        step(k)
+    route, parts = ctx.last_route()
     barrier()
     peak_tf = ctx.fp64_peak(0.3) if rank == 0 else 0.0
     barrier()
@@ -246,128 +396,215 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(K):
-        out = step()
+    for k in range(K):
+        step(k)
+    if world > 1:     # the path's one exchange step: every rank's (1+P) doubles per evaluation, once
+        dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(results.reshape(-1)).to("cuda", non_blocking=True))
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count()
-    exec_flops = ctx.flop_count() / K
+    exec_flops = ctx.flop_count() / (K * B)
     clocks = sampler.summary()
     if world > 1:
         tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms_total = float(tmax.item())
     ms_step = ms_total / K
-    value = world * K / (ms_total * 1e-3)
+    ms_eval = ms_step / B
+    value = world * K * B / (ms_total * 1e-3)
+    out = results[K - 1, B - 1].copy()
 
     # ---- e2e: the public API (drop-in class) with HOST buffers, copies inside the timed region -----------------
-    import contextlib
     with contextlib.redirect_stdout(sys.stderr):      # the drop-in prints like the reference; stdout carries ONE JSON line
-        model = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=train, test_nodes=test, theta=list(theta), relabel_nodes=True,
+        model = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=train, test_nodes=test, theta=list(THETA), relabel_nodes=True,
                                           kerneltype=KERNEL, training_values=False)
     tv = pd.Series(t[train], index=train)
     model.set_training_values(tv)
     from gpnet_b200.engine import register_context
     register_context(ctx)             # same device context (same stream); the engine re-binds the graph in the warm-up calls
     model._engine.device = local
-    for _ in range(2):
-        model.logPosterior_and_grad(theta, train, tv)
+    for b in range(3):
+        model.logPosterior_and_grad(thetas[b % B], train, tv)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        val, grad = model.logPosterior_and_grad(theta, train, tv)
+    for k in range(K):
+        for b in range(B):
+            val, grad = model.logPosterior_and_grad(thetas[b], train, tv)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         tmax = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
-    e2e_value = world * K / e2e_s
+    e2e_value = world * K * B / e2e_s
     assert abs(val - out[0]) <= 1e-12 * abs(val)
 
-    # ---- roofline of the dominant kernel: per-launch CUDA events on the context's stream over one extra (untimed) step ----
-    roof = None
-    cpu = None
-    routes = None
+    roof = cpu = routes = None
+    extras = {}
     if rank == 0:
+        # ---- roofline of the dominant kernel: per-launch CUDA events over one extra (untimed) evaluation.  Launches of one
+        #      kernel that run concurrently (one factorisation per part of the dissection, each on its own stream) share the chip:
+        #      achieved = executed flops of all launches / length of the union of their intervals ----
         ctx.set_profile(True)
-        ctx.gpr_logp_grad(kind, theta, None, True)
+        ctx.gpr_logp_grad(kind, THETA, None, True)
         prof = ctx.profile_summary()
         ctx.set_profile(False)
         algo = algorithmic_flops(N, n)
-        cands = {
-            "gemm_f64_kernel<2,4,6,*,*> (TMA + DMMA.8x8x4, 128x128x16 tiles)": (prof["big_ms"], prof["big_flops"], prof["big_launches"]),
-            "potrf_dataflow_kernel (persistent tile-dataflow Cholesky, TMA + DMMA.8x8x4)": (prof["potrf_ms"], prof["potrf_flops"],
-                                                                                             prof["potrf_launches"]),
+        fam = {
+            "potrf_dataflow_kernel (persistent tile-dataflow Cholesky with appended solve / inverse rows, TMA + DMMA.8x8x4)":
+                (prof["potrf_union_ms"], prof["potrf_flops"], prof["potrf_launches"], prof["potrf_ms"]),
+            "gemm_f64_kernel (TMA + DMMA.8x8x4, 128x128x16 / 64x64x16 tiles)":
+                (prof["gemm_union_ms"], prof["gemm_flops"], prof["gemm_launches"], prof["gemm_ms"]),
         }
-        kname = max(cands, key=lambda k: cands[k][0])
-        k_ms, k_fl, k_cnt = cands[kname]
-        k_tf = k_fl / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else 0.0
+        kname = max(fam, key=lambda k: fam[k][0])
+        k_un, k_fl, k_cnt, k_sum = fam[kname]
+        k_tf = k_fl / (k_un * 1e-3) * 1e-12 if k_un > 0 else 0.0
+        traffic, traffic_src = recorded_traffic(kname)
         roof = {"bound": "tensor", "kernel": kname,
                 "achieved": k_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": k_tf / peak_tf if peak_tf else None,
                 "peak_source": "measured in this run: register-resident DMMA.8x8x4 loop (gpn_fp64_peak); MEASURED_PEAKS.json has no "
                                "FP64 entry; nominal B200 FP64 is 40 TFLOP/s (37.2 at 148 SM x 64 FMA/clk x 1.965 GHz)",
-                "flops_per_launch_avg": k_fl / max(k_cnt, 1), "launch_ms_avg": k_ms / max(k_cnt, 1), "launches_per_step": k_cnt,
-                "kernel_share_of_step": k_ms / ms_step,
-                "other_kernels": {k: {"ms_per_step": v[0], "tflops": v[1] / (v[0] * 1e-3) * 1e-12 if v[0] > 0 else None,
-                                      "launches": v[2], "share_of_step": v[0] / ms_step} for k, v in cands.items() if k != kname},
-                # utilisation is claimed from EXECUTED flops only (SURVEY 8d rule): the default route of this workload reads
-                # K_tt^-1 off the Cholesky factor and executes about half of the conventional count below
-                "step_executed_tflops": exec_flops / (ms_step * 1e-3) * 1e-12,
-                "step_executed_frac_of_measured_peak": exec_flops / (ms_step * 1e-3) * 1e-12 / peak_tf if peak_tf else None,
-                "step_executed_frac_of_nominal_40tf": exec_flops / (ms_step * 1e-3) * 1e-12 / 40.0,
-                "executed_gflop_per_step": exec_flops * 1e-9,
-                "conventional_gflop_per_step": algo * 1e-9,
-                "step_conventional_tflops": algo / (ms_step * 1e-3) * 1e-12,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of the two launches
-                # of this kernel in one step (profiles/r01_ncu_potrf_half.txt: 0.019 GB for each half-block launch,
-                # profiles/r01_ncu_potrf_tt.txt: 3.033 GB);
-                # recorded, not re-measured here (numbers taken under a profiler are never bench values)
-                "traffic": 1.024e9 if kname.startswith("potrf_dataflow") and N == 8192 else None,
-                "traffic_unit": "bytes per launch (average of the step's three launches; ncu captures in profiles/)"}
-        # the same evaluation through the two other exact routes (same outputs to rounding), device-timed like `value`
+                "how": "executed flops of all launches of the kernel in one evaluation / length of the union of their launch intervals "
+                       "(CUDA events on the launching streams); the launches of one evaluation run concurrently on disjoint SM groups",
+                "launches_per_eval": k_cnt, "union_ms": k_un, "sum_of_launch_ms": k_sum,
+                "flops_per_launch_avg": k_fl / max(k_cnt, 1),
+                "kernel_share_of_eval": k_un / ms_eval,
+                "bound_note": "latency: every launch is bound by the per-tile-column dependency chain of a small factorisation "
+                              "(DESIGN.md section 4), not by the tensor pipe",
+                "other_kernels": {k: {"union_ms": v[0], "tflops": v[1] / (v[0] * 1e-3) * 1e-12 if v[0] > 0 else None,
+                                      "launches": v[2], "share_of_eval": v[0] / ms_eval} for k, v in fam.items() if k != kname},
+                # utilisation is claimed from EXECUTED flops only (SURVEY 8d rule)
+                "eval_executed_tflops": exec_flops / (ms_eval * 1e-3) * 1e-12,
+                "eval_executed_frac_of_measured_peak": exec_flops / (ms_eval * 1e-3) * 1e-12 / peak_tf if peak_tf else None,
+                "executed_gflop_per_eval": exec_flops * 1e-9,
+                "conventional_gflop_per_eval": algo * 1e-9,
+                "eval_conventional_tflops": algo / (ms_eval * 1e-3) * 1e-12,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "route": {"level": route, "parts": parts}}
         if world == 1:
+            # the same evaluation through the other exact routes (same outputs to rounding), device-timed like `value`
             routes = {}
             names = {0: "full_kernel (K formed, gathered, K_y factored: the reference's order of operations)",
-                     1: "block (training nodes last, only K[tr,:] formed)", 2: "schur (dense N x N Cholesky + triangular inverse)",
-                     3: "schur_sparse_coupling (separate triangular inverse / product launches)",
+                     2: "schur (dense N x N Cholesky + triangular inverse)",
                      4: "schur_sparse_coupling_augmented (one factorisation of the other-node block)",
-                     5: "schur_sparse_coupling_augmented_dissected (other nodes in two halves)",
+                     5: "schur_sparse_coupling_augmented_dissected (other nodes in two halves; round-1 default)",
                      6: "whole_graph_dissection (default: no dense Schur complement, one augmented factorisation per part)"}
-            for level in (0, 1, 2, 3, 4, 5):
+            for level in (0, 2, 4, 5):
                 ctx.set_fast_paths(level)
                 for _ in range(2):
-                    o2 = ctx.gpr_logp_grad(kind, theta, None, True)[1]
+                    o2 = ctx.gpr_logp_grad(kind, thetas[B - 1], None, True)[1]
                 ctx.reset_counters()
-                kk = max(4, K // 4)
+                kk = 8
+                ctx.set_profile(True)
+                ctx.gpr_logp_grad(kind, thetas[B - 1], None, True)
+                pr = ctx.profile_summary()
+                ctx.set_profile(False)
+                ctx.reset_counters()
                 r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 r0.record(stream)
                 for _ in range(kk):
-                    ctx.gpr_logp_grad(kind, theta, None, True)
+                    ctx.gpr_logp_grad(kind, thetas[B - 1], None, True)
                 r1.record(stream)
                 torch.cuda.synchronize()
                 ms = r0.elapsed_time(r1) / kk
-                routes[names[level]] = {"value": 1e3 / ms, "ms_per_step": ms, "executed_gflop_per_step": ctx.flop_count() / kk * 1e-9,
+                fl = ctx.flop_count() / kk
+                routes[names[level]] = {"value": 1e3 / ms, "ms_per_eval": ms, "executed_gflop_per_eval": fl * 1e-9,
+                                        "executed_tflops": fl / (ms * 1e-3) * 1e-12,
+                                        "frac_of_measured_peak": fl / (ms * 1e-3) * 1e-12 / peak_tf if peak_tf else None,
+                                        "potrf_tflops_over_union": pr["potrf_flops"] / (pr["potrf_union_ms"] * 1e-3) * 1e-12 if pr["potrf_union_ms"] > 0 else None,
                                         "max_rel_diff_vs_default": float(np.max(np.abs(o2 - out) / np.abs(out)))}
-            ctx.set_fast_paths(6)
-            routes[names[6]] = {"value": value, "ms_per_step": ms_step, "executed_gflop_per_step": exec_flops * 1e-9}
+            ctx.set_fast_paths(True)
+            routes[names[6]] = {"value": value, "ms_per_eval": ms_eval, "executed_gflop_per_eval": exec_flops * 1e-9,
+                                "executed_tflops": exec_flops / (ms_eval * 1e-3) * 1e-12}
+            if not args.no_extras:
+                # driver-visible expm evidence: one diffusion logp+grad at N = 8192 (7 N^3 executed: all products symmetric)
+                th_d = np.log([0.6, 0.01])
+                kd = KERNEL_IDS["diffusion"]
+                ctx.gpr_logp_grad(kd, th_d, None, True)
+                ctx.reset_counters()
+                ctx.set_profile(True)
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record(stream)
+                st, od, info = ctx.gpr_logp_grad(kd, th_d, None, True)
+                r1.record(stream)
+                torch.cuda.synchronize()
+                pr = ctx.profile_summary()
+                ctx.set_profile(False)
+                ms = r0.elapsed_time(r1)
+                fl = ctx.flop_count()
+                m_used, s_used = ctx.expm_info()
+                extras["diffusion_n8192_logp_grad"] = {
+                    "ms": ms, "evals_per_s": 1e3 / ms, "pade_order": m_used, "squarings": s_used, "executed_gflop": fl * 1e-9,
+                    "executed_tflops": fl / (ms * 1e-3) * 1e-12, "frac_of_measured_peak": fl / (ms * 1e-3) * 1e-12 / peak_tf if peak_tf else None,
+                    "gemm_tflops_while_active": pr["gemm_flops"] / (pr["gemm_union_ms"] * 1e-3) * 1e-12 if pr["gemm_union_ms"] > 0 else None,
+                    "gemm_share": pr["gemm_union_ms"] / ms, "neg_logp": float(od[0]),
+                    "what": "GPnetRegressor diffusion kernel (expm by Pade + squaring, GPnet.py:338-340) logp+grad on the C3 graph, from scratch"}
         if world == 1 and not args.no_cpu_baseline:
-            dt, cval = cpu_port_eval(problem, N, reference_style=False)
-            cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+            cores = pin_blas_threads()
+            dt, cval = cpu_port_eval(problem, N)
+            st, o0, _ = ctx.gpr_logp_grad(kind, THETA, None, True)
+            cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"1 full-size logp+grad evaluation (N={N}, n={n}) of the dense numpy/scipy restatement with the analytic "
-                             f"gradient ({dt:.1f} s); GPU/CPU -logp agree to {abs(cval - out[0]) / abs(cval):.1e}"}
+                             f"gradient ({dt:.1f} s); GPU/CPU -logp agree to {abs(cval - o0[0]) / abs(cval):.1e}"}
+    if not args.no_extras:
+        # C4 (the sharded landscape north_star names) rides along at every N so that the driver's scaling runs carry it
+        reps = 2 if world == 1 else 3
+        sec, lml, ev_ms = run_c4(ctx, stream, world, rank, local, reps, barrier)
+        if rank == 0:
+            extras["c4_landscape"] = {"seconds_per_landscape": sec, "device_event_ms": ev_ms, "points": int(lml.size),
+                                      "points_per_s": lml.size / sec, "n_gpus": world, "scaling": "strong",
+                                      "lml_max": float(np.max(lml[np.isfinite(lml)])), "argmax": [int(x) for x in np.unravel_index(np.argmax(lml), lml.shape)],
+                                      "what": "GPnetRegressor.lml_landscape (GPnet.py:539-552), diffusion, RGG N=4096, n=2048, 64x64 grid over "
+                                              "(theta0, noise): host axes in, host array out; kernel groups sharded over the ranks (longest "
+                                              "first), one NCCL all-gather of (1+P) doubles per point; best of %d repetitions, max over ranks" % reps}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(N, n, P, world),
-                "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (n + P) + 4 * 0,
-                                          "d2h_bytes_per_step": 8 * 32 + 4 * 16},
+                "config": workload_config("c3", N, n, P, world, B),
+                "ms_per_eval": ms_eval, "timed_region_s": ms_total * 1e-3,
+                "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (8 * (n + P)),
+                                          "d2h_bytes_per_step": B * (8 * 32 + 4 * 16)},
                 "gpu_launches": int(launches), "roofline": roof}
         if routes is not None:
             line["routes"] = routes
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if extras:
+            line["extras"] = extras
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main_c4(args, ctx, stream, world, rank, local, W, K, barrier):
+    """--workload c4: one step = one whole 64 x 64 landscape (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    sampler = ClockSampler(local)
+    run_c4(ctx, stream, world, rank, local, max(W - 1, 1), barrier)          # warm-up landscapes
+    peak_tf = ctx.fp64_peak(0.3) if rank == 0 else 0.0
+    sampler.start()
+    ctx.reset_counters()
+    secs = []
+    for _ in range(K):
+        sec, lml, ev = run_c4(ctx, stream, world, rank, local, 1, barrier)
+        secs.append(sec)
+    clocks = sampler.summary()
+    launches = ctx.launch_count()
+    flops = ctx.flop_count()
+    if rank == 0:
+        sec = float(np.mean(secs))
+        # run_c4 runs one warm-up repetition per call: counters cover 2K landscapes on this rank
+        line = {"metric": "logp landscape points/sec, 64x64 grid at N=4096 nodes (fp64)", "value": lml.size / sec, "unit": "points/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config("c4", 4096, 2048, 2, world, 1),
+                "clocks": clocks, "e2e": {"value": lml.size / sec, "unit": "points/s", "h2d_bytes_per_step": 8 * (2048 + 2 + 128),
+                                          "d2h_bytes_per_step": 8 * 3 * lml.size // world},
+                "gpu_launches": int(launches // 2),
+                "roofline": {"bound": "tensor", "kernel": "gemm_f64_kernel (Pade products of expm)", "achieved": flops / 2 / K / sec * 1e-12,
+                             "peak": peak_tf, "unit": "TFLOP/s", "frac": flops / 2 / K / sec * 1e-12 / peak_tf if peak_tf else None,
+                             "how": "executed flops of this rank's share of one landscape / seconds per landscape", "traffic": None}}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

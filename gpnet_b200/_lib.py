@@ -198,10 +198,11 @@ class Context:
         self.lib.gpn_set_profile(self.h, int(bool(on)))
 
     def profile_summary(self):
-        out = np.zeros(9)
+        out = np.zeros(11)
         self._check(self.lib.gpn_profile_summary(self.h, _dp(out)), "gpn_profile_summary")
         return dict(gemm_ms=out[0], gemm_flops=out[1], gemm_launches=int(out[2]), big_ms=out[3], big_flops=out[4],
-                    big_launches=int(out[5]), potrf_ms=out[6], potrf_flops=out[7], potrf_launches=int(out[8]))
+                    big_launches=int(out[5]), potrf_ms=out[6], potrf_flops=out[7], potrf_launches=int(out[8]),
+                    potrf_union_ms=out[9], gemm_union_ms=out[10])
 
     # -- device-pointer primitives (pointers are ints, e.g. torch.Tensor.data_ptr()) --------------------
     def laplacian_dense(self, alpha, gamma, out_ptr, ld):

@@ -1993,18 +1993,43 @@ void gpn_set_profile(gpn_ctx* c, int on) {
 }
 
 /* out_h[0..2] = summed duration (ms), executed flops and count of the GEMM launches recorded since gpn_set_profile(ctx,1);
- * out_h[3..5] = the same restricted to the 128x128 GEMM configuration; out_h[6..8] = the same for the dataflow Cholesky. */
+ * out_h[3..5] = the same restricted to the 128x128 GEMM configuration; out_h[6..8] = the same for the dataflow Cholesky;
+ * out_h[9] / out_h[10] = length (ms) of the UNION of the launch intervals of the dataflow Cholesky / of all GEMM launches:
+ * launches of one kernel that run concurrently on several streams share the chip, so chip-level throughput is flops / union. */
 int gpn_profile_summary(gpn_ctx* c, double* out_h) {
     GPN_RANGE();
     if (!c) return -1;
     GPN_CK(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < 9; ++i) out_h[i] = 0.0;
+    for (int i = 0; i < 11; ++i) out_h[i] = 0.0;
+    if (c->prof_events.empty()) return 0;
+    std::vector<std::pair<float, float>> iv[2];
+    cudaEvent_t ref = c->prof_events.front().e0;
     for (auto& p : c->prof_events) {
-        float ms = 0.f;
+        GPN_CK(cudaEventSynchronize(p.e1));
+        float ms = 0.f, t0 = 0.f, t1 = 0.f;
         GPN_CK(cudaEventElapsedTime(&ms, p.e0, p.e1));
+        GPN_CK(cudaEventElapsedTime(&t0, ref, p.e0));
+        GPN_CK(cudaEventElapsedTime(&t1, ref, p.e1));
+        iv[p.kind == 2 ? 0 : 1].push_back({t0, t1});
         if (p.kind == 2) { out_h[6] += ms; out_h[7] += p.flops; out_h[8] += 1; continue; }
         out_h[0] += ms; out_h[1] += p.flops; out_h[2] += 1;
         if (p.big) { out_h[3] += ms; out_h[4] += p.flops; out_h[5] += 1; }
+    }
+    for (int f = 0; f < 2; ++f) {
+        std::sort(iv[f].begin(), iv[f].end());
+        double total = 0.0;
+        float cur0 = 0.f, cur1 = -1.f;
+        for (auto& x : iv[f]) {
+            if (cur1 < cur0 || x.first > cur1) {
+                if (cur1 >= cur0) total += cur1 - cur0;
+                cur0 = x.first;
+                cur1 = x.second;
+            } else if (x.second > cur1) {
+                cur1 = x.second;
+            }
+        }
+        if (cur1 >= cur0) total += cur1 - cur0;
+        out_h[9 + f] = total;
     }
     return 0;
 }

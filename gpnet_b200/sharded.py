@@ -38,11 +38,62 @@ def kernel_group_keys(n1: int, n2: int, axidx, P: int, kerneltype: str) -> np.nd
     return flat % n2
 
 
-def shard_indices(keys: np.ndarray, rank: int, world: int) -> np.ndarray:
-    """Flat indices of ``rank``: whole kernel groups are dealt cyclically (group g -> rank g % world), so that a kernel
-    is built on exactly one GPU; with one point per group this is the plain cyclic split."""
+def pade_cost(beta: float) -> float:
+    """Relative cost of one diffusion kernel build as a function of beta = exp(theta0): N^3 products of the Pade order the
+    scaling-and-squaring expm picks (Al-Mohy & Higham thresholds on ||beta L~|| <~ 2 beta) plus the SPD solve Q X = P
+    ((2 (pi_m + s) + 7/3) N^3).  A proxy for load balancing only."""
+    eta = 2.0 * beta
+    if eta < 1.495585217958292e-2:
+        prods = 1
+    elif eta < 2.539398330063230e-1:
+        prods = 2
+    elif eta < 9.504178996162932e-1:
+        prods = 3
+    elif eta < 2.097847961257068:
+        prods = 4
+    else:
+        prods = 6 + max(0, int(np.ceil(np.log2(eta / 4.25))))
+    return 2.0 * (prods + 1) + 7.0 / 3.0
+
+
+def kernel_group_costs(keys: np.ndarray, n1: int, n2: int, axidx, P: int, kerneltype: str, ax1, ax2, theta=None) -> dict:
+    """Estimated cost of every kernel group (key -> cost): the diffusion kernel's Pade order depends on beta, so
+    groups are not equally expensive; the other kernels cost the same for every theta."""
+    uniq, first = np.unique(keys, return_index=True)
+    costs = {}
+    for k, f in zip(uniq, first):
+        c = 1.0
+        if kerneltype == "diffusion":
+            i1, i2 = divmod(int(f), n2)
+            th0 = None
+            if axidx[1] == 0:
+                th0 = ax2[i2]
+            elif axidx[0] == 0:
+                th0 = ax1[i1]
+            elif theta is not None:
+                th0 = np.asarray(theta, dtype=np.float64).reshape(-1)[0]
+            if th0 is not None:
+                c = pade_cost(float(np.exp(th0)))
+        costs[int(k)] = c
+    return costs
+
+
+def shard_indices(keys: np.ndarray, rank: int, world: int, costs: dict | None = None) -> np.ndarray:
+    """Flat indices of ``rank``.  Whole kernel groups go to one rank, so that a kernel is built on exactly one GPU.  Without
+    ``costs`` groups are dealt cyclically (group g -> rank g % world; with one point per group: the plain cyclic split).
+    With ``costs`` (key -> estimated cost) they are dealt longest first to the least loaded rank (LPT), which balances
+    grids whose kernels differ in Pade order."""
     uniq, inverse = np.unique(keys, return_inverse=True)
-    return np.nonzero(inverse % world == rank)[0].astype(np.int64)
+    if costs is None or world == 1:
+        return np.nonzero(inverse % world == rank)[0].astype(np.int64)
+    order = sorted(range(len(uniq)), key=lambda g: (-costs.get(int(uniq[g]), 1.0), g))
+    load = [0.0] * world
+    owner = np.zeros(len(uniq), dtype=np.int64)
+    for g in order:
+        r = min(range(world), key=lambda x: (load[x], x))
+        owner[g] = r
+        load[r] += costs.get(int(uniq[g]), 1.0)
+    return np.nonzero(owner[inverse] == rank)[0].astype(np.int64)
 
 
 def _comm_device(dist, group, device_index=None):
@@ -145,7 +196,8 @@ def sharded_landscape(model, theta, axidx, ax1, ax2, want_grad=False, group=None
     total = n1 * n2
     P = len(model._theta_vec(theta))
     keys = kernel_group_keys(n1, n2, axidx, P, model.kerneltype)
-    shards = [shard_indices(keys, r, world) for r in range(world)]
+    costs = kernel_group_costs(keys, n1, n2, axidx, P, model.kerneltype, ax1, ax2, theta) if len(np.unique(keys)) < total else None
+    shards = [shard_indices(keys, r, world, costs) for r in range(world)]
     err, local = None, np.zeros((len(shards[rank]), 1 + P))
     try:
         local = evaluate_points(model, theta, axidx, ax1, ax2, shards[rank], want_grad)

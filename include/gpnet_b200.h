@@ -45,7 +45,9 @@ void gpn_reset_counters(gpn_ctx* ctx);
 /* measurement hooks (bench.py): sustained FP64 tensor (DMMA.8x8x4) issue-rate ceiling of this GPU, measured for
  * about `seconds`; per-launch CUDA-event profiling of the flop-carrying kernels (out_h[0..2]: ms, executed flops, launches
  * of all GEMM launches since gpn_set_profile(ctx,1); out_h[3..5]: the same for the 128x128 GEMM configuration only;
- * out_h[6..8]: the same for the dataflow Cholesky kernel; out_h has 9 entries). */
+ * out_h[6..8]: the same for the dataflow Cholesky kernel; out_h[9] / out_h[10]: length in ms of the UNION of the launch
+ * intervals of the dataflow Cholesky / of the GEMM launches -- launches of one kernel that run concurrently on several
+ * streams share the chip, so chip-level throughput is executed flops / union; out_h has 11 entries). */
 int gpn_fp64_peak(gpn_ctx* ctx, double seconds, double* tflops_h);
 void gpn_set_profile(gpn_ctx* ctx, int on);
 int gpn_profile_summary(gpn_ctx* ctx, double* out_h);

@@ -258,6 +258,30 @@ def test_kernel_group_shards_cover_the_grid_and_keep_groups_together():
     assert np.array_equal(shard_indices(keys, 1, 3), np.arange(1, 16, 3))
 
 
+def test_cost_balanced_sharding_of_the_c4_grid():
+    """C4 (64 x 64 diffusion grid): kernel groups (one per beta) cost more the higher their Pade order; dealt longest first
+    to the least loaded rank every rank gets the same estimated cost (within one group), whole groups stay together."""
+    from gpnet_b200.sharded import kernel_group_costs, kernel_group_keys, pade_cost, shard_indices
+    ax1 = np.linspace(np.log(0.01), np.log(0.99), 64)
+    ax2 = np.linspace(np.log(0.001), np.log(10.0), 64)
+    keys = kernel_group_keys(64, 64, [0, 1], 2, "diffusion")
+    costs = kernel_group_costs(keys, 64, 64, [0, 1], 2, "diffusion", ax1, ax2)
+    assert len(costs) == 64 and costs[0] < costs[63] and pade_cost(0.001) < pade_cost(0.5) < pade_cost(3.0)
+    for world in (2, 4, 8, 3):
+        shards = [shard_indices(keys, r, world, costs) for r in range(world)]
+        seen = np.zeros(64 * 64, dtype=int)
+        loads = []
+        for sh in shards:
+            seen[sh] += 1
+            groups = np.unique(keys[sh])
+            assert all(np.sum(keys[sh] == g) == 64 for g in groups)          # whole groups
+            loads.append(sum(costs[int(g)] for g in groups))
+        assert np.all(seen == 1)
+        assert max(loads) - min(loads) <= max(costs.values()) + 1e-9
+    # the regularized Laplacian costs the same everywhere: uniform costs
+    assert set(kernel_group_costs(keys, 64, 64, [0, 1], 2, "regularized_laplacian", ax1, ax2).values()) == {1.0}
+
+
 WORKER = r"""
 import os, sys
 import numpy as np
