@@ -15,7 +15,7 @@ import numpy as np
 import pandas as pd
 
 from ._lib import KERNEL_IDS
-from .engine import PredictToken, invalidate_predict, raise_domain
+from .engine import PredictToken, evaluate_batch, invalidate_predict, raise_domain
 from .GPnet import GPnetBase, KERNEL_LIST, _is_false
 
 
@@ -161,6 +161,31 @@ class GPnetRegressor(GPnetBase):
         if info > 0:
             return -np.inf, np.zeros(len(out) - 1)
         return float(out[0]), out[1:].copy()
+
+    def logPosterior_and_grad_batch(self, thetas, *args, lanes=3, want_grad=True):
+        """(-logp, -dlogp/dtheta) for every row of ``thetas`` -- the independent evaluations of a multi-start, of a
+        finite-difference gradient or of a line search (the loops around ``logPosterior`` in GPnet.py:259-274) -- evaluated
+        ``lanes`` at a time on the GPU: one evaluation is bound by its dependency chains and leaves most SMs idle, so
+        concurrent evaluations come almost for free.  Returns ``(values (B,), grads (B, P))``; a failed Cholesky gives
+        ``-inf`` like ``logPosterior`` (A-8)."""
+        data, t = args
+        thetas = [self._theta_vec(th) for th in thetas]
+        tr = self._positions(data)
+        te = self._positions(self.test_nodes) if not _is_false(self.test_nodes) else ()
+        ctxs = self._engine.lanes(lanes, tr, te)
+        for ctx in ctxs[:1]:
+            ctx._kernel_key = None
+            invalidate_predict(ctx)
+        tv = self._values(t)
+        for ctx in ctxs:
+            ctx.set_targets(tv)               # host targets cross once per lane, the evaluations use the resident copy
+        try:
+            out, infos = evaluate_batch(ctxs, self._kind(), thetas, None, want_grad)
+        finally:
+            ctxs[0].set_sm_budget(0)
+        vals = out[:, 0].copy()
+        vals[infos > 0] = -np.inf
+        return vals, out[:, 1:].copy()
 
     # ---- plotting pass-through (presentation only) ---------------------------------------------------
     def gen_cmap(self):

@@ -33,6 +33,9 @@ SIGNATURES = {
     "gpn_set_profile": (None, [C.c_void_p, C.c_int]),
     "gpn_profile_summary": (C.c_int, [C.c_void_p, c_dbl_p]),
     "gpn_debug_leaf_prof": (None, [C.c_void_p, C.c_void_p]),
+    "gpn_debug_scalars": (C.c_int, [C.c_void_p, c_dbl_p]),
+    "gpn_debug_d6_layout": (C.c_int, [C.c_void_p, c_int_p]),
+    "gpn_debug_d6_buffer": (C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]),
     "gpn_debug_df_trace": (None, [C.c_void_p, C.c_void_p]),
     "gpn_debug_leaf_bench": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gpn_set_graph": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_dbl_p]),
@@ -60,6 +63,10 @@ SIGNATURES = {
     "gpn_expm_info": (None, [C.c_void_p, c_int_p, c_int_p]),
     "gpn_kernel_block_h": (C.c_int, [C.c_void_p, c_int_p, C.c_int, c_int_p, C.c_int, C.c_double, c_dbl_p]),
     "gpn_gpr_logp_grad": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_int_p]),
+    "gpn_gpr_logp_grad_begin": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, C.c_int]),
+    "gpn_gpr_logp_grad_end": (C.c_int, [C.c_void_p, c_dbl_p, c_int_p]),
+    "gpn_set_sm_budget": (None, [C.c_void_p, C.c_int]),
+    "gpn_num_sms": (C.c_int, [C.c_void_p]),
     "gpn_set_fast_paths": (None, [C.c_void_p, C.c_int]),
     "gpn_gpr_predict": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p]),
     "gpn_gpr_fetch": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p]),
@@ -308,6 +315,48 @@ class Context:
             return st, out, 0
         self._check(st, "gpn_gpr_logp_grad")
         return 0, out, info.value
+
+    def gpr_logp_grad_begin(self, kind, theta, t, want_grad):
+        """Enqueue one evaluation (asynchronous on the level-6 route); pair with gpr_logp_grad_end.  Returns the status
+        (-100 / -101 for parameter-domain violations, like gpr_logp_grad)."""
+        th = _eth(theta)
+        tt = None if t is None else _f64(t)
+        if tt is not None and len(tt) != self.n_train:
+            raise ValueError("len(t) != number of training nodes")
+        self._pending_P = len(th)
+        st = self.lib.gpn_gpr_logp_grad_begin(self.h, kind, _dp(th), len(th), None if tt is None else _dp(tt), int(want_grad))
+        if st in (-100, -101):
+            return st
+        return self._check(st, "gpn_gpr_logp_grad_begin")
+
+    def gpr_logp_grad_end(self):
+        out = np.zeros(1 + self._pending_P, dtype=np.float64)
+        info = C.c_int(0)
+        self._check(self.lib.gpn_gpr_logp_grad_end(self.h, _dp(out), C.byref(info)), "gpn_gpr_logp_grad_end")
+        return out, info.value
+
+    def debug_scalars(self):
+        out = np.zeros(32)
+        self.lib.gpn_debug_scalars(self.h, _dp(out))
+        return out
+
+    def debug_d6_layout(self):
+        out = (C.c_int * 40)()
+        self.lib.gpn_debug_d6_layout(self.h, out)
+        v = [int(x) for x in out]
+        K = v[0]
+        return dict(K=K, s=v[1], so=v[2], ND=v[3], off=v[4:13][: K + 1], nk=v[13:21][:K], ok=v[21:29][:K], c0=v[29:37][:K])
+
+    def debug_d6_buffer(self, which):
+        n = C.c_longlong(0)
+        p = self.lib.gpn_debug_d6_buffer(self.h, int(which), C.byref(n))
+        return p, n.value
+
+    def set_sm_budget(self, sms=0):
+        self.lib.gpn_set_sm_budget(self.h, int(sms))
+
+    def num_sms(self) -> int:
+        return int(self.lib.gpn_num_sms(self.h))
 
     def set_fast_paths(self, level=True):
         """Route of the regularized-Laplacian regressor likelihood: 0/False full kernel, 1 block route, 2 Schur route,

@@ -94,6 +94,12 @@ struct gpn_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     long flags_rows = 0;                 // layout of `flags`: [ready flags (flags_rows ints) | task counters]
     int potrf_grid_cap = 0;              // > 0: the next dataflow Cholesky may use at most this many CTAs
+    int sm_budget = 0;                   // > 0: SMs this context may fill with co-resident (cooperative) factorisations: several
+                                         // contexts ("lanes") evaluating different thetas at once share the chip (gpn_set_sm_budget)
+    cudaEvent_t ev_done = nullptr;       // end of an evaluation started by gpn_gpr_logp_grad_begin
+    int pend_state = 0;                  // 0 none, 1 asynchronous level-6 evaluation in flight, 2 result already on the host
+    int pend_P = 0, pend_grad = 0, pend_info = 0, pend_status = 0;
+    double pend_out[9] = {0};
     int num_sms = 148;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     long long launches = 0;        // kernels launched through this context (bench "gpu_launches")

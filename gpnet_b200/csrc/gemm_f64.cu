@@ -33,13 +33,23 @@ struct GemmArgs {
 
 // 8-consumer configuration: 12 warps = 2 consumer warpgroups + 1 producer warpgroup, registers rebalanced with
 // setmaxnreg (producer 40, consumers 232) because the register file is allocated in 4-warp granules.
+// Minimum CTAs per SM the 64x64 configuration is compiled for (4 caps it at 168 registers per thread; the 128x128
+// configuration owns its SM).  Compiled for one CTA per SM it took 215 registers and, while CTAs of OTHER kernels were co-resident
+// on the SM under heavy memory traffic (a strided copy on another stream, several contexts evaluating at once), sporadically
+// produced wrong rows 40..63 of its tiles -- the fragments held in the highest registers.  tools/gemm_race.py and
+// tests/test_gpu_primitives.py::test_small_gemm_is_bit_stable_next_to_a_strided_copy reproduce it (9-12 wrong runs of 12 before,
+// none with the cap); the mechanism is not understood, the cap is empirical.
+#ifndef GEMM_SMALL_MIN_CTAS
+#define GEMM_SMALL_MIN_CTAS 4
+#endif
 template <int WM, int WN>
 constexpr int gemm_threads() {
     return (WM * WN == 8) ? 384 : (WM * WN + 1) * 32;
 }
 
+
 template <int WM, int WN, int STAGES, bool AK, bool BK>
-__global__ void __launch_bounds__(gemm_threads<WM, WN>(), 1)
+__global__ void __launch_bounds__((WM * WN == 8) ? 384 : (WM * WN + 1) * 32, (WM * WN == 8) ? 1 : GEMM_SMALL_MIN_CTAS)
 gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
     constexpr int BM = 64 * WM, BN = 32 * WN;
     constexpr int NCONS = WM * WN;
@@ -111,17 +121,18 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_expect_tx(full, STAGE_BYTES);
                 const uint32_t sa = smem0 + s * STAGE_BYTES, sb = sa + A_BYTES;
                 const int k = k_lo + it * KSTEP;
+                const CUtensorMap *pA = &tmA, *pB = &tmB;
                 if (AK) {
-                    tma_load_3d(sa, &tmA, full, k, m0, batch);
+                    tma_load_3d(sa, pA, full, k, m0, batch);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < BM / 16; ++j) tma_load_3d(sa + j * 2048, &tmA, full, m0 + 16 * j, k, batch);
+                    for (int j = 0; j < BM / 16; ++j) tma_load_3d(sa + j * 2048, pA, full, m0 + 16 * j, k, batch);
                 }
                 if (BK) {
-                    tma_load_3d(sb, &tmB, full, k, n0, batch);
+                    tma_load_3d(sb, pB, full, k, n0, batch);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < BN / 16; ++j) tma_load_3d(sb + j * 2048, &tmB, full, n0 + 16 * j, k, batch);
+                    for (int j = 0; j < BN / 16; ++j) tma_load_3d(sb + j * 2048, pB, full, n0 + 16 * j, k, batch);
                 }
             }
         }

@@ -1009,7 +1009,7 @@ int d6_side_stream(gpn_ctx* c, int k) {
     return 0;
 }
 
-int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, RowScalars* rs, int* info_h) {
+int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad) {
     Dissect6& q = c->d6;
     const int N = c->N, n = c->n_train, K = q.K, s = q.s, so = q.so, ND = q.ND;
     GPN_TRY(ensure_vecs(c));
@@ -1047,7 +1047,7 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
         U = (double*)q.work[2].p;
         Uo = (double*)q.work[3].p;
         if (fresh) GPN_CK(cudaMemsetAsync(U, 0, q.work[2].cap, c->stream));                // rows [ND, rowsU) must read as zero
-        GPN_CK(cudaMemsetAsync(Uo, 0, uob, c->stream));
+        GPN_TRY(gpn_k_fill_zero(c, Uo, ldso, (int)rowsU, (int)ldso));
     }
     auto vec = [&](int i) { return (double*)q.work[6].p + (long)i * ld; };
     double *b1 = vec(0), *bt = vec(1), *v1 = vec(2), *vt = vec(3), *y1 = vec(4), *yt = vec(5), *w1 = vec(6), *wt = vec(7), *u1 = vec(8),
@@ -1078,13 +1078,15 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)(woff[K] + Ts + Tso + 2) * 128 * 128));
     double* winv = (double*)c->winv.p;
     cudaStream_t main_stream = c->stream;
+    const int sms = c->sm_budget > 0 ? std::min(c->sm_budget, c->num_sms) : c->num_sms;    // co-resident CTAs this context may use
     {
         double wsum = 0.0;
         for (int k = 0; k < K; ++k) wsum += (double)q.nk[k] * q.nk[k] * q.nk[k];
         int caps[8], used = 0;
-        for (int k = 0; k < K; ++k) { caps[k] = std::max(12, (int)(c->num_sms * ((double)q.nk[k] * q.nk[k] * q.nk[k] / wsum))); used += caps[k]; }
-        for (int k = 0; used > c->num_sms; k = (k + 1) % K)
-            if (caps[k] > 12) { --caps[k]; --used; }
+        const int cap_min = std::max(4, std::min(12, sms / (2 * K)));
+        for (int k = 0; k < K; ++k) { caps[k] = std::max(cap_min, (int)(sms * ((double)q.nk[k] * q.nk[k] * q.nk[k] / wsum))); used += caps[k]; }
+        for (int k = 0; used > sms; k = (k + 1) % K)
+            if (caps[k] > cap_min) { --caps[k]; --used; }
         GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
         int st = 0;
         for (int k = 0; k < K && st == 0; ++k) {
@@ -1140,15 +1142,16 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
     //      factorisations [T; I; U] give L_T, W_T^T and Y = U L_T^-T:  tr(T^-1 (I + U^T U)) = ||W_T||_F^2 + ||Y||_F^2 ----
     const double* E = M + (long)ND * ld + ND;
     double* winvT = winv + (size_t)woff[K] * 128 * 128;
+    constexpr int TS = 9;                                       // stream / flag slot of the other-node separator complement
     if (so > 0) {   // the other-node complement on a side stream, next to the full one
-        GPN_TRY(d6_side_stream(c, 1));
+        GPN_TRY(d6_side_stream(c, TS));
         GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
-        GPN_CK(cudaStreamWaitEvent(c->side[1], c->ev_fork, 0));
-        c->stream = c->side[1];
+        GPN_CK(cudaStreamWaitEvent(c->side[TS], c->ev_fork, 0));
+        c->stream = c->side[TS];
         int st = gpn_d6_t_reduce(c, so, E, ld, (const double*)q.work[8].p, ldso, nb, Tob);
-        c->potrf_grid_cap = c->num_sms / 3;
+        c->potrf_grid_cap = std::max(2, sms / 3);
         if (st == 0) st = gpn_potrf_dataflow(c, so, Tob, ldso, winvT + (size_t)Ts * 128 * 128, iscal(c, 9), 0, want_grad ? Uo : nullptr, ldso,
-                                             want_grad ? ND : 0, WTto, ldso, 1);
+                                             want_grad ? ND : 0, WTto, ldso, TS);
         c->potrf_grid_cap = 0;
         if (st == 0) st = gpn_d6_sep_reduce(c, so, Tob, ldso, want_grad ? WTto : nullptr, ldso, want_grad ? Uo : nullptr, ldso, ND, dscal(c, 11));
         // u_x = M_oo^-1 (M_ot x) for x = 1, t: block-arrow solve through the factors
@@ -1157,17 +1160,17 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
         if (st == 0) st = gpn_d6_tri_solve(c, so, WTto, ldso, r1, rt, v1, vt, us1, ust);
         c->stream = main_stream;
         if (st != 0) return st;
-        GPN_CK(cudaMemcpyAsync(w1, b1, sizeof(double) * ND, cudaMemcpyDeviceToDevice, c->side[1]));
-        GPN_CK(cudaMemcpyAsync(wt, bt, sizeof(double) * ND, cudaMemcpyDeviceToDevice, c->side[1]));
-        GPN_CK(cudaMemsetAsync(u1, 0, sizeof(double) * 2 * ld, c->side[1]));               // u1, ut are adjacent
-        c->stream = c->side[1];
+        GPN_CK(cudaMemcpyAsync(w1, b1, sizeof(double) * ND, cudaMemcpyDeviceToDevice, c->side[TS]));
+        GPN_CK(cudaMemcpyAsync(wt, bt, sizeof(double) * ND, cudaMemcpyDeviceToDevice, c->side[TS]));
+        GPN_CK(cudaMemsetAsync(u1, 0, sizeof(double) * 2 * ld, c->side[TS]));               // u1, ut are adjacent
+        c->stream = c->side[TS];
         st = gpn_d6_sep_scatter(c, beta, us1, ust, w1, wt);
         if (st == 0) st = gpn_d6_block_solve(c, WT, ld, w1, wt, v1, vt, u1, ut);
         c->stream = main_stream;
         if (st != 0) return st;
-        GPN_CK(cudaMemcpyAsync(u1 + ND, us1, sizeof(double) * so, cudaMemcpyDeviceToDevice, c->side[1]));
-        GPN_CK(cudaMemcpyAsync(ut + ND, ust, sizeof(double) * so, cudaMemcpyDeviceToDevice, c->side[1]));
-        GPN_CK(cudaEventRecord(c->ev_side[1], c->side[1]));
+        GPN_CK(cudaMemcpyAsync(u1 + ND, us1, sizeof(double) * so, cudaMemcpyDeviceToDevice, c->side[TS]));
+        GPN_CK(cudaMemcpyAsync(ut + ND, ust, sizeof(double) * so, cudaMemcpyDeviceToDevice, c->side[TS]));
+        GPN_CK(cudaEventRecord(c->ev_side[TS], c->side[TS]));
     } else {
         GPN_CK(cudaMemsetAsync(u1, 0, sizeof(double) * 2 * ld, c->stream));
         GPN_TRY(gpn_d6_block_solve(c, WT, ld, b1, bt, v1, vt, u1, ut));
@@ -1175,7 +1178,7 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
     {
         GPN_TRY(gpn_d6_t_reduce(c, s, E, ld, (const double*)q.work[7].p, lds, nb, Tb));
         mark("T");
-        c->potrf_grid_cap = so > 0 ? c->num_sms - c->num_sms / 3 : 0;
+        c->potrf_grid_cap = so > 0 ? sms - std::max(2, sms / 3) : sms;
         int st = gpn_potrf_dataflow(c, s, Tb, lds, winvT, iscal(c, 8), 0, want_grad ? U : nullptr, lds, want_grad ? ND : 0,
                                     want_grad ? WTt : nullptr, lds, 0);
         c->potrf_grid_cap = 0;
@@ -1183,17 +1186,19 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
         mark("[T; I; U]");
         GPN_TRY(gpn_d6_sep_reduce(c, s, Tb, lds, want_grad ? WTt : nullptr, lds, want_grad ? U : nullptr, lds, ND, dscal(c, 9)));
     }
-    if (so > 0) GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
+    if (so > 0) GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_side[TS], 0));
     {
         const double *dx[6] = {b1, b1, bt, u1, u1, ut}, *dy[6] = {u1, ut, ut, u1, ut, ut};
         const int dn[6] = {N, N, N, N, N, N};
         GPN_TRY(gpn_k_multi_dot(c, 6, dx, dy, dn, dscal(c, 13)));
     }
     mark("reductions, join, dots");
-    double sc[Scal::NDBL];
-    int info[16];
-    GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
+    // the scalar block travels to pinned host memory behind everything above; gpr_reglap_d6_finish waits for it
+    GPN_CK(cudaMemcpyAsync(c->pinned, c->scal.p, sizeof(double) * Scal::NDBL + sizeof(int) * 16, cudaMemcpyDeviceToHost, c->stream));
+    GPN_CK(cudaEventRecord(c->ev_done, c->stream));
+    c->pend_grad = want_grad;
     if (timing) {
+        GPN_CK(cudaStreamSynchronize(c->stream));
         for (size_t i = 1; i < marks.size(); ++i) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
@@ -1201,6 +1206,14 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
         }
         for (auto& m : marks) cudaEventDestroy(m.second);
     }
+    return 0;
+}
+
+int gpr_reglap_d6_finish(gpn_ctx* c, RowScalars* rs, int* info_h) {
+    GPN_CK(cudaEventSynchronize(c->ev_done));
+    const int n = c->n_train;
+    const double* sc = (const double*)c->pinned;
+    const int* info = (const int*)((const char*)c->pinned + sizeof(double) * Scal::NDBL);
     if (info_h) {
         *info_h = 0;
         for (int i = 0; i < 10 && *info_h == 0; ++i) *info_h = info[i];
@@ -1210,7 +1223,7 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
     rs->s = sc[0] - sc[13];
     rs->a = sc[1] - sc[14];
     rs->q = sc[2] - sc[15];
-    if (want_grad) {
+    if (c->pend_grad) {
         const double trM = sc[5] + sc[9], trMoo = sc[6] + sc[11];
         rs->trSD = trM - trMoo - n;
         rs->D11 = sc[16] + n - rs->s;
@@ -1218,6 +1231,11 @@ int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double
         rs->Dtt = sc[18] + sc[4] - rs->q;
     }
     return 0;
+}
+
+int gpr_reglap_d6_scalars(gpn_ctx* c, const double* theta_h, int P, const double* t_h, int want_grad, RowScalars* rs, int* info_h) {
+    GPN_TRY(gpr_reglap_d6_enqueue(c, theta_h, P, t_h, want_grad));
+    return gpr_reglap_d6_finish(c, rs, info_h);
 }
 
 // level 6 applies when the whole graph dissects into parts with thin separators; otherwise the caller takes level 5 / 4
@@ -1804,7 +1822,8 @@ gpn_ctx* gpn_create(int device, void* cuda_stream) {
     c->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) {
         gpn_set_last_error(__FILE__, __LINE__, "side stream / event creation failed");
         delete c;
         return nullptr;
@@ -1854,6 +1873,7 @@ void gpn_destroy(gpn_ctx* c) {
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1976,6 +1996,29 @@ void gpn_set_dissection_parts(gpn_ctx* c, int parts) {
     if (!c) return;
     c->d6_parts = parts < 0 ? 0 : (parts > 8 ? 8 : parts);
     c->d6.built = false;
+}
+int gpn_debug_scalars(gpn_ctx* c, double* out32_h) {
+    if (!c || !c->pinned) return -1;
+    memcpy(out32_h, c->pinned, sizeof(double) * 32);
+    return 0;
+}
+/* development aid: layout of the whole-graph dissection: out40 = [K, s, so, ND, off[9], nk[8], ok[8], c0[8]] */
+int gpn_debug_d6_layout(gpn_ctx* c, int* out40) {
+    if (!c || !c->d6.built) return -1;
+    const Dissect6& q = c->d6;
+    int p = 0;
+    out40[p++] = q.K; out40[p++] = q.s; out40[p++] = q.so; out40[p++] = q.ND;
+    for (int k = 0; k < 9; ++k) out40[p++] = q.off[k];
+    for (int k = 0; k < 8; ++k) out40[p++] = q.nk[k];
+    for (int k = 0; k < 8; ++k) out40[p++] = q.ok[k];
+    for (int k = 0; k < 8; ++k) out40[p++] = q.c0[k];
+    return 0;
+}
+/* development aid: device pointer and capacity (bytes) of work buffer `which` of the whole-graph dissection route */
+void* gpn_debug_d6_buffer(gpn_ctx* c, int which, long long* bytes) {
+    if (!c || which < 0 || which >= 12) return nullptr;
+    if (bytes) *bytes = (long long)c->d6.work[which].cap;
+    return c->d6.work[which].p;
 }
 void gpn_debug_df_trace(gpn_ctx* c, void* dev_buf) {
     if (c) c->df_trace = dev_buf;
@@ -2283,6 +2326,53 @@ int gpn_gpr_logp_grad(gpn_ctx* c, int kind, const double* theta_h, int P, const 
     if (!c) return -1;
     return gpr_logp_grad(c, kind, theta_h, P, t_h, want_grad, out_h, info_h);
 }
+
+/* Asynchronous form of gpn_gpr_logp_grad: _begin enqueues the evaluation on this context's streams and returns; _end waits for
+ * it and delivers the result.  On the whole-graph dissection route (level 6) nothing synchronises in between, so several
+ * contexts bound to the same graph ("lanes", each with an SM budget) evaluate different thetas concurrently; every other
+ * route runs to completion inside _begin. */
+int gpn_gpr_logp_grad_begin(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, int want_grad) {
+    GPN_RANGE();
+    if (!c) return -1;
+    if (c->n_train <= 0) return -1;
+    if (P < 1 || P > 8) return -4;
+    c->pend_state = 0;
+    c->pend_P = P;
+    if (kind == GPN_KERNEL_REGULARIZED_LAPLACIAN && c->fast_reglap >= 6 && c->train_unique && c->n_train < c->N && d6_route(c)) {
+        int st = gpr_reglap_d6_enqueue(c, theta_h, P, t_h, want_grad);
+        if (st != 0) return st;
+        c->pend_state = 1;
+        return 0;
+    }
+    c->pend_status = gpr_logp_grad(c, kind, theta_h, P, t_h, want_grad, c->pend_out, &c->pend_info);
+    c->pend_state = 2;
+    c->pend_grad = want_grad;
+    return c->pend_status;
+}
+int gpn_gpr_logp_grad_end(gpn_ctx* c, double* out_h, int* info_h) {
+    GPN_RANGE();
+    if (!c || c->pend_state == 0) return -1;
+    const int P = c->pend_P;
+    if (c->pend_state == 1) {
+        RowScalars rs;
+        int info = 0;
+        c->pend_state = 0;
+        GPN_TRY(gpr_reglap_d6_finish(c, &rs, &info));
+        row_eval(rs, c->theta_exp[P - 1], P, c->pend_grad, out_h);
+        if (info_h) *info_h = info;
+        return 0;
+    }
+    c->pend_state = 0;
+    for (int j = 0; j < 1 + (c->pend_grad ? P : 0); ++j) out_h[j] = c->pend_out[j];
+    if (info_h) *info_h = c->pend_info;
+    return c->pend_status;
+}
+/* SMs this context may fill with co-resident factorisations (0: the whole chip).  Lanes that run concurrently must not
+ * oversubscribe the chip: cooperative launches that do not fit wait for the others to finish. */
+void gpn_set_sm_budget(gpn_ctx* c, int sms) {
+    if (c) c->sm_budget = sms < 0 ? 0 : sms;
+}
+int gpn_num_sms(gpn_ctx* c) { return c ? c->num_sms : 0; }
 
 int gpn_gpr_predict(gpn_ctx* c, int kind, const double* theta_h, int P, const double* t_h, double* alpha_h, double* fstar_h, double* s_h,
                     double* kss_diag_h, int* info_h) {

@@ -269,7 +269,7 @@ potrf_dataflow_kernel(const __grid_constant__ CUtensorMap tmL, const __grid_cons
                     const long gc = (long)j * TB + cc;
                     double v = (i == j && r == cc) ? -1.0 : 0.0;
                     if (i >= g.id0) v = (j == i - g.id0 && r == cc) ? -1.0 : 0.0;        // identity block: nothing to read
-                    else if (r < row_lim && gc < g.n) v = -tile_ptr[(long)r * tile_ld + cc];
+                    else if (r < row_lim && gc < g.n) v = -__ldcg(tile_ptr + (long)r * tile_ld + cc);   // L2: the tile was written by earlier kernels on other SMs
                     acc[a][b][e] = v;
                 }
         }
@@ -443,7 +443,8 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
         GPN_TRY(gpn_buf_ensure(c, fbuf, sizeof(int) * ((size_t)Trows * T + 4)));
         frows = (long)Trows * T;
         GPN_CK(cudaMemsetAsync(fbuf.p, 0, fbuf.cap, c->stream));
-        fepoch = 0;
+        // the epoch keeps counting across shape changes: a flag of an earlier launch can never match, whatever the order in which
+        // the clearing memset and earlier kernels on other streams touch the buffer
     }
     DfArgs a;
     a.A = A; a.lda = lda; a.n = n; a.T = T; a.ntasks = ntasks; a.winv = winv; a.flags = (int*)fbuf.p;
@@ -504,7 +505,9 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
         pe.kind = 2;
         cudaEventRecord(pe.e0, c->stream);
     }
-    GPN_CK(cudaLaunchCooperativeKernel((const void*)potrf_dataflow_kernel, dim3(grid), dim3(384), args, DF_SMEM, c->stream));
+    static const bool noncoop = getenv("GPNET_B200_DF_NONCOOP") != nullptr;
+    if (noncoop) GPN_CK(cudaLaunchKernel((const void*)potrf_dataflow_kernel, dim3(grid), dim3(384), args, DF_SMEM, c->stream));
+    else GPN_CK(cudaLaunchCooperativeKernel((const void*)potrf_dataflow_kernel, dim3(grid), dim3(384), args, DF_SMEM, c->stream));
     if (c->profile) {
         cudaEventRecord(pe.e1, c->stream);
         c->prof_events.push_back(pe);

@@ -102,6 +102,35 @@ def invalidate_predict(ctx):
                 ctx._predict_token = None
 
 
+def evaluate_batch(ctxs, kind: int, thetas, t, want_grad=True):
+    """(-logp, -grad) rows and Cholesky infos for a batch of independent log-parameter vectors, dealt round robin to the
+    lane contexts ``ctxs`` (all bound to the same graph / node sets): every lane always has one evaluation in flight, so on
+    the asynchronous route the evaluations overlap on the GPU.  ``t``: host targets, or None for the resident ones.
+    Parameter-domain violations raise the reference's AssertionError after the lanes have drained."""
+    thetas = [np.asarray(th, dtype=np.float64).reshape(-1) for th in thetas]
+    B, J = len(thetas), max(len(ctxs), 1)
+    P = len(thetas[0]) if B else 0
+    out = np.zeros((B, 1 + P), dtype=np.float64)
+    infos = np.zeros(B, dtype=np.int64)
+    pending = [None] * J
+    bad = 0
+    for b in range(B + J):
+        lane = b % J
+        if pending[lane] is not None:
+            o, info = ctxs[lane].gpr_logp_grad_end()
+            out[pending[lane], : len(o)] = o
+            infos[pending[lane]] = info
+            pending[lane] = None
+        if b < B and not bad:
+            st = ctxs[lane].gpr_logp_grad_begin(kind, thetas[b], t, want_grad)
+            if st in (-100, -101):
+                bad = st
+            else:
+                pending[lane] = b
+    raise_domain(bad)
+    return out, infos
+
+
 class GraphEngine:
     """Binds one model's graph + node sets to the shared context on demand."""
 
@@ -111,6 +140,29 @@ class GraphEngine:
         self.device = device
         self._ctx = None
         self._pos_cache = {}
+        self._lanes = []
+        self._lanes_key = None
+
+    def lanes(self, count: int, train_pos, test_pos=()):
+        """``count`` contexts bound to this graph and these node sets for concurrent evaluations: lane 0 is the shared
+        context, the others are private to this engine (their buffers are allocated on first use).  Each lane may fill
+        1/count of the SMs with co-resident factorisation kernels."""
+        ctx = self.bind(train_pos, test_pos)
+        count = max(1, int(count))
+        key = (tuple(train_pos), tuple(test_pos or ()))
+        while len(self._lanes) < count - 1:
+            self._lanes.append(Context(ctx.device))
+            self._lanes_key = None
+        extra = self._lanes[: count - 1]
+        if self._lanes_key != key:
+            for lane in self._lanes:
+                lane.set_graph(self.indptr, self.indices, self.weights)
+                lane.set_nodes(train_pos, test_pos or ())
+            self._lanes_key = key
+        share = ctx.num_sms() // count if count > 1 else 0
+        for lane in [ctx] + extra:
+            lane.set_sm_budget(share)
+        return [ctx] + extra
 
     @property
     def ctx(self) -> Context:

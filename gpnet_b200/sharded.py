@@ -215,13 +215,18 @@ def sharded_multistart(model, thetas, want_grad=True, group=None) -> np.ndarray:
     rank, world, dist = dist_info(group)
     thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
     total, P = thetas.shape
-    rows = []
-    for i in range(rank, total, world):
-        if want_grad and hasattr(model, "logPosterior_and_grad"):
-            v, g = model.logPosterior_and_grad(thetas[i], model.training_nodes, model.training_values)
-            rows.append(np.concatenate([[v], g]))
-        else:
-            v = model.logPosterior(thetas[i], model.training_nodes, model.training_values)
-            rows.append(np.concatenate([[float(np.squeeze(v))], np.zeros(P)]))
+    mine = list(range(rank, total, world))
+    if want_grad and hasattr(model, "logPosterior_and_grad_batch") and len(mine) > 1:
+        vals, grads = model.logPosterior_and_grad_batch([thetas[i] for i in mine], model.training_nodes, model.training_values)
+        rows = [np.concatenate([[v], g]) for v, g in zip(vals, grads)]
+    else:
+        rows = []
+        for i in mine:
+            if want_grad and hasattr(model, "logPosterior_and_grad"):
+                v, g = model.logPosterior_and_grad(thetas[i], model.training_nodes, model.training_values)
+                rows.append(np.concatenate([[v], g]))
+            else:
+                v = model.logPosterior(thetas[i], model.training_nodes, model.training_values)
+                rows.append(np.concatenate([[float(np.squeeze(v))], np.zeros(P)]))
     local = np.asarray(rows, dtype=np.float64).reshape(-1, 1 + P)
     return allgather_rows(local, total, rank, world, dist, group)

@@ -55,6 +55,12 @@ int gpn_profile_summary(gpn_ctx* ctx, double* out_h);
 void gpn_debug_leaf_prof(gpn_ctx* ctx, void* dev_buf32);
 /* development aid: run the 128x128 leaf on `copies` stacked blocks (lda 128), one CTA each; block 0 stamps its phases */
 int gpn_debug_leaf_bench(gpn_ctx* ctx, void* A_dev, int copies, void* prof32_dev);
+/* development aid: the 32 device reductions the last evaluation read back (layout private to the route that ran) */
+int gpn_debug_scalars(gpn_ctx* ctx, double* out32_h);
+/* development aid: layout of the whole-graph dissection, out40 = [K, s, so, ND, off[9], nk[8], ok[8], c0[8]] */
+int gpn_debug_d6_layout(gpn_ctx* ctx, int* out40);
+/* development aid: device pointer / capacity in bytes of work buffer `which` (0..11) of the whole-graph dissection route */
+void* gpn_debug_d6_buffer(gpn_ctx* ctx, int which, long long* bytes);
 /* development aid: device buffer receiving 8 int64 %globaltimer stamps per tile of the next dataflow-Cholesky launches
  * (tile (i, j) at slot j * tile_rows + i; tools/gpu_check.py chain / dfbreak / augbreak read it); NULL switches it off */
 void gpn_debug_df_trace(gpn_ctx* ctx, void* dev_buf);
@@ -136,6 +142,17 @@ int gpn_kernel_block_h(gpn_ctx* ctx, const int* rows_h, int nr, const int* cols_
  * (NULL: the resident targets of gpn_set_targets). */
 int gpn_gpr_logp_grad(gpn_ctx* ctx, int kind, const double* etheta_h, int P, const double* t_h, int want_grad,
                       double* out_h, int* info_h);
+/* Asynchronous form of gpn_gpr_logp_grad for batches of independent evaluations (multi-start, finite-difference probes,
+ * landscape rows: the loops of GPnet.py:259-274,539-552): _begin enqueues the evaluation on this context's streams and returns,
+ * _end waits for it and delivers out_h / info_h as gpn_gpr_logp_grad does.  On the whole-graph dissection route (level 6)
+ * nothing synchronises in between, so several contexts bound to the same graph ("lanes") evaluate different thetas at the
+ * same time and fill the SMs that one latency-bound evaluation leaves idle; every other route completes inside _begin.
+ * gpn_set_sm_budget limits the SMs a lane fills with co-resident factorisation kernels (0: the whole chip): concurrent lanes
+ * must not oversubscribe the chip, or their cooperative launches wait for one another. */
+int gpn_gpr_logp_grad_begin(gpn_ctx* ctx, int kind, const double* etheta_h, int P, const double* t_h, int want_grad);
+int gpn_gpr_logp_grad_end(gpn_ctx* ctx, double* out_h, int* info_h);
+void gpn_set_sm_budget(gpn_ctx* ctx, int sms);
+int gpn_num_sms(gpn_ctx* ctx);
 /* GPnetRegressor.predict body (:86-128).  Outputs (host): alpha[n], fstar[m], s[m] (sqrt of the predictive
  * variance), kss_diag[m]; info_h[0]: Cholesky info of k, info_h[1]: info of kstarstar (the two PD gates, A-7). */
 int gpn_gpr_predict(gpn_ctx* ctx, int kind, const double* etheta_h, int P, const double* t_h, double* alpha_h,

@@ -262,3 +262,37 @@ def test_pstep_order_uses_numpy_exp(gpu_ctx):
         gpu_ctx.kernel_block([0, N], [0], 0.0)
     with pytest.raises(IndexError):
         gpu_ctx.kernel_block([0], [-1], 0.0)
+
+
+@pytest.mark.parametrize("mn", [300, 870, 896])
+def test_small_gemm_is_bit_stable_next_to_a_strided_copy(gpu_ctx, mn):
+    """Regression (round 2): the 64x64 GEMM configuration must give bit-identical results while CTAs of another kernel share
+    its SMs under heavy memory traffic (here a strided torch copy on another stream).  Compiled at 215 registers per thread it
+    sporadically produced wrong tile rows in this situation (tools/gemm_race.py); see GEMM_SMALL_MIN_CTAS in gemm_f64.cu."""
+    import torch
+    M = N = mn
+    K, ld = 800, 8192
+    torch.manual_seed(mn)
+    A = torch.randn(M + 64, ld, dtype=torch.float64, device="cuda:0")
+    ldc = (N + 127) // 128 * 128
+    C = torch.zeros(ldc, ldc, dtype=torch.float64, device="cuda:0")
+    big = torch.randn(2048, 32768, dtype=torch.float64, device="cuda:0")       # 512 MB
+    noise = torch.cuda.Stream()
+
+    def run(with_noise):
+        C.zero_()
+        torch.cuda.synchronize()
+        if with_noise:
+            with torch.cuda.stream(noise):
+                for _ in range(4):
+                    big.t().contiguous()
+        gpu_ctx.gemm(0, 1, M, N, K, 1.0, A.data_ptr() + 130 * 8, ld, A.data_ptr() + 130 * 8, ld, 0.0, C.data_ptr(), ldc)
+        gpu_ctx.sync()
+        torch.cuda.synchronize()
+        return C.clone()
+
+    ref = run(False)
+    exact = A[:M, 130:130 + K] @ A[:M, 130:130 + K].T
+    assert (ref[:M, :N] - exact).abs().max().item() < 1e-10
+    for _ in range(8):
+        assert torch.equal(run(True), ref)
