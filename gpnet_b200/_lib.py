@@ -32,6 +32,7 @@ SIGNATURES = {
     "gpn_fp64_peak": (C.c_int, [C.c_void_p, C.c_double, c_dbl_p]),
     "gpn_set_profile": (None, [C.c_void_p, C.c_int]),
     "gpn_profile_summary": (C.c_int, [C.c_void_p, c_dbl_p]),
+    "gpn_profile_intervals": (C.c_int, [C.c_void_p, C.c_void_p, c_dbl_p, C.c_int, c_int_p]),
     "gpn_debug_leaf_prof": (None, [C.c_void_p, C.c_void_p]),
     "gpn_debug_scalars": (C.c_int, [C.c_void_p, c_dbl_p]),
     "gpn_debug_d6_layout": (C.c_int, [C.c_void_p, c_int_p]),
@@ -210,6 +211,15 @@ class Context:
         return dict(gemm_ms=out[0], gemm_flops=out[1], gemm_launches=int(out[2]), big_ms=out[3], big_flops=out[4],
                     big_launches=int(out[5]), potrf_ms=out[6], potrf_flops=out[7], potrf_launches=int(out[8]),
                     potrf_union_ms=out[9], gemm_union_ms=out[10])
+
+    def profile_intervals(self, ref=None, max_rows=4096) -> np.ndarray:
+        """(start ms, end ms, executed flops, kind) of every launch recorded since set_profile(True), relative to the first
+        recorded launch of the context ``ref`` (lanes evaluating concurrently are merged by the caller)."""
+        out = np.zeros((max_rows, 4))
+        rows = C.c_int(0)
+        self._check(self.lib.gpn_profile_intervals(self.h, ref.h if ref is not None else None, _dp(out), max_rows, C.byref(rows)),
+                    "gpn_profile_intervals")
+        return out[: rows.value].copy()
 
     # -- device-pointer primitives (pointers are ints, e.g. torch.Tensor.data_ptr()) --------------------
     def laplacian_dense(self, alpha, gamma, out_ptr, ld):

@@ -54,6 +54,8 @@ enum : int {
     GF_KHI_N = 32,   // contributions only for k <  n0+BN (op(B)[k][n] == 0 for k > n)
     GF_FORCE_SMALL = 64,   // force the 64x64 tile configuration
     GF_FORCE_BIG = 128,    // force the 128x128 tile configuration
+    // debugging aids (GPNET_B200_GEMM_DEBUG, tools/gemm_race.py)
+    GF_DBG_PROD_FENCE = 0x100, GF_DBG_CONS_FENCE = 0x200, GF_DBG_ONE_CTA = 0x400, GF_DBG_PROD_STAY = 0x800,
 };
 
 struct ProfEvent {

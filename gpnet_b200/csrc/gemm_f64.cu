@@ -117,6 +117,7 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(bar_empty + s * 8, ph ^ 1);
+                if (g.flags & GF_DBG_PROD_FENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 const uint32_t full = bar_full + s * 8;
                 mbar_expect_tx(full, STAGE_BYTES);
                 const uint32_t sa = smem0 + s * STAGE_BYTES, sb = sa + A_BYTES;
@@ -134,6 +135,9 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < BN / 16; ++j) tma_load_3d(sb + j * 2048, pB, full, n0 + 16 * j, k, batch);
                 }
+            }
+            if (g.flags & GF_DBG_PROD_STAY) {      // leave only after the consumers have released every stage
+                for (int it = niter; it < niter + STAGES && it - STAGES >= 0; ++it) mbar_wait(bar_empty + (it % STAGES) * 8, ((it / STAGES) & 1) ^ 1);
             }
         }
         return;
@@ -166,6 +170,7 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dmma884(acc[i][j], af[i][u], bf[j][u]);
         }
+        if (g.flags & GF_DBG_CONS_FENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + s * 8);
     }
@@ -250,7 +255,16 @@ int launch_cfg(gpn_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const G
         configured = true;
     }
     dim3 grid(ntiles, batch), block(gemm_threads<WM, WN>());
-    kern<<<grid, block, smem, c->stream>>>(ta, tb, a);
+    size_t smem_req = smem;
+    if ((a.flags & GF_DBG_ONE_CTA) && smem < 120 * 1024) {      // debug: one CTA per SM
+        static bool big_configured = false;
+        if (!big_configured) {
+            GPN_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+            big_configured = true;
+        }
+        smem_req = 120 * 1024;
+    }
+    kern<<<grid, block, smem_req, c->stream>>>(ta, tb, a);
     c->launches++;
     GPN_CK(cudaGetLastError());
     return 0;
@@ -283,6 +297,8 @@ int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, lon
     const long big = count_tiles(128, 128, tm_b, tn_b) * batch;
     const long small = count_tiles(64, 64, tm_s, tn_s) * batch;
     bool use_big = big >= (long)c->num_sms * 3 / 4;
+    static const int dbg = getenv("GPNET_B200_GEMM_DEBUG") ? (int)strtol(getenv("GPNET_B200_GEMM_DEBUG"), nullptr, 0) : 0;
+    flags |= dbg & (GF_DBG_PROD_FENCE | GF_DBG_CONS_FENCE | GF_DBG_ONE_CTA | GF_DBG_PROD_STAY | GF_FORCE_BIG);
     if (flags & GF_FORCE_SMALL) use_big = false;
     if (flags & GF_FORCE_BIG) use_big = true;
     const int bm = use_big ? 128 : 64, bn = bm;

@@ -2077,6 +2077,32 @@ int gpn_profile_summary(gpn_ctx* c, double* out_h) {
     return 0;
 }
 
+/* Launch intervals recorded since gpn_set_profile(ctx,1), for merging ACROSS contexts (lanes that evaluate concurrently): row i of
+ * out_h = (start ms, end ms, executed flops, kind: 0 GEMM / 2 dataflow Cholesky), times relative to the first recorded launch of
+ * `ref` (a context on the same device; NULL: this one).  *rows_h = rows written (at most max_rows). */
+int gpn_profile_intervals(gpn_ctx* c, gpn_ctx* ref, double* out_h, int max_rows, int* rows_h) {
+    GPN_RANGE();
+    if (!c || !rows_h) return -1;
+    *rows_h = 0;
+    if (!ref) ref = c;
+    GPN_CK(cudaStreamSynchronize(c->stream));
+    if (c->prof_events.empty() || ref->prof_events.empty()) return 0;
+    cudaEvent_t e_ref = ref->prof_events.front().e0;
+    GPN_CK(cudaEventSynchronize(e_ref));
+    int r = 0;
+    for (auto& p : c->prof_events) {
+        if (r >= max_rows) break;
+        GPN_CK(cudaEventSynchronize(p.e1));
+        float t0 = 0.f, t1 = 0.f;
+        GPN_CK(cudaEventElapsedTime(&t0, e_ref, p.e0));
+        GPN_CK(cudaEventElapsedTime(&t1, e_ref, p.e1));
+        out_h[4 * r + 0] = t0; out_h[4 * r + 1] = t1; out_h[4 * r + 2] = p.flops; out_h[4 * r + 3] = p.kind;
+        ++r;
+    }
+    *rows_h = r;
+    return 0;
+}
+
 int gpn_set_targets(gpn_ctx* c, const double* t_h, int n) {
     GPN_RANGE();
     if (!c) return -1;

@@ -51,6 +51,10 @@ void gpn_reset_counters(gpn_ctx* ctx);
 int gpn_fp64_peak(gpn_ctx* ctx, double seconds, double* tflops_h);
 void gpn_set_profile(gpn_ctx* ctx, int on);
 int gpn_profile_summary(gpn_ctx* ctx, double* out_h);
+/* the recorded launch intervals themselves, for merging across contexts that evaluate concurrently (lanes): row i of out_h =
+ * (start ms, end ms, executed flops, kind: 0 GEMM, 2 dataflow Cholesky) relative to the first recorded launch of `ref`
+ * (NULL: ctx); *rows_h = rows written, at most max_rows */
+int gpn_profile_intervals(gpn_ctx* ctx, gpn_ctx* ref, double* out_h, int max_rows, int* rows_h);
 /* development aid: device buffer of 32 int64 receiving clock64() stamps of the phases of the next leaf-kernel launch */
 void gpn_debug_leaf_prof(gpn_ctx* ctx, void* dev_buf32);
 /* development aid: run the 128x128 leaf on `copies` stacked blocks (lda 128), one CTA each; block 0 stamps its phases */
