@@ -175,6 +175,16 @@ class GPnetBase:
             print("new parameters: ", self.theta)
         return self
 
+    def use_spectral(self, on=True):
+        """Extension: build every kernel of this model as ``V r(lam) V^T`` from ONE eigendecomposition of the
+        normalized Laplacian (computed on the GPU the first time a kernel is needed; eq. 55-56 of the reference's write-up)
+        instead of expm / inv / matrix_power per theta (GPnet.py:338-349).  Pays for sweeps over many kernel parameters
+        (``lml_landscape``, ``optimize_params``); results agree with the default path to ~1e-12.  With a training set of at
+        most 112 nodes the regressor's landscapes and batches then run one CTA per theta in a single launch."""
+        self._engine.spectral = bool(on)
+        self._engine.invalidate_kernel()
+        return self
+
     def lml_landscape(self, theta, axidx, ax1, ax2):
         """``lml[i, j] = -logPosterior(theta with theta[axidx[0]] = ax1[i], theta[axidx[1]] = ax2[j])``.
         Under torch.distributed with world_size > 1 the grid is sharded cyclically over the ranks and the

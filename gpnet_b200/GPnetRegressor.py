@@ -14,7 +14,7 @@ from __future__ import annotations
 import numpy as np
 import pandas as pd
 
-from ._lib import KERNEL_IDS
+from ._lib import KERNEL_IDS, Context
 from .engine import PredictToken, evaluate_batch, invalidate_predict, raise_domain
 from .GPnet import GPnetBase, KERNEL_LIST, _is_false
 
@@ -172,6 +172,16 @@ class GPnetRegressor(GPnetBase):
         thetas = [self._theta_vec(th) for th in thetas]
         tr = self._positions(data)
         te = self._positions(self.test_nodes) if not _is_false(self.test_nodes) else ()
+        if self._engine.spectral and 0 < len(tr) <= Context.SPECTRAL_BATCH_MAX_N and len(thetas):
+            # small training set on the spectral path: every theta is one CTA of ONE launch (gpn_gpr_logp_grad_batch)
+            ctx = self._engine.bind(tr, te)
+            ctx._kernel_key = None
+            invalidate_predict(ctx)
+            st, out, infos = ctx.gpr_logp_grad_batch(self._kind(), np.asarray(thetas), self._values(t), want_grad)
+            raise_domain(st)
+            vals = out[:, 0].copy()
+            vals[infos > 0] = -np.inf
+            return vals, out[:, 1:].copy()
         ctxs = self._engine.lanes(lanes, tr, te)
         for ctx in ctxs[:1]:
             ctx._kernel_key = None

@@ -32,6 +32,10 @@ SIGNATURES = {
     "gpn_fp64_peak": (C.c_int, [C.c_void_p, C.c_double, c_dbl_p]),
     "gpn_set_profile": (None, [C.c_void_p, C.c_int]),
     "gpn_profile_summary": (C.c_int, [C.c_void_p, c_dbl_p]),
+    "gpn_spectral_prepare": (C.c_int, [C.c_void_p, c_int_p, c_dbl_p]),
+    "gpn_spectral_enable": (None, [C.c_void_p, C.c_int]),
+    "gpn_spectral_get": (C.c_int, [C.c_void_p, c_dbl_p, c_dbl_p]),
+    "gpn_gpr_logp_grad_batch": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_int_p]),
     "gpn_profile_intervals": (C.c_int, [C.c_void_p, C.c_void_p, c_dbl_p, C.c_int, c_int_p]),
     "gpn_debug_leaf_prof": (None, [C.c_void_p, C.c_void_p]),
     "gpn_debug_scalars": (C.c_int, [C.c_void_p, c_dbl_p]),
@@ -344,6 +348,41 @@ class Context:
         info = C.c_int(0)
         self._check(self.lib.gpn_gpr_logp_grad_end(self.h, _dp(out), C.byref(info)), "gpn_gpr_logp_grad_end")
         return out, info.value
+
+    # -- spectral fast path ----------------------------------------------------------------------------
+    SPECTRAL_BATCH_MAX_N = 112
+
+    def spectral_prepare(self):
+        """Eigendecomposition of the bound graph's normalized Laplacian (once per graph); returns (sweeps, offdiag_rel)."""
+        sweeps, off = C.c_int(0), C.c_double(0)
+        self._check(self.lib.gpn_spectral_prepare(self.h, C.byref(sweeps), C.byref(off)), "gpn_spectral_prepare")
+        return sweeps.value, off.value
+
+    def spectral_enable(self, on=True):
+        self.lib.gpn_spectral_enable(self.h, int(bool(on)))
+
+    def spectral_get(self):
+        lam, VT = np.zeros(self.N), np.zeros((self.N, self.N))
+        self._check(self.lib.gpn_spectral_get(self.h, _dp(lam), _dp(VT)), "gpn_spectral_get")
+        return lam, VT
+
+    def gpr_logp_grad_batch(self, kind, thetas, t, want_grad=True):
+        """(-logp, -grad) rows for B log-parameter vectors in one launch (one CTA per theta); t=None: resident targets."""
+        th = np.ascontiguousarray(np.exp(np.asarray(thetas, dtype=np.float64)))
+        if th.ndim != 2:
+            raise ValueError("thetas must be B x P")
+        B, P = th.shape
+        tt = None if t is None else _f64(t)
+        if tt is not None and len(tt) != self.n_train:
+            raise ValueError("len(t) != number of training nodes")
+        out = np.zeros((B, 1 + P))
+        info = np.zeros(B, dtype=np.int32)
+        st = self.lib.gpn_gpr_logp_grad_batch(self.h, kind, _dp(th), B, P, None if tt is None else _dp(tt), int(want_grad), _dp(out),
+                                              info.ctypes.data_as(c_int_p))
+        if st in (-100, -101, -20):
+            return st, out, info
+        self._check(st, "gpn_gpr_logp_grad_batch")
+        return 0, out, info
 
     def debug_scalars(self):
         out = np.zeros(32)

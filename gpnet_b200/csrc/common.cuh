@@ -88,6 +88,21 @@ struct Dissect6 {
     DevBuf work[12];             // G^T, G_o^T, U^T, U_o^T, T, T_o and their factors / inverses, vectors
 };
 
+// Spectral fast path (spectral.cu): L~ = V diag(lam) V^T of the bound graph, computed once (two-sided block Jacobi); every
+// kernel of the reference is then V r(lam) V^T.
+struct Spectral {
+    bool ready = false;          // VT / lam hold the eigendecomposition of the bound graph
+    bool on = false;             // kernel_build goes through V r(lam) V^T (gpn_spectral_enable)
+    bool vt_valid = false;       // Vt holds the training columns of VT for the bound node set
+    int sweeps = 0;              // Jacobi sweeps the decomposition took
+    double off_rel = 0.0;        // ||offdiag||_F / ||A||_F it stopped at
+    std::vector<double> h_lam;   // eigenvalues, ascending
+    DevBuf VT;                   // N x pad128(N): row k = eigenvector k
+    DevBuf lam, rbuf;            // eigenvalues; r(lam) staging (2 x pad128(N))
+    DevBuf Vt;                   // N x n4: Vt[k][i] = VT[k][train_i] (batched evaluator)
+    DevBuf bt, bth, bout;        // batched evaluator: targets, thetas, results
+};
+
 struct gpn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -166,6 +181,7 @@ struct gpn_ctx {
     long flags_rowsK[10] = {0};
     cudaStream_t side[10] = {nullptr};
     cudaEvent_t ev_side[10] = {nullptr};
+    Spectral spec;
     Dissect6 d6;
     int d6_parts = 0;                    // > 0: number of parts forced by gpn_set_dissection_parts (0: chosen from N)
     void* df_trace = nullptr;    // optional device buffer: 8 x int64 globaltimer stamps per dataflow-Cholesky task
@@ -245,6 +261,12 @@ int gpn_k_form_B(gpn_ctx* c, int n, const double* K, long ldk, const double* sw,
 int gpn_k_scale_rows(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* s, double* out, long ldo);
 
 enum { GEMV_FULL = 0, GEMV_LOWER = 1 /* treat entries with col > row as zero */ };
+
+// spectral path (spectral.cu)
+int gpn_spec_invalidate(gpn_ctx* c, bool graph_changed);
+int gpn_spec_prepare(gpn_ctx* c);
+int gpn_spec_build_kernel(gpn_ctx* c, int kind, double th0, int p, double* Kout, long ld, double* pm1, double* scratch);
+const double* gpn_resident_targets(gpn_ctx* c);      // device copy of the targets of gpn_set_targets (gp.cu)
 
 // whole-graph dissection route (dissect.cu)
 int gpn_d6_ensure(gpn_ctx* c);

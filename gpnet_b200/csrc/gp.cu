@@ -481,6 +481,32 @@ int kernel_build(gpn_ctx* c, int kind, const double* theta_h, int P, int want_gr
     c->ldN = pad128(c->N);
     GPN_TRY(clear_info(c));
     int st;
+    if (c->spec.on) {
+        // spectral route (spectral.cu): K = V r(lam) V^T from the eigendecomposition of L~ computed once per graph
+        if (kind != GPN_KERNEL_DIFFUSION && kind != GPN_KERNEL_REGULARIZED_LAPLACIAN && kind != GPN_KERNEL_PSTEP_WALK) return -2;
+        if (kind == GPN_KERNEL_DIFFUSION && !(c->theta_exp[0] < 1.0)) return -100;
+        if (kind == GPN_KERNEL_PSTEP_WALK) {
+            if (!(c->theta_exp[0] >= 2.0)) return -101;
+            if (P < 2) return -4;
+            c->pstep_p = (int)c->theta_exp[1];
+        }
+        for (int i : {0, 1, 4, 5}) GPN_TRY(ensure_mat(c, i));
+        const bool pm1 = kind == GPN_KERNEL_PSTEP_WALK && want_grad && c->pstep_p >= 2;
+        c->have_aux = false;
+        st = gpn_spec_build_kernel(c, kind, c->theta_exp[0], c->pstep_p, mat(c, 5), c->ldN, pm1 ? mat(c, 4) : nullptr, mat(c, 1));
+        if (st != 0) return st;
+        c->mat[9] = c->mat[5];
+        if (kind == GPN_KERNEL_DIFFUSION) {        // the gradient reads A = -beta L~ from mat 0 (gpr_grad_kernel_block)
+            GPN_TRY(laplacian_into(c, -c->theta_exp[0], 0.0, mat(c, 0), c->ldN));
+            c->have_aux = true;
+        } else if (pm1) {
+            c->have_aux = true;
+        }
+        c->expm_m = 0;
+        c->expm_s = 0;
+        c->have_full = true;
+        return 0;
+    }
     if (kind == GPN_KERNEL_DIFFUSION) {
         if (!(c->theta_exp[0] < 1.0)) return -100;                        // GPnet.py:339
         st = build_diffusion(c, c->theta_exp[0]);
@@ -1775,6 +1801,8 @@ int with_matrix_size(gpn_ctx* c, int N, F body) {
 
 }   // namespace
 
+const double* gpn_resident_targets(gpn_ctx* c) { return vecp(c, V_TRES); }
+
 // =====================================================================================================================
 // C-ABI
 // =====================================================================================================================
@@ -1926,6 +1954,7 @@ int gpn_set_graph(gpn_ctx* c, int N, const int* indptr_h, const int* indices_h, 
     c->h_train.clear();
     c->perm_valid = false;
     c->d6.built = false;
+    gpn_spec_invalidate(c, true);
     return gpn_k_degree_dinv(c, N, (const int*)c->indptr.p, (const int*)c->indices.p, (const double*)c->weights.p, (double*)c->dinv.p);
 }
 
@@ -1949,6 +1978,7 @@ int gpn_set_nodes(gpn_ctx* c, int n_train, const int* train_h, int n_test, const
     c->train_unique = std::adjacent_find(c->h_train.begin(), c->h_train.end()) == c->h_train.end();
     c->perm_valid = false;
     c->d6.built = false;
+    gpn_spec_invalidate(c, false);
     return ensure_vecs(c);
 }
 

@@ -142,6 +142,8 @@ class GraphEngine:
         self._pos_cache = {}
         self._lanes = []
         self._lanes_key = None
+        self.spectral = False          # kernels as V r(lam) V^T from one eigendecomposition of L~ (GPnetBase.use_spectral)
+        self.spectral_info = None
 
     def lanes(self, count: int, train_pos, test_pos=()):
         """``count`` contexts bound to this graph and these node sets for concurrent evaluations: lane 0 is the shared
@@ -177,6 +179,14 @@ class GraphEngine:
             ctx.set_graph(self.indptr, self.indices, self.weights)
             ctx._owner = self
             ctx._nodes_key = None
+            ctx._kernel_key = None
+            if self.spectral:
+                self.spectral_info = ctx.spectral_prepare()       # once per bound graph (again if another model took the context)
+        if bool(getattr(ctx, "_spectral_on", False)) != self.spectral:
+            if self.spectral:
+                self.spectral_info = ctx.spectral_prepare()
+            ctx.spectral_enable(self.spectral)
+            ctx._spectral_on = self.spectral
             ctx._kernel_key = None
         if train_pos is not None:
             key = (tuple(train_pos), tuple(test_pos or ()))

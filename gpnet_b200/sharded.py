@@ -181,6 +181,22 @@ def evaluate_points(model, theta, axidx, ax1, ax2, indices, want_grad=False):
     from .engine import raise_domain
     th = model._theta_vec(theta).copy()
     classifier = not hasattr(model, "logPosterior_and_grad")
+    from ._lib import Context
+    n_train = len(model._positions(model.training_nodes))
+    if not classifier and getattr(model._engine, "spectral", False) and 0 < n_train <= Context.SPECTRAL_BATCH_MAX_N and len(indices):
+        # spectral path, small training set: all grid points of this rank in ONE launch, one CTA per point
+        n2 = len(ax2)
+        thetas = np.tile(th, (len(indices), 1))
+        for row, flat in enumerate(np.asarray(indices, dtype=np.int64)):
+            thetas[row, axidx[0]] = ax1[int(flat) // n2]
+            thetas[row, axidx[1]] = ax2[int(flat) % n2]      # the second axis wins when both name the same entry, like the loop of GPnet.py:545-549
+        st, rows, infos = _bound_context(model).gpr_logp_grad_batch(KERNEL_IDS[model.kerneltype], thetas, _targets(model), want_grad)
+        raise_domain(st)
+        out = -rows
+        if not want_grad:
+            out[:, 1:] = 0.0
+        out[infos > 0, 0] = np.inf          # logPosterior returned -inf (A-8) => lml = +inf
+        return out
     st, out = _bound_context(model).landscape_points(KERNEL_IDS[model.kerneltype], classifier, th, axidx, ax1, ax2, _targets(model), indices,
                                                      want_grad)
     raise_domain(st)

@@ -157,6 +157,26 @@ int gpn_gpr_logp_grad_begin(gpn_ctx* ctx, int kind, const double* etheta_h, int 
 int gpn_gpr_logp_grad_end(gpn_ctx* ctx, double* out_h, int* info_h);
 void gpn_set_sm_budget(gpn_ctx* ctx, int sms);
 int gpn_num_sms(gpn_ctx* ctx);
+
+/* ---- spectral fast path for sweeps (the reference's write-up, eq. 55-56: every Kondor kernel of GPnet.py:338-349
+ * is V r(lam) V^T with L~ = V diag(lam) V^T) and batched small-n evaluation --------------------------------------
+ * gpn_spectral_prepare: eigendecomposition of the bound graph's normalized Laplacian, once per graph (two-sided block Jacobi:
+ * 64 x 64 pivot blocks diagonalised in shared memory, rotations applied with batched DMMA GEMMs); *sweeps_h = Jacobi sweeps,
+ * *offdiag_rel_h = ||offdiag||_F / ||L~||_F reached.  gpn_spectral_enable(ctx, 1): every later kernel build of this context
+ * (gpn_kernel_build and all entry points that build a kernel: predict, logp, Newton loop, landscape) forms K = V r(lam) V^T with
+ * ONE symmetric GEMM (N^3 flops) instead of the Pade / inverse / power algorithms; results agree with them to ~1e-12 (own
+ * parity tests).  gpn_spectral_get copies lam (N, ascending) and V^T (N x N row-major: row k = eigenvector k) to the host. */
+int gpn_spectral_prepare(gpn_ctx* ctx, int* sweeps_h, double* offdiag_rel_h);
+void gpn_spectral_enable(gpn_ctx* ctx, int on);
+int gpn_spectral_get(gpn_ctx* ctx, double* lam_h, double* VT_h);
+/* GPnetRegressor.logPosterior (+ gradient) for B parameter vectors in ONE launch, one CTA per theta (training block in shared
+ * memory: n_train <= GPN_SPECTRAL_BATCH_MAX_N, else status -20): the loops of GPnet.py:259-274 / 539-552 around
+ * GPnetRegressor.py:136-150 for the small-n regime where one evaluation is launch- and latency-bound.  etheta_h: B x P
+ * exponentiated parameters, row-major; t_h: targets (NULL: resident); out_h: B x (1+P) rows (-logp, -dlogp/dtheta) like
+ * gpn_gpr_logp_grad; info_h[b] > 0: K_y of row b not positive definite.  Status -100 / -101: parameter domain (GPnet.py:339,344). */
+#define GPN_SPECTRAL_BATCH_MAX_N 112
+int gpn_gpr_logp_grad_batch(gpn_ctx* ctx, int kind, const double* etheta_h, int B, int P, const double* t_h, int want_grad,
+                            double* out_h, int* info_h);
 /* GPnetRegressor.predict body (:86-128).  Outputs (host): alpha[n], fstar[m], s[m] (sqrt of the predictive
  * variance), kss_diag[m]; info_h[0]: Cholesky info of k, info_h[1]: info of kstarstar (the two PD gates, A-7). */
 int gpn_gpr_predict(gpn_ctx* ctx, int kind, const double* etheta_h, int P, const double* t_h, double* alpha_h,

@@ -5,7 +5,7 @@ to CPython bytecode (``py_compile``), the Python counterpart of compiling a C re
     python -m oracle.make_ref
 
 Run by ``__graft_entry__.build()`` in the build container.  No reference SOURCE is copied anywhere; ``oracle/_ref/`` holds
-build outputs only (``*.pyc`` + a manifest with the sha256 of each source), is listed in .gitignore (never enters this
+build outputs only (``*.bytecode`` = CPython bytecode under a neutral extension, because snapshot tools drop ``*.pyc``, + a manifest with the sha256 of each source), is listed in .gitignore (never enters this
 repository) but not in .gpurunignore (travels to the GPU box like the built ``.so``; same image, same interpreter, so the
 bytecode loads there).  ``bench.py --impl reference`` imports it through the shims of oracle/ref_shim.py and drives the
 literal ``GPnetRegressor.logPosterior``.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py)."""
@@ -14,7 +14,7 @@ import os
 import py_compile
 import sys
 
-from oracle.ref_shim import REFERENCE_MODULES, REFERENCE_PATH, VENDORED_PATH
+from oracle.ref_shim import REFERENCE_MODULES, REFERENCE_PATH, VENDORED_EXT, VENDORED_PATH
 
 
 def make_ref(src=REFERENCE_PATH, dst=VENDORED_PATH):
@@ -25,7 +25,7 @@ def make_ref(src=REFERENCE_PATH, dst=VENDORED_PATH):
     out = []
     for f in REFERENCE_MODULES:
         path = os.path.join(src, f)
-        py_compile.compile(path, cfile=os.path.join(dst, f + "c"), dfile=f, doraise=True)      # sourceless import: <dst>/GPnet.pyc
+        py_compile.compile(path, cfile=os.path.join(dst, f[:-3] + VENDORED_EXT), dfile=f, doraise=True)      # sourceless import
         with open(path, "rb") as fh:
             out.append((f, hashlib.sha256(fh.read()).hexdigest()))
     with open(os.path.join(dst, "MANIFEST.txt"), "w") as fh:

@@ -29,7 +29,8 @@ import scipy.sparse.linalg
 
 import os
 
-REFERENCE_PATH = "/root/reference"
+REFERENCE_PATH = os.environ.get("GPNET_REFERENCE_PATH", "/root/reference")
+VENDORED_EXT = ".bytecode"      # CPython bytecode under a neutral extension (snapshot tools drop *.pyc)
 VENDORED_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REFERENCE_MODULES = ("GPnet.py", "GPnetRegressor.py", "GPnetClassifier.py")
 
@@ -39,7 +40,7 @@ def find_reference():
     oracle/_ref (GPU box); None when neither exists."""
     if all(os.path.exists(os.path.join(REFERENCE_PATH, f)) for f in REFERENCE_MODULES):
         return REFERENCE_PATH
-    if all(os.path.exists(os.path.join(VENDORED_PATH, f + "c")) for f in REFERENCE_MODULES):
+    if all(os.path.exists(os.path.join(VENDORED_PATH, f[:-3] + VENDORED_EXT)) for f in REFERENCE_MODULES):
         return VENDORED_PATH
     return None
 
@@ -105,6 +106,19 @@ def load_reference(path=None):
         mod = sys.modules.get(name)
         if mod is not None and not str(getattr(mod, "__file__", "")).startswith(path):
             del sys.modules[name]
+    if path == VENDORED_PATH:      # sourceless import of the compiled copies, in dependency order
+        import importlib.machinery
+        import importlib.util
+        for name in ("GPnet", "GPnetRegressor", "GPnetClassifier"):
+            if name in sys.modules:
+                continue
+            loader = importlib.machinery.SourcelessFileLoader(name, os.path.join(path, name + VENDORED_EXT))
+            spec = importlib.util.spec_from_loader(name, loader)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            if name == "GPnet":       # the shims below must be in place before the subclasses import it
+                pass
+            loader.exec_module(mod)
     gp = importlib.import_module("GPnet")
     gp.sl = _ScipyLinalgProxy()
     gp.GPnetBase.calc_shortest_paths = lambda self: setattr(self, "dist", None)
