@@ -90,9 +90,12 @@ __global__ void __launch_bounds__(256) jacobi64_kernel(const double* __restrict_
             const double app = S[p][p], aqq = S[q][q], apq = S[p][q];
             double c = 1.0, s = 0.0;
             if (fabs(apq) > thresh) {
-                const double tau = (aqq - app) / (2.0 * apq);
-                const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                c = 1.0 / sqrt(1.0 + t * t);
+                // t = tan(theta) of the smaller rotation angle, without the division by a_pq: with d = a_qq - a_pp and
+                // h = sqrt(d^2 + 4 a_pq^2), t = 2 a_pq / (d + sign(d) h)   (one sqrt, one division, one rsqrt on the chain)
+                const double d = aqq - app, b2 = 2.0 * apq;
+                const double h = sqrt(fma(d, d, b2 * b2));
+                const double t = b2 / (d + copysign(h, d));
+                c = rsqrt(fma(t, t, 1.0));
                 s = t * c;
                 rotated = 1;
             }
@@ -218,12 +221,14 @@ int jacobi_run(gpn_ctx* c, int Np, long ld, double* A, double* AP, double* BT, d
     int sweeps = 0;
     bool first = true;
     static const int max_sweeps = getenv("GPNET_B200_JACOBI_SWEEPS") ? atoi(getenv("GPNET_B200_JACOBI_SWEEPS")) : 40;
+    // cyclic sweeps over a 64 x 64 pivot block per visit: one is enough (more did not reduce the number of outer sweeps)
+    static const int inner = getenv("GPNET_B200_JACOBI_INNER") ? atoi(getenv("GPNET_B200_JACOBI_INNER")) : 1;
     while (off_rel > 1e-14 && sweeps < max_sweeps) {
         for (int r = 0; r < nb - 1; ++r) {
             const int* rm = first ? rm0_d : rm1_d;
             first = false;
             GPN_TRY(gpn_k_gather_rows(c, A, ld, rm, Np, Np, AP, ld));
-            jacobi64_kernel<<<npair, 256, jsm, c->stream>>>(AP, ld, rm, Qb, thresh, 2);
+            jacobi64_kernel<<<npair, 256, jsm, c->stream>>>(AP, ld, rm, Qb, thresh, inner);
             c->launches++;
             GPN_CK(cudaGetLastError());
             // B = J^T (P A): only its transpose is kept, B^T = A P^T J
