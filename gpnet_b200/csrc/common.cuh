@@ -254,13 +254,15 @@ int gpn_k_trap_pass(gpn_ctx* c, int rows, int cols, int off, const double* Wb, l
                     double* zb, double* d_fro, bool zero_fro = true);
 int gpn_k_multi_dot(gpn_ctx* c, int count, const double* const* x, const double* const* y, const int* n, double* d_out);
 int gpn_k_colnorm2(gpn_ctx* c, int rows, int cols, const double* V, long ld, double* out);
+int gpn_k_rownorm2(gpn_ctx* c, int rows, int cols, const double* V, long ld, double* out);
+int gpn_k_scale_cols(gpn_ctx* c, int rows, int cols, double* A, long lda, const double* s);
 int gpn_k_diag_gather(gpn_ctx* c, const double* K, long ld, const int* idx, int m, double addc, double* out);
 int gpn_k_grad_trace(gpn_ctx* c, int n, const double* Kinv, long ldi, const double* G, long ldg, const double* Ktt, long ldk,
                      double g_scale, double k_scale, double k_shift, const double* alpha, double* d_out3);
 int gpn_k_form_B(gpn_ctx* c, int n, const double* K, long ldk, const double* sw, double* B, long ldb);
 int gpn_k_scale_rows(gpn_ctx* c, int rows, int cols, const double* A, long lda, const double* s, double* out, long ldo);
 
-enum { GEMV_FULL = 0, GEMV_LOWER = 1 /* treat entries with col > row as zero */ };
+enum { GEMV_FULL = 0, GEMV_LOWER = 1 /* treat entries with col > row as zero */, GEMV_UPPER = 2 /* ... with col < row as zero */ };
 
 // spectral path (spectral.cu)
 int gpn_spec_invalidate(gpn_ctx* c, bool graph_changed);

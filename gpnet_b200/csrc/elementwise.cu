@@ -193,9 +193,11 @@ __global__ void gemv_kernel(int rows, int cols, const double* __restrict__ A, lo
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     const int lim = (mode == GEMV_LOWER) ? min(cols, row + 1) : cols;
+    const int c0 = (mode == GEMV_UPPER) ? (row & ~31) : 0;       // entries with col < row are treated as zero
     const double* a = A + (long)row * lda;
     double s = 0.0;
-    for (int c = lane; c < lim; c += 32) s += a[c] * x[c];
+    for (int c = c0 + lane; c < lim; c += 32)
+        if (mode != GEMV_UPPER || c >= row) s += a[c] * x[c];
     s = warp_sum(s);
     if (lane == 0) y[row] = s;
 }
@@ -206,6 +208,7 @@ __global__ void gemv_t_kernel(int rows, int cols, const double* __restrict__ A, 
     if (c >= cols) return;
     int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
     if (mode == GEMV_LOWER) r0 = max(r0, c);   // A[r][c] nonzero only for r >= c
+    if (mode == GEMV_UPPER) r1 = min(r1, c + 1);   // ... only for r <= c
     double s = 0.0;
     for (int r = r0; r < r1; ++r) s += A[(long)r * lda + c] * x[r];
     if (r1 > r0) atomicAdd(&y[c], s);
@@ -493,6 +496,23 @@ __global__ void colnorm2_kernel(int rows, int cols, const double* __restrict__ V
     atomicAdd(&out[c], s);
 }
 
+// out[r] = sum_c V[r][c]^2 (one warp per row)
+__global__ void rownorm2_kernel(int rows, int cols, const double* __restrict__ V, long ld, double* __restrict__ out) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const double* a = V + (long)row * ld;
+    double s = 0.0;
+    for (int c = lane; c < cols; c += 32) s += a[c] * a[c];
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s;
+}
+// A[r][c] *= s[c]
+__global__ void scale_cols_kernel(int rows, int cols, double* __restrict__ A, long lda, const double* __restrict__ s) {
+    const int r = blockIdx.y;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) A[(long)r * lda + c] *= s[c];
+}
+
 // ---- gradient traces: out[0] = sum_ij Kinv_ij (symmetric, lower stored), out[1] = sum_ij (a_i a_j - Kinv_ij) * D_ij
 //      with D = g_scale*G + k_scale*Ktt (lower triangles; off-diagonal counted twice), out[2] = sum_i a_i -------------
 __global__ void grad_trace_kernel(int n, const double* __restrict__ Kinv, long ldi, const double* __restrict__ G, long ldg,
@@ -770,6 +790,19 @@ int gpn_k_colnorm2(gpn_ctx* c, int rows, int cols, const double* V, long ld, dou
     const int rpb = 128;
     dim3 grid(grid1(cols, 128), (rows + rpb - 1) / rpb);
     colnorm2_kernel<<<grid, 128, 0, c->stream>>>(rows, cols, V, ld, out, rpb);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_rownorm2(gpn_ctx* c, int rows, int cols, const double* V, long ld, double* out) {
+    if (rows <= 0) return 0;
+    rownorm2_kernel<<<grid1((long)rows * 32), TPB, 0, c->stream>>>(rows, cols, V, ld, out);
+    LAUNCHED(c);
+    return 0;
+}
+int gpn_k_scale_cols(gpn_ctx* c, int rows, int cols, double* A, long lda, const double* s) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid(gridx_cols(cols), rows);
+    scale_cols_kernel<<<grid, TPB, 0, c->stream>>>(rows, cols, A, lda, s);
     LAUNCHED(c);
     return 0;
 }

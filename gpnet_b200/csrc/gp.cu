@@ -1604,6 +1604,14 @@ int factor_B(gpn_ctx* c, const NewtonState& s) {
     return gpn_trtri(c, s.n, nbp(c, NB_B), s.ldn, (const double*)c->winv.p, nbp(c, NB_WB), nbp(c, NB_WT), nbp(c, NB_T), s.ldn);
 }
 
+// The same from ONE augmented dataflow factorisation [B; I]: L_B in NB_B and W_B^T = L_B^-T (upper tiles) in
+// NB_WT; the triangular inverse rides along in the Cholesky kernel instead of ten batched GEMM launches.  NB_WB is NOT produced.
+int factor_B_fast(gpn_ctx* c, const NewtonState& s, double* rhs_rows = nullptr, int nrhs = 0) {
+    GPN_TRY(gpn_k_form_B(c, s.n, s.K, s.ldk, vecp(c, V_SW), nbp(c, NB_B), s.ldn));
+    return gpn_potrf_dataflow(c, s.n, nbp(c, NB_B), s.ldn, (double*)c->winv.p, iscal(c, 3), 0, rhs_rows, s.ldn, nrhs,
+                              rhs_rows ? nullptr : nbp(c, NB_WT), s.ldn, 0);
+}
+
 int gpc_newton(gpn_ctx* c, const double* K, long ldk, int n, const double* y_h, double tol, double phif0, double scale, int variant,
                double* f_h, double* a_h, double* logq_h, int* iters_h, int* info_h) {
     GPN_TRY(ensure_vecs(c));
@@ -1619,10 +1627,10 @@ int gpc_newton(gpn_ctx* c, const double* K, long ldk, int n, const double* y_h, 
     GPN_TRY(upload(c, vecp(c, V_Y), y_h, sizeof(double) * n));
     GPN_CK(cudaMemsetAsync(vecp(c, V_F), 0, sizeof(double) * n, c->stream));                    // f = 0 (:96)
     // f^T K^-1 f of the convergence test (:126) through one Cholesky of K (K is fixed during the loop)
+    // [K; I] in one dataflow kernel: W_K^T = L_K^-T (upper tiles) -> NB_WK
     GPN_TRY(gpn_k_fill_zero(c, nbp(c, NB_KC), s.ldn, (int)s.ldn, (int)s.ldn));
     GPN_TRY(gpn_k_copy(c, n, n, K, ldk, nbp(c, NB_KC), s.ldn));
-    GPN_TRY(gpn_potrf(c, n, nbp(c, NB_KC), s.ldn, (double*)c->winv.p, iscal(c, 4)));
-    GPN_TRY(gpn_trtri(c, n, nbp(c, NB_KC), s.ldn, (const double*)c->winv.p, nbp(c, NB_WK), nbp(c, NB_WT), nbp(c, NB_T), s.ldn));
+    GPN_TRY(gpn_potrf_dataflow(c, n, nbp(c, NB_KC), s.ldn, (double*)c->winv.p, iscal(c, 4), 0, nullptr, 0, 0, nbp(c, NB_WK), s.ldn, 0));
     int info[16];
     GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
     s.have_wk = (info[4] == 0);     // K not numerically PD: use f^T a (== f^T K^-1 f since f = K a), see DESIGN.md
@@ -1634,17 +1642,18 @@ int gpc_newton(gpn_ctx* c, const double* K, long ldk, int n, const double* y_h, 
         newton_pre_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_F), vecp(c, V_Y), vecp(c, V_W), vecp(c, V_SW), vecp(c, V_P),
                                                          vecp(c, V_B), vecp(c, V_G));
         c->launches++;
-        GPN_TRY(factor_B(c, s));                                                                 // :110
+        GPN_TRY(factor_B_fast(c, s));                                                            // :110
         GPN_TRY(gpn_k_gemv(c, n, n, K, ldk, vecp(c, V_B), vecp(c, V_KB), GEMV_FULL));            // K b
         vec_mul_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_SW), vecp(c, V_KB), vecp(c, V_RHS));
         c->launches++;
-        GPN_TRY(gpn_k_gemv(c, n, n, nbp(c, NB_WB), s.ldn, vecp(c, V_RHS), vecp(c, V_Z2), GEMV_LOWER));
-        GPN_TRY(gpn_k_gemv_t(c, n, n, nbp(c, NB_WB), s.ldn, vecp(c, V_Z2), vecp(c, V_SOL), GEMV_LOWER));
+        // B^-1 rhs = W^T (W rhs) with W^T = L_B^-T stored upper: W x = (W^T)^T x
+        GPN_TRY(gpn_k_gemv_t(c, n, n, nbp(c, NB_WT), s.ldn, vecp(c, V_RHS), vecp(c, V_Z2), GEMV_UPPER));
+        GPN_TRY(gpn_k_gemv(c, n, n, nbp(c, NB_WT), s.ldn, vecp(c, V_Z2), vecp(c, V_SOL), GEMV_UPPER));
         newton_a_kernel<<<g1(n), 256, 0, c->stream>>>(n, scale, vecp(c, V_B), vecp(c, V_SW), vecp(c, V_SOL), vecp(c, V_A));
         c->launches++;
         GPN_TRY(gpn_k_gemv(c, n, n, K, ldk, vecp(c, V_A), vecp(c, V_F), GEMV_FULL));             // f = K a (:122)
         if (s.have_wk) {
-            GPN_TRY(gpn_k_gemv(c, n, n, nbp(c, NB_WK), s.ldn, vecp(c, V_F), vecp(c, V_U), GEMV_LOWER));
+            GPN_TRY(gpn_k_gemv_t(c, n, n, nbp(c, NB_WK), s.ldn, vecp(c, V_F), vecp(c, V_U), GEMV_UPPER));      // u = W_K f
             GPN_TRY(gpn_k_dot(c, n, vecp(c, V_U), vecp(c, V_U), dscal(c, Scal::Q)));
         } else {
             GPN_TRY(gpn_k_dot(c, n, vecp(c, V_F), vecp(c, V_A), dscal(c, Scal::Q)));
@@ -2499,18 +2508,19 @@ int gpn_gpc_predict(gpn_ctx* c, int kind, const double* theta_h, int P, const do
     newton_pre_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_F), vecp(c, V_Y), vecp(c, V_W), vecp(c, V_SW), vecp(c, V_P), vecp(c, V_B),
                                                      vecp(c, V_G));
     c->launches++;
-    GPN_TRY(factor_B(c, s));
     const int* tr = (const int*)c->train_idx.p;
     const int* te = (const int*)c->test_idx.p;
-    GPN_TRY(ensure_nb(c, NB_KSTAR, ldn, ldm));
-    GPN_TRY(ensure_nb(c, NB_S, ldn, ldm));
-    GPN_TRY(ensure_nb(c, NB_V, ldn, ldm));
-    GPN_TRY(gpn_k_gather(c, kfull(c), c->ldN, tr, n, te, m, 0.0, nbp(c, NB_KSTAR), ldm, n, m));           // kstar n x m, measnoise=0 (:193-199)
-    GPN_TRY(gpn_k_gemv_t(c, n, m, nbp(c, NB_KSTAR), ldm, vecp(c, V_G), vecp(c, V_FSTAR), GEMV_FULL));     // fstar (:210)
-    GPN_TRY(gpn_k_scale_rows(c, n, m, nbp(c, NB_KSTAR), ldm, vecp(c, V_SW), nbp(c, NB_S), ldm));          // sqrtW kstar
-    // v = L_B^-1 (sqrtW kstar) = W_B S                                                                  (:211)
-    GPN_TRY(gpn_gemm(c, n, m, n, 1.0, nbp(c, NB_WB), ldn, true, nbp(c, NB_S), ldm, false, 0.0, nbp(c, NB_V), ldm, GF_KHI_M));
-    GPN_TRY(gpn_k_colnorm2(c, n, m, nbp(c, NB_V), ldm, vecp(c, V_VN)));
+    // kstar^T = K[te, tr] (m x n, measnoise = 0, :193-199) with its rows padded to a multiple of 128 (appended block of the
+    // factorisation below); fstar = kstar^T g (:210)
+    GPN_TRY(ensure_nb(c, NB_KSTAR, ldm, ldn));
+    double* KsT = nbp(c, NB_KSTAR);
+    GPN_TRY(gpn_k_gather(c, kfull(c), c->ldN, te, m, tr, n, 0.0, KsT, ldn));
+    GPN_TRY(gpn_k_gemv(c, m, n, KsT, ldn, vecp(c, V_G), vecp(c, V_FSTAR), GEMV_FULL));
+    // v = L_B^-1 (sqrtW kstar) (:211): its transpose (kstar^T sqrtW) L_B^-T is the appended right-hand-side block of the
+    // SAME dataflow kernel that factors B (:208) -- no triangular inverse, no separate product; ||v_i||^2 = row norms
+    GPN_TRY(gpn_k_scale_cols(c, m, n, KsT, ldn, vecp(c, V_SW)));
+    GPN_TRY(factor_B_fast(c, s, KsT, m));
+    GPN_TRY(gpn_k_rownorm2(c, m, n, KsT, ldn, vecp(c, V_VN)));
     GPN_TRY(gpn_k_diag_gather(c, kfull(c), c->ldN, te, m, 0.0, vecp(c, V_KSS)));                          // :212-214
     pistar_kernel<<<g1(m), 256, 0, c->stream>>>(m, vecp(c, V_FSTAR), vecp(c, V_KSS), vecp(c, V_VN), vecp(c, V_VV), vecp(c, V_PI));
     c->launches++;
