@@ -264,6 +264,13 @@ int symm_mul(gpn_ctx* c, const double* A, const double* B, double* C) {
 // SPD inverse of the N x N matrix in `a` (destroyed -> L); result (full symmetric) in `out`; w/t scratch
 int spd_inverse(gpn_ctx* c, int n, double* a, long ld, double* w, double* wt, double* tt, double* out, int info_slot) {
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(n) * 128));
+    static const int aug_max = getenv("GPNET_B200_INV_AUG_MAX") ? atoi(getenv("GPNET_B200_INV_AUG_MAX")) : 3072;
+    if (n <= aug_max && c->potrf_mode == 0) {
+        // small n: the factorisation is bound by its dependency chain, so W^T = L^-T rides along as the identity block of the same
+        // dataflow kernel ([A; I]) instead of a dozen triangular-inverse launches behind it
+        GPN_TRY(gpn_potrf_dataflow(c, n, a, ld, (double*)c->winv.p, iscal(c, info_slot), 0, nullptr, 0, 0, wt, ld, 0));
+        return gpn_lauum_t(c, n, wt, ld, out, ld, true);
+    }
     GPN_TRY(gpn_potrf(c, n, a, ld, (double*)c->winv.p, iscal(c, info_slot)));
     GPN_TRY(gpn_trtri(c, n, a, ld, (const double*)c->winv.p, w, wt, tt, ld));
     return gpn_lauum_t(c, n, wt, ld, out, ld, true);
@@ -449,6 +456,7 @@ int expm_of_mat0(gpn_ctx* c) {
     }
     {   // Q = V - U -> Z (zero padded);  P = V + U -> X8
         GPN_TRY(gpn_k_fill_zero(c, Z, ld, (int)pad128(N), (int)pad128(N)));
+        GPN_TRY(gpn_k_fill_zero(c, X8, ld, (int)pad128(N), (int)pad128(N)));       // P is an appended row block of [Q; P; I]: zero padded rows
         const double* X2[2] = {V, U};
         const long l2[2] = {ld, ld};
         const double cq[2] = {1.0, -1.0}, cp[2] = {1.0, 1.0};
@@ -456,8 +464,18 @@ int expm_of_mat0(gpn_ctx* c) {
         GPN_TRY(gpn_k_lincomb(c, N, X8, ld, 0.0, 2, X2, l2, cp));
     }
     // X = Q^-1 P  (Q SPD: q_m(x) = p_m(-x) has positive coefficients and spec(A) <= 0)
-    GPN_TRY(spd_inverse(c, N, Z, ld, A2, A4, V, A6, 0));       // Qinv -> A6 (A2, A4, V scratch: U and V are dead once Q, P exist)
-    GPN_TRY(symm_mul(c, A6, X8, U));                            // X -> U
+    static const int aug_max = getenv("GPNET_B200_EXPM_AUG_MAX") ? atoi(getenv("GPNET_B200_EXPM_AUG_MAX")) : 3072;
+    if (N <= aug_max) {
+        // small N: the Cholesky of Q is bound by its dependency chain, so the solve rides along in the SAME dataflow kernel:
+        // [Q; P; I] -> L, Y = P L^-T, W^T = L^-T, then X = Y W = P Q^-1 = Q^-1 P (polynomials in A commute) as one product with a
+        // triangular k-range.  Replaces potrf + triangular inverse (a dozen launches) + W^T W + Q^-1 P.
+        GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(N) * 128));
+        GPN_TRY(gpn_potrf_dataflow(c, N, Z, ld, (double*)c->winv.p, iscal(c, 0), 0, X8, ld, N, A2, ld, 0));
+        GPN_TRY(gpn_gemm(c, N, N, N, 1.0, X8, ld, true, A2, ld, true, 0.0, U, ld, GF_LOWER | GF_MIRROR | GF_KLO_N));
+    } else {
+        GPN_TRY(spd_inverse(c, N, Z, ld, A2, A4, V, A6, 0));       // Qinv -> A6 (A2, A4, V scratch: U and V are dead once Q, P exist)
+        GPN_TRY(symm_mul(c, A6, X8, U));                            // X -> U
+    }
     double* cur = U;
     double* oth = V;
     for (int i = 0; i < s; ++i) {
