@@ -246,6 +246,25 @@ class GPnetBase:
         self._engine.invalidate_kernel()
         return info == 0
 
+    # ``df`` (GPnet.py:576-605) is assembled on first access after a predict(): building the pandas frame (and the pivot
+    # distances it needs) costs more host time than the whole device side of a C1 / C2 prediction (3-6 ms against 1.5-7 ms), and
+    # most callers of predict() in an optimisation loop never look at it.  generate_df() itself stays eager and public.
+    @property
+    def df(self):
+        if self.__dict__.get("_df_pending"):
+            self.__dict__["_df_pending"] = False
+            self.generate_df()
+        return self.__dict__.get("_df")
+
+    @df.setter
+    def df(self, value):
+        self.__dict__["_df"] = value
+        self.__dict__["_df_pending"] = False
+
+    def _defer_df(self):
+        """predict() calls this where the reference calls generate_df()."""
+        self.__dict__["_df_pending"] = True
+
     def generate_df(self):
         fstar_series = pd.Series(index=self.test_nodes, data=self.fstar)
         s_series = pd.Series(index=self.test_nodes, data=self.s)

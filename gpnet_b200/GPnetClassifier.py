@@ -79,7 +79,7 @@ class GPnetClassifier(GPnetBase):
         self.s = np.sqrt(self.V)
         print("succesfully trained model")
         self.is_trained = True
-        self.generate_df()
+        self._defer_df()       # the reference's generate_df() (GPnet.py:576-605), materialised on first access of self.df
         return (self.fstar.T, self.V, self.predicted_probs)
 
     def gradLogPosterior(self, theta, *args):

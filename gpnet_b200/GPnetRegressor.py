@@ -127,7 +127,7 @@ class GPnetRegressor(GPnetBase):
         self.s = res["s"]
         print("succesfully trained model")
         self.is_trained = True
-        self.generate_df()
+        self._defer_df()       # the reference's generate_df() (GPnet.py:576-605), materialised on first access of self.df
         return self
 
     # ---- GPnetRegressor.py:136-150 ---------------------------------------------------------------------

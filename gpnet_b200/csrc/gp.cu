@@ -119,10 +119,13 @@ __global__ void newton_a_kernel(int n, double scale, const double* __restrict__ 
     if (i < n) a[i] = scale * (b[i] - sw[i] * sol[i]);
 }
 // phif_i = log p_i - q/2 - logdet/2 - n/2 log 2pi; conv = sum (old - new)^2 (:124-132).  Single block.
-__global__ void newton_phif_kernel(int n, const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ logdet,
-                                   double* __restrict__ phif, int first, double phif0, double* __restrict__ conv) {
+__global__ void newton_phif_kernel(int n, const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ q_alt,
+                                   const int* __restrict__ info_k, const double* __restrict__ logdet, double* __restrict__ phif, int first,
+                                   double phif0, double* __restrict__ conv) {
     __shared__ double sh[32];
-    const double common = -0.5 * (*q) - 0.5 * (*logdet) - 0.5 * n * LOG_2PI;
+    // f^T K^-1 f through the Cholesky of K; if K is not numerically positive definite: f^T a (the same quantity, f = K a)
+    const double qq = (*info_k == 0) ? *q : *q_alt;
+    const double common = -0.5 * qq - 0.5 * (*logdet) - 0.5 * n * LOG_2PI;
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double v = log(p[i]) + common;
@@ -1643,17 +1646,30 @@ int gpc_newton(gpn_ctx* c, const double* K, long ldk, int n, const double* y_h, 
     GPN_TRY(ensure_nb(c, NB_WK, s.ldn, s.ldn));
     GPN_TRY(ensure_nb(c, NB_KC, s.ldn, s.ldn));
     GPN_TRY(ensure_nb(c, NB_WT, s.ldn, s.ldn));
-    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)pad128(std::max(n, c->N)) * 128));
+    const size_t wblk = (size_t)pad128(std::max(n, c->N)) * 128;
+    GPN_TRY(gpn_winv_ensure(c, sizeof(double) * 2 * wblk));
     GPN_TRY(upload(c, vecp(c, V_Y), y_h, sizeof(double) * n));
     GPN_CK(cudaMemsetAsync(vecp(c, V_F), 0, sizeof(double) * n, c->stream));                    // f = 0 (:96)
-    // f^T K^-1 f of the convergence test (:126) through one Cholesky of K (K is fixed during the loop)
-    // [K; I] in one dataflow kernel: W_K^T = L_K^-T (upper tiles) -> NB_WK
-    GPN_TRY(gpn_k_fill_zero(c, nbp(c, NB_KC), s.ldn, (int)s.ldn, (int)s.ldn));
-    GPN_TRY(gpn_k_copy(c, n, n, K, ldk, nbp(c, NB_KC), s.ldn));
-    GPN_TRY(gpn_potrf_dataflow(c, n, nbp(c, NB_KC), s.ldn, (double*)c->winv.p, iscal(c, 4), 0, nullptr, 0, 0, nbp(c, NB_WK), s.ldn, 0));
+    // f^T K^-1 f of the convergence test (:126) through ONE Cholesky of K (K is fixed during the loop): [K; I] in one dataflow
+    // kernel gives W_K^T = L_K^-T (upper tiles) -> NB_WK.  It runs on the side stream, on half of the SMs, next to the first
+    // factorisation of B (own flag slot, own block of inverted diagonal tiles); the loop joins it before its first use.
     int info[16];
-    GPN_TRY(read_scalars(c, nullptr, 0, info, 16));
-    s.have_wk = (info[4] == 0);     // K not numerically PD: use f^T a (== f^T K^-1 f since f = K a), see DESIGN.md
+    cudaStream_t main_stream = c->stream;
+    {
+        GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
+        GPN_CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        c->stream = c->stream2;
+        int st = gpn_k_fill_zero(c, nbp(c, NB_KC), s.ldn, (int)s.ldn, (int)s.ldn);
+        if (st == 0) st = gpn_k_copy(c, n, n, K, ldk, nbp(c, NB_KC), s.ldn);
+        c->potrf_grid_cap = c->num_sms / 2;
+        if (st == 0) st = gpn_potrf_dataflow(c, n, nbp(c, NB_KC), s.ldn, (double*)c->winv.p + wblk, iscal(c, 4), 0, nullptr, 0, 0, nbp(c, NB_WK), s.ldn, 1);
+        c->potrf_grid_cap = 0;
+        c->stream = main_stream;
+        if (st != 0) return st;
+        GPN_CK(cudaEventRecord(c->ev_join, c->stream2));
+    }
+    s.have_wk = true;      // decided on the device from the Cholesky's info (newton_phif_kernel)
+    bool joined = false;
     int count = 0, iters = 0;
     double sc[Scal::NDBL];
     while (true) {
@@ -1662,7 +1678,12 @@ int gpc_newton(gpn_ctx* c, const double* K, long ldk, int n, const double* y_h, 
         newton_pre_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_F), vecp(c, V_Y), vecp(c, V_W), vecp(c, V_SW), vecp(c, V_P),
                                                          vecp(c, V_B), vecp(c, V_G));
         c->launches++;
-        GPN_TRY(factor_B_fast(c, s));                                                            // :110
+        if (!joined) c->potrf_grid_cap = c->num_sms - c->num_sms / 2;                             // next to [K; I]
+        {
+            const int stf = factor_B_fast(c, s);                                                 // :110
+            c->potrf_grid_cap = 0;
+            if (stf != 0) return stf;
+        }
         GPN_TRY(gpn_k_gemv(c, n, n, K, ldk, vecp(c, V_B), vecp(c, V_KB), GEMV_FULL));            // K b
         vec_mul_kernel<<<g1(n), 256, 0, c->stream>>>(n, vecp(c, V_SW), vecp(c, V_KB), vecp(c, V_RHS));
         c->launches++;
@@ -1672,15 +1693,16 @@ int gpc_newton(gpn_ctx* c, const double* K, long ldk, int n, const double* y_h, 
         newton_a_kernel<<<g1(n), 256, 0, c->stream>>>(n, scale, vecp(c, V_B), vecp(c, V_SW), vecp(c, V_SOL), vecp(c, V_A));
         c->launches++;
         GPN_TRY(gpn_k_gemv(c, n, n, K, ldk, vecp(c, V_A), vecp(c, V_F), GEMV_FULL));             // f = K a (:122)
-        if (s.have_wk) {
-            GPN_TRY(gpn_k_gemv_t(c, n, n, nbp(c, NB_WK), s.ldn, vecp(c, V_F), vecp(c, V_U), GEMV_UPPER));      // u = W_K f
-            GPN_TRY(gpn_k_dot(c, n, vecp(c, V_U), vecp(c, V_U), dscal(c, Scal::Q)));
-        } else {
-            GPN_TRY(gpn_k_dot(c, n, vecp(c, V_F), vecp(c, V_A), dscal(c, Scal::Q)));
+        if (!joined) {
+            GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+            joined = true;
         }
+        GPN_TRY(gpn_k_gemv_t(c, n, n, nbp(c, NB_WK), s.ldn, vecp(c, V_F), vecp(c, V_U), GEMV_UPPER));          // u = W_K f
+        GPN_TRY(gpn_k_dot(c, n, vecp(c, V_U), vecp(c, V_U), dscal(c, Scal::Q)));
+        GPN_TRY(gpn_k_dot(c, n, vecp(c, V_F), vecp(c, V_A), dscal(c, Scal::AF)));                              // the fall-back: f^T a
         GPN_TRY(gpn_k_sumlogdiag(c, n, nbp(c, NB_B), s.ldn, dscal(c, Scal::LOGDET)));
-        newton_phif_kernel<<<1, 1024, 0, c->stream>>>(n, vecp(c, V_P), dscal(c, Scal::Q), dscal(c, Scal::LOGDET), vecp(c, V_PHIF),
-                                                       iters == 1, phif0, dscal(c, Scal::CONV));
+        newton_phif_kernel<<<1, 1024, 0, c->stream>>>(n, vecp(c, V_P), dscal(c, Scal::Q), dscal(c, Scal::AF), iscal(c, 4),
+                                                       dscal(c, Scal::LOGDET), vecp(c, V_PHIF), iters == 1, phif0, dscal(c, Scal::CONV));
         c->launches++;
         GPN_TRY(read_scalars(c, sc, Scal::NDBL, info, 16));
         if (info[3] != 0) {     // np.linalg.cholesky raised inside the loop: propagate (GPnetClassifier.py:110)
