@@ -172,3 +172,38 @@ def test_spectral_landscape_n2048_equals_default_path():
     a = regressor(G, tr, [], t, "diffusion", th, True).lml_landscape(list(th), [0, 1], ax1, ax2)
     b = regressor(G, tr, [], t, "diffusion", th, False).lml_landscape(list(th), [0, 1], ax1, ax2)
     assert nrel(a, b) <= TOL
+
+
+@pytest.mark.parametrize("N,n", [(70, 7), (130, 1), (333, 111), (400, 112)])
+def test_batched_evaluator_ragged_sizes_and_weighted_graph(N, n):
+    """Training-set sizes that are not multiples of the 4 x 4 register tiles (down to one node, up to the 112-node limit), a graph
+    size that needs padding in the eigensolver, and edge weights (GPnet.py:329 honours the "weight" attribute)."""
+    import networkx as nx
+    rng = np.random.RandomState(N)
+    G = nx.connected_watts_strogatz_graph(N, 6, 0.3, seed=1)
+    for u, v in G.edges():
+        G[u][v]["weight"] = float(rng.uniform(0.5, 2.0))
+    tr, te = cfg.split(N, n, min(20, N - n))
+    t = rng.randn(N)
+    for kt, th in KERNELS:
+        m = regressor(G, tr, te, t, kt, th, True)
+        thetas = [np.array(th, dtype=float), np.array(th, dtype=float) + 0.1 * np.array([(-1.0 if kt == "diffusion" else 1.0)] + [0.0] * (len(th) - 2) + [0.5])]
+        vals, grads = m.logPosterior_and_grad_batch(thetas, tr, m.training_values)
+        assert m._engine.ctx.last_route()[0] == 7
+        orc = go.OracleGP(G, kerneltype=kt, expm_mode="dense")
+        for b, thb in enumerate(thetas):
+            oval, ograd = orc.neg_logp_grad(thb, tr, t[tr])
+            assert abs(vals[b] - oval) <= TOL * max(abs(oval), 1.0), (kt, N, n, b)
+            assert np.max(np.abs(grads[b] - ograd)) <= 1e-8 * max(np.max(np.abs(ograd)), 1.0), (kt, N, n, b)
+
+
+def test_training_sets_above_the_batch_limit_fall_back_to_the_lanes():
+    G, tr, te, t = cfg.grid_case(20, 20, 150, 100)
+    th = np.log([0.6, 0.01])
+    m = regressor(G, tr, te, t, "regularized_laplacian", th, True)
+    vals, grads = m.logPosterior_and_grad_batch([th, th + 0.05], tr, m.training_values, lanes=2)
+    assert m._engine.ctx.last_route()[0] != 7
+    orc = go.OracleGP(G, kerneltype="regularized_laplacian", expm_mode="dense")
+    for b, thb in enumerate([th, th + 0.05]):
+        oval, ograd = orc.neg_logp_grad(thb, tr, t[tr])
+        assert abs(vals[b] - oval) <= TOL * abs(oval) and nrel(grads[b], ograd) <= 1e-8
