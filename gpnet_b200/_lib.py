@@ -266,7 +266,7 @@ class Context:
 
     def last_route(self):
         """(level, parts) of the last regressor likelihood evaluation: parts = [number of parts, separator size, sizes...]."""
-        parts = (C.c_int * 10)()
+        parts = (C.c_int * 16)()
         level = int(self.lib.gpn_last_route(self.h, parts))
         k = parts[0]
         return level, [int(x) for x in parts[: 2 + k]]

@@ -69,15 +69,18 @@ struct ProfEvent {
 // the nodes are numbered [P_1 | ... | P_K | Sep], no edge joins two different parts, every part is numbered [others | training]
 // and so is the separator.  M = I + beta L~ is then block-arrow, and the leading block of every M_kk (and of Sep) is the
 // corresponding block of M_oo: ONE factorisation per part serves both M and M_oo.
+constexpr int D6_MAXP = 12;      // parts of the whole-graph dissection (each has its own stream, flag slot and info slot)
+constexpr int D6_SLOTS = 16;     // streams / flag slots: parts 0..11, 15 = other-node separator complement
 struct Dissect6 {
     bool built = false;          // the analysis below was run for the current graph / node set
     bool usable = false;         // ... and found thin separators
     int K = 0;                   // parts
     int s = 0, so = 0;           // separator nodes, of which other (non-training) nodes (numbered first)
     int ND = 0;                  // N - s: nodes in the parts
-    int off[9] = {0};            // first row of part k (even), off[K] = ND
-    int nk[8] = {0}, ok[8] = {0};   // nodes of part k, of which others (numbered first)
-    int c0[8] = {0};             // first row of part k (multiple of 128) that has a neighbour in the separator: inside the other-node
+    int off[D6_MAXP + 1] = {0};  // first row of part k (even), off[K] = ND
+    int nk[D6_MAXP] = {0}, ok[D6_MAXP] = {0};   // nodes of part k, of which others (numbered first)
+    int strips = 0, cells = 0;   // the parts are `strips` BFS strips of the graph, each cut again into `cells` pieces (strips x cells = K)
+    int c0[D6_MAXP] = {0};             // first row of part k (multiple of 128) that has a neighbour in the separator: inside the other-node
                                  // group and inside the training group the interior nodes are numbered before the boundary nodes,
                                  // so G = W C is zero above row c0 of the part
     long long sep_nnz = 0;
@@ -176,11 +179,11 @@ struct gpn_ctx {
     int epoch2 = 0;
     long flags_rows2 = 0;
     // slots 2..9: further concurrent factorisations (one per part of the whole-graph dissection), each on its own side stream
-    DevBuf flagsK[10];
-    int epochK[10] = {0};
-    long flags_rowsK[10] = {0};
-    cudaStream_t side[10] = {nullptr};
-    cudaEvent_t ev_side[10] = {nullptr};
+    DevBuf flagsK[D6_SLOTS];
+    int epochK[D6_SLOTS] = {0};
+    long flags_rowsK[D6_SLOTS] = {0};
+    cudaStream_t side[D6_SLOTS] = {nullptr};
+    cudaEvent_t ev_side[D6_SLOTS] = {nullptr};
     Spectral spec;
     Dissect6 d6;
     int d6_parts = 0;                    // > 0: number of parts forced by gpn_set_dissection_parts (0: chosen from N)

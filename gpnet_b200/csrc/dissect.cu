@@ -25,8 +25,8 @@ constexpr int TPB = 256;
 
 struct D6Desc {
     int K, s, so, ND;
-    int off[9];
-    int nk[8], ok[8];
+    int off[D6_MAXP + 1];
+    int nk[D6_MAXP], ok[D6_MAXP];
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -296,8 +296,8 @@ int up(gpn_ctx* c, DevBuf& b, const std::vector<T>& v) {
 D6Desc make_desc(const Dissect6& q) {
     D6Desc d;
     d.K = q.K; d.s = q.s; d.so = q.so; d.ND = q.ND;
-    for (int k = 0; k < 9; ++k) d.off[k] = q.off[k];
-    for (int k = 0; k < 8; ++k) { d.nk[k] = q.nk[k]; d.ok[k] = q.ok[k]; }
+    for (int k = 0; k <= D6_MAXP; ++k) d.off[k] = q.off[k];
+    for (int k = 0; k < D6_MAXP; ++k) { d.nk[k] = q.nk[k]; d.ok[k] = q.ok[k]; }
     return d;
 }
 
@@ -307,17 +307,48 @@ D6Desc make_desc(const Dissect6& q) {
 // levels at the quantiles of the node count (a level separates the levels below it from those above it exactly: edges only
 // join equal or adjacent levels), separator nodes without a neighbour in the next level pushed back into the part below.
 // usable = false (the caller falls back to level 5) when the graph is too small or its separators are fat.
+static int d6_analyse(gpn_ctx* c, bool allow_cells);
 int gpn_d6_ensure(gpn_ctx* c) {
     Dissect6& q = c->d6;
     if (q.built) return 0;
     q.built = true;
     q.usable = false;
+    GPN_TRY(d6_analyse(c, true));
+    if (!q.usable) GPN_TRY(d6_analyse(c, false));      // the strips do not split into cells (or the result is poor): plain strips
+    return 0;
+}
+static int d6_analyse(gpn_ctx* c, bool allow_cells) {
+    Dissect6& q = c->d6;
+    q.usable = false;
     const int N = c->N, n = c->n_train;
     static const int k_env = getenv("GPNET_B200_D6_PARTS") ? atoi(getenv("GPNET_B200_D6_PARTS")) : 0;
     const int forced = c->d6_parts > 0 ? c->d6_parts : k_env;      // forced: tests exercise the route on small graphs too
-    int K = forced > 0 ? forced : (N + 820) / 1640;        // ~1600 nodes per part (a sweep at N = 8192 is flat between 5 and 6 parts)
-    if (K > 8) K = 8;
-    const int min_nodes = forced > 0 ? 64 : 2048, min_part = forced > 0 ? 8 : 256;
+    // Parts = `strips` BFS strips of the whole graph, each cut again into `cells` pieces by the level sets of a BFS INSIDE the strip
+    // (its levels run along the strip): on a planar-like graph the separator of a strips x cells grid of ~N / (strips cells)-node
+    // parts is hardly larger than that of strips x 1, while the dependency chain of a part's factorisation shrinks with its size:
+    // N = 8192: 5 x 1 parts of ~1500 nodes + 870 separator nodes = 13 + 7 tile columns on the critical path, 3 x 2 parts of ~1250
+    // + 674 = 10 + 6 (and a separator phase with 0.6 of the flops).  Forced part counts (tests, GPNET_B200_D6_PARTS) are plain strips.
+    static const int cells_env = getenv("GPNET_B200_D6_CELLS") ? atoi(getenv("GPNET_B200_D6_CELLS")) : -1;
+    int K, cells = 1;
+    if (forced > 0) {
+        K = forced;
+    } else {
+        // ~1350 nodes per part, two pieces per strip when that gives at least four parts.  Measured at N = 8192 (evals/s with one /
+        // two lanes): strips x cells = 5x1: 433 / 575, 4x1: 403 / 528, 2x2: 420 / 553, 2x3: 494 / 638, 3x2: 516 / 674 (default),
+        // 4x2: 517 / 466, 2x4: 535 / 483, 3x3: 398 / 455, 4x3: 399 / 432 -- smaller parts shorten the chains but every extra cut adds
+        // separator nodes, and the separator's work grows with its square; many small parts also starve two lanes of SMs
+        const int want = std::max(2, (N + 675) / 1350);
+        cells = want >= 4 ? 2 : 1;
+        K = std::max(2, (int)std::lround((double)want / cells));
+        static const int strips_env = getenv("GPNET_B200_D6_STRIPS") ? atoi(getenv("GPNET_B200_D6_STRIPS")) : -1;
+        if (strips_env >= 2) K = strips_env;
+        if (cells_env >= 1) cells = cells_env;
+        if (!allow_cells) cells = 1;
+        while (K * cells > D6_MAXP && cells > 1) --cells;
+        if (cells == 1 && !(strips_env >= 2 && allow_cells)) K = (N + 820) / 1640;                    // strips only: ~1600 nodes per part (flat between 5 and 6 at N = 8192)
+    }
+    if (K > (cells > 1 ? D6_MAXP / cells : 8)) K = cells > 1 ? D6_MAXP / cells : 8;
+    const int min_nodes = forced > 0 ? 64 : 2048, min_part = forced > 0 ? 8 : 128;
     if (K < 2 || N < min_nodes || n <= 0 || n >= N) return 0;
     std::vector<char> is_train(N, 0);
     for (int v : c->h_train) is_train[v] = 1;
@@ -381,6 +412,81 @@ int gpn_d6_ensure(gpn_ctx* c) {
             part[v] = p;
         }
     }
+    const int strips = K;
+    if (cells > 1) {
+        // second stage: inside every strip, BFS levels of the INDUCED subgraph from a pseudo-peripheral node of the strip; cells - 1
+        // cut levels at the quantiles; cut nodes without a neighbour in the next level stay in the piece below.  Pieces of one
+        // strip are separated by the cut levels (edges of the induced subgraph join equal or adjacent levels only), different
+        // strips by the first stage.  Nodes the BFS does not reach (other components of the strip) join the strip's last piece.
+        std::vector<int> lev2(N, -1), newpart(N, -1), q2;
+        bool ok = true;
+        for (int p = 0; p < strips && ok; ++p) {
+            std::vector<int> nodes;
+            for (int v = 0; v < N; ++v)
+                if (part[v] == p) nodes.push_back(v);
+            if (nodes.empty()) { ok = false; break; }
+            auto bfs2 = [&](int root) {
+                for (int v : nodes) lev2[v] = -1;
+                q2.clear();
+                q2.push_back(root);
+                lev2[root] = 0;
+                for (size_t h = 0; h < q2.size(); ++h) {
+                    const int u = q2[h];
+                    for (int e = c->h_indptr[u]; e < c->h_indptr[u + 1]; ++e) {
+                        const int v = c->h_indices[e];
+                        if (part[v] == p && lev2[v] < 0) { lev2[v] = lev2[u] + 1; q2.push_back(v); }
+                    }
+                }
+                return q2.back();
+            };
+            int r2 = nodes[0];
+            for (int v : nodes)
+                if (c->h_indptr[v + 1] - c->h_indptr[v] > c->h_indptr[r2 + 1] - c->h_indptr[r2]) r2 = v;
+            for (int sweep = 0; sweep < 2; ++sweep) r2 = bfs2(r2);
+            bfs2(r2);
+            const int reached2 = (int)q2.size();
+            int nl2 = 0;
+            for (int v : q2) nl2 = std::max(nl2, lev2[v] + 1);
+            if (nl2 < 3 * cells) { ok = false; break; }
+            std::vector<int> cnt2(nl2, 0);
+            for (int v : q2) cnt2[lev2[v]]++;
+            std::vector<int> cuts2;
+            int l = 0;
+            long cum = 0;
+            for (int k = 1; k < cells && ok; ++k) {
+                const long target = (long)reached2 * k / cells;
+                while (l < nl2 - 1 && cum + cnt2[l] < target) cum += cnt2[l++];
+                if ((!cuts2.empty() && l <= cuts2.back() + 1) || l <= 0 || l >= nl2 - 1) ok = false;
+                else cuts2.push_back(l);
+            }
+            if (!ok) break;
+            for (int v : nodes) {
+                if (lev2[v] < 0) { newpart[v] = p * cells + cells - 1; continue; }
+                int piece = 0;
+                bool on_cut = false;
+                for (int lc : cuts2) {
+                    if (lev2[v] > lc) ++piece;
+                    if (lev2[v] == lc) on_cut = true;
+                }
+                if (on_cut) {
+                    bool up_nb = false;
+                    for (int e = c->h_indptr[v]; e < c->h_indptr[v + 1] && !up_nb; ++e) {
+                        const int u = c->h_indices[e];
+                        up_nb = part[u] == p && lev2[u] == lev2[v] + 1;
+                    }
+                    newpart[v] = up_nb ? -1 : p * cells + piece;
+                } else {
+                    newpart[v] = p * cells + piece;
+                }
+            }
+        }
+        if (ok) {
+            for (int v = 0; v < N; ++v) part[v] = part[v] < 0 ? -1 : newpart[v];
+            K = strips * cells;
+        } else {
+            return 0;             // the strips do not split: the caller retries with plain strips
+        }
+    }
     std::vector<std::vector<int>> po(K), pt(K);
     std::vector<int> so_nodes, st_nodes;
     for (int v = 0; v < N; ++v) {
@@ -418,6 +524,7 @@ int gpn_d6_ensure(gpn_ctx* c) {
     for (int k = 0; k < K; ++k) minpart = std::min(minpart, (int)(po[k].size() + pt[k].size()));
     if (s < 1 || s > N / (forced > 0 ? 2 : 4) || minpart < min_part) return 0;
     q.K = K; q.s = s; q.so = (int)so_nodes.size(); q.ND = N - s;
+    q.strips = strips; q.cells = cells;
     std::vector<int> perm(N), inv(N);
     int pos = 0;
     for (int k = 0; k < K; ++k) {
@@ -427,8 +534,8 @@ int gpn_d6_ensure(gpn_ctx* c) {
         for (int v : po[k]) { perm[v] = pos; inv[pos++] = v; }
         for (int v : pt[k]) { perm[v] = pos; inv[pos++] = v; }
     }
-    for (int k = K; k < 9; ++k) q.off[k] = pos;
-    for (int k = K; k < 8; ++k) q.nk[k] = q.ok[k] = 0;
+    for (int k = K; k <= D6_MAXP; ++k) q.off[k] = pos;
+    for (int k = K; k < D6_MAXP; ++k) q.nk[k] = q.ok[k] = 0;
     for (int v : so_nodes) { perm[v] = pos; inv[pos++] = v; }
     for (int v : st_nodes) { perm[v] = pos; inv[pos++] = v; }
     // permuted graph, training ranks
@@ -548,7 +655,7 @@ int gpn_d6_tri_solve(gpn_ctx* c, int n, const double* WTf, long ld, const double
     if (n <= 0) return 0;
     D6Desc d = {};
     d.K = 1; d.ND = n; d.nk[0] = n; d.ok[0] = n; d.off[0] = 0;
-    for (int k = 1; k < 9; ++k) d.off[k] = n;
+    for (int k = 1; k <= D6_MAXP; ++k) d.off[k] = n;
     d6_w_mul_kernel<<<dim3((n + 31) / 32, 1), dim3(32, 8), 0, c->stream>>>(d, WTf, ld, xa, xb, va, vb);
     d6_wt_mul_kernel<<<(n * 32 + TPB - 1) / TPB, TPB, 0, c->stream>>>(d, WTf, ld, va, vb, ua, ub);
     c->launches += 2;

@@ -1121,7 +1121,7 @@ int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double
     // (all products below use the 128x128 GEMM configuration even when they have few tiles: the parts run concurrently, so the chip is
     //  filled across streams, and the big tiles are the efficient ones: 513.7 -> 555.4 evals/s with two lanes)
     // ---- one stream per part: [M_kk; I] -> L_k, W_k^T;  G_k^T = (W_k C_k)^T;  U_k = W_k^T G_k (gradient only) ----
-    int Tk[8], woff[9] = {0};
+    int Tk[D6_MAXP], woff[D6_MAXP + 1] = {0};
     for (int k = 0; k < K; ++k) { Tk[k] = (q.nk[k] + 127) / 128; woff[k + 1] = woff[k] + Tk[k]; }
     const int Ts = (s + 127) / 128, Tso = (std::max(so, 1) + 127) / 128;
     GPN_TRY(gpn_winv_ensure(c, sizeof(double) * (size_t)(woff[K] + Ts + Tso + 2) * 128 * 128));
@@ -1131,7 +1131,7 @@ int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double
     {
         double wsum = 0.0;
         for (int k = 0; k < K; ++k) wsum += (double)q.nk[k] * q.nk[k] * q.nk[k];
-        int caps[8], used = 0;
+        int caps[D6_MAXP], used = 0;
         const int cap_min = std::max(4, std::min(12, sms / (2 * K)));
         for (int k = 0; k < K; ++k) { caps[k] = std::max(cap_min, (int)(sms * ((double)q.nk[k] * q.nk[k] * q.nk[k] / wsum))); used += caps[k]; }
         for (int k = 0; used > sms; k = (k + 1) % K)
@@ -1191,7 +1191,7 @@ int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double
     //      factorisations [T; I; U] give L_T, W_T^T and Y = U L_T^-T:  tr(T^-1 (I + U^T U)) = ||W_T||_F^2 + ||Y||_F^2 ----
     const double* E = M + (long)ND * ld + ND;
     double* winvT = winv + (size_t)woff[K] * 128 * 128;
-    constexpr int TS = 9;                                       // stream / flag slot of the other-node separator complement
+    constexpr int TS = D6_SLOTS - 1;                            // stream / flag slot of the other-node separator complement
     if (so > 0) {   // the other-node complement on a side stream, next to the full one
         GPN_TRY(d6_side_stream(c, TS));
         GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
@@ -1199,7 +1199,7 @@ int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double
         c->stream = c->side[TS];
         int st = gpn_d6_t_reduce(c, so, E, ld, (const double*)q.work[8].p, ldso, nb, Tob);
         c->potrf_grid_cap = std::max(2, sms / 3);
-        if (st == 0) st = gpn_potrf_dataflow(c, so, Tob, ldso, winvT + (size_t)Ts * 128 * 128, iscal(c, 9), 0, want_grad ? Uo : nullptr, ldso,
+        if (st == 0) st = gpn_potrf_dataflow(c, so, Tob, ldso, winvT + (size_t)Ts * 128 * 128, iscal(c, 15), 0, want_grad ? Uo : nullptr, ldso,
                                              want_grad ? ND : 0, WTto, ldso, TS);
         c->potrf_grid_cap = 0;
         if (st == 0) st = gpn_d6_sep_reduce(c, so, Tob, ldso, want_grad ? WTto : nullptr, ldso, want_grad ? Uo : nullptr, ldso, ND, dscal(c, 11));
@@ -1228,7 +1228,7 @@ int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double
         GPN_TRY(gpn_d6_t_reduce(c, s, E, ld, (const double*)q.work[7].p, lds, nb, Tb));
         mark("T");
         c->potrf_grid_cap = so > 0 ? sms - std::max(2, sms / 3) : sms;
-        int st = gpn_potrf_dataflow(c, s, Tb, lds, winvT, iscal(c, 8), 0, want_grad ? U : nullptr, lds, want_grad ? ND : 0,
+        int st = gpn_potrf_dataflow(c, s, Tb, lds, winvT, iscal(c, 14), 0, want_grad ? U : nullptr, lds, want_grad ? ND : 0,
                                     want_grad ? WTt : nullptr, lds, 0);
         c->potrf_grid_cap = 0;
         if (st != 0) return st;
@@ -1265,7 +1265,7 @@ int gpr_reglap_d6_finish(gpn_ctx* c, RowScalars* rs, int* info_h) {
     const int* info = (const int*)((const char*)c->pinned + sizeof(double) * Scal::NDBL);
     if (info_h) {
         *info_h = 0;
-        for (int i = 0; i < 10 && *info_h == 0; ++i) *info_h = info[i];
+        for (int i = 0; i < 16 && *info_h == 0; ++i) *info_h = info[i];      // parts 0..11, 14 / 15 = separator complements
     }
     rs->n = n;
     rs->half_logdet = -((sc[7] + sc[10]) - (sc[8] + sc[12]));          // (1/2) log det K_tt = -(1/2) (log det M - log det M_oo)
@@ -1943,7 +1943,7 @@ void gpn_destroy(gpn_ctx* c) {
             if (b.p) cudaFree(b.p);
         for (auto& b : c->flagsK)
             if (b.p) cudaFree(b.p);
-        for (int k = 0; k < 10; ++k) {
+        for (int k = 0; k < D6_SLOTS; ++k) {
             if (c->side[k]) { cudaStreamSynchronize(c->side[k]); cudaStreamDestroy(c->side[k]); }
             if (c->ev_side[k]) cudaEventDestroy(c->ev_side[k]);
         }
@@ -2089,7 +2089,7 @@ int gpn_debug_d6_layout(gpn_ctx* c, int* out40) {
     const Dissect6& q = c->d6;
     int p = 0;
     out40[p++] = q.K; out40[p++] = q.s; out40[p++] = q.so; out40[p++] = q.ND;
-    for (int k = 0; k < 9; ++k) out40[p++] = q.off[k];
+    for (int k = 0; k < 9; ++k) out40[p++] = q.off[k];      // (the first eight parts only: development aid)
     for (int k = 0; k < 8; ++k) out40[p++] = q.nk[k];
     for (int k = 0; k < 8; ++k) out40[p++] = q.ok[k];
     for (int k = 0; k < 8; ++k) out40[p++] = q.c0[k];
@@ -2339,11 +2339,11 @@ int gpn_matpow_f64(gpn_ctx* c, int N, const double* B, long ldb, int p, double* 
 }
 
 /* Route the last gpn_gpr_logp_grad / landscape evaluation took (see gpn_set_fast_paths; -1: none yet).  parts_h (may be NULL,
- * room for 10 ints): [number of parts of the node dissection used (0: none), separator size, part sizes...]. */
+ * room for 16 ints): [number of parts of the node dissection used (0: none), separator size, part sizes...]. */
 int gpn_last_route(gpn_ctx* c, int* parts_h) {
     if (!c) return -1;
     if (parts_h) {
-        for (int i = 0; i < 10; ++i) parts_h[i] = 0;
+        for (int i = 0; i < 16; ++i) parts_h[i] = 0;
         if (c->last_route == 5) {
             parts_h[0] = 2; parts_h[1] = c->dis_s; parts_h[2] = c->dis_a; parts_h[3] = c->dis_b;
         } else if (c->last_route == 6) {

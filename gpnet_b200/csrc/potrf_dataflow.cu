@@ -429,7 +429,7 @@ int gpn_potrf_dataflow(gpn_ctx* c, int n, double* A, long lda, double* winv, int
                        double* Wt, long ldwt, int slot) {
     // slot 1: own flag / counter buffer, for a factorisation that runs concurrently with another one (side stream)
     c->winv_for = nullptr;
-    if (slot < 0 || slot >= 10) return -13;
+    if (slot < 0 || slot >= D6_SLOTS) return -13;
     DevBuf& fbuf = slot >= 2 ? c->flagsK[slot] : (slot ? c->flags2 : c->flags);
     int& fepoch = slot >= 2 ? c->epochK[slot] : (slot ? c->epoch2 : c->epoch);
     long& frows = slot >= 2 ? c->flags_rowsK[slot] : (slot ? c->flags_rows2 : c->flags_rows);

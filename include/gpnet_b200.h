@@ -205,7 +205,7 @@ void gpn_set_fast_paths(gpn_ctx* ctx, int level);
 void gpn_set_dissection_parts(gpn_ctx* ctx, int parts);
 /* Route the last regressor likelihood evaluation (gpn_gpr_logp_grad, landscape rows) actually took, after the fallbacks a
  * level applies on its own (e.g. 5 -> 4 where the other nodes have no thin separator); -1 before the first evaluation.
- * parts_h (may be NULL; room for 10 ints): [parts of the node dissection used (0: none), separator size, part sizes ...]. */
+ * parts_h (may be NULL; room for 16 ints): [parts of the node dissection used (0: none), separator size, part sizes ...]. */
 int gpn_last_route(gpn_ctx* ctx, int* parts_h);
 
 /* ---- GP classification, Laplace approximation (GPnetClassifier.py:90-147,184-240) ---------------------------- */
