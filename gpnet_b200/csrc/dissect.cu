@@ -307,6 +307,71 @@ D6Desc make_desc(const Dissect6& q) {
 // levels at the quantiles of the node count (a level separates the levels below it from those above it exactly: edges only
 // join equal or adjacent levels), separator nodes without a neighbour in the next level pushed back into the part below.
 // usable = false (the caller falls back to level 5) when the graph is too small or its separators are fat.
+// Minimum vertex separator between BFS level l and level l + 1 of the subgraph whose nodes satisfy scope(v): the edges between
+// the two levels form a bipartite graph, and by Koenig's theorem its minimum vertex cover (from a maximum matching: Kuhn's
+// augmenting paths, a few hundred nodes) is the smallest node set whose removal disconnects everything at or below level l
+// from everything at or above level l + 1.  Typically 25-40 % fewer nodes than the boundary nodes of one level.
+template <class Scope>
+static void level_cut_cover(const gpn_ctx* c, const std::vector<int>& level, const std::vector<int>& nodes_l, Scope scope, int l,
+                            std::vector<int>& cover) {
+    cover.clear();
+    std::vector<int> A, B;
+    std::vector<int> bidx;                       // node -> index in B (lazy, via map vector sized on demand)
+    std::vector<std::vector<int>> adj;
+    std::vector<std::pair<int, int>> bmap;       // (node, index) sorted for lookup
+    for (int u : nodes_l) {
+        std::vector<int> nb;
+        for (int e = c->h_indptr[u]; e < c->h_indptr[u + 1]; ++e) {
+            const int v = c->h_indices[e];
+            if (scope(v) && level[v] == l + 1) nb.push_back(v);
+        }
+        if (!nb.empty()) { A.push_back(u); adj.push_back(nb); }
+    }
+    for (auto& nb : adj)
+        for (int v : nb) bmap.push_back({v, 0});
+    std::sort(bmap.begin(), bmap.end());
+    bmap.erase(std::unique(bmap.begin(), bmap.end()), bmap.end());
+    for (size_t i = 0; i < bmap.size(); ++i) { bmap[i].second = (int)i; B.push_back(bmap[i].first); }
+    auto bindex = [&](int v) { return std::lower_bound(bmap.begin(), bmap.end(), std::make_pair(v, 0))->second; };
+    for (auto& nb : adj)
+        for (int& v : nb) v = bindex(v);
+    const int na = (int)A.size(), nbn = (int)B.size();
+    std::vector<int> matchA(na, -1), matchB(nbn, -1), seen(nbn, -1);
+    // Kuhn's algorithm (iterative DFS would be overkill at these sizes: recursion depth <= na)
+    struct Aug {
+        const std::vector<std::vector<int>>& adj;
+        std::vector<int>&matchA, &matchB, &seen;
+        bool run(int a, int stamp) {
+            for (int b : adj[a]) {
+                if (seen[b] == stamp) continue;
+                seen[b] = stamp;
+                if (matchB[b] < 0 || run(matchB[b], stamp)) { matchA[a] = b; matchB[b] = a; return true; }
+            }
+            return false;
+        }
+    } aug{adj, matchA, matchB, seen};
+    for (int a = 0; a < na; ++a) aug.run(a, a);
+    // Koenig: Z = vertices reachable from unmatched A-vertices by alternating paths; cover = (A \ Z) + (B & Z)
+    std::vector<char> za(na, 0), zb(nbn, 0);
+    std::vector<int> stack;
+    for (int a = 0; a < na; ++a)
+        if (matchA[a] < 0) { za[a] = 1; stack.push_back(a); }
+    while (!stack.empty()) {
+        const int a = stack.back();
+        stack.pop_back();
+        for (int b : adj[a]) {
+            if (zb[b] || matchA[a] == b) continue;
+            zb[b] = 1;
+            const int a2 = matchB[b];
+            if (a2 >= 0 && !za[a2]) { za[a2] = 1; stack.push_back(a2); }
+        }
+    }
+    for (int a = 0; a < na; ++a)
+        if (!za[a]) cover.push_back(A[a]);
+    for (int b = 0; b < nbn; ++b)
+        if (zb[b]) cover.push_back(B[b]);
+}
+
 static int d6_analyse(gpn_ctx* c, bool allow_cells);
 int gpn_d6_ensure(gpn_ctx* c) {
     Dissect6& q = c->d6;
@@ -382,35 +447,64 @@ static int d6_analyse(gpn_ctx* c, bool allow_cells) {
     if (nlev < (forced > 0 ? 2 * K + 1 : 3 * K)) return 0;
     std::vector<int> cnt(nlev, 0);
     for (int v : queue) cnt[lev[v]]++;
+    // Cut k separates the levels <= l_k from the levels > l_k; l_k is the quantile level of the node count (optionally the thinnest cut in a
+    // window around it), and the separator itself is the
+    // minimum vertex cover of the edges between level l_k and l_k + 1 (level_cut_cover), not a whole boundary layer.
+    // Default: the separator of a cut is the set of nodes of level l_k with a neighbour in level l_k + 1.  GPNET_B200_D6_THIN=1 takes
+    // the minimum vertex cover of the edges between the two levels instead (level_cut_cover): 674 -> 562 separator nodes at N = 8192,
+    // but measured SLOWER with two lanes (647 against 672 evals/s, three A/B repetitions on one box; 520 against 515 with one lane),
+    // so it stays an experiment switch.
+    static const bool thin = getenv("GPNET_B200_D6_THIN") && atoi(getenv("GPNET_B200_D6_THIN")) == 1;
+    // levels searched on either side of the quantile level for a thinner cut: 0 by default -- at N = 8192 a shift by two levels
+    // (~400 nodes) unbalances the parts, and the longest part's chain costs more than the thinner separator saves (3 x 2 parts:
+    // window 2: separator 502, parts 1066..1698, 467 / 563 evals/s; window 0: see the default)
+    static const int window = getenv("GPNET_B200_D6_WINDOW") ? atoi(getenv("GPNET_B200_D6_WINDOW")) : 0;
+    std::vector<std::vector<int>> bylev(nlev);
+    for (int v : queue) bylev[lev[v]].push_back(v);
     std::vector<int> cuts;
+    std::vector<char> in_sep(N, 0);
     {
         int l = 0;
         long cum = 0;
+        std::vector<int> cover, best;
+        auto whole = [](int) { return true; };
         for (int k = 1; k < K; ++k) {
             const long target = (long)reached * k / K;
             while (l < nlev - 1 && cum + cnt[l] < target) cum += cnt[l++];
-            if (!cuts.empty() && l <= cuts.back() + 1) return 0;
-            if (l <= 0 || l >= nlev - 1) return 0;
-            cuts.push_back(l);
+            const int lo_ok = cuts.empty() ? 1 : cuts.back() + 2;
+            if (l < lo_ok || l <= 0 || l >= nlev - 1) return 0;
+            int lbest = l;
+            if (thin) level_cut_cover(c, lev, bylev[l], whole, l, best);
+            if (thin && forced <= 0) {
+                for (int dl = -window; dl <= window; ++dl) {
+                    const int lc = l + dl;
+                    if (dl == 0 || lc < lo_ok || lc <= 0 || lc >= nlev - 1) continue;
+                    level_cut_cover(c, lev, bylev[lc], whole, lc, cover);
+                    if (cover.size() < best.size()) { best = cover; lbest = lc; }
+                }
+            }
+            if (!thin) {      // round-2 first version: the boundary nodes of level l (those with a neighbour in level l + 1)
+                best.clear();
+                for (int v : bylev[l]) {
+                    bool up_nb = false;
+                    for (int e = c->h_indptr[v]; e < c->h_indptr[v + 1] && !up_nb; ++e) up_nb = lev[c->h_indices[e]] == l + 1;
+                    if (up_nb) best.push_back(v);
+                }
+            }
+            cuts.push_back(lbest);
+            for (int v : best) in_sep[v] = 1;
+            // the running count continues from the quantile level (the window may have moved the cut by up to two levels)
         }
     }
     // part of every node (unreached components join the last part: they have no edge to anything else); -1 = separator
     std::vector<int> part(N);
     for (int v = 0; v < N; ++v) {
         if (lev[v] < 0) { part[v] = K - 1; continue; }
+        if (in_sep[v]) { part[v] = -1; continue; }
         int p = 0;
-        bool on_cut = false;
-        for (int l : cuts) {
+        for (int l : cuts)
             if (lev[v] > l) ++p;
-            if (lev[v] == l) on_cut = true;
-        }
-        if (on_cut) {
-            bool up_nb = false;
-            for (int e = c->h_indptr[v]; e < c->h_indptr[v + 1] && !up_nb; ++e) up_nb = lev[c->h_indices[e]] == lev[v] + 1;
-            part[v] = up_nb ? -1 : p;           // no neighbour above: the node belongs to the part below
-        } else {
-            part[v] = p;
-        }
+        part[v] = p;
     }
     const int strips = K;
     if (cells > 1) {
@@ -450,35 +544,50 @@ static int d6_analyse(gpn_ctx* c, bool allow_cells) {
             if (nl2 < 3 * cells) { ok = false; break; }
             std::vector<int> cnt2(nl2, 0);
             for (int v : q2) cnt2[lev2[v]]++;
-            std::vector<int> cuts2;
+            std::vector<std::vector<int>> bylev2(nl2);
+            for (int v : q2) bylev2[lev2[v]].push_back(v);
+            auto in_strip = [&](int v) { return part[v] == p; };
+            std::vector<int> cuts2, cover, best;
+            std::vector<int> sep2;
             int l = 0;
             long cum = 0;
             for (int k = 1; k < cells && ok; ++k) {
                 const long target = (long)reached2 * k / cells;
                 while (l < nl2 - 1 && cum + cnt2[l] < target) cum += cnt2[l++];
-                if ((!cuts2.empty() && l <= cuts2.back() + 1) || l <= 0 || l >= nl2 - 1) ok = false;
-                else cuts2.push_back(l);
+                const int lo_ok = cuts2.empty() ? 1 : cuts2.back() + 2;
+                if (l < lo_ok || l <= 0 || l >= nl2 - 1) { ok = false; break; }
+                int lbest = l;
+                if (thin) {
+                    level_cut_cover(c, lev2, bylev2[l], in_strip, l, best);
+                    for (int dl = -window; dl <= window; ++dl) {
+                        const int lc = l + dl;
+                        if (dl == 0 || lc < lo_ok || lc <= 0 || lc >= nl2 - 1) continue;
+                        level_cut_cover(c, lev2, bylev2[lc], in_strip, lc, cover);
+                        if (cover.size() < best.size()) { best = cover; lbest = lc; }
+                    }
+                } else {
+                    best.clear();
+                    for (int v : bylev2[l]) {
+                        bool up_nb = false;
+                        for (int e = c->h_indptr[v]; e < c->h_indptr[v + 1] && !up_nb; ++e) {
+                            const int u = c->h_indices[e];
+                            up_nb = part[u] == p && lev2[u] == l + 1;
+                        }
+                        if (up_nb) best.push_back(v);
+                    }
+                }
+                cuts2.push_back(lbest);
+                sep2.insert(sep2.end(), best.begin(), best.end());
             }
             if (!ok) break;
             for (int v : nodes) {
                 if (lev2[v] < 0) { newpart[v] = p * cells + cells - 1; continue; }
                 int piece = 0;
-                bool on_cut = false;
-                for (int lc : cuts2) {
+                for (int lc : cuts2)
                     if (lev2[v] > lc) ++piece;
-                    if (lev2[v] == lc) on_cut = true;
-                }
-                if (on_cut) {
-                    bool up_nb = false;
-                    for (int e = c->h_indptr[v]; e < c->h_indptr[v + 1] && !up_nb; ++e) {
-                        const int u = c->h_indices[e];
-                        up_nb = part[u] == p && lev2[u] == lev2[v] + 1;
-                    }
-                    newpart[v] = up_nb ? -1 : p * cells + piece;
-                } else {
-                    newpart[v] = p * cells + piece;
-                }
+                newpart[v] = p * cells + piece;
             }
+            for (int v : sep2) newpart[v] = -1;
         }
         if (ok) {
             for (int v = 0; v < N; ++v) part[v] = part[v] < 0 ? -1 : newpart[v];
