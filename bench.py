@@ -521,6 +521,39 @@ def main():
                 "eval_conventional_tflops": algo / (ms_eval * 1e-3) * 1e-12,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "route": {"level": route, "parts": parts}}
+        if world == 1 and not args.no_extras:
+            # the SAME two kernels at flop-bound sizes, measured live: what the kernels reach when the work, not a dependency chain
+            # of a small factorisation, is the bound (M = I + 0.6 L~ of the C3 graph: a plain 8192 Cholesky; A A^T with lower tiles +
+            # mirrored store: one Pade product of the N = 8192 expm)
+            Nf = N
+            ldf = (Nf + 127) // 128 * 128
+            A_t = torch.zeros((ldf, ldf), dtype=torch.float64, device="cuda")
+            C_t = torch.zeros((ldf, ldf), dtype=torch.float64, device="cuda")
+            fb = {}
+            for what in ("potrf", "pade_product"):
+                best_ms = None
+                for rep in range(3):
+                    ctx.laplacian_dense(0.6 if what == "potrf" else -0.6, 1.0 if what == "potrf" else 0.0, A_t.data_ptr(), ldf)
+                    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    r0.record(stream)
+                    if what == "potrf":
+                        info_f = ctx.potrf(Nf, A_t.data_ptr(), ldf)
+                    else:
+                        ctx.syrk(Nf, Nf, 1.0, A_t.data_ptr(), ldf, 0.0, C_t.data_ptr(), ldf)
+                    r1.record(stream)
+                    torch.cuda.synchronize()
+                    ms = r0.elapsed_time(r1)
+                    best_ms = ms if best_ms is None else min(best_ms, ms)
+                T128 = (Nf + 127) // 128
+                fl = Nf ** 3 / 3.0 if what == "potrf" else 2.0 * 128 * 128 * Nf * (T128 * (T128 + 1) // 2)
+                fb[what] = {"n": Nf, "ms": best_ms, "tflops": fl / (best_ms * 1e-3) * 1e-12,
+                            "frac_of_measured_peak": fl / (best_ms * 1e-3) * 1e-12 / peak_tf if peak_tf else None,
+                            "flops": "n^3/3 (standard count)" if what == "potrf" else "executed: 2080 lower 128x128 tiles x K"}
+            roof["same_kernels_at_flop_bound_sizes"] = {
+                "potrf_dataflow_kernel, plain Cholesky": fb["potrf"], "gemm_f64_kernel, symmetric N x N x N product": fb["pade_product"],
+                "note": "best of 3, CUDA events on the launching stream; the timed step's launches are 1200-1300-row factorisations"}
+            del A_t, C_t
+            torch.cuda.empty_cache()
         if world == 1:
             # the same evaluation through the other exact routes (same outputs to rounding), device-timed like `value`
             routes = {}
