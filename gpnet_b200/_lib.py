@@ -36,6 +36,8 @@ SIGNATURES = {
     "gpn_spectral_enable": (None, [C.c_void_p, C.c_int]),
     "gpn_spectral_get": (C.c_int, [C.c_void_p, c_dbl_p, c_dbl_p]),
     "gpn_gpr_logp_grad_batch": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, C.c_int, c_dbl_p, C.c_int, c_dbl_p, c_int_p]),
+    "gpn_gpc_newton_batch": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, C.c_int, C.c_int, c_dbl_p, C.c_double, C.c_double, C.c_double, c_dbl_p,
+                                      c_int_p, c_int_p]),
     "gpn_profile_intervals": (C.c_int, [C.c_void_p, C.c_void_p, c_dbl_p, C.c_int, c_int_p]),
     "gpn_debug_leaf_prof": (None, [C.c_void_p, C.c_void_p]),
     "gpn_debug_scalars": (C.c_int, [C.c_void_p, c_dbl_p]),
@@ -383,6 +385,25 @@ class Context:
             return st, out, info
         self._check(st, "gpn_gpr_logp_grad_batch")
         return 0, out, info
+
+    def gpc_newton_batch(self, kind, thetas, y, tol=0.1, phif=1e100, scale=1.0):
+        """logq, Newton iteration counts and Cholesky infos of the Laplace loop for B log-parameter vectors in one launch."""
+        th = np.ascontiguousarray(np.exp(np.asarray(thetas, dtype=np.float64)))
+        if th.ndim != 2:
+            raise ValueError("thetas must be B x P")
+        B, P = th.shape
+        yy = _f64(y)
+        if len(yy) != self.n_train:
+            raise ValueError("len(y) != number of training nodes")
+        logq = np.zeros(B)
+        iters = np.zeros(B, dtype=np.int32)
+        info = np.zeros(B, dtype=np.int32)
+        st = self.lib.gpn_gpc_newton_batch(self.h, kind, _dp(th), B, P, _dp(yy), tol, phif, scale, _dp(logq), iters.ctypes.data_as(c_int_p),
+                                           info.ctypes.data_as(c_int_p))
+        if st in (-100, -101, -20):
+            return st, logq, iters, info
+        self._check(st, "gpn_gpc_newton_batch")
+        return 0, logq, iters, info
 
     def debug_scalars(self):
         out = np.zeros(32)

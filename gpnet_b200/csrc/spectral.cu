@@ -483,6 +483,250 @@ __global__ void __launch_bounds__(256) spectral_batch_kernel(SpecBatchArgs a) {
     }
 }
 
+
+// ---- batched small-n Laplace Newton loop (GPnetClassifier.NRiteration, GPnetClassifier.py:90-147) ------------------------------
+// One CTA per theta: K = V_t r(lam) V_t^T + c in shared memory, then the reference's loop line for line (the same statements as
+// gpc_newton in gp.cu): W, p, b from f; B = I + sqrtW K sqrtW; L = chol(B); a = scale (b - sqrtW (B^-1 (sqrtW (K b)))); f = K a;
+// phif from f^T K^-1 f (one Cholesky of K per theta; f^T a if K is not numerically positive definite), log det B and log p;
+// stop when sum (phif_old - phif)^2 < tol; logq = -a^T f / 2 - sum log(1 + log(1 + exp(y f))) - sum log diag L   (quirk A-10).
+// Shared memory: X[n][n+1]: K (lower), L_K (entry (i,j), j <= i, at X[j][i+1]);  Y[n][n+1]: B -> L_B (lower).
+struct SpecNewtonArgs {
+    int N, n, ldv, P, kind, B;
+    const double *Vt, *lam, *y, *thetas;
+    double tol, phif0, scale0;
+    double* logq;      // B
+    int* iters;        // B
+    int* info;         // B
+};
+
+// in-place lower Cholesky of the n x n matrix A (row stride ldx) by the whole CTA; returns 0 or the failing minor (uniform)
+__device__ __forceinline__ int cta_cholesky(double* A, int ldx, int n, int tid, int tx, int ty) {
+    for (int k = 0; k < n; ++k) {
+        const double d = A[(size_t)k * ldx + k];
+        if (!(d > 0.0)) return k + 1;
+        const double lkk = sqrt(d), inv = 1.0 / lkk;
+        __syncthreads();
+        for (int i = k + 1 + tid; i < n; i += 256) A[(size_t)i * ldx + k] *= inv;
+        if (tid == 0) A[(size_t)k * ldx + k] = lkk;
+        __syncthreads();
+        for (int i = k + 1 + ty; i < n; i += 16) {
+            const double lik = A[(size_t)i * ldx + k];
+            for (int j = k + 1 + tx; j <= i; j += 16) A[(size_t)i * ldx + j] -= lik * A[(size_t)j * ldx + k];
+        }
+        __syncthreads();
+    }
+    return 0;
+}
+// v <- L^-1 v (forward) for L lower in A;  TRANS_STORE: L[i][k] is read from A[k][i+1] (the packed upper half)
+template <bool TRANS_STORE>
+__device__ __forceinline__ void cta_forward(const double* A, int ldx, int n, double* v, int tid) {
+    for (int k = 0; k < n; ++k) {
+        __syncthreads();
+        const double lkk = TRANS_STORE ? A[(size_t)k * ldx + k + 1] : A[(size_t)k * ldx + k];
+        const double vk = v[k] / lkk;
+        __syncthreads();
+        if (tid == 0) v[k] = vk;
+        for (int i = k + 1 + tid; i < n; i += 256) v[i] -= (TRANS_STORE ? A[(size_t)k * ldx + i + 1] : A[(size_t)i * ldx + k]) * vk;
+    }
+    __syncthreads();
+}
+// v <- L^-T v (backward) for L lower in A
+__device__ __forceinline__ void cta_backward(const double* A, int ldx, int n, double* v, int tid) {
+    for (int k = n - 1; k >= 0; --k) {
+        __syncthreads();
+        const double vk = v[k] / A[(size_t)k * ldx + k];
+        __syncthreads();
+        if (tid == 0) v[k] = vk;
+        for (int j = tid; j < k; j += 256) v[j] -= A[(size_t)k * ldx + j] * vk;
+    }
+    __syncthreads();
+}
+// out = K x for the symmetric K held in the lower triangle of X
+__device__ __forceinline__ void cta_symv(const double* X, int ldx, int n, const double* x, double* out, int tid) {
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) s = fma(j <= i ? X[(size_t)i * ldx + j] : X[(size_t)j * ldx + i], x[j], s);
+        out[i] = s;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) spectral_newton_kernel(SpecNewtonArgs a) {
+    extern __shared__ double sm[];
+    const int n = a.n, ldx = n + 1, n4 = (n + 3) / 4 * 4;
+    double* X = sm;
+    double* Y = X + (size_t)n * ldx;
+    const size_t ysz = max((size_t)n * ldx, (size_t)KC * n4 + 2 * KC);
+    double* yv = Y + ysz;          // labels
+    double* f = yv + n4;
+    double* av = f + n4;
+    double* bv = av + n4;
+    double* pv = bv + n4;
+    double* sw = pv + n4;
+    double* tmp = sw + n4;
+    double* phif = tmp + n4;
+    double* red = phif + n4;       // 33 doubles
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int nb4 = n4 / 4, nlb = nb4 * (nb4 + 1) / 2;
+
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const double* th = a.thetas + (long)b * a.P;
+        const double th0 = th[0], noise = th[a.P - 1];
+        const int pw = (a.kind == GPN_KERNEL_PSTEP_WALK && a.P >= 2) ? (int)th[1] : 0;
+        __syncthreads();
+        for (int i = tid; i < n4; i += 256) { yv[i] = i < n ? a.y[i] : 0.0; f[i] = 0.0; }
+        // ---- K_tt on 4x4 register tiles of the lower triangle (see spectral_batch_kernel) ----
+        int bi[2], bj[2];
+        double accK[2][4][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = tid + 256 * u;
+            int i = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+            while ((long)i * (i + 1) / 2 > e) --i;
+            while ((long)(i + 1) * (i + 2) / 2 <= e) ++i;
+            bi[u] = e < nlb ? i : -1;
+            bj[u] = e - i * (i + 1) / 2;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) accK[u][x][y] = 0.0;
+        }
+        double* chunk = Y;
+        double* rk = Y + (size_t)KC * n4;
+        for (int k0 = 0; k0 < a.N; k0 += KC) {
+            __syncthreads();
+            const int kc = min(KC, a.N - k0);
+            for (int idx = tid; idx < KC * n4; idx += 256) {
+                const int kk = idx / n4, i = idx - kk * n4;
+                chunk[idx] = (kk < kc && i < n) ? a.Vt[(long)(k0 + kk) * a.ldv + i] : 0.0;
+            }
+            if (tid < KC) {
+                double r = 0.0, rd = 0.0;
+                if (tid < kc) spectral_weights(a.kind, a.lam[k0 + tid], th0, pw, r, rd);
+                rk[tid] = r;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (bi[u] < 0) continue;
+                const double* vi = chunk + 4 * bi[u];
+                const double* vj = chunk + 4 * bj[u];
+                for (int kk = 0; kk < KC; ++kk) {
+                    const double r = rk[kk];
+                    double xi[4], xj[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) { xi[x] = vi[kk * n4 + x]; xj[x] = vj[kk * n4 + x]; }
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const double ur = r * xi[x];
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) accK[u][x][y] = fma(ur, xj[y], accK[u][x][y]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (bi[u] < 0) continue;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int i = 4 * bi[u] + x, j = 4 * bj[u] + y;
+                    if (i < n && j <= i) {
+                        const double v = accK[u][x][y] + noise;       // kernel(train, train): noise on EVERY entry (A-3)
+                        X[(size_t)i * ldx + j] = v;
+                        Y[(size_t)i * ldx + j] = v;
+                    }
+                }
+        }
+        __syncthreads();
+        // ---- L_K = chol(K) (in Y), parked in the upper half of X; K not positive definite: q = f^T a instead ----
+        const int info_k = cta_cholesky(Y, ldx, n, tid, tx, ty);
+        __syncthreads();
+        if (info_k == 0)
+            for (int i = ty; i < n; i += 16)
+                for (int j = tx; j <= i; j += 16) X[(size_t)j * ldx + i + 1] = Y[(size_t)i * ldx + j];
+        __syncthreads();
+        // ---- Newton loop ----
+        double scale = a.scale0, logdet = 0.0;
+        int count = 0, iters = 0, fail = 0;
+        for (;;) {
+            ++count;
+            ++iters;
+            for (int i = tid; i < n; i += 256) {
+                const double fi = f[i];
+                const double e = exp(-fabs(fi));
+                const double d = 1.0 + e;
+                const double pi = (fi >= 0.0) ? 1.0 / d : e / d;
+                const double wi = e / (d * d);
+                pv[i] = pi;
+                sw[i] = sqrt(wi);
+                bv[i] = wi * fi + (0.5 * (yv[i] + 1.0) - pi);
+            }
+            __syncthreads();
+            for (int i = ty; i < n; i += 16)
+                for (int j = tx; j <= i; j += 16) Y[(size_t)i * ldx + j] = (i == j ? 1.0 : 0.0) + sw[i] * X[(size_t)i * ldx + j] * sw[j];
+            __syncthreads();
+            fail = cta_cholesky(Y, ldx, n, tid, tx, ty);
+            __syncthreads();
+            if (fail) break;
+            cta_symv(X, ldx, n, bv, tmp, tid);                                  // K b
+            for (int i = tid; i < n; i += 256) tmp[i] *= sw[i];
+            cta_forward<false>(Y, ldx, n, tmp, tid);
+            cta_backward(Y, ldx, n, tmp, tid);                                   // B^-1 (sqrtW K b)
+            for (int i = tid; i < n; i += 256) av[i] = scale * (bv[i] - sw[i] * tmp[i]);
+            cta_symv(X, ldx, n, av, f, tid);                                     // f = K a
+            double q;
+            if (info_k == 0) {
+                for (int i = tid; i < n; i += 256) tmp[i] = f[i];
+                cta_forward<true>(X, ldx, n, tmp, tid);                          // u = L_K^-1 f
+                double s = 0.0;
+                for (int i = tid; i < n; i += 256) s += tmp[i] * tmp[i];
+                q = block_sum_all(s, red);
+            } else {
+                double s = 0.0;
+                for (int i = tid; i < n; i += 256) s += f[i] * av[i];
+                q = block_sum_all(s, red);
+            }
+            double ld_ = 0.0;
+            for (int i = tid; i < n; i += 256) ld_ += log(Y[(size_t)i * ldx + i]);
+            logdet = block_sum_all(ld_, red);
+            const double common = -0.5 * q - 0.5 * logdet - 0.5 * n * LOG_2PI;
+            double cs = 0.0;
+            for (int i = tid; i < n; i += 256) {
+                const double v = log(pv[i]) + common;
+                const double old = iters == 1 ? a.phif0 : phif[i];
+                const double dd = old - v;
+                cs += dd * dd;
+                phif[i] = v;
+            }
+            const double conv = block_sum_all(cs, red);
+            if (conv < a.tol) break;
+            if (count > 100) { count = 0; scale *= 0.5; }
+            if (iters > 100000) { fail = -1; break; }
+        }
+        double af = 0.0, lik = 0.0;
+        if (!fail) {
+            for (int i = tid; i < n; i += 256) {
+                af += av[i] * f[i];
+                const double sv = -yv[i] * f[i];
+                lik += log(1.0 + log(1.0 + exp(-sv)));
+            }
+        }
+        af = block_sum_all(af, red);
+        lik = block_sum_all(lik, red);
+        if (tid == 0) {
+            a.info[b] = fail;
+            a.iters[b] = iters;
+            a.logq[b] = -0.5 * af - lik - logdet;
+        }
+        __syncthreads();
+    }
+}
+
 }   // namespace
 
 // =====================================================================================================================
@@ -601,6 +845,23 @@ int gpn_spec_build_kernel(gpn_ctx* c, int kind, double th0, int p, double* Kout,
     return 0;
 }
 
+// the training columns of V^T for the bound node set (once per node set): Vt[k][i] = VT[k][train_i]
+static int spec_training_columns(gpn_ctx* c) {
+    GPN_TRY(gpn_spec_prepare(c));
+    Spectral& sp = c->spec;
+    if (sp.vt_valid) return 0;
+    const int n = c->n_train, N = c->N;
+    const long ldN = pad128(N);
+    const int ldv = (n + 3) / 4 * 4;
+    GPN_TRY(gpn_buf_ensure(c, sp.Vt, sizeof(double) * (size_t)N * ldv));
+    dim3 grid(1, N);
+    gather_cols_kernel<<<grid, 128, 0, c->stream>>>(N, n, (const double*)sp.VT.p, ldN, (const int*)c->train_idx.p, (double*)sp.Vt.p, ldv);
+    c->launches++;
+    GPN_CK(cudaGetLastError());
+    sp.vt_valid = true;
+    return 0;
+}
+
 extern "C" {
 
 int gpn_spectral_prepare(gpn_ctx* c, int* sweeps_h, double* offdiag_rel_h) {
@@ -645,18 +906,9 @@ int gpn_gpr_logp_grad_batch(gpn_ctx* c, int kind, const double* thetas_h, int B,
         if (kind == GPN_KERNEL_PSTEP_WALK && !(thetas_h[(long)b * P] >= 2.0)) return -101;
     }
     GPN_CK(cudaSetDevice(c->device));
-    GPN_TRY(gpn_spec_prepare(c));
+    GPN_TRY(spec_training_columns(c));
     Spectral& sp = c->spec;
-    const long ldN = pad128(N);
     const int ldv = (n + 3) / 4 * 4;
-    if (!sp.vt_valid) {
-        GPN_TRY(gpn_buf_ensure(c, sp.Vt, sizeof(double) * (size_t)N * ldv));
-        dim3 grid(1, N);
-        gather_cols_kernel<<<grid, 128, 0, c->stream>>>(N, n, (const double*)sp.VT.p, ldN, (const int*)c->train_idx.p, (double*)sp.Vt.p, ldv);
-        c->launches++;
-        GPN_CK(cudaGetLastError());
-        sp.vt_valid = true;
-    }
     GPN_TRY(gpn_buf_ensure(c, sp.bt, sizeof(double) * (size_t)(n + 8)));
     GPN_TRY(gpn_buf_ensure(c, sp.bth, sizeof(double) * (size_t)B * P));
     GPN_TRY(gpn_buf_ensure(c, sp.bout, sizeof(double) * (size_t)B * (1 + P) + sizeof(int) * (size_t)B));
@@ -682,6 +934,56 @@ int gpn_gpr_logp_grad_batch(gpn_ctx* c, int kind, const double* thetas_h, int B,
     GPN_CK(cudaGetLastError());
     c->flops += (double)B * (want_grad ? 4.0 : 2.0) * 0.5 * n * (double)n * N;      // DFMA flops of the K / D accumulation (lower halves)
     GPN_TRY(sync_read(c, out_h, a.out, sizeof(double) * (size_t)B * (1 + P)));
+    GPN_TRY(sync_read(c, info_h, a.info, sizeof(int) * (size_t)B));
+    c->last_route = 7;
+    return 0;
+}
+
+int gpn_gpc_newton_batch(gpn_ctx* c, int kind, const double* thetas_h, int B, int P, const double* y_h, double tol, double phif0, double scale,
+                         double* logq_h, int* iters_h, int* info_h) {
+    GPN_RANGE();
+    if (!c) return -1;
+    if (B <= 0) return 0;
+    if (P < 1 || P > 8) return -5;
+    if (kind < 0 || kind > 2) return -2;
+    const int n = c->n_train, N = c->N;
+    if (n <= 0 || n > GPN_SPECTRAL_BATCH_MAX_N) return -20;
+    if (!y_h) return -6;
+    if (kind == GPN_KERNEL_PSTEP_WALK && P < 2) return -5;
+    for (int b = 0; b < B; ++b) {
+        if (kind == GPN_KERNEL_DIFFUSION && !(thetas_h[(long)b * P] < 1.0)) return -100;
+        if (kind == GPN_KERNEL_PSTEP_WALK && !(thetas_h[(long)b * P] >= 2.0)) return -101;
+    }
+    GPN_CK(cudaSetDevice(c->device));
+    GPN_TRY(spec_training_columns(c));
+    Spectral& sp = c->spec;
+    const int ldv = (n + 3) / 4 * 4, n4 = ldv;
+    GPN_TRY(gpn_buf_ensure(c, sp.bt, sizeof(double) * (size_t)(n + 8)));
+    GPN_TRY(gpn_buf_ensure(c, sp.bth, sizeof(double) * (size_t)B * P));
+    GPN_TRY(gpn_buf_ensure(c, sp.bout, sizeof(double) * (size_t)B + sizeof(int) * (size_t)B * 2 + 64));
+    GPN_TRY(sync_write(c, sp.bt.p, y_h, sizeof(double) * n));
+    GPN_TRY(sync_write(c, sp.bth.p, thetas_h, sizeof(double) * (size_t)B * P));
+    SpecNewtonArgs a;
+    a.N = N; a.n = n; a.ldv = ldv; a.P = P; a.kind = kind; a.B = B;
+    a.Vt = (const double*)sp.Vt.p; a.lam = (const double*)sp.lam.p; a.y = (const double*)sp.bt.p; a.thetas = (const double*)sp.bth.p;
+    a.tol = tol; a.phif0 = phif0; a.scale0 = scale;
+    a.logq = (double*)sp.bout.p;
+    a.iters = (int*)(a.logq + B);
+    a.info = a.iters + B;
+    const size_t ysz = std::max((size_t)n * (n + 1), (size_t)KC * n4 + 2 * KC);
+    const size_t smem = sizeof(double) * ((size_t)n * (n + 1) + ysz + 8 * (size_t)n4 + 40);
+    static size_t configured = 0;
+    if (smem > configured) {
+        GPN_CK(cudaFuncSetAttribute(spectral_newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int grid = std::min(B, 4 * c->num_sms);
+    spectral_newton_kernel<<<grid, 256, smem, c->stream>>>(a);
+    c->launches++;
+    GPN_CK(cudaGetLastError());
+    c->flops += (double)B * n * (double)n * N;
+    GPN_TRY(sync_read(c, logq_h, a.logq, sizeof(double) * (size_t)B));
+    GPN_TRY(sync_read(c, iters_h, a.iters, sizeof(int) * (size_t)B));
     GPN_TRY(sync_read(c, info_h, a.info, sizeof(int) * (size_t)B));
     c->last_route = 7;
     return 0;

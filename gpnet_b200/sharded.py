@@ -183,6 +183,19 @@ def evaluate_points(model, theta, axidx, ax1, ax2, indices, want_grad=False):
     classifier = not hasattr(model, "logPosterior_and_grad")
     from ._lib import Context
     n_train = len(model._positions(model.training_nodes))
+    if classifier and not want_grad and getattr(model._engine, "spectral", False) and 0 < n_train <= Context.SPECTRAL_BATCH_MAX_N and len(indices):
+        # the classifier's landscape: the Laplace Newton loop of every grid point of this rank in ONE launch, one CTA per point
+        n2 = len(ax2)
+        thetas = np.tile(th, (len(indices), 1))
+        for row, flat in enumerate(np.asarray(indices, dtype=np.int64)):
+            thetas[row, axidx[0]] = ax1[int(flat) // n2]
+            thetas[row, axidx[1]] = ax2[int(flat) % n2]
+        st, logq, iters, infos = _bound_context(model).gpc_newton_batch(KERNEL_IDS[model.kerneltype], thetas, _targets(model))
+        raise_domain(st)
+        out = np.zeros((len(indices), 1 + len(th)))
+        out[:, 0] = logq
+        out[infos != 0, 0] = np.nan          # np.linalg.cholesky raised inside the loop (gpn_landscape_points reports NaN too)
+        return out
     if not classifier and getattr(model._engine, "spectral", False) and 0 < n_train <= Context.SPECTRAL_BATCH_MAX_N and len(indices):
         # spectral path, small training set: all grid points of this rank in ONE launch, one CTA per point
         n2 = len(ax2)

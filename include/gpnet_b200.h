@@ -177,6 +177,12 @@ int gpn_spectral_get(gpn_ctx* ctx, double* lam_h, double* VT_h);
 #define GPN_SPECTRAL_BATCH_MAX_N 112
 int gpn_gpr_logp_grad_batch(gpn_ctx* ctx, int kind, const double* etheta_h, int B, int P, const double* t_h, int want_grad,
                             double* out_h, int* info_h);
+/* GPnetClassifier.NRiteration (GPnetClassifier.py:90-147; the loop GPnet.py:539-552 runs per grid point for a classifier) for B
+ * parameter vectors in ONE launch, one CTA per theta, same size limit and statuses as gpn_gpr_logp_grad_batch: y_h = the +-1
+ * labels of the training nodes, tol / phif0 / scale = the reference's defaults 0.1 / 1e100 / 1.0; logq_h[b], iters_h[b] (Newton
+ * iterations), info_h[b] (> 0: B not positive definite in some iteration, as np.linalg.cholesky raising inside the loop). */
+int gpn_gpc_newton_batch(gpn_ctx* ctx, int kind, const double* etheta_h, int B, int P, const double* y_h, double tol, double phif0,
+                         double scale, double* logq_h, int* iters_h, int* info_h);
 /* GPnetRegressor.predict body (:86-128).  Outputs (host): alpha[n], fstar[m], s[m] (sqrt of the predictive
  * variance), kss_diag[m]; info_h[0]: Cholesky info of k, info_h[1]: info of kstarstar (the two PD gates, A-7). */
 int gpn_gpr_predict(gpn_ctx* ctx, int kind, const double* etheta_h, int P, const double* t_h, double* alpha_h,

@@ -207,3 +207,53 @@ def test_training_sets_above_the_batch_limit_fall_back_to_the_lanes():
     for b, thb in enumerate([th, th + 0.05]):
         oval, ograd = orc.neg_logp_grad(thb, tr, t[tr])
         assert abs(vals[b] - oval) <= TOL * abs(oval) and nrel(grads[b], ograd) <= 1e-8
+
+
+@pytest.mark.parametrize("kt,th", [("diffusion", np.log([0.6, 0.1])), ("regularized_laplacian", np.log([0.6, 0.1])), ("pstep_walk", np.log([2.3, 4, 0.1]))])
+def test_batched_newton_loop_against_the_oracle_and_the_default_path(kt, th):
+    """GPnetClassifier.NRiteration for a batch of thetas in one launch (one CTA each): logq to 1e-9 and IDENTICAL Newton iteration
+    counts against the oracle's loop and against the default CUDA loop."""
+    import gpnet_b200
+    from gpnet_b200._lib import KERNEL_IDS
+    G, tr, te, y = cfg.ba_case(300, 100, 100)
+    ys = pd.Series(y[tr], index=tr)
+    m = gpnet_b200.GPnetClassifier(Graph=G, training_nodes=tr, test_nodes=te, theta=list(th), relabel_nodes=True, kerneltype=kt,
+                                   training_values=ys).use_spectral()
+    rng = np.random.RandomState(5)
+    thetas = [np.array(th, dtype=float)]
+    for _ in range(4):
+        d = rng.uniform(-0.4, 0.4, len(th))
+        if kt == "diffusion":
+            d[0] = -abs(d[0])
+        if kt == "pstep_walk":
+            d[0] = abs(d[0])
+        thetas.append(np.array(th) + d)
+    ctx = m._engine.bind(m._positions(tr), m._positions(te))
+    st, logq, iters, infos = ctx.gpc_newton_batch(KERNEL_IDS[kt], np.asarray(thetas), y[tr].astype(float))
+    assert st == 0 and np.all(infos == 0)
+    orc = go.OracleGP(G, kerneltype=kt, expm_mode="dense")
+    ref = gpnet_b200.GPnetClassifier(Graph=G, training_nodes=tr, test_nodes=te, theta=list(th), relabel_nodes=True, kerneltype=kt,
+                                     training_values=ys)
+    for b, thb in enumerate(thetas):
+        o_f, o_logq, o_a, o_iters = orc.newton(thb, tr, y[tr])[:4]
+        assert abs(logq[b] - o_logq) <= TOL * abs(o_logq), (kt, b, logq[b], o_logq)
+        assert int(iters[b]) == o_iters, (kt, b)
+        f, lq, a = ref.NRiteration(tr, ys, thb)
+        assert abs(logq[b] - float(lq[0, 0])) <= TOL * abs(logq[b]) and int(iters[b]) == ref.newton_iterations
+
+
+def test_classifier_landscape_through_the_batched_newton_loop():
+    import gpnet_b200
+    G, tr, te, y = cfg.ba_case(300, 100, 100)
+    ys = pd.Series(y[tr], index=tr)
+    th = np.log([0.6, 0.1])
+    ax1 = np.linspace(np.log(0.05), np.log(0.9), 6)
+    ax2 = np.linspace(np.log(0.01), np.log(1.0), 5)
+
+    def model(spectral):
+        m = gpnet_b200.GPnetClassifier(Graph=G, training_nodes=tr, test_nodes=te, theta=list(th), relabel_nodes=True, kerneltype="diffusion",
+                                       training_values=ys)
+        return m.use_spectral() if spectral else m
+    a = model(True).lml_landscape(list(th), [0, 1], ax1, ax2)
+    b = model(False).lml_landscape(list(th), [0, 1], ax1, ax2)
+    assert a.shape == (6, 5) and nrel(a, b) <= TOL
