@@ -164,3 +164,45 @@ def test_spectral_landscape_branch_builds_the_reference_loop_thetas():
         sharded._bound_context = orig
     assert np.array_equal(ctx.thetas, np.array([[0.1, -1.0], [0.2, -2.0], [0.3, -2.0]]))
     assert out[0, 0] == -1.0 and np.isposinf(out[1, 0]) and out[2, 0] == -3.0 and np.all(out[:, 1:] == 0.0)
+
+
+def test_spectral_landscape_branch_of_a_classifier_uses_the_batched_newton_loop():
+    """The classifier's landscape on the spectral path hands the same loop thetas to gpn_gpc_newton_batch and maps a failed
+    Cholesky inside the loop to NaN (like gpn_landscape_points)."""
+    from gpnet_b200 import sharded
+
+    class Ctx:
+        def gpc_newton_batch(self, kind, thetas, y):
+            self.thetas, self.y = np.array(thetas), np.array(y)
+            B = len(thetas)
+            info = np.zeros(B, dtype=np.int32)
+            info[2] = 5
+            return 0, -np.arange(1.0, B + 1.0), np.full(B, 4, dtype=np.int32), info
+
+    class Engine:
+        spectral = True
+
+    class Model:                                  # no logPosterior_and_grad attribute: a classifier
+        kerneltype = "regularized_laplacian"
+        training_nodes = list(range(6))
+        test_nodes = []
+        training_values = np.array([1, -1, 1, 1, -1, -1])
+        _engine = Engine()
+
+        def _theta_vec(self, th):
+            return np.asarray(th, dtype=float)
+
+        def _positions(self, nodes):
+            return list(nodes)
+
+    ctx = Ctx()
+    orig = sharded._bound_context
+    sharded._bound_context = lambda model: ctx
+    try:
+        out = sharded.evaluate_points(Model(), [0.0, 0.0], [1, 0], np.array([0.5, 0.6]), np.array([-1.0, -2.0, -3.0]), [0, 1, 5])
+    finally:
+        sharded._bound_context = orig
+    # axidx = [1, 0]: the first axis writes entry 1, the second entry 0
+    assert np.array_equal(ctx.thetas, np.array([[-1.0, 0.5], [-2.0, 0.5], [-3.0, 0.6]]))
+    assert np.array_equal(ctx.y, Model.training_values.astype(float))
+    assert out[0, 0] == -1.0 and out[1, 0] == -2.0 and np.isnan(out[2, 0]) and out.shape == (3, 3)
