@@ -324,6 +324,42 @@ def run_c4(ctx, stream, world, rank, local, reps, barrier, spectral=False, first
     return best, lml, best_ev
 
 
+def c1_batched_landscapes(ctx, local):
+    import pandas as pd
+    import torch
+    import gpnet_b200
+    from gpnet_b200.engine import register_context
+    from oracle import configs as cfg      # canonical synthetic inputs only
+    G, tr, te, t = cfg.grid_case(30, 30, 90, 810)
+    ax1 = np.linspace(np.log(0.01), np.log(0.99), 64)
+    ax2 = np.linspace(np.log(0.001), np.log(10.0), 64)
+    out = {"what": "C1: 30x30 grid, n = 90, diffusion kernel, 64x64 landscape over (theta0, noise) through lml_landscape with "
+                   "use_spectral(): regressor = gpn_gpr_logp_grad_batch, classifier = gpn_gpc_newton_batch (whole Laplace Newton loop per "
+                   "CTA); wall clock of the second landscape (the first pays for the eigendecomposition of L~)"}
+    with contextlib.redirect_stdout(sys.stderr):
+        reg = gpnet_b200.GPnetRegressor(Graph=G, training_nodes=tr, test_nodes=te, theta=list(np.log([0.6, 0.01])), relabel_nodes=True,
+                                        kerneltype="diffusion", training_values=False)
+        reg.set_training_values(pd.Series(t[tr], index=tr))
+        y = np.where(t > 0, 1, -1).astype(np.int64)
+        cls = gpnet_b200.GPnetClassifier(Graph=G, training_nodes=tr, test_nodes=te, theta=list(np.log([0.6, 0.1])), relabel_nodes=True,
+                                         kerneltype="diffusion", training_values=pd.Series(y[tr], index=tr))
+        register_context(ctx)
+        for name, m in (("regressor", reg), ("classifier", cls)):
+            m._engine.device = local
+            m.use_spectral()
+            m.lml_landscape([0.0, 0.0], [0, 1], ax1, ax2)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lml = m.lml_landscape([0.0, 0.0], [0, 1], ax1, ax2)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out[name] = {"landscape_ms": dt * 1e3, "us_per_point": dt / lml.size * 1e6, "points": int(lml.size),
+                         "finite_points": int(np.isfinite(lml).sum()), "jacobi_sweeps_and_offdiag_rel": list(m._engine.spectral_info or ())}
+            m.use_spectral(False)
+            m._engine.bind()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -649,6 +685,13 @@ def main():
                                                "max_rel_diff_vs_default_path": float(np.max(np.abs(lml_s[fin] - lml[fin]) / np.abs(lml[fin]))),
                                                "what": "use_spectral(): K = V exp(-beta lam) V^T from one GPU eigendecomposition (two-sided block "
                                                        "Jacobi) of the normalized Laplacian instead of one Pade expm per kernel group"}
+        if rank == 0 and world == 1:
+            # config C1 (30 x 30 grid, 90 training nodes): the launch-bound regime.  64 x 64 landscapes of the regressor and of the
+            # classifier through the drop-in classes on the spectral path: ONE launch, one CTA per grid point
+            try:
+                extras["c1_batched_landscapes"] = c1_batched_landscapes(ctx, local)
+            except Exception as e:      # evidence only: never lose the headline line over it
+                extras["c1_batched_landscapes"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
