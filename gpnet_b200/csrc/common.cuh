@@ -204,7 +204,8 @@ int gpn_winv_ensure(gpn_ctx* c, size_t bytes);
 // b_kmajor: B stored [N][K]; else [K][N].  Batched over `batch` problems with element strides sA/sB/sC.
 int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, long lda, bool a_kmajor, const double* B,
              long ldb, bool b_kmajor, double beta, double* C, long ldc, int flags, int batch = 1, long sA = 0,
-             long sB = 0, long sC = 0, double* CT = nullptr, long ldct = 0, long sCT = 0);   // CT: optional transposed copy
+             long sB = 0, long sC = 0, double* CT = nullptr, long ldct = 0, long sCT = 0,    // CT: optional transposed copy
+             int klo_shift = 0);   // GF_KLO_M relative to row m0 - klo_shift (trapezoidal op(A))
 
 // Cholesky (lower, in place, row-major), triangular inverse and SPD inverse.  info: device int (0 = ok).
 int gpn_potrf(gpn_ctx* c, int n, double* A, long lda, double* winv, int* d_info, int info_offset = 0);

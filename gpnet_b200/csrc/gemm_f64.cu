@@ -29,6 +29,7 @@ struct GemmArgs {
     double alpha, beta;
     int flags;
     int tiles_m, tiles_n;
+    int klo_shift;   // GF_KLO_M counts from m0 - klo_shift (>= 0): op(A)[m][k] == 0 for k < m - klo_shift (a trapezoidal operand)
 };
 
 // 8-consumer configuration: 12 warps = 2 consumer warpgroups + 1 producer warpgroup, registers rebalanced with
@@ -91,7 +92,7 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     const int m0 = tm * BM, n0 = tn * BN;
     int k_lo = 0, k_hi = g.K;
-    if (g.flags & GF_KLO_M) k_lo = max(k_lo, m0);
+    if (g.flags & GF_KLO_M) k_lo = max(k_lo, m0 - g.klo_shift);
     if (g.flags & GF_KLO_N) k_lo = max(k_lo, n0);
     if (g.flags & GF_KHI_M) k_hi = min(k_hi, m0 + BM);
     if (g.flags & GF_KHI_N) k_hi = min(k_hi, n0 + BN);
@@ -283,7 +284,7 @@ int launch_layout(gpn_ctx* c, bool ak, bool bk, const CUtensorMap& ta, const CUt
 
 int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, long lda, bool a_kmajor, const double* B, long ldb,
              bool b_kmajor, double beta, double* C, long ldc, int flags, int batch, long sA, long sB, long sC, double* CT, long ldct,
-             long sCT) {
+             long sCT, int klo_shift) {
     if (M <= 0 || N <= 0 || batch <= 0) return 0;
     if (K < 0) return -4;
     if ((flags & GF_LOWER) && M != N) return -2;
@@ -303,7 +304,7 @@ int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, lon
     if (flags & GF_FORCE_BIG) use_big = true;
     const int bm = use_big ? 128 : 64, bn = bm;
     GemmArgs a;
-    a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = ldc; a.sC = sC; a.CT = CT; a.ldct = ldct; a.sCT = sCT; a.alpha = alpha; a.beta = beta; a.flags = flags;
+    a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = ldc; a.sC = sC; a.CT = CT; a.ldct = ldct; a.sCT = sCT; a.alpha = alpha; a.beta = beta; a.flags = flags; a.klo_shift = klo_shift;
     a.tiles_m = use_big ? tm_b : tm_s;
     a.tiles_n = use_big ? tn_b : tn_s;
     const long ntiles = (use_big ? big : small) / batch;
@@ -316,7 +317,7 @@ int gpn_gemm(gpn_ctx* c, int M, int N, int K, double alpha, const double* A, lon
         for (int tm = 0; tm < a.tiles_m; ++tm)
             for (int tn = 0; tn < ((flags & GF_LOWER) ? tm + 1 : a.tiles_n); ++tn) {
                 int k_lo = 0, k_hi = K;
-                if (flags & GF_KLO_M) k_lo = k_lo > tm * bm ? k_lo : tm * bm;
+                if (flags & GF_KLO_M) k_lo = k_lo > tm * bm - klo_shift ? k_lo : tm * bm - klo_shift;
                 if (flags & GF_KLO_N) k_lo = k_lo > tn * bn ? k_lo : tn * bn;
                 if (flags & GF_KHI_M) k_hi = k_hi < (tm + 1) * bm ? k_hi : (tm + 1) * bm;
                 if (flags & GF_KHI_N) k_hi = k_hi < (tn + 1) * bn ? k_hi : (tn + 1) * bn;

@@ -1165,14 +1165,14 @@ int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double
             if (st == 0 && want_grad && kr > 0) {
                 // U_k[m][r] = sum_{j >= max(m, c0)} WT_k[m][j] G^T[r][j]: rows above c0 see the full range, the rest is triangular
                 double* Uk = U + (long)q.off[k] * lds;
-                if (c0 > 0) st = gpn_gemm(c, c0, s, kr, 1.0, WTk + c0, ld, true, GTk, ldg, true, 0.0, Uk, lds, GF_FORCE_BIG);
-                if (st == 0) st = gpn_gemm(c, kr, s, kr, 1.0, WTk + (long)c0 * ld + c0, ld, true, GTk, ldg, true, 0.0, Uk + (long)c0 * lds, lds, GF_KLO_M | GF_FORCE_BIG);
+                // ONE launch: the operand W_k^T[:, c0:] is trapezoidal (c0 is a multiple of the tile size: GF_KLO_M shifted by c0)
+                st = gpn_gemm(c, q.nk[k], s, kr, 1.0, WTk + c0, ld, true, GTk, ldg, true, 0.0, Uk, lds, GF_KLO_M | GF_FORCE_BIG, 1, 0, 0, 0, nullptr, 0, 0,
+                              c0);
                 if (st == 0 && so > 0 && kro > 0) {
                     double* Uok = Uo + (long)q.off[k] * ldso;
                     const double* GTok = GTo + q.off[k] + c0o;
-                    if (c0o > 0) st = gpn_gemm(c, c0o, so, kro, 1.0, WTk + c0o, ld, true, GTok, ldg, true, 0.0, Uok, ldso, GF_FORCE_BIG);
-                    if (st == 0) st = gpn_gemm(c, kro, so, kro, 1.0, WTk + (long)c0o * ld + c0o, ld, true, GTok, ldg, true, 0.0, Uok + (long)c0o * ldso, ldso,
-                                               GF_KLO_M | GF_FORCE_BIG);
+                    st = gpn_gemm(c, q.ok[k], so, kro, 1.0, WTk + c0o, ld, true, GTok, ldg, true, 0.0, Uok, ldso, GF_KLO_M | GF_FORCE_BIG, 1, 0, 0, 0, nullptr, 0,
+                                  0, c0o);
                 }
             }
             if (k > 0 && st == 0) {

@@ -22,6 +22,7 @@ for J in [int(x) for x in os.environ.get("LANES", "1,2,3,4,6").split(",")]:
             c.set_sm_budget(int(bud) if bud is not None else (c.num_sms() // J if J > 1 else 0))
         out, infos = evaluate_batch(ctxs, 1, thetas, None, True)       # warm-up
         torch.cuda.synchronize()
+        for c in ctxs: c.reset_counters()
         t0 = time.perf_counter()
         for _ in range(3):
             out, infos = evaluate_batch(ctxs, 1, thetas, None, True)
@@ -30,5 +31,5 @@ for J in [int(x) for x in os.environ.get("LANES", "1,2,3,4,6").split(",")]:
         if ref is None: ref = out
         bad = np.nonzero(np.max(np.abs(out-ref)/np.abs(ref), axis=1) > 1e-11)[0]
         print("  rows off:", bad.tolist(), "cols:", [int(np.argmax(np.abs(out[i]-ref[i])/np.abs(ref[i]))) for i in bad])
-        print(f"lanes={J} parts={K} route={ctxs[0].last_route()} evals/s={B/dt:.1f} ms/eval={dt/B*1e3:.3f} max_rel_diff_vs_first={np.max(np.abs(out-ref)/np.abs(ref)):.1e} infos={infos.max()}", flush=True)
+        print(f"lanes={J} parts={K} route={ctxs[0].last_route()} evals/s={B/dt:.1f} ms/eval={dt/B*1e3:.3f} max_rel_diff_vs_first={np.max(np.abs(out-ref)/np.abs(ref)):.1e} infos={infos.max()} gflop/eval={sum(c.flop_count() for c in ctxs) / (3 * B) * 1e-9:.2f} layout={ctxs[0].debug_d6_layout() if os.environ.get('LAYOUT') else ''}", flush=True)
         for c in ctxs: c.close()
