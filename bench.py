@@ -17,6 +17,8 @@ at every N so that the driver's scaling runs carry it.  Prints ONE JSON line; ra
 import os
 import sys
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # before CUDA is initialised: see gpnet_b200/__init__.py
+
 if "--impl" in sys.argv and "reference" in sys.argv:
     # the CPU arm runs single-process on ALL host cores: torchrun exports OMP_NUM_THREADS=1, undo that before numpy loads its BLAS
     for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
@@ -368,7 +370,7 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4"])
     ap.add_argument("--evals-per-step", type=int, default=80)
-    ap.add_argument("--lanes", type=int, default=2, help="evaluations in flight per GPU (contexts sharing the SMs)")
+    ap.add_argument("--lanes", type=int, default=3, help="evaluations in flight per GPU (contexts sharing the SMs)")
     ap.add_argument("--nodes", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -416,17 +418,17 @@ def main():
     G, csr, train, test, t = problem
     P = len(THETA)
     kind = KERNEL_IDS[KERNEL]
-    from gpnet_b200.engine import evaluate_batch
+    from gpnet_b200.engine import evaluate_batch, lane_sm_budget
     J = max(args.lanes, 1)
-    # J lanes = J contexts bound to the same graph, each with 1/J of the SMs for its co-resident factorisation kernels: one
-    # evaluation is bound by its dependency chains and leaves SMs idle, two in flight fill them (measured: 401 -> 513 evals/s;
-    # four lanes lose again: the factorisations turn flop-bound on a quarter of the chip)
+    # J lanes = J contexts bound to the same graph, each with an SM budget for its co-resident factorisation kernels: one
+    # evaluation is bound by its dependency chains and leaves SMs idle, three in flight fill them (measured: 1 / 2 / 3 / 4 lanes:
+    # 569 / 733 / 820 / 784 evals/s; engine.lane_sm_budget has the budget sweep)
     ctxs = [ctx] + [Context(local) for _ in range(J - 1)]
     for cx in ctxs:
         cx.set_graph(*csr)
         cx.set_nodes(train, test)
         cx.set_targets(t[train])
-        cx.set_sm_budget(ctx.num_sms() // J if J > 1 else 0)
+        cx.set_sm_budget(lane_sm_budget(ctx.num_sms(), J))
     thetas = multistart_thetas(rank, B)
     results = np.zeros((K, B, 1 + P))
     gathered = torch.zeros((world, K * B * (1 + P)), dtype=torch.float64, device="cuda") if world > 1 else None

@@ -184,6 +184,9 @@ struct gpn_ctx {
     long flags_rowsK[D6_SLOTS] = {0};
     cudaStream_t side[D6_SLOTS] = {nullptr};
     cudaEvent_t ev_side[D6_SLOTS] = {nullptr};
+    // a second stream per part: the U_k products run beside the G_k^T G_k products of the same part (both only need G_k)
+    cudaStream_t side2[D6_SLOTS] = {nullptr};
+    cudaEvent_t ev_g[D6_SLOTS] = {nullptr}, ev_u[D6_SLOTS] = {nullptr};
     Spectral spec;
     Dissect6 d6;
     int d6_parts = 0;                    // > 0: number of parts forced by gpn_set_dissection_parts (0: chosen from N)

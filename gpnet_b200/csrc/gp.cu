@@ -1048,6 +1048,14 @@ int reglap_inverse_oo_dissected(gpn_ctx* c, double* M, long ld, int* info_slot_u
 // forms and the gradient traces come from log det / tr(inverse) / two solves with M and M_oo, which K concurrent augmented
 // factorisations [M_kk; I] (one per part) and the small separator complements T, T_o deliver.
 // ---------------------------------------------------------------------------------------------------------------------
+int d6_second_stream(gpn_ctx* c, int k) {
+    if (!c->side2[k]) {
+        GPN_CK(cudaStreamCreateWithFlags(&c->side2[k], cudaStreamNonBlocking));
+        GPN_CK(cudaEventCreateWithFlags(&c->ev_g[k], cudaEventDisableTiming));
+        GPN_CK(cudaEventCreateWithFlags(&c->ev_u[k], cudaEventDisableTiming));
+    }
+    return 0;
+}
 int d6_side_stream(gpn_ctx* c, int k) {
     if (!c->side[k]) {
         GPN_CK(cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking));
@@ -1138,6 +1146,7 @@ int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double
             if (caps[k] > cap_min) { --caps[k]; --used; }
         GPN_CK(cudaEventRecord(c->ev_fork, main_stream));
         int st = 0;
+        bool forked_u[D6_MAXP] = {false};
         for (int k = 0; k < K && st == 0; ++k) {
             if (k > 0) {
                 st = d6_side_stream(c, k);
@@ -1153,6 +1162,39 @@ int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double
             // G_k is zero above row c0 of the part (interior nodes come first): every product below starts there
             const int c0 = q.c0[k], kr = q.nk[k] - c0, c0o = std::min(c0, q.ok[k]), kro = q.ok[k] - c0o;
             const double* GTk = GT + q.off[k] + c0;
+            bool u_forked = false;
+            if (st == 0 && want_grad && kr > 0) {
+                // U_k = W_k^T G_k (and its other-node counterpart) on the part's SECOND stream, beside the G_k^T G_k products below:
+                // both only need G_k, and a launch of 20-70 tiles of ~115 us leaves most of the chip to the other one
+                cudaStream_t part_stream = c->stream;
+                st = d6_second_stream(c, k);
+                if (st == 0) {
+                    cudaError_t e = cudaEventRecord(c->ev_g[k], part_stream);
+                    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->side2[k], c->ev_g[k], 0);
+                    if (e != cudaSuccess) st = GPN_CUDA_ERR(e);
+                }
+                if (st == 0) {
+                    c->stream = c->side2[k];
+                    // U_k[m][r] = sum_{j >= max(m, c0)} WT_k[m][j] G^T[r][j]: ONE launch, the operand W_k^T[:, c0:] is trapezoidal (c0 is a
+                    // multiple of the tile size: GF_KLO_M shifted by c0)
+                    double* Uk = U + (long)q.off[k] * lds;
+                    st = gpn_gemm(c, q.nk[k], s, kr, 1.0, WTk + c0, ld, true, GTk, ldg, true, 0.0, Uk, lds, GF_KLO_M | GF_FORCE_BIG, 1, 0, 0, 0, nullptr, 0,
+                                  0, c0);
+                    if (st == 0 && so > 0 && kro > 0) {
+                        double* Uok = Uo + (long)q.off[k] * ldso;
+                        const double* GTok = GTo + q.off[k] + c0o;
+                        st = gpn_gemm(c, q.ok[k], so, kro, 1.0, WTk + c0o, ld, true, GTok, ldg, true, 0.0, Uok, ldso, GF_KLO_M | GF_FORCE_BIG, 1, 0, 0, 0,
+                                      nullptr, 0, 0, c0o);
+                    }
+                    if (st == 0) {
+                        cudaError_t e = cudaEventRecord(c->ev_u[k], c->side2[k]);
+                        if (e != cudaSuccess) st = GPN_CUDA_ERR(e);
+                        else u_forked = true;
+                    }
+                    c->stream = part_stream;
+                }
+            }
+            forked_u[k] = u_forked;
             double *Cb = (double*)q.work[7].p + (size_t)k * lds * lds, *Cbo = (double*)q.work[8].p + (size_t)k * ldso * ldso;
             if (st == 0) {
                 if (kr > 0) st = gpn_gemm(c, s, s, kr, 1.0, GTk, ldg, true, GTk, ldg, true, 0.0, Cb, lds, GF_LOWER | GF_FORCE_BIG);
@@ -1161,19 +1203,6 @@ int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double
             if (st == 0 && so > 0) {
                 if (kro > 0) st = gpn_gemm(c, so, so, kro, 1.0, GTo + q.off[k] + c0o, ldg, true, GTo + q.off[k] + c0o, ldg, true, 0.0, Cbo, ldso, GF_LOWER | GF_FORCE_BIG);
                 else st = gpn_k_fill_zero(c, Cbo, ldso, so, (int)ldso);
-            }
-            if (st == 0 && want_grad && kr > 0) {
-                // U_k[m][r] = sum_{j >= max(m, c0)} WT_k[m][j] G^T[r][j]: rows above c0 see the full range, the rest is triangular
-                double* Uk = U + (long)q.off[k] * lds;
-                // ONE launch: the operand W_k^T[:, c0:] is trapezoidal (c0 is a multiple of the tile size: GF_KLO_M shifted by c0)
-                st = gpn_gemm(c, q.nk[k], s, kr, 1.0, WTk + c0, ld, true, GTk, ldg, true, 0.0, Uk, lds, GF_KLO_M | GF_FORCE_BIG, 1, 0, 0, 0, nullptr, 0, 0,
-                              c0);
-                if (st == 0 && so > 0 && kro > 0) {
-                    double* Uok = Uo + (long)q.off[k] * ldso;
-                    const double* GTok = GTo + q.off[k] + c0o;
-                    st = gpn_gemm(c, q.ok[k], so, kro, 1.0, WTk + c0o, ld, true, GTok, ldg, true, 0.0, Uok, ldso, GF_KLO_M | GF_FORCE_BIG, 1, 0, 0, 0, nullptr, 0,
-                                  0, c0o);
-                }
             }
             if (k > 0 && st == 0) {
                 cudaError_t e = cudaEventRecord(c->ev_side[k], c->side[k]);
@@ -1184,6 +1213,8 @@ int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double
         c->potrf_grid_cap = 0;
         if (st != 0) return st;
         for (int k = 1; k < K; ++k) GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_side[k], 0));
+        for (int k = 0; k < K; ++k)
+            if (forked_u[k]) GPN_CK(cudaStreamWaitEvent(c->stream, c->ev_u[k], 0));
     }
     mark("parts: factor, G, U");
     GPN_TRY(gpn_d6_factor_reduce(c, M, WT, ld, dscal(c, 5)));
@@ -1946,6 +1977,9 @@ void gpn_destroy(gpn_ctx* c) {
         for (int k = 0; k < D6_SLOTS; ++k) {
             if (c->side[k]) { cudaStreamSynchronize(c->side[k]); cudaStreamDestroy(c->side[k]); }
             if (c->ev_side[k]) cudaEventDestroy(c->ev_side[k]);
+            if (c->side2[k]) { cudaStreamSynchronize(c->side2[k]); cudaStreamDestroy(c->side2[k]); }
+            if (c->ev_g[k]) cudaEventDestroy(c->ev_g[k]);
+            if (c->ev_u[k]) cudaEventDestroy(c->ev_u[k]);
         }
     }
     if (c->pinned) cudaFreeHost(c->pinned);

@@ -102,6 +102,18 @@ def invalidate_predict(ctx):
                 ctx._predict_token = None
 
 
+def lane_sm_budget(num_sms: int, lanes: int) -> int:
+    """SMs each of ``lanes`` concurrent contexts may fill with co-resident factorisation kernels (0: the whole chip).  An even split
+    for two lanes; from three lanes on a mild over-subscription (40 % of the chip each: a cooperative launch that does not fit
+    simply waits) measured best at C3: 3 lanes with 40 / 49 / 60 / 74 SMs: 738 / 804 / 820 / 817 evals/s; 2 lanes with 60 / 74 / 90:
+    689 / 733 / 730; 4 lanes with 37 / 49 / 60: 702 / 762 / 784."""
+    if lanes <= 1:
+        return 0
+    if lanes == 2:
+        return num_sms // 2
+    return max(num_sms // lanes, (2 * num_sms) // 5)
+
+
 def evaluate_batch(ctxs, kind: int, thetas, t, want_grad=True):
     """(-logp, -grad) rows and Cholesky infos for a batch of independent log-parameter vectors, dealt round robin to the
     lane contexts ``ctxs`` (all bound to the same graph / node sets): every lane always has one evaluation in flight, so on
@@ -161,7 +173,7 @@ class GraphEngine:
                 lane.set_graph(self.indptr, self.indices, self.weights)
                 lane.set_nodes(train_pos, test_pos or ())
             self._lanes_key = key
-        share = ctx.num_sms() // count if count > 1 else 0
+        share = lane_sm_budget(ctx.num_sms(), count)
         for lane in [ctx] + extra:
             lane.set_sm_budget(share)
         return [ctx] + extra

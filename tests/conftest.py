@@ -2,6 +2,8 @@ import glob
 import os
 import sys
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # before CUDA is initialised: see gpnet_b200/__init__.py
+
 import numpy as np
 import pytest
 

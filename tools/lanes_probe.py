@@ -1,5 +1,6 @@
 """Throughput of batches of independent logp+grad evaluations at C3 with J concurrent lanes (contexts sharing the chip)."""
 import os, sys, time
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
