@@ -1163,7 +1163,16 @@ int gpr_reglap_d6_enqueue(gpn_ctx* c, const double* theta_h, int P, const double
             const int c0 = q.c0[k], kr = q.nk[k] - c0, c0o = std::min(c0, q.ok[k]), kro = q.ok[k] - c0o;
             const double* GTk = GT + q.off[k] + c0;
             bool u_forked = false;
-            if (st == 0 && want_grad && kr > 0) {
+            static const bool second = !(getenv("GPNET_B200_D6_SECOND") && atoi(getenv("GPNET_B200_D6_SECOND")) == 0);
+            if (st == 0 && want_grad && kr > 0 && !second) {      // A/B switch: the U products behind the G^T G products on the part's stream
+                double* Uk = U + (long)q.off[k] * lds;
+                st = gpn_gemm(c, q.nk[k], s, kr, 1.0, WTk + c0, ld, true, GTk, ldg, true, 0.0, Uk, lds, GF_KLO_M | GF_FORCE_BIG, 1, 0, 0, 0, nullptr, 0, 0,
+                              c0);
+                if (st == 0 && so > 0 && kro > 0)
+                    st = gpn_gemm(c, q.ok[k], so, kro, 1.0, WTk + c0o, ld, true, GTo + q.off[k] + c0o, ldg, true, 0.0, Uo + (long)q.off[k] * ldso, ldso,
+                                  GF_KLO_M | GF_FORCE_BIG, 1, 0, 0, 0, nullptr, 0, 0, c0o);
+            }
+            if (st == 0 && want_grad && kr > 0 && second) {
                 // U_k = W_k^T G_k (and its other-node counterpart) on the part's SECOND stream, beside the G_k^T G_k products below:
                 // both only need G_k, and a launch of 20-70 tiles of ~115 us leaves most of the chip to the other one
                 cudaStream_t part_stream = c->stream;
