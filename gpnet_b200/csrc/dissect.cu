@@ -450,14 +450,14 @@ static int d6_analyse(gpn_ctx* c, bool allow_cells) {
     // Cut k separates the levels <= l_k from the levels > l_k; l_k is the quantile level of the node count (optionally the thinnest cut in a
     // window around it), and the separator itself is the
     // minimum vertex cover of the edges between level l_k and l_k + 1 (level_cut_cover), not a whole boundary layer.
-    // Default: the separator of a cut is the set of nodes of level l_k with a neighbour in level l_k + 1.  GPNET_B200_D6_THIN=1 takes
-    // the minimum vertex cover of the edges between the two levels instead (level_cut_cover): 674 -> 562 separator nodes at N = 8192,
-    // but measured SLOWER with two lanes (647 against 672 evals/s, three A/B repetitions on one box; 520 against 515 with one lane),
-    // so it stays an experiment switch.
-    static const bool thin = getenv("GPNET_B200_D6_THIN") && atoi(getenv("GPNET_B200_D6_THIN")) == 1;
+    // The separator of a cut is the minimum vertex cover of the edges between level l_k and level l_k + 1 (level_cut_cover), not the
+    // whole boundary layer of level l_k (GPNET_B200_D6_THIN=0: the first round-2 version): 674 -> 562 separator nodes and 26.8 ->
+    // 24.1 GFLOP per evaluation at N = 8192; 822 -> 875 evals/s with three lanes, 569 -> 588 with one (with 8 hardware queues it had
+    // measured slower, like every configuration with more concurrent work).
+    static const bool thin = !(getenv("GPNET_B200_D6_THIN") && atoi(getenv("GPNET_B200_D6_THIN")) == 0);
     // levels searched on either side of the quantile level for a thinner cut: 0 by default -- at N = 8192 a shift by two levels
     // (~400 nodes) unbalances the parts, and the longest part's chain costs more than the thinner separator saves (3 x 2 parts:
-    // window 2: separator 502, parts 1066..1698, 467 / 563 evals/s; window 0: see the default)
+    // window 2: separator 502 but parts of 1066..1698 nodes)
     static const int window = getenv("GPNET_B200_D6_WINDOW") ? atoi(getenv("GPNET_B200_D6_WINDOW")) : 0;
     std::vector<std::vector<int>> bylev(nlev);
     for (int v : queue) bylev[lev[v]].push_back(v);
