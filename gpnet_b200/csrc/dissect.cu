@@ -455,10 +455,12 @@ static int d6_analyse(gpn_ctx* c, bool allow_cells) {
     // 24.1 GFLOP per evaluation at N = 8192; 822 -> 875 evals/s with three lanes, 569 -> 588 with one (with 8 hardware queues it had
     // measured slower, like every configuration with more concurrent work).
     static const bool thin = !(getenv("GPNET_B200_D6_THIN") && atoi(getenv("GPNET_B200_D6_THIN")) == 0);
-    // levels searched on either side of the quantile level for a thinner cut: 0 by default -- at N = 8192 a shift by two levels
-    // (~400 nodes) unbalances the parts, and the longest part's chain costs more than the thinner separator saves (3 x 2 parts:
-    // window 2: separator 502 but parts of 1066..1698 nodes)
-    static const int window = getenv("GPNET_B200_D6_WINDOW") ? atoi(getenv("GPNET_B200_D6_WINDOW")) : 0;
+    // Levels searched on either side of the quantile level for the THINNEST cut (smallest vertex cover), as long as the cut stays within
+    // 20 % of a part's node count of the quantile: the work of the separator phase and of the per-part products falls with the
+    // separator (N = 8192: 562 -> 502 nodes, 24.1 -> 21.8 GFLOP per evaluation), which is what counts once three evaluations in flight
+    // fill the chip (873 -> 926 evals/s); a single evaluation alone is bound by its longest part instead (parts of 1066..1698 nodes
+    // instead of 1212..1356) and pays for it.  GPNET_B200_D6_WINDOW=0 keeps the balanced cuts.
+    static const int window = getenv("GPNET_B200_D6_WINDOW") ? atoi(getenv("GPNET_B200_D6_WINDOW")) : 2;
     std::vector<std::vector<int>> bylev(nlev);
     for (int v : queue) bylev[lev[v]].push_back(v);
     std::vector<int> cuts;
@@ -479,6 +481,9 @@ static int d6_analyse(gpn_ctx* c, bool allow_cells) {
                 for (int dl = -window; dl <= window; ++dl) {
                     const int lc = l + dl;
                     if (dl == 0 || lc < lo_ok || lc <= 0 || lc >= nlev - 1) continue;
+                    long below = 0;
+                    for (int x = 0; x < lc; ++x) below += cnt[x];
+                    if (std::labs(below - target) * 5 > reached / K) continue;          // keep the parts within 20 % of their share
                     level_cut_cover(c, lev, bylev[lc], whole, lc, cover);
                     if (cover.size() < best.size()) { best = cover; lbest = lc; }
                 }
@@ -562,6 +567,9 @@ static int d6_analyse(gpn_ctx* c, bool allow_cells) {
                     for (int dl = -window; dl <= window; ++dl) {
                         const int lc = l + dl;
                         if (dl == 0 || lc < lo_ok || lc <= 0 || lc >= nl2 - 1) continue;
+                        long below = 0;
+                        for (int x = 0; x < lc; ++x) below += cnt2[x];
+                        if (std::labs(below - target) * 5 > reached2 / cells) continue;
                         level_cut_cover(c, lev2, bylev2[lc], in_strip, lc, cover);
                         if (cover.size() < best.size()) { best = cover; lbest = lc; }
                     }
