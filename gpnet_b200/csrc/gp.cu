@@ -1975,6 +1975,12 @@ void gpn_destroy(gpn_ctx* c) {
     for (auto& b : c->nb)
         if (b.p) cudaFree(b.p);
     {
+        Spectral& sp = c->spec;
+        DevBuf* spb[] = {&sp.VT, &sp.lam, &sp.rbuf, &sp.Vt, &sp.bt, &sp.bth, &sp.bout};
+        for (DevBuf* b : spb)
+            if (b->p) cudaFree(b->p);
+    }
+    {
         Dissect6& q = c->d6;
         DevBuf* d6b[] = {&q.indptr, &q.indices, &q.weights, &q.dinv, &q.trank, &q.sep_ptr, &q.sep_idx, &q.sep_w, &q.sep_pp};
         for (DevBuf* b : d6b)
