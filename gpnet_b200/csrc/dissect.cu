@@ -391,20 +391,21 @@ static int d6_analyse(gpn_ctx* c, bool allow_cells) {
     // Parts = `strips` BFS strips of the whole graph, each cut again into `cells` pieces by the level sets of a BFS INSIDE the strip
     // (its levels run along the strip): on a planar-like graph the separator of a strips x cells grid of ~N / (strips cells)-node
     // parts is hardly larger than that of strips x 1, while the dependency chain of a part's factorisation shrinks with its size:
-    // N = 8192: 5 x 1 parts of ~1500 nodes + 870 separator nodes = 13 + 7 tile columns on the critical path, 3 x 2 parts of ~1250
-    // + 674 = 10 + 6 (and a separator phase with 0.6 of the flops).  Forced part counts (tests, GPNET_B200_D6_PARTS) are plain strips.
+    // N = 8192: 5 x 1 parts of ~1500 nodes + 870 separator nodes = 13 + 7 tile columns on the critical path, 4 x 2 parts of ~950
+    // + 636 = 8-10 + 5 (and half of the flops).  Forced part counts (tests, GPNET_B200_D6_PARTS) are plain strips.
     static const int cells_env = getenv("GPNET_B200_D6_CELLS") ? atoi(getenv("GPNET_B200_D6_CELLS")) : -1;
     int K, cells = 1;
     if (forced > 0) {
         K = forced;
     } else {
-        // ~1350 nodes per part, two pieces per strip when that gives at least four parts.  Measured at N = 8192 (evals/s with one /
-        // two lanes): strips x cells = 5x1: 433 / 575, 4x1: 403 / 528, 2x2: 420 / 553, 2x3: 494 / 638, 3x2: 516 / 674 (default),
-        // 4x2: 517 / 466, 2x4: 535 / 483, 3x3: 398 / 455, 4x3: 399 / 432 -- smaller parts shorten the chains but every extra cut adds
-        // separator nodes, and the separator's work grows with its square; many small parts also starve two lanes of SMs
-        const int want = std::max(2, (N + 675) / 1350);
+        // ~1000 nodes per part, two pieces per strip when that gives at least four parts.  Measured at N = 8192 with the final separator
+        // rule and 32 hardware queues (evals/s with one / three lanes): strips x cells = 3x2: 610 / 907, 2x3: 580 / 916, 4x2: 657 / 981
+        // (default), 3x3: 635 / 931, 5x2: 600 / 837, 4x3: 622 / 834, 6x2: 553 / 758 -- smaller parts shorten the chains, but every extra
+        // cut adds separator nodes, and the separator's work grows with its square
+        const int want = std::max(2, (N + 512) / 1024);
         cells = want >= 4 ? 2 : 1;
         K = std::max(2, (int)std::lround((double)want / cells));
+        if (cells > 1 && K * cells > D6_MAXP) K = D6_MAXP / cells;
         static const int strips_env = getenv("GPNET_B200_D6_STRIPS") ? atoi(getenv("GPNET_B200_D6_STRIPS")) : -1;
         if (strips_env >= 2) K = strips_env;
         if (cells_env >= 1) cells = cells_env;

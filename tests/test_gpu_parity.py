@@ -510,7 +510,7 @@ def test_c3_full_size_logp_and_gradient_against_oracle(c3_case, level):
             assert parts[0] == 2 and min(parts[2:4]) >= 512 and 0 < parts[1] <= min(parts[2:4]) // 2
         if level == 6:
             K = parts[0]
-            assert K >= 4 and min(parts[2:2 + K]) >= 1024 and sum(parts[1:2 + K]) == 8192 and parts[1] < 1024
+            assert K >= 4 and min(parts[2:2 + K]) >= 256 and sum(parts[1:2 + K]) == 8192 and parts[1] < 1024
 
 
 @pytest.mark.parametrize("N,n,seed", [(4096, 1500, 1), (5000, 2500, 2), (6000, 2000, 3)])
