@@ -369,7 +369,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4"])
-    ap.add_argument("--evals-per-step", type=int, default=96)
+    ap.add_argument("--evals-per-step", type=int, default=120)
     ap.add_argument("--lanes", type=int, default=3, help="evaluations in flight per GPU (contexts sharing the SMs)")
     ap.add_argument("--nodes", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
