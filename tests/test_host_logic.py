@@ -334,3 +334,14 @@ def test_allgather_world_size_2_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out.decode()
+
+
+def test_lane_sm_budgets():
+    """SM budget per lane (engine.lane_sm_budget): whole chip for one lane, an even split for two, a mild over-subscription
+    (40 % each) from three lanes on -- never less than the even share."""
+    from gpnet_b200.engine import lane_sm_budget
+    assert lane_sm_budget(148, 1) == 0 and lane_sm_budget(148, 0) == 0
+    assert lane_sm_budget(148, 2) == 74
+    assert lane_sm_budget(148, 3) == 59 and lane_sm_budget(148, 4) == 59
+    for lanes in range(2, 9):
+        assert lane_sm_budget(148, lanes) >= 148 // lanes
